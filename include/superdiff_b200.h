@@ -1,0 +1,198 @@
+/* superdiff_b200 — C ABI of the B200-native SuperDiff sampling path.
+ *
+ * The reference (mo-rsa24/super-diffusion) is pure Python and has no FFI
+ * layer; the seams this library plugs into are its Python closures
+ * (SURVEY.md §8b).  Each entry point names the reference code whose per-step
+ * body it replaces.  Conventions:
+ *   - every pointer is a BORROWED DEVICE pointer unless the name ends in
+ *     `_host`; the caller (PyTorch) owns all memory;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*),
+ *     never synchronise the device, and may be captured into a CUDA graph;
+ *   - return value: 0 on success, negative error code otherwise
+ *     (SD_ERR_*); sd_last_error() returns a thread-local message;
+ *   - stateless and re-entrant.  There is NO CPU fallback: without an
+ *     sm_100 device the launch fails and the error code says so.
+ */
+#ifndef SUPERDIFF_B200_H_
+#define SUPERDIFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SD_OK 0
+#define SD_ERR_INVALID_ARG (-1)
+#define SD_ERR_UNSUPPORTED (-2)
+#define SD_ERR_CUDA (-3)
+
+#define SD_MAX_MODELS 8
+
+/* how the mixing weights kappa_j (sum_j kappa_j = 1) are chosen */
+enum sd_mode {
+  SD_MODE_OR = 0,    /* softmax_j(T*(logq_j + logp_j)): cifar/dynamics.py:124 (T=1e6),
+                        notebooks/superposition_edu.ipynb:813 (T=1), clip_eval.py:402 */
+  SD_MODE_AND = 1,   /* equalise the density increments: superposition_edu.ipynb:899-905
+                        (M=2 closed form), general M by the linear solve of SURVEY.md A.3 */
+  SD_MODE_AVG = 2,   /* kappa_j = 1/M: cifar/dynamics.py:155-171 */
+  SD_MODE_FIXED = 3  /* kappa read from `weights` (caller supplied) */
+};
+
+/* which log-density increment is accumulated into logq */
+enum sd_dlogq_mode {
+  SD_DLOGQ_CIFAR_MAXSUB = 0, /* cifar/dynamics.py:131-135: increment minus its max over models */
+  SD_DLOGQ_ITO = 1,          /* superposition_edu.ipynb:777-780: R_i + ito_scale*dt*a */
+  SD_DLOGQ_NONE = 2          /* logq left untouched (cifar/dynamics.py:171 returns zeros) */
+};
+
+/* Fused VP-SDE SuperDiff step (one launch per timestep).
+ * Replaces the body of get_joint_stoch_vf.joint_vf (cifar/dynamics.py:123-136),
+ * get_avg_vf.joint_vf (:155-171) and the toy notebook's per-step cells
+ * (superposition_edu.ipynb:813-819, :899-905, :938-946), after the M score
+ * evaluations:
+ *     kappa   = mode(logq | Gram reductions)
+ *     dx      = -dt*(a*x - 2*b*sum_j kappa_j s_j) + sqrt(2*sigma*b*dt)*noise
+ *     x_out   = x + dx                      (x_out may alias x)
+ *     logq_i += dlogq_mode(R_i),  R_i = [<dx,s_i> + dt*a*<x,s_i> - dt*b*|s_i|^2]/sigma
+ * x, noise, scores[j], x_out: [B, D] fp32 contiguous; logq, weights: [B, M].
+ * `sched` (optional, device): table of per-step (a, b, sigma, dt) quadruples;
+ * when non-NULL the scalars are read from sched[4 * (*step_counter)] instead of
+ * the by-value arguments so that a captured CUDA graph can be replayed for
+ * every timestep (step_counter NULL = row 0).
+ * `logp_bias` (optional): [M] additive bias inside the OR softmax.
+ * `ito_scale`: constant multiplier of dt*a in SD_DLOGQ_ITO mode; the notebook's
+ * value is ndim*D (= 4 for the 2-D toy, superposition_edu.ipynb:778). */
+int sd_step_vpsde(const float* x, const float* noise, const float* const* scores_host /* M device ptrs, host array */,
+                  int M, int B, int D,
+                  float a_t, float b_t, float sigma_t, float dt,
+                  const float* sched, const int* step_counter,
+                  int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
+                  float* logq, float* x_out, float* weights, void* stream);
+
+/* Same as sd_step_vpsde with explicit launch shape (tuning / benchmarks):
+ * threads per CTA (64..256, multiple of 32), float4 chunks per thread (1..4),
+ * CTAs per sample (thread-block cluster size 1,2,4,8).  0 = heuristic. */
+int sd_step_vpsde_ex(const float* x, const float* noise, const float* const* scores_host,
+                     int M, int B, int D,
+                     float a_t, float b_t, float sigma_t, float dt,
+                     const float* sched, const int* step_counter,
+                     int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
+                     float* logq, float* x_out, float* weights, void* stream,
+                     int threads, int vec_per_thread, int cluster);
+
+/* Fused EDM-sigma SuperDiff step on Stable-Diffusion latents with
+ * classifier-free guidance.  Replaces applications/images/clip_eval.py:395-413
+ * (methods "and", "or") and :417-424 ("avg"):
+ *     noise = sqrt(2|dsigma|sigma) * z
+ *     kappa = AND closed form (:398-400) | softmax([T(ll_obj+logp), T ll_bg])[0] (:402) | kappa_fixed
+ *     vf    = v_unc + g*((v_bg - v_unc) + kappa*(v_obj - v_bg));  latents_out = latents + 2*dsigma*vf + noise
+ *     ll_k += and/avg: sum(-|dsigma|/sigma v_k^2 - dx v_k/sigma) (:409-410) | or: -sum(v_k(dx + dsigma v_k))/sigma (:412-413)
+ * latents, z, v_obj, v_bg, v_unc, latents_out: [B, D] fp32; ll: [B, 2] in/out
+ * (obj, bg); kappa_out: [B].  lift_term = sigma*lift/num_inference_steps (:399). */
+int sd_step_edm_cfg(const float* latents, const float* z, const float* v_obj, const float* v_bg, const float* v_unc,
+                    int B, int D, float sigma, float dsigma, float guidance, float lift_term,
+                    int mode /* SD_MODE_AND | SD_MODE_OR | SD_MODE_AVG (kappa_fixed) */,
+                    float temperature, float logp, float kappa_fixed,
+                    float* ll, float* latents_out, float* kappa_out, void* stream);
+
+/* In-graph helper: *counter += delta (single thread).  Lets a captured graph
+ * advance the row of `sched` it reads. */
+int sd_counter_add(int* counter, int delta, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Score-network ops (cifar/models/ddpm.py:47-101 and the layers it uses).
+ * Activations are NHWC; GEMM operands are bf16, accumulation fp32 in TMEM.
+ * ------------------------------------------------------------------------ */
+
+/* One A-operand segment of an implicit GEMM: an NHWC bf16 tensor [B,H,W,C]
+ * read through `taps` filter taps (9 = 3x3 SAME stride 1, 1 = 1x1 / NIN). */
+typedef struct sd_gemm_src {
+  const void* ptr; /* bf16 [B, H, W, C] */
+  int C;           /* channels (multiple of 64) */
+  int taps;        /* 1 or 9 */
+} sd_gemm_src;
+
+#define SD_EPI_SWISH 1u     /* out = swish(out) after everything else */
+#define SD_EPI_OUT_F32 2u   /* `out` is fp32 instead of bf16 */
+
+/* out[b,h,w,n] = sum_seg sum_tap sum_c src[b,h+dh,w+dw,c] * Wt[n, k(seg,tap,c)]
+ *               + bias[n] + rowbias[b, n] + residual[b,h,w,n]
+ * Replaces nn.Conv 3x3 / NIN / nn.Dense call sites: cifar/models/layers.py:95-107,
+ * :464-475, :556, and the residual add of :565 / :511.
+ * Wt: bf16 [N, K] row-major (K = sum_seg taps*C, segment-major, tap-major, then
+ * channel).  bias: fp32 [N] or NULL.  rowbias: fp32 [B, rowbias_ld] or NULL
+ * (the per-sample time-embedding projection, layers.py:556).  residual: bf16
+ * [B,H,W,N] or NULL.  N multiple of 16, <= 256 per tile (larger N is tiled). */
+int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W,
+                 const void* Wt, int N, const float* bias,
+                 const float* rowbias, int rowbias_ld,
+                 const void* residual, unsigned flags, void* out, int out_ld, void* stream);
+
+/* Batched "NT" GEMM on the same tcgen05 kernel:
+ *     out[b][m][n] = sum_k A[b][m][k] * Bt[b][n][k] + bias[n] + residual[b][m][n]
+ * A: bf16 [batch][M][lda], Bt: bf16 [batch][N][ldb] (both K-contiguous); a batch
+ * stride of 0 shares the operand across the batch.  Used for nn.Dense call sites
+ * (batch = 1) and for the S = 256 attention products q k^T and p v of
+ * cifar/models/layers.py:505-509.  K multiple of 64. */
+int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                    int batch, int M, int N, int K, const float* bias, const void* residual, unsigned flags,
+                    void* out, int ldc, long long strideC, void* stream);
+
+/* Row softmax P[r,:] = softmax(scale * X[r,:]); X fp32 [rows, cols] -> P bf16
+ * (jax.nn.softmax at cifar/models/layers.py:507 with the C^-1/2 scale of :505). */
+int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale, void* stream);
+
+/* GroupNorm(32 groups, eps) + optional swish over the channel-concatenation of
+ * up to two NHWC bf16 tensors; writes bf16 [B,H,W,C0+C1].
+ * Replaces act(normalize()(x)) at cifar/models/layers.py:552,557,498 and
+ * cifar/models/ddpm.py:98 (flax nn.GroupNorm defaults, normalization.py:38-39). */
+int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                       const float* gamma, const float* beta, float eps, int apply_swish,
+                       void* out, void* stream);
+
+/* Single-head self-attention over HW tokens (cifar/models/layers.py:505-509):
+ * out = softmax_{HW}(q k^T * C^-1/2) v.  qkv: bf16 [B, S, 3C] (q | k | v
+ * channel blocks), out: bf16 [B, S, C].  CUDA-core kernel for the low-resolution
+ * blocks (S in {4, 16, 64}); S = 256 runs as sd_batched_gemm + sd_softmax_rows. */
+int sd_attention(const void* qkv, int B, int S, int C, void* out, void* stream);
+
+/* Nearest-neighbour x2 upsample of an NHWC bf16 tensor
+ * (jax.image.resize 'nearest', cifar/models/layers.py:520). */
+int sd_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream);
+
+/* Gather for the stride-2 SAME conv (cifar/models/layers.py:533, pad (0,1)):
+ * out[b,ho,wo, tap*C + c] = x[b, 2ho+kh, 2wo+kw, c] (0 outside). bf16. */
+int sd_im2col_s2(const void* x, int B, int H, int W, int C, void* out, void* stream);
+
+/* First conv (cifar/models/ddpm.py:71): fp32 NHWC [B,H,W,Cin<=4] -> bf16
+ * [B,H,W,Cout], 3x3 SAME, fp32 weights [3,3,Cin,Cout] (Flax HWIO) + bias. */
+int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio, const float* bias,
+               int Cout, void* out, void* stream);
+
+/* Sinusoidal time embedding + Dense + swish + Dense (+ class embedding) and the
+ * swish that feeds every ResBlock's Dense (cifar/models/ddpm.py:64-68,
+ * layers.py:450-461,556): writes act_temb = swish(temb) as bf16 [B, 4nf].
+ * t comes from t_dev[0] scaled per sample, or from sched/step_counter
+ * (sigma column == t for this SDE). */
+int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, const int* step_counter,
+                      int B, int nf,
+                      const float* w0 /*[nf,4nf]*/, const float* b0, const float* w1 /*[4nf,4nf]*/, const float* b1,
+                      const float* class_emb /*[ncls,4nf] or NULL*/, const int* labels,
+                      float* temb_scratch /* fp32 [B,4nf] ([1,4nf] when t is shared) */,
+                      void* act_temb_out /* bf16 [B,4nf] */, void* stream);
+
+/* fp32 -> bf16 and bf16 -> fp32 converts (weights upload, debugging). */
+int sd_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
+int sd_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream);
+
+const char* sd_last_error(void);
+int sd_version(void);
+/* 1 when the current device is compute capability 10.x (sm_100 family). */
+int sd_device_ok(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUPERDIFF_B200_H_ */

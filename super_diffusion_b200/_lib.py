@@ -1,0 +1,84 @@
+"""ctypes loader for ``libsuperdiff_b200.so`` (the C ABI in include/superdiff_b200.h).
+
+There is no fallback: if the shared library has not been built, or a call
+fails, a RuntimeError is raised.  Nothing here imports ``oracle/``.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsuperdiff_b200.so")
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+c_void_p = ctypes.c_void_p
+
+
+class GemmSrc(ctypes.Structure):
+    """struct sd_gemm_src (include/superdiff_b200.h)."""
+    _fields_ = [("ptr", ctypes.c_void_p), ("C", ctypes.c_int), ("taps", ctypes.c_int)]
+
+
+# name -> (restype, argtypes); must list every symbol include/superdiff_b200.h declares
+_F, _I, _V, _U, _SZ = ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t
+_LL = ctypes.c_longlong
+SIGNATURES = {
+    "sd_step_vpsde": (_I, [_V, _V, ctypes.POINTER(_V), _I, _I, _I, _F, _F, _F, _F, _V, _V,
+                           _I, _I, _F, _V, _F, _V, _V, _V, _V]),
+    "sd_step_vpsde_ex": (_I, [_V, _V, ctypes.POINTER(_V), _I, _I, _I, _F, _F, _F, _F, _V, _V,
+                              _I, _I, _F, _V, _F, _V, _V, _V, _V, _I, _I, _I]),
+    "sd_step_edm_cfg": (_I, [_V, _V, _V, _V, _V, _I, _I, _F, _F, _F, _F, _I, _F, _F, _F, _V, _V, _V, _V]),
+    "sd_counter_add": (_I, [_V, _I, _V]),
+    "sd_conv_gemm": (_I, [ctypes.POINTER(GemmSrc), _I, _I, _I, _I, _V, _I, _V, _V, _I, _V, _U, _V, _I, _V]),
+    "sd_groupnorm_swish": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _V]),
+    "sd_attention": (_I, [_V, _I, _I, _I, _V, _V]),
+    "sd_upsample2x": (_I, [_V, _I, _I, _I, _I, _V, _V]),
+    "sd_im2col_s2": (_I, [_V, _I, _I, _I, _I, _V, _V]),
+    "sd_conv_in": (_I, [_V, _I, _I, _I, _I, _V, _V, _I, _V, _V]),
+    "sd_time_embedding": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
+    "sd_batched_gemm": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _I, _V, _V, _U, _V, _I, _LL, _V]),
+    "sd_softmax_rows": (_I, [_V, _V, ctypes.c_long, _I, _F, _V]),
+    "sd_cast_f32_to_bf16": (_I, [_V, _V, _SZ, _V]),
+    "sd_cast_bf16_to_f32": (_I, [_V, _V, _SZ, _V]),
+    "sd_last_error": (ctypes.c_char_p, []),
+    "sd_version": (_I, []),
+    "sd_device_ok": (_I, []),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library once; raise loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the sm_100a CUDA extension has not been built. "
+            "Run `python -m super_diffusion_b200.build` (or __graft_entry__.build()). "
+            "There is no CPU / PyTorch fallback for this path.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().sd_last_error()
+        raise RuntimeError(f"superdiff_b200 {what} failed (code {rc}): {msg.decode() if msg else '?'}")
+
+
+def require_device():
+    """Raise unless the current CUDA device is an sm_100-family GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("superdiff_b200 needs a CUDA device (B200, sm_100a); none is visible and "
+                           "there is no CPU fallback")
+    if not load().sd_device_ok():
+        raise RuntimeError("superdiff_b200 kernels are compiled for sm_100a only; the current device is not "
+                           "compute capability 10.x")

@@ -1,0 +1,66 @@
+// C-ABI glue shared by every entry point: error plumbing, version, device check, casts.
+#include "common.cuh"
+#include "../../include/superdiff_b200.h"
+#include <cuda_bf16.h>
+
+namespace sdb {
+
+static thread_local std::string g_last_error;
+
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+
+int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return SD_OK;
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return kErrCuda;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+}  // namespace sdb
+
+extern "C" {
+
+const char* sd_last_error(void) { return sdb::g_last_error.c_str(); }
+
+int sd_version(void) { return 100; }  // 0.1.0
+
+int sd_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  int major = 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int sd_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream) {
+  if (!in || !out) return sdb::fail(sdb::kErrInvalidArg, "sd_cast_f32_to_bf16: null pointer");
+  if (n == 0) return SD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads < 148u * 16u ? (n + threads - 1) / threads : 148u * 16u);
+  sdb::cast_f32_bf16_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(in, (__nv_bfloat16*)out, n);
+  return sdb::check_cuda(cudaGetLastError(), "sd_cast_f32_to_bf16 launch");
+}
+
+int sd_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream) {
+  if (!in || !out) return sdb::fail(sdb::kErrInvalidArg, "sd_cast_bf16_to_f32: null pointer");
+  if (n == 0) return SD_OK;
+  const int threads = 256;
+  const unsigned blocks = (unsigned)((n + threads - 1) / threads < 148u * 16u ? (n + threads - 1) / threads : 148u * 16u);
+  sdb::cast_bf16_f32_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, out, n);
+  return sdb::check_cuda(cudaGetLastError(), "sd_cast_bf16_to_f32 launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+// Shared device/host helpers for the superdiff_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <stdint.h>
+#include <string>
+
+namespace sdb {
+
+namespace cg = cooperative_groups;
+
+// ---- error plumbing for the C ABI (no exceptions cross the boundary) --------
+void set_last_error(const std::string& msg);
+int fail(int code, const std::string& msg);
+int check_cuda(cudaError_t e, const char* what);
+
+constexpr int kErrInvalidArg = -1;
+constexpr int kErrUnsupported = -2;
+constexpr int kErrCuda = -3;
+
+// ---- streaming 128-bit global accesses ---------------------------------------
+// Inputs of the fused step are read exactly once: keep them out of L1.
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st4(float* p, const float4& v) {
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Reduce K per-thread fp32 partials over the CTA and (optionally) over the
+// thread-block cluster that shares one sample.  Partials are widened to fp64
+// before the first cross-thread add, so the result does not depend on the
+// CTA/cluster shape beyond fp64 rounding.  Returns a shared-memory pointer to
+// the K totals, valid for every thread of every CTA in the cluster.
+//   scratch: shared double[ (nwarps + 2) * K ]
+template <int K, bool CLUSTER>
+__device__ __forceinline__ const double* block_cluster_sum(const float (&part)[K], double* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  double* cta_tot = scratch + nwarps * K;
+  double* full = cta_tot + K;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    double v = warp_sum((double)part[k]);
+    if (lane == 0) scratch[warp * K + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += scratch[w * K + threadIdx.x];
+    cta_tot[threadIdx.x] = s;
+    if (!CLUSTER) full[threadIdx.x] = s;
+  }
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    cluster.sync();  // every CTA's cta_tot is written and visible cluster-wide
+    if (threadIdx.x < K) {
+      double s = 0.0;
+      const unsigned n = cluster.num_blocks();
+      for (unsigned r = 0; r < n; ++r) s += *cluster.map_shared_rank(&cta_tot[threadIdx.x], r);
+      full[threadIdx.x] = s;
+    }
+    cluster.sync();  // nobody exits (or reuses cta_tot) while peers still read it
+  } else {
+    __syncthreads();
+  }
+  return full;
+}
+
+}  // namespace sdb

@@ -1,0 +1,522 @@
+// Implicit-GEMM convolution / NIN / Dense on the 5th-gen tensor cores (sm_100a).
+//
+// Replaces the nn.Conv 3x3 (reference cifar/models/layers.py:95-107), NIN (:464-475)
+// and nn.Dense (:556, cifar/models/ddpm.py:65-66) call sites of the CIFAR score-net.
+//
+//   out[m, n] = sum_k A[m, k] * Wt[n, k] + bias[n] + rowbias[img(m), n] + residual[m, n]
+//
+// m enumerates output pixels (b, h, w) of an NHWC tensor, k enumerates
+// (segment, tap, channel).  A is never materialised: for every 64-channel
+// K-block the producer warp issues ONE 4-D TMA load of the (channel, w, h, b)
+// box shifted by the filter tap; out-of-bounds coordinates are zero-filled by
+// the TMA unit, which is exactly SAME padding.  The box lands in shared memory
+// as 128 rows x 128 B with the 128-byte swizzle, i.e. the canonical K-major
+// UMMA operand layout, and is consumed by tcgen05.mma (M=128, N<=256, K=16)
+// with the fp32 accumulator in tensor memory.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld -> bias /
+// time-embedding / residual / swish -> global).  Persistent over output tiles,
+// 4-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps
+// the MMAs of tile i+1.
+#include "common.cuh"
+#include "../../include/superdiff_b200.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
+namespace sdb {
+
+constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
+constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int MAX_BN = 256;
+constexpr int A_BYTES = BM * BK * 2;          // 16 KB
+constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
+constexpr int MAX_SEGS = 3;
+constexpr int GEMM_THREADS = 192;
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+
+struct GemmParams {
+  CUtensorMap a_map[MAX_SEGS];
+  CUtensorMap b_map;
+  int nseg;
+  int seg_kb_end[MAX_SEGS];   // cumulative K-block count at the end of each segment
+  int seg_taps[MAX_SEGS];
+  int seg_cblocks[MAX_SEGS];  // C / 64
+  int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
+  int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
+  int m_tiles_per_batch, M_per_batch;
+  long long out_batch_stride; // elements
+  int h_box, tiles_per_img, imgs_per_tile;
+  int M_total, HW, N_out, block_n, n_tiles, m_tiles, num_kb;
+  const float* bias;
+  const float* rowbias;
+  int rowbias_ld;
+  const __nv_bfloat16* residual;
+  int res_ld;
+  void* out;
+  int out_ld;
+  unsigned flags;
+};
+
+// ---- PTX wrappers ------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s
+  }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// K-major operand tile, 128-byte rows, SWIZZLE_128B (8-row atoms of 1024 B):
+// start>>4 | LBO=1 (ignored for swizzled K-major) | SBO=1024>>4 | version=1 (sm_100) | layout=2 (SW128)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float swishf(float v) { return v / (1.f + __expf(-v)); }
+
+// Epilogue for 16 consecutive output columns of one row.
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0, int img) {
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  const bool full = (n0 + 16 <= p.N_out);
+  if (full) {
+    if (p.bias) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (p.rowbias) {
+      const float* rb = p.rowbias + (size_t)img * p.rowbias_ld + n0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        const float4 b = *reinterpret_cast<const float4*>(rb + j);
+        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+      }
+    }
+    if (p.residual) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint4 u = rp[h];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          v[h * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+          v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        }
+      }
+    }
+    if (p.flags & SD_EPI_SWISH) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = swishf(v[j]);
+    }
+    if (p.flags & SD_EPI_OUT_F32) {
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off + n0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint32_t w[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0);
+      op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+  } else {
+    // ragged N tail (e.g. the 3-channel output conv): scalar, masked
+    for (int j = 0; j < 16; ++j) {
+      const int n = n0 + j;
+      if (n >= p.N_out) break;
+      float x = v[j];
+      if (p.bias) x += p.bias[n];
+      if (p.rowbias) x += p.rowbias[(size_t)img * p.rowbias_ld + n];
+      if (p.residual) x += __bfloat162float(p.residual[row_off + n]);
+      if (p.flags & SD_EPI_SWISH) x = swishf(x);
+      if (p.flags & SD_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[row_off + n] = x;
+      else reinterpret_cast<__nv_bfloat16*>(p.out)[row_off + n] = __float2bfloat16_rn(x);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.a_map[s]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.b_map) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // whole TMEM (512 columns): two 256-column fp32 accumulators; 1 CTA / SM by construction (smem)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.block_n * BK * 2;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int c1, c2, c3, bz = 0;
+        if (p.flat) {
+          const int batch = m_tile / p.m_tiles_per_batch;
+          c1 = (m_tile - batch * p.m_tiles_per_batch) * BM; c2 = 0;
+          c3 = p.a_batched ? batch : 0;
+          bz = p.b_batched ? batch : 0;
+        } else {
+          c1 = 0;
+          c2 = (m_tile % p.tiles_per_img) * p.h_box;
+          c3 = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
+        }
+        int seg = 0, seg_start = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          while (kb >= p.seg_kb_end[seg]) { seg_start = p.seg_kb_end[seg]; ++seg; }
+          const int local = kb - seg_start;
+          const int tap = local / p.seg_cblocks[seg];
+          const int cb = local - tap * p.seg_cblocks[seg];
+          int dh = 0, dw = 0;
+          if (p.seg_taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+          tma_load_4d(&p.a_map[seg], sa, &full_bar[stage], cb * BK, c1 + dw, c2 + dh, c3);
+          tma_load_3d(&p.b_map, sa + A_BYTES, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(sa);
+          const uint64_t b_desc = umma_desc_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom
+            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = q * 32 + lane;
+      bool row_ok;
+      size_t row_off;
+      int img;
+      if (p.flat) {
+        const int batch = m_tile / p.m_tiles_per_batch;
+        const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + row;
+        row_ok = rl < p.M_per_batch;
+        row_off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
+        img = batch;
+      } else {
+        const int m = m_tile * BM + row;
+        row_ok = m < p.M_total;
+        row_off = (size_t)m * p.out_ld;
+        img = m / p.HW;
+      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+      const int n_base = n_tile * p.block_n;
+      for (int c = 0; c < p.block_n; c += 32) {
+        uint32_t r0[16], r1[16];
+        tmem_ld16(taddr + c, r0);
+        const bool second = (c + 16 < p.block_n);
+        if (second) tmem_ld16(taddr + c + 16, r1);
+        tmem_wait_ld();
+        if (row_ok) {
+          if (n_base + c < p.N_out) epilogue_store16(p, r0, row_off, n_base + c, img);
+          if (second && n_base + c + 16 < p.N_out) epilogue_store16(p, r1, row_off, n_base + c + 16, img);
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                      const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return fail(kErrCuda, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(kErrCuda, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  return SD_OK;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+
+static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, long long strideB, int nbatchB,
+                       const float* bias, const float* rowbias, int rowbias_ld, const void* residual, unsigned flags,
+                       void* out, int out_ld, cudaStream_t st, const char* who) {
+  const int n_pad = (N + 15) / 16 * 16;
+  p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
+  p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
+  if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
+  {
+    // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
+    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)nbatchB};
+    cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)(nbatchB > 1 ? strideB : (long long)N * ldb) * 2};
+    cuuint32_t box[3] = {BK, (cuuint32_t)p.block_n, 1};
+    int rc = encode_map(&p.b_map, Wt, 3, dims, strides, box);
+    if (rc != SD_OK) return rc;
+  }
+  p.N_out = N;
+  p.bias = bias;
+  p.rowbias = rowbias;
+  p.rowbias_ld = rowbias_ld;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.res_ld = out_ld;
+  p.out = out;
+  p.out_ld = out_ld;
+  p.flags = flags;
+  const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
+  const bool vec_ok = (out_ld % out_align == 0) && ((uintptr_t)out % 16 == 0) && (!residual || ((uintptr_t)residual % 16 == 0 && out_ld % 8 == 0)) &&
+                      (!bias || (uintptr_t)bias % 16 == 0) && (!rowbias || ((uintptr_t)rowbias % 16 == 0 && rowbias_ld % 4 == 0)) &&
+                      (p.out_batch_stride % out_align == 0);
+  if (!vec_ok && N >= 16) return fail(kErrInvalidArg, std::string(who) + ": out/residual/bias must be 16-byte aligned (ld multiple of 8 bf16 / 4 fp32)");
+
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
+  return check_cuda(cudaGetLastError(), who);
+}
+
+}  // namespace sdb
+
+extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
+                            const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
+                            unsigned flags, void* out, int out_ld, void* stream) {
+  using namespace sdb;
+  if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, "sd_conv_gemm: 1..3 sources required");
+  if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, "sd_conv_gemm: bad argument");
+  if (B == 0) return SD_OK;
+  GemmParams p{};
+  if (W > BM || (BM % W) != 0) return fail(kErrUnsupported, "sd_conv_gemm: W must divide 128");
+  const int h_box = (H * W >= BM) ? BM / W : H;
+  if ((H % h_box) != 0 || (BM % (W * h_box)) != 0)
+    return fail(kErrUnsupported, "sd_conv_gemm: H*W must divide or be a multiple of 128 in whole rows");
+  p.h_box = h_box;
+  p.tiles_per_img = (H * W >= BM) ? (H * W) / BM : 1;
+  p.imgs_per_tile = (H * W >= BM) ? 1 : BM / (H * W);
+  p.flat = 0;
+  int kb = 0;
+  long K = 0;
+  for (int s = 0; s < num_srcs; ++s) {
+    const sd_gemm_src& src = srcs[s];
+    if (!src.ptr || src.C < BK || (src.C % BK) != 0) return fail(kErrInvalidArg, "sd_conv_gemm: source channels must be a multiple of 64");
+    if (!(src.taps == 1 || src.taps == 9)) return fail(kErrInvalidArg, "sd_conv_gemm: taps must be 1 or 9");
+    if (((uintptr_t)src.ptr % 16) != 0) return fail(kErrInvalidArg, "sd_conv_gemm: source must be 16-byte aligned");
+    p.seg_taps[s] = src.taps;
+    p.seg_cblocks[s] = src.C / BK;
+    kb += src.taps * (src.C / BK);
+    p.seg_kb_end[s] = kb;
+    K += (long)src.taps * src.C;
+    cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * W, (cuuint64_t)src.C * 2 * W * H};
+    cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)p.h_box, (cuuint32_t)p.imgs_per_tile};
+    int rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box);
+    if (rc != SD_OK) return rc;
+  }
+  for (int s = num_srcs; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
+  p.nseg = num_srcs;
+  p.num_kb = kb;
+  p.M_total = B * H * W;
+  p.HW = H * W;
+  p.m_tiles = (p.M_total + BM - 1) / BM;
+  p.m_tiles_per_batch = 1;
+  return launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
+                     (cudaStream_t)stream, "sd_conv_gemm");
+}
+
+extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                               int batch, int M, int N, int K, const float* bias, const void* residual,
+                               unsigned flags, void* out, int ldc, long long strideC, void* stream) {
+  using namespace sdb;
+  if (!A || !Bt || !out || batch < 0 || M < 1 || N < 1 || K < BK || (K % BK) != 0)
+    return fail(kErrInvalidArg, "sd_batched_gemm: bad argument (K must be a multiple of 64)");
+  if (batch == 0) return SD_OK;
+  if (((uintptr_t)A % 16) != 0 || (lda % 8) != 0 || (strideA % 8) != 0 || (strideB % 8) != 0)
+    return fail(kErrInvalidArg, "sd_batched_gemm: A must be 16-byte aligned with lda, strides multiples of 8");
+  GemmParams p{};
+  p.flat = 1;
+  p.a_batched = strideA != 0;
+  p.b_batched = strideB != 0;
+  p.M_per_batch = M;
+  p.m_tiles_per_batch = (M + BM - 1) / BM;
+  p.m_tiles = p.m_tiles_per_batch * batch;
+  p.out_batch_stride = strideC;
+  p.nseg = 1;
+  p.seg_taps[0] = 1;
+  p.seg_cblocks[0] = K / BK;
+  p.seg_kb_end[0] = K / BK;
+  for (int s = 1; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
+  p.num_kb = K / BK;
+  p.M_total = M * batch;
+  p.HW = 1;
+  const int nbA = p.a_batched ? batch : 1;
+  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)M, 1, (cuuint64_t)nbA};
+  const cuuint64_t bstride = (cuuint64_t)(p.a_batched ? strideA : (long long)M * lda) * 2;
+  cuuint64_t strides[3] = {(cuuint64_t)lda * 2, bstride, bstride};
+  cuuint32_t box[4] = {BK, BM, 1, 1};
+  int rc = encode_map(&p.a_map[0], A, 4, dims, strides, box);
+  if (rc != SD_OK) return rc;
+  return launch_gemm(p, N, K, Bt, ldb, strideB, p.b_batched ? batch : 1, bias, nullptr, 0, residual, flags, out, ldc,
+                     (cudaStream_t)stream, "sd_batched_gemm");
+}

@@ -1,0 +1,183 @@
+// Fused EDM-sigma SuperDiff step on Stable-Diffusion latents (sm_100a).
+//
+// Replaces reference applications/images/clip_eval.py:395-413 ("and", "or")
+// and :417-424 ("avg"): ~25 eager PyTorch elementwise/reduce launches become
+// one kernel that reads latents, z, v_obj, v_bg, v_unc once and writes the new
+// latents, kappa and the two log-likelihoods.
+// One thread-block cluster per sample (D = 16384 for 64x64x4 latents); the
+// slice stays in registers between the reduction and the write pass.
+// HBM bytes per sample: 4*D*6.
+#include "common.cuh"
+#include "../../include/superdiff_b200.h"
+
+namespace sdb {
+
+struct EdmParams {
+  const float* x; const float* z; const float* vo; const float* vb; const float* vu;
+  float* ll; float* x_out; float* kappa_out;
+  int B, D;
+  float sigma, dsigma, g, lift_term, temperature, logp, kappa_fixed;
+  int mode;
+};
+
+// reductions (all per sample):
+//  0 dd=<d,d>  1 bd=<base,d>  2 zd=<z,d>  3 oo=<vo,vo>  4 bb=<vb,vb>  5 ob=<vo,base>  6 od=<vo,d>  7 oz=<vo,z>
+//  with d = vo - vb, base = vu + g (vb - vu)
+template <int NV, bool CLUSTER>
+__global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ EdmParams p) {
+  extern __shared__ double scratch[];
+  unsigned csize = 1, crank = 0;
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    csize = cluster.num_blocks();
+    crank = cluster.block_rank();
+  }
+  const int sample = blockIdx.x / csize;
+  const int nunits = p.D / 4;
+  const int per_cta = (nunits + csize - 1) / csize;
+  const int u0 = crank * per_cta, u1 = min(nunits, u0 + per_cta);
+  const size_t base_off = (size_t)sample * p.D;
+  const float cn = sqrtf(2.f * fabsf(p.dsigma) * p.sigma);
+
+  float4 x[NV], z[NV], d[NV], bs[NV], vo[NV];
+  bool ok[NV];
+  float part[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[k] = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int u = u0 + j * blockDim.x + threadIdx.x;
+    ok[j] = u < u1;
+    x[j] = z[j] = d[j] = bs[j] = vo[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok[j]) {
+      const size_t off = base_off + (size_t)u * 4;
+      x[j] = ld_stream4(p.x + off);
+      z[j] = ld_stream4(p.z + off);
+      vo[j] = ld_stream4(p.vo + off);
+      const float4 vb = ld_stream4(p.vb + off);
+      const float4 vu = ld_stream4(p.vu + off);
+      d[j] = make_float4(vo[j].x - vb.x, vo[j].y - vb.y, vo[j].z - vb.z, vo[j].w - vb.w);
+      bs[j] = make_float4(vu.x + p.g * (vb.x - vu.x), vu.y + p.g * (vb.y - vu.y),
+                          vu.z + p.g * (vb.z - vu.z), vu.w + p.g * (vb.w - vu.w));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const float dd[4] = {d[j].x, d[j].y, d[j].z, d[j].w};
+    const float bb[4] = {bs[j].x, bs[j].y, bs[j].z, bs[j].w};
+    const float zz[4] = {z[j].x, z[j].y, z[j].z, z[j].w};
+    const float oo[4] = {vo[j].x, vo[j].y, vo[j].z, vo[j].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float vbe = oo[e] - dd[e];
+      part[0] = fmaf(dd[e], dd[e], part[0]);
+      part[1] = fmaf(bb[e], dd[e], part[1]);
+      part[2] = fmaf(zz[e], dd[e], part[2]);
+      part[3] = fmaf(oo[e], oo[e], part[3]);
+      part[4] = fmaf(vbe, vbe, part[4]);
+      part[5] = fmaf(oo[e], bb[e], part[5]);
+      part[6] = fmaf(oo[e], dd[e], part[6]);
+      part[7] = fmaf(oo[e], zz[e], part[7]);
+    }
+  }
+  const double* t = block_cluster_sum<8, CLUSTER>(part, scratch);
+  const double DD = t[0], BD = t[1], ZD = t[2], OO = t[3], BB = t[4], OB = t[5], OD = t[6], OZ = t[7];
+  const double ds = p.dsigma, sg = p.sigma, g = p.g;
+  double kappa;
+  if (p.mode == SD_MODE_AND) {
+    // clip_eval.py:398-400 with dx_ind = 2 dsigma base + cn z
+    const double num = fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term;
+    kappa = num / (2.0 * ds * g * DD);
+  } else if (p.mode == SD_MODE_OR) {
+    // clip_eval.py:402: softmax([T (ll_obj + logp), T ll_bg])[0], fp32 like the reference
+    const float z0 = p.temperature * (p.ll[2 * sample] + p.logp), z1 = p.temperature * p.ll[2 * sample + 1];
+    const float m = fmaxf(z0, z1);
+    const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+    kappa = (double)(e0 / (e0 + e1));
+  } else {
+    kappa = (double)p.kappa_fixed;
+  }
+  const float kf = (float)kappa;
+  const float two_ds = 2.f * p.dsigma;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (!ok[j]) continue;
+    float4 o;
+    // vf = base + g kappa d ; dx = 2 dsigma vf + cn z   (clip_eval.py:404-405)
+    o.x = x[j].x + (two_ds * (bs[j].x + p.g * kf * d[j].x) + cn * z[j].x);
+    o.y = x[j].y + (two_ds * (bs[j].y + p.g * kf * d[j].y) + cn * z[j].y);
+    o.z = x[j].z + (two_ds * (bs[j].z + p.g * kf * d[j].z) + cn * z[j].z);
+    o.w = x[j].w + (two_ds * (bs[j].w + p.g * kf * d[j].w) + cn * z[j].w);
+    st4(p.x_out + base_off + (size_t)(u0 + j * blockDim.x + threadIdx.x) * 4, o);
+  }
+  if (crank == 0 && threadIdx.x == 0) {
+    // <vo,dx> = 2ds(OB + g k OD) + cn OZ ; <vb,dx> = <vo,dx> - <d,dx>, <d,dx> = 2ds(BD + g k DD) + cn ZD
+    const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
+    const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
+    const double b_dx = o_dx - d_dx;
+    const double q = (p.mode == SD_MODE_OR) ? (-ds / sg) : (-fabs(ds) / sg);   // :412-413 vs :409-410
+    p.ll[2 * sample] = p.ll[2 * sample] + (float)(-o_dx / sg + q * OO);
+    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(-b_dx / sg + q * BB);
+    p.kappa_out[sample] = kf;
+  }
+}
+
+template <int NV>
+static cudaError_t launch_edm(const EdmParams& p, int threads, int cluster, cudaStream_t st) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.B * cluster);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = sizeof(double) * (size_t)(threads / 32 + 2) * 8;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, true>, p);
+  }
+  return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, false>, p);
+}
+
+}  // namespace sdb
+
+extern "C" int sd_step_edm_cfg(const float* latents, const float* z, const float* v_obj, const float* v_bg,
+                               const float* v_unc, int B, int D, float sigma, float dsigma, float guidance,
+                               float lift_term, int mode, float temperature, float logp, float kappa_fixed, float* ll,
+                               float* latents_out, float* kappa_out, void* stream) {
+  using namespace sdb;
+  if (!latents || !z || !v_obj || !v_bg || !v_unc || !ll || !latents_out || !kappa_out)
+    return fail(kErrInvalidArg, "sd_step_edm_cfg: null pointer argument");
+  if (B < 0 || D < 4 || D % 4) return fail(kErrInvalidArg, "sd_step_edm_cfg: D must be a positive multiple of 4");
+  if (!(mode == SD_MODE_AND || mode == SD_MODE_OR || mode == SD_MODE_AVG))
+    return fail(kErrInvalidArg, "sd_step_edm_cfg: mode must be AND, OR or AVG");
+  if (!(sigma > 0.f)) return fail(kErrInvalidArg, "sd_step_edm_cfg: sigma must be > 0");
+  if ((((uintptr_t)latents | (uintptr_t)z | (uintptr_t)v_obj | (uintptr_t)v_bg | (uintptr_t)v_unc |
+        (uintptr_t)latents_out) % 16) != 0)
+    return fail(kErrInvalidArg, "sd_step_edm_cfg: tensors must be 16-byte aligned");
+  if (B == 0) return SD_OK;
+  EdmParams p{latents, z, v_obj, v_bg, v_unc, ll, latents_out, kappa_out, B, D,
+              sigma, dsigma, guidance, lift_term, temperature, logp, kappa_fixed, mode};
+  const int nunits = D / 4;
+  // smallest (cluster, threads, NV <= 2) that keeps the sample resident; prefer more CTAs when B is small
+  int best_c = 0, best_t = 0, best_nv = 0;
+  long best_cost = -1;
+  for (int c = 1; c <= 8; c *= 2)
+    for (int t = 64; t <= 256; t *= 2)
+      for (int n = 1; n <= 2; ++n) {
+        const long cap = (long)c * t * n;
+        if (cap < nunits) continue;
+        long cost = (cap - nunits) * 4 + (c > 1 ? 64 * c : 0);
+        const long ctas = (long)B * c;
+        if (ctas < 148 * 4) cost += (148 * 4 - ctas);
+        if (t < 128) cost += 32;
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; best_t = t; best_nv = n; }
+      }
+  if (best_cost < 0) return fail(kErrUnsupported, "sd_step_edm_cfg: D too large (max 8*256*2 float4 per sample)");
+  cudaError_t err = best_nv == 1 ? launch_edm<1>(p, best_t, best_c, (cudaStream_t)stream)
+                                 : launch_edm<2>(p, best_t, best_c, (cudaStream_t)stream);
+  return check_cuda(err, "sd_step_edm_cfg launch");
+}

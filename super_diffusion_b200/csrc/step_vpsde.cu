@@ -1,0 +1,126 @@
+// Host dispatch + C ABI of the fused VP-SDE SuperDiff step (kernels: step_vpsde_kernel.cuh,
+// instantiated per model count in step_vpsde_m*.cu so the build parallelises).
+#include "common.cuh"
+#include "../../include/superdiff_b200.h"
+
+#include "step_vpsde_params.cuh"
+
+namespace sdb {
+
+template <int M> cudaError_t launch_m(const StepParams& p, int threads, int nv, int cluster, int vec, cudaStream_t st);
+template <int M> cudaError_t launch_small(const StepParams& p, cudaStream_t st);
+
+}  // namespace sdb
+
+namespace sdb {
+
+static int step_vpsde_impl(const float* x, const float* noise, const float* const* scores, int M, int B, int D,
+                           float a_t, float b_t, float sigma_t, float dt, const float* sched, const int* step_counter,
+                           int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
+                           float* logq, float* x_out, float* weights, void* stream, int threads, int nv, int cluster) {
+  if (M < 1 || M > SD_MAX_MODELS) return fail(kErrInvalidArg, "sd_step_vpsde: M must be in [1, 8]");
+  if (B < 0 || D < 1) return fail(kErrInvalidArg, "sd_step_vpsde: B >= 0 and D >= 1 required");
+  if (mode < SD_MODE_OR || mode > SD_MODE_FIXED) return fail(kErrInvalidArg, "sd_step_vpsde: unknown mode");
+  if (dlogq_mode < SD_DLOGQ_CIFAR_MAXSUB || dlogq_mode > SD_DLOGQ_NONE)
+    return fail(kErrInvalidArg, "sd_step_vpsde: unknown dlogq_mode");
+  if (!x || !noise || !scores || !x_out || !weights || (!logq && (mode == SD_MODE_OR || dlogq_mode != SD_DLOGQ_NONE)))
+    return fail(kErrInvalidArg, "sd_step_vpsde: null pointer argument");
+  if (B == 0) return SD_OK;  // empty batch: nothing to launch
+  StepParams p{};
+  p.x = x; p.noise = noise;
+  for (int i = 0; i < M; ++i) {
+    if (!scores[i]) return fail(kErrInvalidArg, "sd_step_vpsde: null score pointer");
+    p.s[i] = scores[i];
+  }
+  p.logq = logq; p.x_out = x_out; p.weights = weights; p.logp_bias = logp_bias;
+  p.sched = sched; p.step_counter = step_counter;
+  p.M = M; p.B = B; p.D = D;
+  p.a = a_t; p.b = b_t; p.sigma = sigma_t; p.dt = dt;
+  p.mode = mode; p.dlogq_mode = dlogq_mode; p.temperature = temperature; p.ito_scale = ito_scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t err;
+
+  if (D <= 64 && threads == 0) {
+#define SDB_SMALL(Mv) case Mv: err = launch_small<Mv>(p, st); break;
+    switch (M) {
+      SDB_SMALL(1) SDB_SMALL(2) SDB_SMALL(3) SDB_SMALL(4) SDB_SMALL(5) SDB_SMALL(6) SDB_SMALL(7) SDB_SMALL(8)
+      default: err = cudaErrorInvalidValue;
+    }
+#undef SDB_SMALL
+    return check_cuda(err, "sd_step_vpsde (small-D launch)");
+  }
+
+  // vector width: float4 when every base pointer is 16B aligned and D % 4 == 0
+  bool aligned = (D % 4 == 0) && (((uintptr_t)x | (uintptr_t)noise | (uintptr_t)x_out) % 16 == 0);
+  for (int i = 0; i < M; ++i) aligned = aligned && ((uintptr_t)scores[i] % 16 == 0);
+  const int vec = aligned ? 4 : 1;
+  const int nunits = D / vec;
+  const bool is_and = mode == SD_MODE_AND;
+  if (threads == 0 || nv == 0 || cluster == 0) {
+    // Heuristic: keep (M+2)*NV float4 registers per thread <= 24, prefer 128..256 threads and
+    // enough CTAs (>= ~8 per SM) that the 148 SMs stay balanced.
+    const int nv_cap = max(1, min(4, 24 / (M + 2)));
+    int best_t = 256, best_nv = nv_cap, best_c = 8;
+    long best_cost = -1;
+    for (int c = 1; c <= 8; c *= 2)
+      for (int t = 64; t <= 256; t *= 2)
+        for (int n = 1; n <= nv_cap; ++n) {
+          const long cap = (long)c * t * n;
+          if (is_and && cap < nunits) continue;            // AND needs the sample resident
+          const long rounds = (nunits + cap - 1) / cap;
+          const long waste = rounds * cap - nunits;          // idle lanes
+          const long ctas = (long)B * c;
+          long cost = waste * 4 + (c > 1 ? 64 * c : 0) + rounds * 16;
+          if (ctas < 148 * 8) cost += (148 * 8 - ctas);     // too few CTAs: prefer splitting samples
+          if (t < 128) cost += 32;
+          if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_t = t; best_nv = n; best_c = c; }
+        }
+    if (best_cost < 0)
+      return fail(kErrUnsupported, "sd_step_vpsde: D too large for the register-resident AND step (max 8*256*4 float4 per sample)");
+    threads = best_t; nv = best_nv; cluster = best_c;
+  }
+  if (threads < 32 || threads > 256 || threads % 32 || nv < 1 || nv > 4 ||
+      !(cluster == 1 || cluster == 2 || cluster == 4 || cluster == 8))
+    return fail(kErrInvalidArg, "sd_step_vpsde_ex: bad launch shape");
+  if (is_and && (long)cluster * threads * nv < nunits)
+    return fail(kErrUnsupported, "sd_step_vpsde_ex: launch shape does not hold one sample (AND mode)");
+#define SDB_M(Mv) case Mv: err = launch_m<Mv>(p, threads, nv, cluster, vec, st); break;
+  switch (M) {
+    SDB_M(1) SDB_M(2) SDB_M(3) SDB_M(4) SDB_M(5) SDB_M(6) SDB_M(7) SDB_M(8)
+    default: err = cudaErrorInvalidValue;
+  }
+#undef SDB_M
+  return check_cuda(err, "sd_step_vpsde launch");
+}
+
+__global__ void counter_add_kernel(int* c, int d) { *c += d; }
+
+}  // namespace sdb
+
+extern "C" {
+
+int sd_step_vpsde(const float* x, const float* noise, const float* const* scores_host, int M, int B, int D,
+                  float a_t, float b_t, float sigma_t, float dt, const float* sched, const int* step_counter,
+                  int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
+                  float* logq, float* x_out, float* weights, void* stream) {
+  return sdb::step_vpsde_impl(x, noise, scores_host, M, B, D, a_t, b_t, sigma_t, dt, sched, step_counter, mode,
+                              dlogq_mode, temperature, logp_bias, ito_scale, logq, x_out, weights, stream, 0, 0, 0);
+}
+
+int sd_step_vpsde_ex(const float* x, const float* noise, const float* const* scores_host, int M, int B, int D,
+                     float a_t, float b_t, float sigma_t, float dt, const float* sched, const int* step_counter,
+                     int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
+                     float* logq, float* x_out, float* weights, void* stream, int threads, int vec_per_thread,
+                     int cluster) {
+  return sdb::step_vpsde_impl(x, noise, scores_host, M, B, D, a_t, b_t, sigma_t, dt, sched, step_counter, mode,
+                              dlogq_mode, temperature, logp_bias, ito_scale, logq, x_out, weights, stream, threads,
+                              vec_per_thread, cluster);
+}
+
+int sd_counter_add(int* counter, int delta, void* stream) {
+  if (!counter) return sdb::fail(sdb::kErrInvalidArg, "sd_counter_add: null counter");
+  sdb::counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
+  return sdb::check_cuda(cudaGetLastError(), "sd_counter_add launch");
+}
+
+}  // extern "C"

@@ -1,0 +1,409 @@
+// Fused VP-SDE SuperDiff step for sm_100a: ONE launch per timestep.
+//
+// Replaces the body of get_joint_stoch_vf.joint_vf (reference cifar/dynamics.py:123-136),
+// get_avg_vf.joint_vf (:155-171) and the toy notebook cells
+// (notebooks/superposition_edu.ipynb:813-819, :899-905, :938-946).
+//
+// Layout: one thread-block CLUSTER per sample.  Each CTA owns a contiguous
+// slice of the sample's D elements, keeps x / noise / all M scores for that
+// slice in registers (one HBM read per element), and the cluster exchanges
+// the K per-sample partial reductions through distributed shared memory.
+//   weights known up front (OR / AVG / FIXED): K = M          (R_i * sigma)
+//   AND (weights depend on the reductions):    K = M(M+1)/2+M (Gram G_ij, N_i)
+// HBM bytes per sample: 4*D*(M+3)  (read x, noise, M scores; write x_out).
+#pragma once
+#include "common.cuh"
+#include "../../include/superdiff_b200.h"
+#include "step_vpsde_params.cuh"
+
+namespace sdb {
+
+
+__device__ __forceinline__ void ldv4(float (&d)[4], const float* p) {
+  const float4 t = ld_stream4(p);
+  d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+}
+
+struct StepScalars {
+  float a, b, sigma, dt;
+};
+
+__device__ __forceinline__ StepScalars load_scalars(const StepParams& p) {
+  StepScalars s{p.a, p.b, p.sigma, p.dt};
+  if (p.sched != nullptr) {
+    const int row = p.step_counter ? *p.step_counter : 0;
+    const float4 v = *reinterpret_cast<const float4*>(p.sched + 4 * (size_t)row);
+    s.a = v.x; s.b = v.y; s.sigma = v.z; s.dt = v.w;
+  }
+  return s;
+}
+
+// Mixing weights that do not need this step's reductions.
+template <int M>
+__device__ __forceinline__ void known_weights(const StepParams& p, int sample, float (&w)[M]) {
+  if (p.mode == SD_MODE_OR) {
+    float z[M], zmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      float l = p.logq[(size_t)sample * M + i];
+      if (p.logp_bias) l += p.logp_bias[i];
+      z[i] = p.temperature * l;
+      zmax = fmaxf(zmax, z[i]);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) { z[i] = expf(z[i] - zmax); den += z[i]; }
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = z[i] / den;
+  } else if (p.mode == SD_MODE_AVG) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = 1.0f / (float)M;
+  } else {  // FIXED
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = p.weights[(size_t)sample * M + i];
+  }
+}
+
+// Solve the AND system in fp64.  G packed upper
+// triangular: idx(i,j) for i<=j.  M == 2 uses the notebook's closed form.
+template <int M>
+__device__ void and_solve(const double* G /*packed*/, const double* N, double dtb, double c, double* kappa) {
+  auto g = [&](int i, int j) {
+    if (i > j) { int t = i; i = j; j = t; }
+    return G[i * M - (i * (i - 1)) / 2 + (j - i)];
+  };
+  if (M == 1) { kappa[0] = 1.0; return; }
+  if (M == 2) {
+    const double num = dtb * (g(0, 0) - g(1, 1)) - 2.0 * dtb * (g(0, 1) - g(1, 1)) - c * (N[0] - N[1]);
+    const double den = 2.0 * dtb * (g(0, 0) - 2.0 * g(0, 1) + g(1, 1));
+    kappa[0] = num / den;
+    kappa[1] = 1.0 - kappa[0];
+    return;
+  }
+  double A[M][M + 1];
+  for (int i = 0; i < M - 1; ++i) {
+    for (int j = 0; j < M; ++j) A[i][j] = 2.0 * dtb * (g(i, j) - g(M - 1, j));
+    A[i][M] = dtb * (g(i, i) - g(M - 1, M - 1)) - c * (N[i] - N[M - 1]);
+  }
+  for (int j = 0; j <= M; ++j) A[M - 1][j] = 1.0;
+  for (int col = 0; col < M; ++col) {  // Gaussian elimination, partial pivoting
+    int piv = col;
+    double best = fabs(A[col][col]);
+    for (int r = col + 1; r < M; ++r)
+      if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
+    if (piv != col)
+      for (int j = 0; j <= M; ++j) { double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
+    const double inv = 1.0 / A[col][col];
+    for (int r = col + 1; r < M; ++r) {
+      const double f = A[r][col] * inv;
+      for (int j = col; j <= M; ++j) A[r][j] -= f * A[col][j];
+    }
+  }
+  for (int i = M - 1; i >= 0; --i) {
+    double s = A[i][M];
+    for (int j = i + 1; j < M; ++j) s -= A[i][j] * kappa[j];
+    kappa[i] = s / A[i][i];
+  }
+}
+
+__device__ __forceinline__ void write_logq(const StepParams& p, const StepScalars& sc, int sample, int M,
+                                           const double* R /* already divided by sigma */) {
+  if (p.dlogq_mode == SD_DLOGQ_NONE) return;
+  double sub = 0.0;
+  if (p.dlogq_mode == SD_DLOGQ_CIFAR_MAXSUB) {
+    sub = -R[0];
+    for (int i = 1; i < M; ++i) sub = fmin(sub, -R[i]);   // -max_i R_i
+  } else {
+    sub = (double)p.ito_scale * (double)sc.dt * (double)sc.a;
+  }
+  for (int i = 0; i < M; ++i) {
+    float* q = p.logq + (size_t)sample * M + i;
+    // the reference accumulates logq in fp32 (cifar/eval_utils.py:84)
+    *q = *q + (float)(R[i] + sub);
+  }
+}
+
+// VEC = 4: float4 accesses (D % 4 == 0, 16B-aligned bases); VEC = 1: scalar.
+template <int M, int NV, int VEC, bool AND, bool CLUSTER>
+__global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__ StepParams p) {
+  extern __shared__ double scratch[];
+  unsigned csize = 1, crank = 0;
+  if (CLUSTER) {
+    cg::cluster_group cluster = cg::this_cluster();
+    csize = cluster.num_blocks();
+    crank = cluster.block_rank();
+  }
+  const int sample = blockIdx.x / csize;
+  const StepScalars sc = load_scalars(p);
+  const float dta = sc.dt * sc.a, dtb = sc.dt * sc.b;
+  const float c = sqrtf(2.f * sc.sigma * sc.b * sc.dt);
+  const int nunits = p.D / VEC;                                   // float4 (or scalar) units per sample
+  const int per_cta = (nunits + csize - 1) / csize;
+  const int u0 = crank * per_cta;
+  const int u1 = min(nunits, u0 + per_cta);
+  const size_t base = (size_t)sample * p.D;
+
+  constexpr int KAND = M * (M + 1) / 2 + M;
+  constexpr int K = AND ? KAND : M;
+  float part[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) part[k] = 0.f;
+
+  if (!AND) {
+    float w[M];
+    known_weights<M>(p, sample, w);
+    // weights known: stream the slice in rounds of NV units per thread
+    for (int r0 = u0; r0 < u1; r0 += NV * blockDim.x) {
+      float xv[NV][VEC], ev[NV][VEC], sv[M][NV][VEC];
+      bool ok[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int u = r0 + j * blockDim.x + threadIdx.x;
+        ok[j] = u < u1;
+        if (ok[j]) {
+          const size_t off = base + (size_t)u * VEC;
+          if constexpr (VEC == 4) {
+            ldv4(xv[j], p.x + off);
+            ldv4(ev[j], p.noise + off);
+#pragma unroll
+            for (int i = 0; i < M; ++i) ldv4(sv[i][j], p.s[i] + off);
+          } else {
+            xv[j][0] = ld_stream1(p.x + off);
+            ev[j][0] = ld_stream1(p.noise + off);
+#pragma unroll
+            for (int i = 0; i < M; ++i) sv[i][j][0] = ld_stream1(p.s[i] + off);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (!ok[j]) continue;
+        float o[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) {
+          float mix = 0.f;
+#pragma unroll
+          for (int i = 0; i < M; ++i) mix = fmaf(w[i], sv[i][j][e], mix);
+          const float xe = xv[j][e];
+          const float dx = -dta * xe + 2.f * dtb * mix + c * ev[j][e];
+          o[e] = xe + dx;
+          const float q = dx + dta * xe;                // dx + dt*a*x
+#pragma unroll
+          for (int i = 0; i < M; ++i) {
+            const float s = sv[i][j][e];
+            part[i] = fmaf(s, q - dtb * s, part[i]);    // s_i*(dx + dt*a*x - dt*b*s_i)
+          }
+        }
+        const size_t off = base + (size_t)(r0 + j * blockDim.x + threadIdx.x) * VEC;
+        if constexpr (VEC == 4) st4(p.x_out + off, make_float4(o[0], o[1], o[2], o[3]));
+        else p.x_out[off] = o[0];
+      }
+    }
+    const double* tot = block_cluster_sum<K, CLUSTER>(part, scratch);
+    if (crank == 0 && threadIdx.x == 0) {
+      double R[M];
+#pragma unroll
+      for (int i = 0; i < M; ++i) R[i] = tot[i] / (double)sc.sigma;
+      write_logq(p, sc, sample, M, R);
+      if (p.mode != SD_MODE_FIXED)
+        for (int i = 0; i < M; ++i) p.weights[(size_t)sample * M + i] = w[i];
+    }
+  } else {
+    // AND: the slice stays resident in registers between the reduction pass and the write pass
+    float xv[NV][VEC], ev[NV][VEC], sv[M][NV][VEC];
+    bool ok[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int u = u0 + j * blockDim.x + threadIdx.x;
+      ok[j] = u < u1;
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        xv[j][e] = 0.f; ev[j][e] = 0.f;
+#pragma unroll
+        for (int i = 0; i < M; ++i) sv[i][j][e] = 0.f;
+      }
+      if (ok[j]) {
+        const size_t off = base + (size_t)u * VEC;
+        if constexpr (VEC == 4) {
+          ldv4(xv[j], p.x + off);
+          ldv4(ev[j], p.noise + off);
+#pragma unroll
+          for (int i = 0; i < M; ++i) ldv4(sv[i][j], p.s[i] + off);
+        } else {
+          xv[j][0] = ld_stream1(p.x + off);
+          ev[j][0] = ld_stream1(p.noise + off);
+#pragma unroll
+          for (int i = 0; i < M; ++i) sv[i][j][0] = ld_stream1(p.s[i] + off);
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < M; ++i)
+#pragma unroll
+          for (int l = i; l < M; ++l) { part[k] = fmaf(sv[i][j][e], sv[l][j][e], part[k]); ++k; }
+#pragma unroll
+        for (int i = 0; i < M; ++i) part[M * (M + 1) / 2 + i] = fmaf(sv[i][j][e], ev[j][e], part[M * (M + 1) / 2 + i]);
+      }
+    const double* tot = block_cluster_sum<K, CLUSTER>(part, scratch);
+    // kappa: closed form for M <= 2 (every thread), one solver thread + smem broadcast otherwise
+    double* kappa_sh = scratch + ((blockDim.x + 31) / 32 + 2) * K;
+    double kappa[M];
+    if (M <= 2) {
+      and_solve<M>(tot, tot + M * (M + 1) / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
+    } else {
+      if (threadIdx.x == 0) {
+        and_solve<M>(tot, tot + M * (M + 1) / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
+        for (int i = 0; i < M; ++i) kappa_sh[i] = kappa[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < M; ++i) kappa[i] = kappa_sh[i];
+    }
+    float w[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = (float)kappa[i];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      if (!ok[j]) continue;
+      float o[VEC];
+#pragma unroll
+      for (int e = 0; e < VEC; ++e) {
+        float mix = 0.f;
+#pragma unroll
+        for (int i = 0; i < M; ++i) mix = fmaf(w[i], sv[i][j][e], mix);
+        o[e] = xv[j][e] + (-dta * xv[j][e] + 2.f * dtb * mix + c * ev[j][e]);
+      }
+      const size_t off = base + (size_t)(u0 + j * blockDim.x + threadIdx.x) * VEC;
+      if constexpr (VEC == 4) st4(p.x_out + off, make_float4(o[0], o[1], o[2], o[3]));
+      else p.x_out[off] = o[0];
+    }
+    if (crank == 0 && threadIdx.x == 0) {
+      // R_i = [2 dt b sum_j kappa_j G_ij + c N_i - dt b G_ii] / sigma   (Appendix A.2 with A.1 substituted)
+      auto g = [&](int i, int j) {
+        if (i > j) { int t = i; i = j; j = t; }
+        return tot[i * M - (i * (i - 1)) / 2 + (j - i)];
+      };
+      const double dtbd = (double)sc.dt * (double)sc.b;
+      double R[M];
+      for (int i = 0; i < M; ++i) {
+        double acc = 0.0;
+        for (int j = 0; j < M; ++j) acc += kappa[j] * g(i, j);
+        R[i] = (2.0 * dtbd * acc + (double)c * tot[M * (M + 1) / 2 + i] - dtbd * g(i, i)) / (double)sc.sigma;
+      }
+      write_logq(p, sc, sample, M, R);
+      for (int i = 0; i < M; ++i) p.weights[(size_t)sample * M + i] = w[i];
+    }
+  }
+}
+
+// Tiny-D path (toy 2-D notebook, D <= 64): one thread per sample, fp64 reductions.
+template <int M>
+__global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_constant__ StepParams p) {
+  const int sample = blockIdx.x * blockDim.x + threadIdx.x;
+  if (sample >= p.B) return;
+  const StepScalars sc = load_scalars(p);
+  const float dta = sc.dt * sc.a, dtb = sc.dt * sc.b;
+  const float c = sqrtf(2.f * sc.sigma * sc.b * sc.dt);
+  const size_t base = (size_t)sample * p.D;
+  float w[M];
+  double R[M];
+  if (p.mode == SD_MODE_AND) {
+    double G[M * (M + 1) / 2], N[M];
+    for (int k = 0; k < M * (M + 1) / 2; ++k) G[k] = 0.0;
+    for (int i = 0; i < M; ++i) N[i] = 0.0;
+    for (int d = 0; d < p.D; ++d) {
+      float s[M];
+#pragma unroll
+      for (int i = 0; i < M; ++i) s[i] = p.s[i][base + d];
+      const float e = p.noise[base + d];
+      int k = 0;
+#pragma unroll
+      for (int i = 0; i < M; ++i) {
+#pragma unroll
+        for (int l = i; l < M; ++l) G[k++] += (double)(s[i] * s[l]);
+        N[i] += (double)(s[i] * e);
+      }
+    }
+    double kappa[M];
+    and_solve<M>(G, N, (double)sc.dt * (double)sc.b, (double)c, kappa);
+#pragma unroll
+    for (int i = 0; i < M; ++i) w[i] = (float)kappa[i];
+  } else {
+    known_weights<M>(p, sample, w);
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) R[i] = 0.0;
+  for (int d = 0; d < p.D; ++d) {
+    float s[M];
+    float mix = 0.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) { s[i] = p.s[i][base + d]; mix = fmaf(w[i], s[i], mix); }
+    const float xe = p.x[base + d];
+    const float dx = -dta * xe + 2.f * dtb * mix + c * p.noise[base + d];
+    const float q = dx + dta * xe;
+#pragma unroll
+    for (int i = 0; i < M; ++i) R[i] += (double)(s[i] * (q - dtb * s[i]));
+    p.x_out[base + d] = xe + dx;
+  }
+#pragma unroll
+  for (int i = 0; i < M; ++i) R[i] /= (double)sc.sigma;
+  write_logq(p, sc, sample, M, R);
+  if (p.mode != SD_MODE_FIXED)
+    for (int i = 0; i < M; ++i) p.weights[(size_t)sample * M + i] = w[i];
+}
+
+template <int M, int NV, int VEC, bool AND>
+static cudaError_t launch_cfg(const StepParams& p, int threads, int cluster, cudaStream_t st) {
+  constexpr int K = AND ? (M * (M + 1) / 2 + M) : M;
+  const size_t smem = sizeof(double) * ((size_t)(threads / 32 + 2) * K + M);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.B * cluster);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, step_vpsde_kernel<M, NV, VEC, AND, true>, p);
+  }
+  return cudaLaunchKernelEx(&cfg, step_vpsde_kernel<M, NV, VEC, AND, false>, p);
+}
+
+template <int M>
+cudaError_t launch_m(const StepParams& p, int threads, int nv, int cluster, int vec, cudaStream_t st) {
+  const bool is_and = p.mode == SD_MODE_AND;
+#define SDB_CASE(NVv)                                                                        \
+  case NVv:                                                                                  \
+    if (vec == 4) return is_and ? launch_cfg<M, NVv, 4, true>(p, threads, cluster, st)        \
+                                : launch_cfg<M, NVv, 4, false>(p, threads, cluster, st);      \
+    return is_and ? launch_cfg<M, NVv, 1, true>(p, threads, cluster, st)                      \
+                  : launch_cfg<M, NVv, 1, false>(p, threads, cluster, st);
+  switch (nv) {
+    SDB_CASE(1)
+    SDB_CASE(2)
+    SDB_CASE(3)
+    SDB_CASE(4)
+  }
+#undef SDB_CASE
+  return cudaErrorInvalidValue;
+}
+
+template <int M>
+cudaError_t launch_small(const StepParams& p, cudaStream_t st) {
+  const int threads = 128;
+  step_vpsde_small_kernel<M><<<(p.B + threads - 1) / threads, threads, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+
+}  // namespace sdb

@@ -1,0 +1,291 @@
+"""Tensor-level wrappers over the C ABI (one Python call = one kernel launch)."""
+import ctypes
+
+import torch
+
+from . import _lib
+
+MODE_OR, MODE_AND, MODE_AVG, MODE_FIXED = 0, 1, 2, 3
+DLOGQ_CIFAR_MAXSUB, DLOGQ_ITO, DLOGQ_NONE = 0, 1, 2
+MODES = {"or": MODE_OR, "and": MODE_AND, "avg": MODE_AVG, "fixed": MODE_FIXED}
+DLOGQ_MODES = {"cifar": DLOGQ_CIFAR_MAXSUB, "ito": DLOGQ_ITO, "none": DLOGQ_NONE}
+
+_launches = 0  # kernels launched through this module (bench.py reports it as gpu_launches)
+
+
+def launch_count():
+    return _launches
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, name):
+    if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous float32 CUDA tensor")
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def step_vpsde(x, noise, scores, logq, a, b, sigma, dt, mode, dlogq_mode, temperature=1.0,
+               logp_bias=None, ito_scale=0.0, x_out=None, weights=None, sched=None, step_counter=None,
+               launch_shape=None):
+    """Fused VP-SDE SuperDiff step (sd_step_vpsde).  x, noise: (B, ...); scores:
+    list of M tensors shaped like x (or one stacked (M, B, ...) tensor); logq,
+    weights: (B, M), updated in place.  Returns (x_out, logq, weights)."""
+    lib = _lib.load()
+    if isinstance(scores, torch.Tensor):
+        scores = list(scores.unbind(0))
+    M = len(scores)
+    B = x.shape[0]
+    D = x[0].numel() if B > 0 else int(torch.tensor(x.shape[1:]).prod())
+    _f32c(x, "x"); _f32c(noise, "noise"); _f32c(logq, "logq")
+    for i, s in enumerate(scores):
+        _f32c(s, f"scores[{i}]")
+        if s.shape != x.shape:
+            raise ValueError("score shape mismatch")
+    if noise.shape != x.shape or logq.shape != (B, M):
+        raise ValueError("noise must match x and logq must be (B, M)")
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    if weights is None:
+        weights = torch.empty(B, M, device=x.device, dtype=torch.float32)
+    _f32c(x_out, "x_out"); _f32c(weights, "weights")
+    if isinstance(mode, str):
+        mode = MODES[mode]
+    if isinstance(dlogq_mode, str):
+        dlogq_mode = DLOGQ_MODES[dlogq_mode]
+    sp = (ctypes.c_void_p * M)(*[s.data_ptr() for s in scores])
+    common = (_ptr(x), _ptr(noise), sp, M, B, D, float(a), float(b), float(sigma), float(dt),
+              _ptr(sched), _ptr(step_counter), int(mode), int(dlogq_mode), float(temperature),
+              _ptr(logp_bias), float(ito_scale), _ptr(logq), _ptr(x_out), _ptr(weights), _stream())
+    if launch_shape is None:
+        rc = lib.sd_step_vpsde(*common)
+    else:
+        rc = lib.sd_step_vpsde_ex(*common, *[int(v) for v in launch_shape])
+    _lib.check(rc, "sd_step_vpsde")
+    if B > 0:
+        _count()
+    return x_out, logq, weights
+
+
+def step_edm_cfg(latents, z, v_obj, v_bg, v_unc, ll, sigma, dsigma, mode, guidance=7.5, lift_term=0.0,
+                 temperature=1.0, logp=0.0, kappa_fixed=0.5, latents_out=None, kappa_out=None):
+    """Fused EDM/CFG SuperDiff step on SD latents (sd_step_edm_cfg).  ll: (B, 2)
+    updated in place.  Returns (latents_out, ll, kappa)."""
+    lib = _lib.load()
+    B = latents.shape[0]
+    D = latents[0].numel()
+    for n, t in (("latents", latents), ("z", z), ("v_obj", v_obj), ("v_bg", v_bg), ("v_unc", v_unc), ("ll", ll)):
+        _f32c(t, n)
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    if kappa_out is None:
+        kappa_out = torch.empty(B, device=latents.device, dtype=torch.float32)
+    if isinstance(mode, str):
+        mode = MODES[mode]
+    rc = lib.sd_step_edm_cfg(_ptr(latents), _ptr(z), _ptr(v_obj), _ptr(v_bg), _ptr(v_unc), B, D,
+                             float(sigma), float(dsigma), float(guidance), float(lift_term), int(mode),
+                             float(temperature), float(logp), float(kappa_fixed),
+                             _ptr(ll), _ptr(latents_out), _ptr(kappa_out), _stream())
+    _lib.check(rc, "sd_step_edm_cfg")
+    if B > 0:
+        _count()
+    return latents_out, ll, kappa_out
+
+
+def counter_add(counter, delta=1):
+    _lib.check(_lib.load().sd_counter_add(_ptr(counter), int(delta), _stream()), "sd_counter_add")
+    _count()
+
+
+# ---------------------------------------------------------------------------
+# score-net ops (NHWC bf16 activations)
+# ---------------------------------------------------------------------------
+EPI_SWISH, EPI_OUT_F32 = 1, 2
+
+
+def _bf16c(t, name):
+    if not (t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous()):
+        raise ValueError(f"{name} must be a contiguous bfloat16 CUDA tensor")
+    return t
+
+
+def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False, out_f32=False, out=None,
+              n_out=None):
+    """Implicit GEMM over NHWC bf16 sources (sd_conv_gemm).  srcs: list of
+    (tensor [B,H,W,C], taps) with taps in {1, 9}; weight: bf16 [N, K]."""
+    lib = _lib.load()
+    x0 = srcs[0][0]
+    B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
+    arr = (_lib.GemmSrc * len(srcs))()
+    K = 0
+    for i, (t, taps) in enumerate(srcs):
+        _bf16c(t, f"srcs[{i}]")
+        if t.shape[:3] != x0.shape[:3]:
+            raise ValueError("all sources must share (B, H, W)")
+        arr[i].ptr = t.data_ptr()
+        arr[i].C = t.shape[3]
+        arr[i].taps = taps
+        K += taps * t.shape[3]
+    _bf16c(weight, "weight")
+    N = weight.shape[0] if n_out is None else n_out
+    if weight.shape[1] != K:
+        raise ValueError(f"weight K {weight.shape[1]} != {K}")
+    if out is None:
+        out = torch.empty(B, H, W, N, device=x0.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    rb_ld = rowbias.stride(0) if rowbias is not None else 0
+    if residual is not None:
+        _bf16c(residual, "residual")
+    rc = lib.sd_conv_gemm(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld,
+                          _ptr(residual), flags, _ptr(out), out.shape[-1], _stream())
+    _lib.check(rc, "sd_conv_gemm")
+    if B > 0:
+        _count()
+    return out
+
+
+def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None):
+    """out[b] = A[b] @ Bt[b]^T (sd_batched_gemm).  A: bf16 [batch, M, >=K] or [M, K]
+    (shared), Bt: bf16 [batch, N, >=K] or [N, K] (shared); row strides may exceed K."""
+    lib = _lib.load()
+    a3 = A if A.dim() == 3 else A.unsqueeze(0)
+    b3 = Bt if Bt.dim() == 3 else Bt.unsqueeze(0)
+    batch = max(a3.shape[0], b3.shape[0])
+    M, N = a3.shape[1], b3.shape[1]
+    if K is None:
+        K = a3.shape[2]
+    for t in (a3, b3):
+        if t.dtype != torch.bfloat16 or not t.is_cuda or t.stride(2) != 1:
+            raise ValueError("operands must be bf16 CUDA tensors with unit inner stride")
+    sA = a3.stride(0) if (A.dim() == 3 and a3.shape[0] > 1) else 0
+    sB = b3.stride(0) if (Bt.dim() == 3 and b3.shape[0] > 1) else 0
+    if out is None:
+        out = torch.empty(batch, M, N, device=A.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0)
+    rc = lib.sd_batched_gemm(_ptr(a3), a3.stride(1), sA, _ptr(b3), b3.stride(1), sB, batch, M, N, K,
+                             _ptr(bias), _ptr(residual), flags, _ptr(out), out.stride(-2),
+                             out.stride(0) if out.dim() == 3 else 0, _stream())
+    _lib.check(rc, "sd_batched_gemm")
+    if batch > 0:
+        _count()
+    return out
+
+
+def softmax_rows(x, scale, out=None):
+    lib = _lib.load()
+    _f32c(x, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_softmax_rows(_ptr(x), _ptr(out), rows, cols, float(scale), _stream()), "sd_softmax_rows")
+    _count()
+    return out
+
+
+def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
+    lib = _lib.load()
+    _bf16c(x0, "x0")
+    B = x0.shape[0]
+    HW = x0.shape[1] * x0.shape[2]
+    C0 = x0.shape[3]
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1, "x1")
+        C1 = x1.shape[3]
+    if out is None:
+        out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
+    rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
+                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(out), _stream())
+    _lib.check(rc, "sd_groupnorm_swish")
+    if B > 0:
+        _count()
+    return out
+
+
+def attention_small(qkv, C, out=None):
+    lib = _lib.load()
+    _bf16c(qkv, "qkv")
+    B, S = qkv.shape[0], qkv.shape[1]
+    if out is None:
+        out = torch.empty(B, S, C, device=qkv.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_attention(_ptr(qkv), B, S, C, _ptr(out), _stream()), "sd_attention")
+    if B > 0:
+        _count()
+    return out
+
+
+def upsample2x(x, out=None):
+    lib = _lib.load()
+    _bf16c(x, "x")
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, C, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_upsample2x(_ptr(x), B, H, W, C, _ptr(out), _stream()), "sd_upsample2x")
+    if B > 0:
+        _count()
+    return out
+
+
+def im2col_s2(x, out=None):
+    lib = _lib.load()
+    _bf16c(x, "x")
+    B, H, W, C = x.shape
+    if out is None:
+        out = torch.empty(B, H // 2, W // 2, 9 * C, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_im2col_s2(_ptr(x), B, H, W, C, _ptr(out), _stream()), "sd_im2col_s2")
+    if B > 0:
+        _count()
+    return out
+
+
+def conv_in(x, w_hwio, bias, out=None):
+    lib = _lib.load()
+    _f32c(x, "x")
+    B, H, W, Cin = x.shape
+    Cout = w_hwio.shape[-1]
+    if out is None:
+        out = torch.empty(B, H, W, Cout, device=x.device, dtype=torch.bfloat16)
+    rc = lib.sd_conv_in(_ptr(x), B, H, W, Cin, _ptr(_f32c(w_hwio, "w")), _ptr(bias), Cout, _ptr(out), _stream())
+    _lib.check(rc, "sd_conv_in")
+    if B > 0:
+        _count()
+    return out
+
+
+def time_embedding(B, nf, w0, b0, w1, b1, t=None, t_stride=0, sched=None, step_counter=None, class_emb=None,
+                   labels=None, scratch=None, out=None):
+    lib = _lib.load()
+    dev = w0.device
+    shared = sched is not None or t_stride == 0
+    if scratch is None:
+        scratch = torch.empty(1 if shared else B, 4 * nf, device=dev, dtype=torch.float32)
+    if out is None:
+        out = torch.empty(B, 4 * nf, device=dev, dtype=torch.bfloat16)
+    rc = lib.sd_time_embedding(_ptr(t), int(t_stride), _ptr(sched), _ptr(step_counter), B, nf, _ptr(w0), _ptr(b0),
+                               _ptr(w1), _ptr(b1), _ptr(class_emb), _ptr(labels), _ptr(scratch), _ptr(out), _stream())
+    _lib.check(rc, "sd_time_embedding")
+    if B > 0:
+        _count(2)
+    return out
+
+
+def cast_bf16(x, out=None):
+    lib = _lib.load()
+    _f32c(x, "x")
+    if out is None:
+        out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_cast_f32_to_bf16(_ptr(x), _ptr(out), x.numel(), _stream()), "sd_cast_f32_to_bf16")
+    _count()
+    return out

@@ -1,0 +1,193 @@
+"""GPU parity of the score-net building blocks against plain torch math on the
+same bf16-rounded inputs (fp32/fp64 reference; tolerance = bf16 output rounding,
+2^-8 relative, plus fp32 accumulation-order noise)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from super_diffusion_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _close(got, ref, rtol=1.2e-2, atol=None):
+    got = got.float().cpu().double()
+    ref = ref.double().cpu()
+    if atol is None:
+        atol = 1.2e-2 * ref.abs().max().item() / 4 + 1e-6
+    err = (got - ref).abs()
+    bad = err > atol + rtol * ref.abs()
+    assert not bad.any(), (err.max().item(), ref.abs().max().item(), int(bad.sum()))
+
+
+def _conv_ref(x, w_nk, taps, C):
+    # x: [B,H,W,C] float; w_nk: [N, taps*C] float (tap-major, then channel)
+    N = w_nk.shape[0]
+    if taps == 1:
+        return torch.einsum("bhwc,nc->bhwn", x, w_nk)
+    w = w_nk.reshape(N, 3, 3, C).permute(0, 3, 1, 2)  # OIHW
+    return F.conv2d(x.permute(0, 3, 1, 2), w, padding=1).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("B,H,W,C,N,taps", [
+    (2, 32, 32, 128, 128, 9), (3, 16, 16, 256, 256, 9), (5, 8, 8, 128, 256, 9), (9, 4, 4, 256, 256, 9),
+    (2, 32, 32, 64, 16, 9), (2, 32, 32, 128, 3, 9), (4, 16, 16, 256, 768, 1), (2, 32, 32, 256, 128, 1),
+    (1, 32, 32, 64, 64, 9), (16, 4, 4, 512, 256, 1), (3, 8, 8, 256, 48, 1),
+])
+def test_conv_gemm_single_source(cuda, B, H, W, C, N, taps):
+    g = torch.Generator().manual_seed(B * 1000 + H + C + N)
+    x = _bf(torch.randn(B, H, W, C, generator=g))
+    w = _bf(torch.randn(N, taps * C, generator=g) / math.sqrt(taps * C))
+    bias = torch.randn(N, generator=g)
+    out = ops.conv_gemm([(x.to(cuda), taps)], w.to(cuda), bias=bias.to(cuda))
+    torch.cuda.synchronize()
+    ref = _conv_ref(x.double(), w.double(), taps, C) + bias.double()
+    assert out.shape == (B, H, W, N)
+    _close(out, ref)
+
+
+def test_conv_gemm_fused_resblock_tail(cuda):
+    """conv2 (9 taps) + NIN shortcut over a 2-tensor concat (1 tap each) + bias + time-embedding row bias,
+    i.e. the tail of ResnetBlockDDPM (cifar/models/layers.py:556-565) as ONE GEMM; then residual/swish/f32 flags."""
+    B, H, W, Co, C0, C1 = 3, 16, 16, 256, 256, 128
+    g = torch.Generator().manual_seed(7)
+    a2 = _bf(torch.randn(B, H, W, Co, generator=g))
+    xa = _bf(torch.randn(B, H, W, C0, generator=g))
+    xb = _bf(torch.randn(B, H, W, C1, generator=g))
+    w_conv = torch.randn(Co, 9 * Co, generator=g) / math.sqrt(9 * Co)
+    w_nin = torch.randn(Co, C0 + C1, generator=g) / math.sqrt(C0 + C1)
+    w = _bf(torch.cat([w_conv, w_nin], dim=1))
+    bias = torch.randn(Co, generator=g)
+    rowbias = torch.randn(B, 640, generator=g)
+    out = ops.conv_gemm([(a2.to(cuda), 9), (xa.to(cuda), 1), (xb.to(cuda), 1)], w.to(cuda), bias=bias.to(cuda),
+                        rowbias=rowbias.to(cuda)[:, 128:128 + Co])
+    wd = w.double()
+    ref = _conv_ref(a2.double(), wd[:, :9 * Co], 9, Co) \
+        + torch.einsum("bhwc,nc->bhwn", torch.cat([xa, xb], -1).double(), wd[:, 9 * Co:]) \
+        + bias.double() + rowbias.double()[:, None, None, 128:128 + Co]
+    _close(out, ref)
+    res = _bf(torch.randn(B, H, W, Co, generator=g))
+    out2 = ops.conv_gemm([(a2.to(cuda), 9)], w[:, :9 * Co].contiguous().to(cuda), bias=bias.to(cuda),
+                         residual=res.to(cuda), swish=True, out_f32=True)
+    r2 = _conv_ref(a2.double(), wd[:, :9 * Co], 9, Co) + bias.double() + res.double()
+    r2 = r2 * torch.sigmoid(r2)
+    assert out2.dtype == torch.float32
+    _close(out2, r2, rtol=2e-3, atol=2e-3)
+
+
+def test_conv_gemm_many_tiles_persistent(cuda):
+    """More tiles than SMs (B=64 at 32x32 -> 512 tiles): exercises the persistent loop, the smem ring
+    wrap-around and the two TMEM accumulators."""
+    B, H, W, C, N = 64, 32, 32, 128, 128
+    g = torch.Generator().manual_seed(3)
+    x = _bf(torch.randn(B, H, W, C, generator=g))
+    w = _bf(torch.randn(N, 9 * C, generator=g) / math.sqrt(9 * C))
+    out = ops.conv_gemm([(x.to(cuda), 9)], w.to(cuda))
+    ref = F.conv2d(x.to(cuda).float().permute(0, 3, 1, 2), w.to(cuda).float().reshape(N, 3, 3, C).permute(0, 3, 1, 2),
+                   padding=1).permute(0, 2, 3, 1)
+    _close(out, ref.cpu())
+
+
+@pytest.mark.parametrize("batch,M,N,K,shareA,shareB", [
+    (1, 512, 640, 512, False, True), (1, 100, 256, 128, False, True), (6, 256, 256, 256, False, False),
+    (5, 256, 256, 256, True, False), (3, 128, 64, 64, False, False), (2, 200, 40, 192, False, False),
+])
+def test_batched_gemm(cuda, batch, M, N, K, shareA, shareB):
+    g = torch.Generator().manual_seed(batch + M + N + K)
+    A = _bf(torch.randn(*( (M, K) if shareA else (batch, M, K)), generator=g))
+    Bt = _bf(torch.randn(*( (N, K) if shareB else (batch, N, K)), generator=g) / math.sqrt(K))
+    bias = torch.randn(N, generator=g)
+    out = ops.batched_gemm(A.to(cuda), Bt.to(cuda), bias=bias.to(cuda), out_f32=True)
+    Ad = A.double() if A.dim() == 3 else A.double()[None]
+    Bd = Bt.double() if Bt.dim() == 3 else Bt.double()[None]
+    ref = torch.einsum("bmk,bnk->bmn", Ad.expand(batch, -1, -1), Bd.expand(batch, -1, -1)) + bias.double()
+    _close(out, ref, rtol=1e-4, atol=1e-4)
+
+
+def test_batched_gemm_strided_qkv_views(cuda):
+    """q k^T on strided views of a packed [B, S, 3C] tensor (the attention layout)."""
+    B, S, C = 4, 256, 256
+    g = torch.Generator().manual_seed(11)
+    qkv = _bf(torch.randn(B, S, 3 * C, generator=g)).to(cuda)
+    q, k = qkv[:, :, :C], qkv[:, :, C:2 * C]
+    out = ops.batched_gemm(q, k, out_f32=True, K=C)
+    ref = torch.einsum("bsc,btc->bst", q.double(), k.double())
+    _close(out, ref.cpu(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("B,H,C0,C1,swish", [(3, 32, 128, 0, True), (2, 32, 256, 128, True), (2, 16, 256, 256, True),
+                                            (5, 8, 256, 0, False), (9, 4, 256, 256, True), (2, 32, 128, 128, True),
+                                            (2, 16, 128, 0, True), (1, 16, 256, 128, True)])
+def test_groupnorm_swish(cuda, B, H, C0, C1, swish):
+    g = torch.Generator().manual_seed(B + H + C0 + C1)
+    x0 = _bf(1.5 * torch.randn(B, H, H, C0, generator=g) + 0.3)
+    x1 = _bf(0.7 * torch.randn(B, H, H, C1, generator=g) - 0.2) if C1 else None
+    C = C0 + C1
+    gamma = 1 + 0.1 * torch.randn(C, generator=g)
+    beta = 0.1 * torch.randn(C, generator=g)
+    out = ops.groupnorm_swish(x0.to(cuda), gamma.to(cuda), beta.to(cuda), x1=x1.to(cuda) if C1 else None, swish=swish)
+    x = torch.cat([x0, x1], -1).double() if C1 else x0.double()
+    xr = x.reshape(B, H * H, 32, C // 32)
+    mean = xr.mean(dim=(1, 3), keepdim=True)
+    var = (xr * xr).mean(dim=(1, 3), keepdim=True) - mean * mean
+    y = ((xr - mean) / torch.sqrt(var + 1e-6)).reshape(B, H, H, C) * gamma.double() + beta.double()
+    if swish:
+        y = y * torch.sigmoid(y)
+    _close(out, y, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("S", [16, 64])
+def test_attention_small(cuda, S):
+    B, C = 5, 256
+    g = torch.Generator().manual_seed(S)
+    qkv = _bf(torch.randn(B, S, 3 * C, generator=g))
+    out = ops.attention_small(qkv.to(cuda), C)
+    q, k, v = qkv.double().split(C, dim=-1)
+    w = torch.softmax(torch.einsum("bsc,btc->bst", q, k) * C ** -0.5, dim=-1)
+    _close(out, torch.einsum("bst,btc->bsc", w, v), rtol=1e-2, atol=1e-2)
+
+
+def test_softmax_rows(cuda):
+    x = torch.randn(3, 256, 256) * 8
+    out = ops.softmax_rows(x.to(cuda), 1 / 16)
+    _close(out, torch.softmax(x.double() / 16, -1), rtol=1e-2, atol=1e-4)
+
+
+def test_upsample_im2col_convin_temb(cuda):
+    g = torch.Generator().manual_seed(5)
+    x = _bf(torch.randn(3, 8, 8, 256, generator=g))
+    up = ops.upsample2x(x.to(cuda))
+    assert torch.equal(up.cpu(), x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    col = ops.im2col_s2(x.to(cuda)).cpu()
+    xp = F.pad(x, (0, 0, 0, 1, 0, 1))
+    ref = torch.stack([xp[:, kh:kh + 8:2, kw:kw + 8:2, :] for kh in range(3) for kw in range(3)], dim=3).reshape(3, 4, 4, 9 * 256)
+    assert torch.equal(col, ref)
+    xi = torch.randn(4, 32, 32, 3, generator=g)
+    w = torch.randn(3, 3, 3, 128, generator=g) / math.sqrt(27)
+    b = torch.randn(128, generator=g)
+    ci = ops.conv_in(xi.to(cuda), w.to(cuda), b.to(cuda))
+    ref = F.conv2d(xi.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), b.double(), padding=1).permute(0, 2, 3, 1)
+    _close(ci, ref, rtol=1e-2, atol=1e-2)
+    # time embedding (cifar/models/layers.py:450-461 + ddpm.py:64-68) -> swish(temb) in bf16
+    nf, B = 128, 6
+    w0, b0 = torch.randn(nf, 4 * nf, generator=g) / math.sqrt(nf), 0.1 * torch.randn(4 * nf, generator=g)
+    w1, b1 = torch.randn(4 * nf, 4 * nf, generator=g) / math.sqrt(4 * nf), 0.1 * torch.randn(4 * nf, generator=g)
+    emb_tab = torch.randn(10, 4 * nf, generator=g)
+    labels = torch.arange(B, dtype=torch.int32) % 10
+    for t_val, per_sample in ((0.37, False), (None, True)):
+        tt = torch.rand(B, generator=g) if per_sample else torch.full((1,), t_val)
+        got = ops.time_embedding(B, nf, w0.to(cuda), b0.to(cuda), w1.to(cuda), b1.to(cuda), t=tt.to(cuda),
+                                 t_stride=1 if per_sample else 0, class_emb=emb_tab.to(cuda), labels=labels.to(cuda))
+        tv = (tt if per_sample else tt.expand(B)).double()
+        half = nf // 2
+        f = torch.exp(torch.arange(half, dtype=torch.float32) * -(math.log(10000) / (half - 1))).double()
+        e = torch.cat([torch.sin(tv[:, None] * f), torch.cos(tv[:, None] * f)], 1)
+        h = e @ w0.double() + b0.double()
+        h = (h * torch.sigmoid(h)) @ w1.double() + b1.double() + emb_tab.double()[labels.long()]
+        _close(got, h * torch.sigmoid(h), rtol=1e-2, atol=1e-2)
