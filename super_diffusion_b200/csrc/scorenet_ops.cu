@@ -373,24 +373,17 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   if (B == 0) return SD_OK;
   GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, gamma, beta, eps, apply_swish, (__nv_bfloat16*)out};
   const int VC = C / 8;
-  int k = 256 / VC;
-  if (k < 1) k = 1;
-  while (VC * k > 512) --k;
-  if (k < 1) return fail(kErrUnsupported, "sd_groupnorm_swish: too many channels");
-  const int threads = VC * k;     // multiple of VC; rows_per_pass = k
-  if (threads % 32) {
-    // keep whole warps: pad k until threads is a multiple of 32 (VC is a multiple of 4 since C % 32 == 0)
-    int kk = k;
-    while ((VC * kk) % 32 && VC * (kk + 1) <= 512) ++kk;
-    if ((VC * kk) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
-    k = kk;
-  }
-  const int T = VC * k;
-  int cluster = 0, nv = 0;
-  for (int c = 1; c <= 8; c *= 2) {
+  // threads = VC * k (k pixel rows per pass, whole warps, <= 512); smallest cluster, then fewest threads >= 256,
+  // such that a CTA's pixel slice fits in NV <= 16 vectors per thread
+  int cluster = 0, nv = 0, T = 0;
+  for (int c = 1; c <= 8 && !cluster; c *= 2) {
     const int px = (HW + c - 1) / c;
-    const int need = (px + k - 1) / k;
-    if (need <= 16) { cluster = c; nv = need; break; }
+    for (int k = 1; VC * k <= 512; ++k) {
+      if ((VC * k) % 32) continue;
+      const int need = (px + k - 1) / k;
+      const bool big_enough = VC * k >= 256 || VC * (k + 1) > 512;
+      if (need <= 16 && (big_enough || need <= 1)) { cluster = c; nv = need; T = VC * k; break; }
+    }
   }
   if (!cluster) return fail(kErrUnsupported, "sd_groupnorm_swish: H*W*C too large for the register-resident path");
   cudaError_t err;

@@ -1,0 +1,253 @@
+"""B200-native 'score-net' (the reference's DDPM U-Net, cifar/models/ddpm.py:41-101).
+
+Same registry name, config fields and call signature as the reference
+(``model_fn(t, x, y)`` with t (B,1,1,1), x (B,H,W,C) NHWC fp32, y (B,) labels;
+returns (B,H,W,C) fp32 = sigma_t * grad log q_t), but the forward is a fixed
+sequence of hand-written sm_100a kernels reached through the C ABI:
+
+* every 3x3 conv / NIN / Dense is the tcgen05 implicit GEMM (``ops.conv_gemm``,
+  ``ops.batched_gemm``) with bf16 operands and fp32 accumulation in TMEM;
+  conv bias, the time-embedding projection (layers.py:556), the NIN shortcut
+  (:560-564, fused as extra K-blocks) and the residual add (:565, :511) live in
+  the GEMM epilogue / K loop;
+* GroupNorm+swish (normalization.py:38-39 + layers.py:552,557) is one
+  cluster-per-sample kernel that also performs the skip concat of ddpm.py:90;
+* attention (layers.py:505-509) is batched tcgen05 GEMMs + a row softmax at
+  S = 256 and a small CUDA-core kernel at S <= 64.
+
+Activations are NHWC bf16 between kernels; the output score is fp32.
+There is no PyTorch / CPU fallback for the forward.
+"""
+import math
+
+import torch
+
+from .. import _lib, ops
+from . import utils
+
+
+def _conv_w(p):
+    """Flax HWIO [3,3,Cin,Cout] -> bf16 [Cout, 9*Cin] (tap-major, then channel)."""
+    k = p["kernel"]
+    return k.permute(3, 0, 1, 2).reshape(k.shape[3], -1).contiguous()
+
+
+class _Bound:
+    """ScoreNet bound to one parameter tree, weights resident on the device in GEMM layout."""
+
+    def __init__(self, model, params, device):
+        self.model = model
+        self.config = model.config
+        self.device = device
+        self._prepare(params)
+
+    # -- weight upload -------------------------------------------------------
+    def _dev(self, t, dtype=torch.float32):
+        return t.detach().to(device=self.device, dtype=dtype).contiguous()
+
+    def _prepare(self, P):
+        cfg = self.config
+        m = cfg.model
+        nf, ch_mult, nrb = m.nf, tuple(m.ch_mult), m.num_res_blocks
+        attn_res = tuple(m.attn_resolutions)
+        bf = torch.bfloat16
+        self.nf = nf
+        self.temb_w0 = self._dev(P["Dense_0"]["kernel"]); self.temb_b0 = self._dev(P["Dense_0"]["bias"])
+        self.temb_w1 = self._dev(P["Dense_1"]["kernel"]); self.temb_b1 = self._dev(P["Dense_1"]["bias"])
+        self.class_emb = self._dev(P["Embed_0"]["embedding"]) if m.conditioned else None
+        self.conv_in_w = self._dev(P["Conv_0"]["kernel"]); self.conv_in_b = self._dev(P["Conv_0"]["bias"])
+
+        dense_w, dense_b = [], []
+        self.res = []
+        self.attn = []
+        self.down = []
+        self.up = []
+        self.plan = []     # op list mirroring the control flow of ddpm.py:70-99
+        off = 0
+        counters = {"res": 0, "attn": 0, "down": 0, "up": 0}
+
+        def add_res(cin_parts, cout):
+            nonlocal off
+            blk = P[f"ResnetBlockDDPM_{counters['res']}"]
+            cin = sum(cin_parts)
+            w2 = _conv_w(blk["Conv_1"])
+            b2 = blk["Conv_1"]["bias"].clone()
+            nin = "NIN_0" in blk
+            if nin:
+                w2 = torch.cat([w2, blk["NIN_0"]["W"].T], dim=1)
+                b2 = b2 + blk["NIN_0"]["b"]
+            dense_w.append(blk["Dense_0"]["kernel"].T)                       # [cout, 4nf]
+            dense_b.append(blk["Dense_0"]["bias"] + blk["Conv_0"]["bias"])   # conv1 bias folded into the row bias
+            r = dict(g1=self._dev(blk["GroupNorm_0"]["scale"]), be1=self._dev(blk["GroupNorm_0"]["bias"]),
+                     w1=self._dev(_conv_w(blk["Conv_0"]), bf),
+                     g2=self._dev(blk["GroupNorm_1"]["scale"]), be2=self._dev(blk["GroupNorm_1"]["bias"]),
+                     w2=self._dev(w2, bf), b2=self._dev(b2), nin=nin, cout=cout, off=off, cin=cin)
+            off += cout
+            self.res.append(r)
+            counters["res"] += 1
+            return len(self.res) - 1
+
+        def add_attn(c):
+            blk = P[f"AttnBlock_{counters['attn']}"]
+            wq, wk, wv, wo = (blk[f"NIN_{i}"]["W"] for i in range(4))
+            bq, bk, bv, bo = (blk[f"NIN_{i}"]["b"] for i in range(4))
+            a = dict(g=self._dev(blk["GroupNorm_0"]["scale"]), be=self._dev(blk["GroupNorm_0"]["bias"]),
+                     w_qkv=self._dev(torch.cat([wq.T, wk.T, wv.T], 0), bf), b_qkv=self._dev(torch.cat([bq, bk, bv])),
+                     w_qk=self._dev(torch.cat([wq.T, wk.T], 0), bf), b_qk=self._dev(torch.cat([bq, bk])),
+                     w_vT=self._dev(wv.T, bf), b_v=self._dev(bv),
+                     w_o=self._dev(wo.T, bf), b_o=self._dev(bo), c=c)
+            self.attn.append(a)
+            counters["attn"] += 1
+            return len(self.attn) - 1
+
+        size = cfg.data.image_size
+        c = nf
+        chans = [nf]
+        nres = len(ch_mult)
+        for lvl in range(nres):
+            for _ in range(nrb):
+                ri = add_res([c], nf * ch_mult[lvl])
+                c = nf * ch_mult[lvl]
+                ai = add_attn(c) if size in attn_res else None
+                self.plan.append(("down_block", ri, ai))
+                chans.append(c)
+            if lvl != nres - 1:
+                blk = P[f"Downsample_{counters['down']}"]["Conv_0"]
+                self.down.append(dict(w=self._dev(_conv_w(blk), bf), b=self._dev(blk["bias"])))
+                self.plan.append(("downsample", len(self.down) - 1))
+                counters["down"] += 1
+                size //= 2
+                chans.append(c)
+        r0 = add_res([c], c); a0 = add_attn(c); r1 = add_res([c], c)
+        self.plan.append(("mid", r0, a0, r1))
+        for lvl in reversed(range(nres)):
+            for _ in range(nrb + 1):
+                ri = add_res([c, chans.pop()], nf * ch_mult[lvl])
+                c = nf * ch_mult[lvl]
+                self.plan.append(("up_block", ri))
+            if size in attn_res:
+                self.plan.append(("attn", add_attn(c)))
+            if lvl != 0:
+                blk = P[f"Upsample_{counters['up']}"]["Conv_0"]
+                self.up.append(dict(w=self._dev(_conv_w(blk), bf), b=self._dev(blk["bias"])))
+                self.plan.append(("upsample", len(self.up) - 1))
+                counters["up"] += 1
+                size *= 2
+        assert not chans
+        self.out_g = self._dev(P["GroupNorm_0"]["scale"]); self.out_be = self._dev(P["GroupNorm_0"]["bias"])
+        wout = _conv_w(P["Conv_1"])                       # [C_img, 9*nf]
+        self.n_img = wout.shape[0]
+        pad = (-wout.shape[0]) % 16
+        self.out_w = self._dev(torch.cat([wout, torch.zeros(pad, wout.shape[1])], 0), bf)
+        self.out_b = self._dev(P["Conv_1"]["bias"])
+        self.dense_w = self._dev(torch.cat(dense_w, 0), bf)   # [sum cout, 4nf]
+        self.dense_b = self._dev(torch.cat(dense_b, 0))
+        self.dense_n = off
+
+    # -- forward ---------------------------------------------------------------
+    def _res(self, srcs, i, rowbias):
+        r = self.res[i]
+        x0 = srcs[0]
+        x1 = srcs[1] if len(srcs) > 1 else None
+        a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1)
+        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]])
+        a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"])
+        if r["nin"]:
+            return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"])
+        return ops.conv_gemm([(a2, 9)], r["w2"], bias=r["b2"], residual=x0)
+
+    def _attn(self, x, i):
+        a = self.attn[i]
+        B, H, W, C = x.shape
+        S = H * W
+        h = ops.groupnorm_swish(x, a["g"], a["be"], swish=False)
+        if S <= 64:
+            qkv = ops.conv_gemm([(h, 1)], a["w_qkv"], bias=a["b_qkv"])
+            o = ops.attention_small(qkv.view(B, S, 3 * C), C)
+        else:
+            qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(B, S, 2 * C)
+            vt = ops.batched_gemm(a["w_vT"], h.view(B, S, C))                       # [B, C, S] = V^T (bias deferred)
+            sc = ops.batched_gemm(qk[:, :, :C], qk[:, :, C:], out_f32=True, K=C)    # [B, S, S]
+            p = ops.softmax_rows(sc, C ** -0.5)
+            o = ops.batched_gemm(p, vt, bias=a["b_v"])                              # rows of p sum to 1 -> + b_v
+        return ops.conv_gemm([(o.view(B, H, W, C), 1)], a["w_o"], bias=a["b_o"], residual=x)
+
+    def __call__(self, t, x, y=None, *, sched=None, step_counter=None, out=None):
+        """t: (B,1,1,1)/(B,)/scalar tensor or float; x: (B,H,W,C) fp32 NHWC on the device."""
+        _lib.require_device()
+        B = x.shape[0]
+        if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
+            raise ValueError("x must be a contiguous float32 CUDA tensor (NHWC)")
+        labels = None
+        if self.class_emb is not None:
+            if y is None:
+                raise ValueError("conditioned score-net needs labels")
+            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
+        if sched is not None:
+            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
+                                     sched=sched, step_counter=step_counter, class_emb=self.class_emb, labels=labels)
+        else:
+            if not torch.is_tensor(t):
+                t = torch.full((1,), float(t), device=x.device, dtype=torch.float32)
+            t = t.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+            stride = 0 if t.numel() == 1 else 1
+            if stride and t.numel() != B:
+                raise ValueError("t must have one entry per sample")
+            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
+                                     t=t, t_stride=stride, class_emb=self.class_emb, labels=labels)
+        rowbias = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0]    # [B, sum cout]
+        h = ops.conv_in(x, self.conv_in_w, self.conv_in_b)
+        hs = [h]
+        for op in self.plan:
+            kind = op[0]
+            if kind == "down_block":
+                h = self._res([hs[-1]], op[1], rowbias)
+                if op[2] is not None:
+                    h = self._attn(h, op[2])
+                hs.append(h)
+            elif kind == "downsample":
+                d = self.down[op[1]]
+                h = ops.conv_gemm([(ops.im2col_s2(hs[-1]), 1)], d["w"], bias=d["b"])
+                hs.append(h)
+            elif kind == "mid":
+                h = self._res([hs[-1]], op[1], rowbias)
+                h = self._attn(h, op[2])
+                h = self._res([h], op[3], rowbias)
+            elif kind == "up_block":
+                h = self._res([h, hs.pop()], op[1], rowbias)
+            elif kind == "attn":
+                h = self._attn(h, op[1])
+            elif kind == "upsample":
+                u = self.up[op[1]]
+                h = ops.conv_gemm([(ops.upsample2x(h), 9)], u["w"], bias=u["b"])
+        assert not hs
+        a = ops.groupnorm_swish(h, self.out_g, self.out_be)
+        return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)
+
+
+@utils.register_model(name="score-net")
+class ScoreNet:
+    """cifar/models/ddpm.py:41-101.  ``ScoreNet(config).bind(params)`` gives the callable."""
+
+    def __init__(self, config):
+        self.config = config
+        m = config.model
+        if m.normalization != "GroupNorm" or m.nonlinearity.lower() != "swish" or not m.resamp_with_conv:
+            raise NotImplementedError("the B200 score-net implements the reference's CIFAR config family: "
+                                      "GroupNorm + swish + conv resampling (cifar/configs/sm/cifar/vpsde*.py)")
+        if m.nf % 64 or config.data.num_channels > 4:
+            raise NotImplementedError("nf must be a multiple of 64 and the image must have <= 4 channels")
+
+    def bind(self, params, device=None):
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        return _Bound(self, params, device)
+
+    def apply(self, variables, t, x, y, train=False, mutable=False, rngs=None):
+        """Flax-style entry used by the reference's get_model_fn (models/utils.py:91-95)."""
+        if train:
+            raise NotImplementedError("train=True (dropout) is outside the sampling path")
+        key = id(variables["params"])
+        cache = self.__dict__.setdefault("_bound_cache", {})
+        if key not in cache:
+            cache[key] = self.bind(variables["params"], x.device)
+        return cache[key](t, x, y)

@@ -1,0 +1,206 @@
+"""SuperDiff OR / AND sampling loops over the fused sm_100a step kernels.
+
+Entry points mirror the reference's three superposition loops:
+
+* ``superdiff_or`` / ``superdiff_and`` — notebooks/superposition_edu.ipynb:797-822
+  (stochastic OR) and :922-949 (stochastic AND): caller-supplied score models
+  ``score_fn(t, x) -> sigma_t * grad log q_t(x)``, VP-SDE schedule, ``t`` accumulated
+  in float32 like the notebook, log-density trajectories returned.
+* ``sd_superdiff`` — applications/images/clip_eval.py:348-415 (methods and / or /
+  avg): caller-supplied velocity function (the UNet stays PyTorch), EDM sigma table.
+* ``SuperDiffSampler`` — the CIFAR loop (cifar/eval_utils.py:72-86 over
+  cifar/dynamics.py:115-136) with the whole timestep (M score-net forwards + fused
+  step) captured once into a CUDA graph and replayed per step; per-step scalars come
+  from a device-side schedule table, so no host value is baked into the graph.
+"""
+import math
+
+import torch
+
+from . import _lib, ops, sde
+
+
+def _noise_iter(noise, n, shape, device, seed):
+    """noise: None (draw with torch.randn from `seed`), a [n, *shape] tensor (device or pinned host),
+    or a callable i -> tensor."""
+    if noise is None:
+        g = torch.Generator(device=device)
+        g.manual_seed(int(seed))
+        return lambda i: torch.randn(shape, generator=g, device=device, dtype=torch.float32)
+    if callable(noise):
+        return noise
+    if noise.shape[0] < n:
+        raise ValueError("noise tensor has fewer steps than n_steps")
+    return lambda i: noise[i].to(device, non_blocking=True)
+
+
+def _vpsde_loop(score_fns, x0, mode, dlogq_mode, n_steps, dt, noise, seed, temperature, logp_bias, ito_scale,
+                ll0, accumulate, record):
+    _lib.require_device()
+    M = len(score_fns)
+    x = x0.clone().contiguous()
+    B = x.shape[0]
+    dev = x.device
+    ll = torch.zeros(B, M, device=dev, dtype=torch.float32) if ll0 is None else ll0.to(dev, torch.float32).clone().contiguous()
+    w = torch.empty(B, M, device=dev, dtype=torch.float32)
+    ts = sde.time_grid(n_steps, dt, accumulate)
+    nz = _noise_iter(noise, n_steps, x.shape, dev, seed)
+    bias = None if logp_bias is None else torch.as_tensor(logp_bias, dtype=torch.float32, device=dev)
+    traj = {"ll": [ll.clone()], "kappa": [], "x": [x.clone()]} if record else None
+    for i in range(n_steps):
+        t = float(ts[i])
+        tt = torch.full((B, 1), t, device=dev, dtype=torch.float32)
+        scores = [f(tt, x).contiguous() for f in score_fns]
+        ops.step_vpsde(x, nz(i), scores, ll, sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t), dt, mode, dlogq_mode,
+                       temperature=temperature, logp_bias=bias, ito_scale=ito_scale, x_out=x, weights=w)
+        if record:
+            traj["ll"].append(ll.clone()); traj["kappa"].append(w.clone()); traj["x"].append(x.clone())
+    if record:
+        traj = {k: torch.stack(v) for k, v in traj.items()}
+    return x, ll, w, traj
+
+
+def superdiff_or(score_fns, x0, n_steps=1000, dt=1e-3, noise=None, seed=0, temperature=1.0, logp_bias=None,
+                 ito_scale=None, accumulate="float32", record=False):
+    """Stochastic SuperDiff-OR (superposition_edu.ipynb:797-822): kappa = softmax(T * ll) (:813, T = 1),
+    ll_k(0) = 0 (:806-807), ll_k += get_stoch_dll (:818-819).  ``ito_scale`` defaults to the notebook's
+    ndim * D (the ``ndim*dt*a`` term broadcast over D elements, :778)."""
+    D = x0[0].numel()
+    ito = float(D * D) if ito_scale is None else float(ito_scale)
+    return _vpsde_loop(score_fns, x0, ops.MODE_OR, ops.DLOGQ_ITO, n_steps, dt, noise, seed, temperature, logp_bias,
+                       ito, None, accumulate, record)
+
+
+def superdiff_and(score_fns, x0, n_steps=1000, dt=1e-3, noise=None, seed=0, ito_scale=None, accumulate="float32",
+                  record=False):
+    """Stochastic SuperDiff-AND (superposition_edu.ipynb:922-949): kappa from select_kappa (:899-905; the
+    general-M linear solve of SURVEY.md A.3 for M > 2, which the reference does not have),
+    ll_k(0) = -|x0|^2/2 - ndim*log(2 pi) (:932), same noise inside kappa and dx (:900,943)."""
+    D = x0[0].numel()
+    ito = float(D * D) if ito_scale is None else float(ito_scale)
+    M = len(score_fns)
+    ll0 = (-0.5 * (x0.reshape(x0.shape[0], -1) ** 2).sum(1) - D * math.log(2 * math.pi))[:, None].expand(-1, M)
+    return _vpsde_loop(score_fns, x0, ops.MODE_AND, ops.DLOGQ_ITO, n_steps, dt, noise, seed, 1.0, None, ito, ll0,
+                       accumulate, record)
+
+
+def sd_superdiff(get_vel, latents0, method="and", num_inference_steps=50, guidance_scale=7.5, lift=0.0, T=1.0,
+                 logp=0.0, kappa_avg=0.5, noise=None, seed=1, record=False):
+    """Stable-Diffusion latent SuperDiff (clip_eval.py:348-415).  ``get_vel(t, sigma, latents, which)`` with
+    which in {'obj', 'bg', 'uncond'} returns the velocity tensor (the reference's get_vel over its UNet,
+    :89-105); ``latents0`` is the unit-variance draw of :329-333 and is scaled by init_noise_sigma (:340).
+    Returns (latents, ll (B,2), kappa trajectory or last kappa, traj)."""
+    _lib.require_device()
+    mode = {"and": ops.MODE_AND, "or": ops.MODE_OR, "avg": ops.MODE_AVG}[method]
+    sigmas, timesteps, init_sigma = sde.edm_sigmas(num_inference_steps)
+    x = (latents0 * init_sigma).contiguous()
+    B, dev = x.shape[0], x.device
+    ll = torch.ones(B, 2, device=dev, dtype=torch.float32)                       # :348-349
+    kappa = torch.full((B,), 0.5, device=dev, dtype=torch.float32)               # :308
+    nz = _noise_iter(noise, num_inference_steps, x.shape, dev, seed)
+    traj = {"ll": [ll.clone()], "kappa": [kappa.clone()]} if record else None
+    for i in range(num_inference_steps):
+        sigma, dsigma = float(sigmas[i]), float(sigmas[i + 1] - sigmas[i])       # :352-353
+        t = float(timesteps[i])
+        v_obj = get_vel(t, sigma, x, "obj").contiguous()
+        v_unc = get_vel(t, sigma, x, "uncond").contiguous()
+        v_bg = get_vel(t, sigma, x, "bg").contiguous()
+        ops.step_edm_cfg(x, nz(i), v_obj, v_bg, v_unc, ll, sigma, dsigma, mode, guidance=guidance_scale,
+                         lift_term=sigma * lift / num_inference_steps, temperature=T, logp=logp,
+                         kappa_fixed=kappa_avg, latents_out=x, kappa_out=kappa)
+        if record:
+            traj["ll"].append(ll.clone()); traj["kappa"].append(kappa.clone())
+    if record:
+        traj = {k: torch.stack(v) for k, v in traj.items()}
+    return x, ll, kappa, traj
+
+
+class SuperDiffSampler:
+    """CIFAR SuperDiff sampler with one CUDA graph per timestep.
+
+    nets: list of bound score-nets (``ScoreNet(config).bind(params)``); mode 'or' reproduces
+    get_joint_stoch_vf (cifar/dynamics.py:115-136, T = 1e6, max-subtracted dlogq), 'and' applies the
+    notebook's kappa to image tensors (BASELINE config 3), 'avg' is get_avg_vf (:155-171).
+    """
+
+    def __init__(self, nets, batch, image_shape=(32, 32, 3), mode="or", n_steps=1000, dt=None, temperature=1e6,
+                 labels=None, device=None, use_graph=True):
+        _lib.require_device()
+        self.nets = list(nets)
+        self.M = len(self.nets)
+        self.B = int(batch)
+        self.shape = (self.B,) + tuple(image_shape)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.mode = {"or": ops.MODE_OR, "and": ops.MODE_AND, "avg": ops.MODE_AVG}[mode]
+        self.dlogq_mode = {"or": ops.DLOGQ_CIFAR_MAXSUB, "and": ops.DLOGQ_ITO, "avg": ops.DLOGQ_NONE}[mode]
+        self.temperature = float(temperature)
+        self.n_steps = int(n_steps)
+        self.dt = float(dt) if dt is not None else 1.0 / self.n_steps
+        ts = sde.time_grid(self.n_steps, self.dt, "float64")                   # cifar/eval_utils.py:76,85
+        self.sched = sde.schedule_table(ts, self.dt, self.device)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        dev = self.device
+        self.x = torch.zeros(self.shape, device=dev, dtype=torch.float32)
+        self.noise = torch.zeros(self.shape, device=dev, dtype=torch.float32)
+        self.logq = torch.zeros(self.B, self.M, device=dev, dtype=torch.float32)
+        self.weights = torch.zeros(self.B, self.M, device=dev, dtype=torch.float32)
+        self.scores = [torch.zeros(self.shape, device=dev, dtype=torch.float32) for _ in range(self.M)]
+        self.labels = None if labels is None else labels.to(dev)
+        self.use_graph = use_graph
+        self.graph = None
+        self.launches_per_step = None
+
+    def _step_body(self):
+        for i, net in enumerate(self.nets):
+            net(None, self.x, self.labels, sched=self.sched, step_counter=self.counter, out=self.scores[i])
+        ops.step_vpsde(self.x, self.noise, self.scores, self.logq, 0.0, 0.0, 1.0, 0.0, self.mode, self.dlogq_mode,
+                       temperature=self.temperature, x_out=self.x, weights=self.weights, sched=self.sched,
+                       step_counter=self.counter)
+        ops.counter_add(self.counter, 1)
+
+    def capture(self):
+        """Warm up once on a side stream (lazy init, allocator), then capture one timestep."""
+        before = ops.launch_count()
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._step_body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.launches_per_step = ops.launch_count() - before
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step_body()
+        self.reset()
+
+    def reset(self, x0=None):
+        self.counter.zero_()
+        self.logq.zero_()
+        if x0 is not None:
+            self.x.copy_(x0)
+
+    def step(self, noise=None):
+        """One Euler-Maruyama timestep at the schedule row the device counter points to."""
+        if noise is not None:
+            self.noise.copy_(noise, non_blocking=True)
+        if self.launches_per_step is None:
+            self.capture()
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step_body()
+
+    def sample(self, x0=None, noise=None, seed=0):
+        """Run all n_steps from x0 (default N(0, I) from `seed`).  Returns (x, logq, weights)."""
+        g = torch.Generator(device=self.device)
+        g.manual_seed(int(seed))
+        if self.launches_per_step is None:
+            self.capture()
+        if x0 is None:
+            x0 = torch.randn(self.shape, generator=g, device=self.device, dtype=torch.float32)
+        self.reset(x0)
+        nz = _noise_iter(noise, self.n_steps, self.shape, self.device, seed + 1)
+        for i in range(self.n_steps):
+            self.step(nz(i))
+        return self.x, self.logq, self.weights

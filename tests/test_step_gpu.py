@@ -83,6 +83,8 @@ def test_step_matches_oracle(cuda, B, D, M, mode, dmode):
 @pytest.mark.parametrize("mode", [O.MODE_OR, O.MODE_AND])
 def test_explicit_launch_shapes(cuda, shape, mode):
     B, D, M, t, dt = 6, 3072, 2, 0.81, 5e-3
+    if mode == O.MODE_AND and shape[0] * shape[1] * shape[2] * 4 < D:
+        pytest.skip("AND keeps the sample register-resident: this shape cannot hold D=3072")
     x, eps, s, logq = _mk(B, D, M, seed=17, dev=cuda, logq_scale=1e-6)
     got = _run(x, eps, s, logq, t, dt, mode, O.DLOGQ_CIFAR_MAXSUB, cuda, temperature=1e6, launch_shape=shape)
     ref = _ref(x, eps, s, logq, t, dt, mode, O.DLOGQ_CIFAR_MAXSUB, temperature=1e6)
