@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — SuperDiff CIFAR samples/s (2 models, 1000 steps) on B200.
+
+One "step" = one Euler-Maruyama timestep of the SuperDiff-OR sampler over one batch:
+M = 2 score-net forwards + the fused superposition step (BASELINE.json configs[1]:
+CIFAR-10 VP-SDE, 32x32x3, batch 512 per GPU, random-init weights, synthetic noise).
+samples/s = batch / (n_steps * seconds_per_step) with n_steps = 1000.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 runs under torchrun (one rank per GPU, NCCL); every rank samples its own shard
+with no per-step communication (weak scaling: 512 samples per GPU), timing is the max
+over ranks, and one all-gather of the final samples + log-densities follows the loop.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_STEPS = 1000          # BASELINE.json configs[1]: 1000 Euler-Maruyama steps
+BATCH_PER_GPU = 512
+M_MODELS = 2
+D = 32 * 32 * 3
+GFLOP_PER_SAMPLE_FWD = 12.154
+METRIC = "SuperDiff CIFAR samples/s (2 models,1000 steps) @1/2/4/8 B200; step HBM GB/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def _cpu_oracle_step(batch, threads):
+    """One SuperDiff-OR timestep (M score-net forwards + superposition step) of the CPU oracle on `batch`
+    samples; returns seconds.  This is the reference's CPU path as restated in oracle/ (the reference
+    itself needs JAX/Flax, absent from this image — SURVEY.md F8)."""
+    import torch
+    from oracle import scorenet as OS
+    from oracle import steps as O
+    from super_diffusion_b200.configs import vpsde
+    from super_diffusion_b200.models import utils as mutils
+    torch.set_num_threads(threads)
+    cfg = vpsde.get_config()
+    params = [mutils.init_model(10 + m, cfg, zero_init_scale=1.0)[1] for m in range(M_MODELS)]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 32, 32, 3, generator=g)
+    eps = torch.randn(batch, 32, 32, 3, generator=g)
+    logq = torch.zeros(batch, M_MODELS)
+    tt = torch.full((batch, 1, 1, 1), 0.5)
+
+    def one():
+        with torch.no_grad():
+            s = torch.stack([OS.scorenet_apply(p, cfg, tt, x, None) for p in params])
+            return O.or_step_cifar_literal(x, logq, s, eps, 0.5, 1e-3)
+    return one
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement of the reference path on the host cores, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample_b = 16
+    one = _cpu_oracle_step(sample_b, threads)
+    for _ in range(min(args.warmup, 1)):
+        one()
+    k = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(k):
+        one()
+    sec = (time.perf_counter() - t0) / k
+    value = sample_b / (N_STEPS * sec)
+    sample = (f"{k} timed step(s) at batch {sample_b} (2 oracle score-net forwards + OR step each), "
+              f"scaled to samples/s over {N_STEPS} steps")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": args.gpus,
+            "steps": k, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cifar_superdiff_or_b512_m2_1000steps", "batch_per_gpu": BATCH_PER_GPU,
+                       "models": M_MODELS, "n_steps": N_STEPS, "image": "32x32x3"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from super_diffusion_b200 import _lib, ops, sde
+    from super_diffusion_b200 import distributed as D_
+    from super_diffusion_b200.configs import vpsde
+    from super_diffusion_b200.models import utils as mutils
+    from super_diffusion_b200.superposition import SuperDiffSampler
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.require_device()
+    hbm_peak, tf_peak, peak_kind = _peaks()
+    B = args.batch
+    cfg = vpsde.get_config()
+    nets = []
+    for m in range(M_MODELS):
+        model, params = mutils.init_model(10 + m, cfg, zero_init_scale=1.0)   # random init, non-degenerate
+        nets.append(model.bind(params, dev))
+    sampler = SuperDiffSampler(nets, B, mode="or", n_steps=N_STEPS, temperature=1e6, device=dev)
+    sampler.capture()
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    x0 = torch.randn(sampler.shape, generator=g, device=dev)
+    n_noise = 4
+    noise_dev = [torch.randn(sampler.shape, generator=g, device=dev) for _ in range(n_noise)]
+    noise_host = [n.cpu().pin_memory() for n in noise_dev]
+    logq_host = torch.empty(B, M_MODELS).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(kind, K, W):
+        sampler.reset(x0)
+        for i in range(W):
+            sampler.step(noise_dev[i % n_noise] if kind == "device" else noise_host[i % n_noise])
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(K):
+            if kind == "device":
+                sampler.step(noise_dev[i % n_noise])
+            else:   # e2e: host noise in, log-densities out, every step
+                sampler.step(noise_host[i % n_noise])
+                logq_host.copy_(sampler.logq, non_blocking=True)
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e) / K
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = ops.launch_count()
+    ms_dev = timed("device", args.steps, args.warmup)
+    clk = clocks.stop() if rank == 0 else None
+    launches = (sampler.launches_per_step + 0) * args.steps
+    ms_e2e = timed("host", args.steps, args.warmup)
+
+    # final gather of samples + log-densities (the only communication of the job)
+    gather_ms = None
+    if world > 1:
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        xs = D_.gather_samples(sampler.x, world * B)
+        lq = D_.gather_samples(sampler.logq, world * B)
+        e.record()
+        torch.cuda.synchronize()
+        gather_ms = s.elapsed_time(e)
+        assert xs.shape[0] == world * B and lq.shape == (world * B, M_MODELS)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit GEMM), measured live with CUDA events ----
+    gemm_ms, gemm_flop, other_ms = _instrumented_step(sampler, ops, torch)
+    gemm_tf = gemm_flop / (gemm_ms * 1e-3) / 1e12
+    # ---- fused step kernel alone, L2 flushed between launches ----
+    step_us, step_bytes = _step_kernel_time(sampler, ops, torch, noise_dev[0])
+    step_gbs = step_bytes / (step_us * 1e-6) / 1e9
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total_b = world * B
+    value = total_b / (N_STEPS * ms_dev * 1e-3)
+    e2e = total_b / (N_STEPS * ms_e2e * 1e-3)
+    fwd_tf = M_MODELS * B * GFLOP_PER_SAMPLE_FWD * 1e9 / (ms_dev * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "cifar_superdiff_or_b512_m2_1000steps", "batch_per_gpu": B, "models": M_MODELS,
+                   "n_steps": N_STEPS, "image": "32x32x3", "mode": "OR T=1e6 (cifar/dynamics.py:124)",
+                   "weights": "random init, zero-init layers drawn at scale 1",
+                   "step": "one Euler-Maruyama timestep = 2 score-net forwards + fused SuperDiff step, CUDA graph",
+                   "l2": "per-step working set (>2 GB of activations at batch 512) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * M_MODELS * 4,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
+                     "traffic": None, "kernel": "gemm_tcgen05_kernel", "peak_kind": f"{peak_kind} sustained bf16",
+                     "share_of_step": gemm_ms / (gemm_ms + other_ms),
+                     "note": "sum of algorithmic conv/NIN/Dense/attention GEMM flops of one timestep / sum of that kernel's "
+                             "launch durations (CUDA events around every launch, eager pass after the timed region)"},
+        "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
+                          "traffic": None, "kernel": "step_vpsde_kernel", "us_per_launch": step_us,
+                          "bytes_per_launch": step_bytes, "peak_kind": f"{peak_kind} copy bandwidth",
+                          "note": "4*B*D*(M+3) algorithmic bytes; standalone launches with a 256 MB L2 flush between them"},
+        "scorenet_tflops_whole_step": fwd_tf,
+        "gather_ms": gather_ms,
+    }
+    if world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        sample_b = 16
+        one = _cpu_oracle_step(sample_b, threads)
+        one()
+        t0 = time.perf_counter()
+        one()
+        sec = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": sample_b / (N_STEPS * sec), "unit": "samples/s", "cores": threads, "kind": "port",
+                                "sample": f"1 timed step at batch {sample_b} (2 fp32 oracle score-net forwards + OR step), "
+                                          f"scaled linearly to {N_STEPS} steps"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _instrumented_step(sampler, ops, torch):
+    """One eager timestep with CUDA events around every kernel launch made through ops.*; returns
+    (gemm kernel ms, gemm algorithmic flop, all other kernels ms)."""
+    recs = []
+    names = ["conv_gemm", "batched_gemm", "groupnorm_swish", "attention_small", "softmax_rows", "upsample2x",
+             "im2col_s2", "conv_in", "time_embedding", "step_vpsde", "counter_add"]
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(n):
+        f = orig[n]
+
+        def g(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = f(*a, **k)
+            e.record()
+            flop = 0.0
+            if n == "conv_gemm":
+                srcs, w = a[0], a[1]
+                t0 = srcs[0][0]
+                nout = k.get("n_out") or w.shape[0]
+                flop = 2.0 * t0.shape[0] * t0.shape[1] * t0.shape[2] * w.shape[1] * nout
+            elif n == "batched_gemm":
+                flop = 2.0 * r.numel() * (k.get("K") or a[0].shape[-1])
+            recs.append((n, s, e, flop))
+            return r
+        return g
+    for n in names:
+        setattr(ops, n, wrap(n))
+    try:
+        sampler._step_body()
+        recs.clear()
+        sampler._step_body()
+        torch.cuda.synchronize()
+    finally:
+        for n in names:
+            setattr(ops, n, orig[n])
+    gemm_ms = sum(s.elapsed_time(e) for n, s, e, _ in recs if n in ("conv_gemm", "batched_gemm"))
+    other_ms = sum(s.elapsed_time(e) for n, s, e, _ in recs if n not in ("conv_gemm", "batched_gemm"))
+    gemm_flop = sum(f for *_, f in recs)
+    return gemm_ms, gemm_flop, other_ms
+
+
+def _step_kernel_time(sampler, ops, torch, noise):
+    B, M = sampler.B, sampler.M
+    flush = torch.empty(64 * 1024 * 1024, device=sampler.device, dtype=torch.float32)   # 256 MB > 126 MB L2
+    x = torch.randn(B, D, device=sampler.device)
+    xo = torch.empty_like(x)
+    sc = [torch.randn(B, D, device=sampler.device) for _ in range(M)]
+    nz = noise.reshape(B, D)
+    lq = torch.zeros(B, M, device=sampler.device)
+    w = torch.zeros(B, M, device=sampler.device)
+    ts = []
+    for i in range(13):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6,
+                       x_out=xo, weights=w)
+        e.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            ts.append(s.elapsed_time(e) * 1e3)
+    return statistics.median(ts), 4 * B * D * (M + 3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU (default: BASELINE config, 512)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

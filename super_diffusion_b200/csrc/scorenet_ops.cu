@@ -43,13 +43,14 @@ struct GnParams {
 
 template <int NV, bool CLUSTER>
 __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_constant__ GnParams p) {
-  extern __shared__ float gn_smem[];   // [2*C] channel sums / sumsq, then [2*32] group mean / rstd
+  extern __shared__ float gn_smem[];   // [2*C] channel sums / sumsq, [2*32] group mean / rstd, [rows][2*C] partials
   const int C = p.C0 + p.C1;
   const int VC = C / 8;                // 16-byte vectors per pixel
   float* ch_sum = gn_smem;
   float* ch_sq = gn_smem + C;
   float* g_mean = gn_smem + 2 * C;
   float* g_rstd = g_mean + 32;
+  float* part = g_rstd + 32;           // [rows_per_pass][2*C]
   unsigned csize = 1, crank = 0;
   if (CLUSTER) {
     cg::cluster_group cluster = cg::this_cluster();
@@ -60,9 +61,6 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
   const int px_per_cta = (p.HW + csize - 1) / csize;
   const int p0 = crank * px_per_cta, p1 = min(p.HW, p0 + px_per_cta);
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) gn_smem[i] = 0.f;
-  __syncthreads();
-
   const bool from0 = cv * 8 < p.C0;
   const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + cv * 8
                                    : p.x1 + (size_t)sample * p.HW * p.C1 + (cv * 8 - p.C0);
@@ -86,10 +84,17 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
   }
+  // fixed-order (deterministic) reduction over the pixel rows handled by this CTA
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    atomicAdd(&ch_sum[cv * 8 + e], s[e]);
-    atomicAdd(&ch_sq[cv * 8 + e], q[e]);
+    part[(size_t)r * 2 * C + cv * 8 + e] = s[e];
+    part[(size_t)r * 2 * C + C + cv * 8 + e] = q[e];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int rr = 0; rr < rows_per_pass; ++rr) a += part[(size_t)rr * 2 * C + i];
+    gn_smem[i] = a;
   }
   __syncthreads();
   if (CLUSTER) {
@@ -153,7 +158,7 @@ static cudaError_t launch_gn(const GnParams& p, int threads, int cluster, cudaSt
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)p.B * cluster);
   cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = sizeof(float) * (2 * (p.C0 + p.C1) + 64);
+  cfg.dynamicSmemBytes = sizeof(float) * (2 * (p.C0 + p.C1) * (1 + threads / ((p.C0 + p.C1) / 8)) + 64);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   if (cluster > 1) {
@@ -373,16 +378,21 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   if (B == 0) return SD_OK;
   GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, gamma, beta, eps, apply_swish, (__nv_bfloat16*)out};
   const int VC = C / 8;
-  // threads = VC * k (k pixel rows per pass, whole warps, <= 512); smallest cluster, then fewest threads >= 256,
-  // such that a CTA's pixel slice fits in NV <= 16 vectors per thread
+  // threads = VC * k (k pixel rows per pass, whole warps, 256..512); pick the launch with the fewest vectors per
+  // thread (more CTAs resident per SM so load and store phases of different CTAs overlap), then the smallest cluster
   int cluster = 0, nv = 0, T = 0;
-  for (int c = 1; c <= 8 && !cluster; c *= 2) {
+  long best = -1;
+  for (int c = 1; c <= 8; c *= 2) {
     const int px = (HW + c - 1) / c;
     for (int k = 1; VC * k <= 512; ++k) {
       if ((VC * k) % 32) continue;
+      if (VC * k < 256 && VC * (k + 1) <= 512 && px > k) continue;     // keep CTAs at >= 256 threads when there is work
       const int need = (px + k - 1) / k;
-      const bool big_enough = VC * k >= 256 || VC * (k + 1) > 512;
-      if (need <= 16 && (big_enough || need <= 1)) { cluster = c; nv = need; T = VC * k; break; }
+      if (need > 16) continue;
+      int nvt = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
+      const long regs = (long)(nvt <= 4 ? 80 : nvt == 8 ? 108 : 128) * VC * k;
+      const long cost = (long)nvt * 1000 + (regs > 32768 ? 400 : 0) + c * 10 + (VC * k) / 64;
+      if (best < 0 || cost < best) { best = cost; cluster = c; nv = need; T = VC * k; }
     }
   }
   if (!cluster) return fail(kErrUnsupported, "sd_groupnorm_swish: H*W*C too large for the register-resident path");

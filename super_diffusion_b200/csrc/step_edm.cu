@@ -149,6 +149,7 @@ extern "C" int sd_step_edm_cfg(const float* latents, const float* z, const float
                                float lift_term, int mode, float temperature, float logp, float kappa_fixed, float* ll,
                                float* latents_out, float* kappa_out, void* stream) {
   using namespace sdb;
+  if (B == 0) return SD_OK;
   if (!latents || !z || !v_obj || !v_bg || !v_unc || !ll || !latents_out || !kappa_out)
     return fail(kErrInvalidArg, "sd_step_edm_cfg: null pointer argument");
   if (B < 0 || D < 4 || D % 4) return fail(kErrInvalidArg, "sd_step_edm_cfg: D must be a positive multiple of 4");

@@ -23,9 +23,9 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
   if (mode < SD_MODE_OR || mode > SD_MODE_FIXED) return fail(kErrInvalidArg, "sd_step_vpsde: unknown mode");
   if (dlogq_mode < SD_DLOGQ_CIFAR_MAXSUB || dlogq_mode > SD_DLOGQ_NONE)
     return fail(kErrInvalidArg, "sd_step_vpsde: unknown dlogq_mode");
+  if (B == 0) return SD_OK;  // empty batch: nothing to launch (pointers may be null)
   if (!x || !noise || !scores || !x_out || !weights || (!logq && (mode == SD_MODE_OR || dlogq_mode != SD_DLOGQ_NONE)))
     return fail(kErrInvalidArg, "sd_step_vpsde: null pointer argument");
-  if (B == 0) return SD_OK;  // empty batch: nothing to launch
   StepParams p{};
   p.x = x; p.noise = noise;
   for (int i = 0; i < M; ++i) {
@@ -70,8 +70,10 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
           const long rounds = (nunits + cap - 1) / cap;
           const long waste = rounds * cap - nunits;          // idle lanes
           const long ctas = (long)B * c;
-          long cost = waste * 4 + (c > 1 ? 64 * c : 0) + rounds * 16;
-          if (ctas < 148 * 8) cost += (148 * 8 - ctas);     // too few CTAs: prefer splitting samples
+          // measured on B200 (tools/time_forward.py): one CTA per sample beats cluster splits at every
+          // batch size that fills the chip, so clusters are only for residency (AND, large D) or tiny batches
+          long cost = waste * 4 + (c > 1 ? 2000L * c : 0) + rounds * 16;
+          if (ctas < 148) cost += (148 - ctas) * 50;
           if (t < 128) cost += 32;
           if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_t = t; best_nv = n; best_c = c; }
         }
