@@ -49,6 +49,7 @@ struct GemmParams {
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
+  int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   long long out_batch_stride; // elements
   int h_box, tiles_per_img, imgs_per_tile;
   int M_total, HW, N_out, block_n, n_tiles, m_tiles, num_kb;
@@ -212,7 +213,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int m_units = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int total_tiles = m_units * p.n_tiles;
+  const int nsub = p.dual ? 2 : 1;
+  const uint32_t b_off = p.dual ? 2 * A_BYTES : A_BYTES;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s)
@@ -240,19 +244,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.block_n * BK * 2;
+      const uint32_t tx_bytes = (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        int c1, c2, c3, bz = 0;
-        if (p.flat) {
-          const int batch = m_tile / p.m_tiles_per_batch;
-          c1 = (m_tile - batch * p.m_tiles_per_batch) * BM; c2 = 0;
-          c3 = p.a_batched ? batch : 0;
-          bz = p.b_batched ? batch : 0;
-        } else {
-          c1 = 0;
-          c2 = (m_tile % p.tiles_per_img) * p.h_box;
-          c3 = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
+        const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
+        int c1[2], c2[2], c3[2], bz = 0;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const int m_tile = m_unit * nsub + sub;     // may be == m_tiles for an odd tail: TMA zero-fills, epilogue masks
+          if (p.flat) {
+            const int batch = m_tile / p.m_tiles_per_batch;
+            c1[sub] = (m_tile - batch * p.m_tiles_per_batch) * BM; c2[sub] = 0;
+            c3[sub] = p.a_batched ? batch : 0;
+            if (sub == 0) bz = p.b_batched ? batch : 0;
+          } else {
+            c1[sub] = 0;
+            c2[sub] = (m_tile % p.tiles_per_img) * p.h_box;
+            c3[sub] = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
+          }
         }
         int seg = 0, seg_start = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -265,8 +272,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          tma_load_4d(&p.a_map[seg], sa, &full_bar[stage], cb * BK, c1 + dw, c2 + dh, c3);
-          tma_load_3d(&p.b_map, sa + A_BYTES, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
+          for (int sub = 0; sub < nsub; ++sub)
+            tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
+          tma_load_3d(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -288,11 +296,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_sw128(sa);
-          const uint64_t b_desc = umma_desc_sw128(sa + A_BYTES);
+          const uint64_t b_desc = umma_desc_sw128(sa + b_off);
+          for (int sub = 0; sub < nsub; ++sub) {
+            const uint64_t a_desc = umma_desc_sw128(sa + sub * A_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom
-            umma_bf16(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom
+              umma_bf16(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
           umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -307,36 +317,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int row = q * 32 + lane;
-      bool row_ok;
-      size_t row_off;
-      int img;
-      if (p.flat) {
-        const int batch = m_tile / p.m_tiles_per_batch;
-        const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + row;
-        row_ok = rl < p.M_per_batch;
-        row_off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
-        img = batch;
-      } else {
-        const int m = m_tile * BM + row;
-        row_ok = m < p.M_total;
-        row_off = (size_t)m * p.out_ld;
-        img = m / p.HW;
-      }
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
       const int n_base = n_tile * p.block_n;
-      for (int c = 0; c < p.block_n; c += 32) {
-        uint32_t r0[16], r1[16];
-        tmem_ld16(taddr + c, r0);
-        const bool second = (c + 16 < p.block_n);
-        if (second) tmem_ld16(taddr + c + 16, r1);
-        tmem_wait_ld();
-        if (row_ok) {
-          if (n_base + c < p.N_out) epilogue_store16(p, r0, row_off, n_base + c, img);
-          if (second && n_base + c + 16 < p.N_out) epilogue_store16(p, r1, row_off, n_base + c + 16, img);
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int m_tile = m_unit * nsub + sub;
+        bool row_ok;
+        size_t row_off;
+        int img;
+        if (p.flat) {
+          const int batch = m_tile / p.m_tiles_per_batch;
+          const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + row;
+          row_ok = rl < p.M_per_batch && m_tile < p.m_tiles;
+          row_off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
+          img = batch;
+        } else {
+          const int m = m_tile * BM + row;
+          row_ok = m < p.M_total;
+          row_off = (size_t)m * p.out_ld;
+          img = m / p.HW;
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
+        for (int c = 0; c < p.block_n; c += 32) {
+          uint32_t r0[16], r1[16];
+          tmem_ld16(taddr + c, r0);
+          const bool second = (c + 16 < p.block_n);
+          if (second) tmem_ld16(taddr + c + 16, r1);
+          tmem_wait_ld();
+          if (row_ok) {
+            if (n_base + c < p.N_out) epilogue_store16(p, r0, row_off, n_base + c, img);
+            if (second && n_base + c + 16 < p.N_out) epilogue_store16(p, r1, row_off, n_base + c + 16, img);
+          }
         }
       }
       tcgen05_fence_before();
@@ -401,7 +414,13 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
                        void* out, int out_ld, cudaStream_t st, const char* who) {
   const int n_pad = (N + 15) / 16 * 16;
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
+  // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
+  if (p.block_n > 128 && p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
   p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
+  // narrow N: pair two m-tiles per CTA tile so the B tile is fetched once per 256 rows (same smem traffic per
+  // MMA cycle as the 128x256 tile, which runs near the tensor peak)
+  p.dual = (p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
+            (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
@@ -432,7 +451,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = (p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
   gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
   return check_cuda(cudaGetLastError(), who);

@@ -4,6 +4,7 @@
 #include "common.cuh"
 #include "../../include/superdiff_b200.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace sdb {
 
@@ -29,41 +30,38 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // ---------------------------------------------------------------------------
 // GroupNorm(32) + swish over concat(x0, x1) along channels.
-// One thread-block cluster per sample; each CTA keeps its pixel slice in
-// registers (read once), the cluster exchanges 2*C per-channel partial sums
-// through distributed shared memory.  HBM/L2 traffic: read + write, once each.
+// Groups are independent, so the work is split over (sample, channel block): one CTA owns all H*W pixels of
+// `Cs` consecutive channels (a whole number of groups), keeps them in registers (read once), reduces per-channel
+// partials through shared memory in a fixed order (deterministic) and writes the normalised block.  No clusters,
+// no cross-CTA traffic (measured on B200: cluster launches of memory-bound kernels cost 2-3x).
 // ---------------------------------------------------------------------------
 struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
   int C0, C1, B, HW;
+  int Cs, nsplit;            // channels per CTA, CTAs per sample
   const float* gamma; const float* beta;
   float eps; int apply_swish;
   __nv_bfloat16* out;
 };
 
-template <int NV, bool CLUSTER>
+template <int NV>
 __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_constant__ GnParams p) {
-  extern __shared__ float gn_smem[];   // [2*C] channel sums / sumsq, [2*32] group mean / rstd, [rows][2*C] partials
-  const int C = p.C0 + p.C1;
-  const int VC = C / 8;                // 16-byte vectors per pixel
+  extern __shared__ float gn_smem[];   // [2*Cs] channel sums / sumsq, [2*32] group mean / rstd, [rows][2*Cs] partials
+  const int C = p.C0 + p.C1, Cs = p.Cs;
+  const int VC = Cs / 8;               // 16-byte vectors per pixel owned by this CTA
   float* ch_sum = gn_smem;
-  float* ch_sq = gn_smem + C;
-  float* g_mean = gn_smem + 2 * C;
+  float* ch_sq = gn_smem + Cs;
+  float* g_mean = gn_smem + 2 * Cs;
   float* g_rstd = g_mean + 32;
-  float* part = g_rstd + 32;           // [rows_per_pass][2*C]
-  unsigned csize = 1, crank = 0;
-  if (CLUSTER) {
-    cg::cluster_group cluster = cg::this_cluster();
-    csize = cluster.num_blocks();
-    crank = cluster.block_rank();
-  }
-  const int sample = blockIdx.x / csize;
-  const int px_per_cta = (p.HW + csize - 1) / csize;
-  const int p0 = crank * px_per_cta, p1 = min(p.HW, p0 + px_per_cta);
+  float* part = g_rstd + 32;           // [rows_per_pass][2*Cs]
+  const int sample = blockIdx.x / p.nsplit;
+  const int c_base = (blockIdx.x - sample * p.nsplit) * Cs;
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
-  const bool from0 = cv * 8 < p.C0;
-  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + cv * 8
-                                   : p.x1 + (size_t)sample * p.HW * p.C1 + (cv * 8 - p.C0);
+  const int c0 = c_base + cv * 8;      // first of this thread's 8 channels (never straddles x0 | x1: C0 % 8 == 0)
+
+  const bool from0 = c0 < p.C0;
+  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0
+                                   : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
   const int src_ld = from0 ? p.C0 : p.C1;
   uint4 v[NV];
   bool ok[NV];
@@ -72,8 +70,8 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    const int px = p0 + r + j * rows_per_pass;
-    ok[j] = px < p1;
+    const int px = r + j * rows_per_pass;
+    ok[j] = px < p.HW;
     if (ok[j]) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)px * src_ld);
   }
 #pragma unroll
@@ -84,36 +82,24 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
   }
-  // fixed-order (deterministic) reduction over the pixel rows handled by this CTA
+  // fixed-order (deterministic) reduction over the pixel rows
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    part[(size_t)r * 2 * C + cv * 8 + e] = s[e];
-    part[(size_t)r * 2 * C + C + cv * 8 + e] = q[e];
+    part[(size_t)r * 2 * Cs + cv * 8 + e] = s[e];
+    part[(size_t)r * 2 * Cs + Cs + cv * 8 + e] = q[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) {
     float a = 0.f;
-    for (int rr = 0; rr < rows_per_pass; ++rr) a += part[(size_t)rr * 2 * C + i];
+    for (int rr = 0; rr < rows_per_pass; ++rr) a += part[(size_t)rr * 2 * Cs + i];
     gn_smem[i] = a;
   }
   __syncthreads();
-  if (CLUSTER) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();
-  }
-  if (threadIdx.x < 32) {
-    const int cpg = C / 32;
+  const int cpg = C / 32;
+  const int ngroups = Cs / cpg;
+  if (threadIdx.x < ngroups) {
     double sum = 0.0, sq = 0.0;
-    for (unsigned rk = 0; rk < csize; ++rk) {
-      const float* rs = ch_sum;
-      const float* rq = ch_sq;
-      if (CLUSTER) {
-        cg::cluster_group cluster = cg::this_cluster();
-        rs = cluster.map_shared_rank(ch_sum, rk);
-        rq = cluster.map_shared_rank(ch_sq, rk);
-      }
-      for (int c = 0; c < cpg; ++c) { sum += (double)rs[threadIdx.x * cpg + c]; sq += (double)rq[threadIdx.x * cpg + c]; }
-    }
+    for (int c = 0; c < cpg; ++c) { sum += (double)ch_sum[threadIdx.x * cpg + c]; sq += (double)ch_sq[threadIdx.x * cpg + c]; }
     const double n = (double)p.HW * cpg;
     const double mean = sum / n;
     double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
@@ -121,23 +107,17 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
     g_mean[threadIdx.x] = (float)mean;
     g_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
-  if (CLUSTER) {
-    cg::cluster_group cluster = cg::this_cluster();
-    cluster.sync();                         // peers finished reading my channel sums; g_* visible CTA-wide
-  } else {
-    __syncthreads();
-  }
-  const int cpg = C / 32;
+  __syncthreads();
   float mu[8], rs[8], ga[8], be[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int c = cv * 8 + e;
-    mu[e] = g_mean[c / cpg];
-    rs[e] = g_rstd[c / cpg];
-    ga[e] = p.gamma[c];
-    be[e] = p.beta[c];
+    const int cl = cv * 8 + e;
+    mu[e] = g_mean[cl / cpg];
+    rs[e] = g_rstd[cl / cpg];
+    ga[e] = p.gamma[c_base + cl];
+    be[e] = p.beta[c_base + cl];
   }
-  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + cv * 8;
+  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     if (!ok[j]) continue;
@@ -148,29 +128,17 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
       float y = (f[e] - mu[e]) * rs[e] * ga[e] + be[e];
       f[e] = p.apply_swish ? swish_f(y) : y;
     }
-    const int px = p0 + r + j * rows_per_pass;
+    const int px = r + j * rows_per_pass;
     *reinterpret_cast<uint4*>(dst + (size_t)px * C) = pack8(f);
   }
 }
 
 template <int NV>
-static cudaError_t launch_gn(const GnParams& p, int threads, int cluster, cudaStream_t st) {
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)p.B * cluster);
-  cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = sizeof(float) * (2 * (p.C0 + p.C1) * (1 + threads / ((p.C0 + p.C1) / 8)) + 64);
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  if (cluster > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, groupnorm_swish_kernel<NV, true>, p);
-  }
-  return cudaLaunchKernelEx(&cfg, groupnorm_swish_kernel<NV, false>, p);
+static cudaError_t launch_gn(const GnParams& p, int threads, cudaStream_t st) {
+  const int rows = threads / (p.Cs / 8);
+  const size_t smem = sizeof(float) * ((size_t)2 * p.Cs * (1 + rows) + 64);
+  groupnorm_swish_kernel<NV><<<(unsigned)(p.B * p.nsplit), threads, smem, st>>>(p);
+  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -279,33 +247,57 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict_
   }
 }
 
-// First conv: fp32 NHWC [B,H,W,Cin<=4] -> bf16 [B,H,W,Cout], one CTA per image row, thread = output channel.
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int H, int W, int Cin,
+// First conv: fp32 NHWC [B,H,W,Cin<=4] -> bf16 [B,H,W,Cout].  Weights (9*Cin x Cout fp32, <= 18 KB) sit in
+// shared memory; a thread owns one pixel x 32 output channels (its 9*Cin inputs in registers) and writes
+// 64 contiguous bytes, so a pixel's 256-byte row is covered by 4 adjacent threads (coalesced).
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       int Cout, __nv_bfloat16* __restrict__ out) {
-  extern __shared__ float cin_smem[];   // [3][W+2][Cin]
-  const int b = blockIdx.x / H, h = blockIdx.x % H;
-  const int row_elems = (W + 2) * Cin;
-  for (int i = threadIdx.x; i < 3 * row_elems; i += blockDim.x) {
-    const int kr = i / row_elems, rem = i % row_elems;
-    const int wi = rem / Cin - 1, c = rem % Cin;
-    const int hi = h + kr - 1;
-    float v = 0.f;
-    if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = x[(((size_t)b * H + hi) * W + wi) * Cin + c];
-    cin_smem[i] = v;
-  }
+  extern __shared__ float cin_smem[];   // [9*Cin][Cout] weights, then [Cout] bias
+  const int K = 9 * Cin;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) cin_smem[i] = w[i];
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) cin_smem[K * Cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
-  for (int co = threadIdx.x; co < Cout; co += blockDim.x) {
-    float wr[36];
-    for (int k = 0; k < 9 * Cin; ++k) wr[k] = w[(size_t)k * Cout + co];   // HWIO: ((kh*3+kw)*Cin + c)*Cout + co
-    const float bv = bias ? bias[co] : 0.f;
-    for (int wo = 0; wo < W; ++wo) {
-      float acc = bv;
-      for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw)
-          for (int c = 0; c < Cin; ++c)
-            acc = fmaf(cin_smem[kh * row_elems + (wo + kw) * Cin + c], wr[(kh * 3 + kw) * Cin + c], acc);
-      out[(((size_t)b * H + h) * W + wo) * Cout + co] = __float2bfloat16_rn(acc);
+  const int groups = Cout / 32;
+  const size_t total = (size_t)B * H * W * groups;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int cg0 = (int)(i % groups) * 32;
+    size_t pix = i / groups;
+    const int wo = pix % W; pix /= W;
+    const int ho = pix % H;
+    const int b = (int)(pix / H);
+    float in[36];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int hi = ho + kh - 1, wi = wo + kw - 1;
+        const bool okp = hi >= 0 && hi < H && wi >= 0 && wi < W;
+        for (int c = 0; c < Cin; ++c)
+          in[(kh * 3 + kw) * 4 + c] = okp ? x[(((size_t)b * H + hi) * W + wi) * Cin + c] : 0.f;
+      }
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = cin_smem[K * Cout + cg0 + j];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+      for (int c = 0; c < Cin; ++c) {
+        const float v = in[t * 4 + c];
+        const float4* wr = reinterpret_cast<const float4*>(cin_smem + (size_t)(t * Cin + c) * Cout + cg0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 w4 = wr[j];
+          acc[4 * j] = fmaf(v, w4.x, acc[4 * j]); acc[4 * j + 1] = fmaf(v, w4.y, acc[4 * j + 1]);
+          acc[4 * j + 2] = fmaf(v, w4.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(v, w4.w, acc[4 * j + 3]);
+        }
+      }
+    uint4* op = reinterpret_cast<uint4*>(out + ((((size_t)b * H + ho) * W + wo) * Cout + cg0));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = acc[8 * j + e];
+      op[j] = pack8(f);
     }
   }
 }
@@ -376,33 +368,52 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   if (C0 < 8 || C0 % 8 || C1 % 8 || C % 32 || C > 2048) return fail(kErrInvalidArg, "sd_groupnorm_swish: channels must be multiples of 8, total a multiple of 32");
   if (B < 0 || HW < 1) return fail(kErrInvalidArg, "sd_groupnorm_swish: bad shape");
   if (B == 0) return SD_OK;
-  GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, gamma, beta, eps, apply_swish, (__nv_bfloat16*)out};
-  const int VC = C / 8;
-  // threads = VC * k (k pixel rows per pass, whole warps, 256..512); pick the launch with the fewest vectors per
-  // thread (more CTAs resident per SM so load and store phases of different CTAs overlap), then the smallest cluster
-  int cluster = 0, nv = 0, T = 0;
-  long best = -1;
-  for (int c = 1; c <= 8; c *= 2) {
-    const int px = (HW + c - 1) / c;
+  GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, 0, 0, gamma, beta, eps, apply_swish,
+             (__nv_bfloat16*)out};
+  const int cpg = C / 32;
+  // channel block per CTA: a multiple of lcm(cpg, 8) channels dividing C; threads = (Cs/8) * k pixel rows per pass.
+  // Prefer <= 8 vectors per thread (3+ CTAs resident per SM), then wide channel blocks (longer contiguous segments).
+  int unit = cpg;
+  while (unit % 8) unit += cpg;
+  static const int min_cs = [] { const char* e = getenv("SDB_GN_MIN_CS"); return e ? atoi(e) : 32; }();   // tuning knob
+  int best_cs = 0, best_t = 0, best_nv = 0;
+  long best_cost = -1;
+  for (int Cs = unit; Cs <= C; Cs += unit) {
+    if (C % Cs) continue;
+    const int VC = Cs / 8;
     for (int k = 1; VC * k <= 512; ++k) {
-      if ((VC * k) % 32) continue;
-      if (VC * k < 256 && VC * (k + 1) <= 512 && px > k) continue;     // keep CTAs at >= 256 threads when there is work
-      const int need = (px + k - 1) / k;
+      const int T = VC * k;
+      if (T % 32) continue;
+      const int need = (HW + k - 1) / k;
       if (need > 16) continue;
-      int nvt = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
-      const long regs = (long)(nvt <= 4 ? 80 : nvt == 8 ? 108 : 128) * VC * k;
-      const long cost = (long)nvt * 1000 + (regs > 32768 ? 400 : 0) + c * 10 + (VC * k) / 64;
-      if (best < 0 || cost < best) { best = cost; cluster = c; nv = need; T = VC * k; }
+      const int nvt = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
+      const size_t smem = sizeof(float) * ((size_t)2 * Cs * (1 + k) + 64);
+      if (smem > 96 * 1024) continue;
+      long cost = (nvt > 8 ? 4000 : 0) + (T < 128 ? 1500 : 0) + (T > 384 ? 300 : 0) + (long)(nvt * k - HW) * 4  // idle lanes
+                  + 2048 / Cs + (Cs < min_cs ? 1000 : 0) + (smem > 32 * 1024 ? 500 : 0);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_cs = Cs; best_t = T; best_nv = need; }
     }
   }
-  if (!cluster) return fail(kErrUnsupported, "sd_groupnorm_swish: H*W*C too large for the register-resident path");
+  if (best_cost < 0) return fail(kErrUnsupported, "sd_groupnorm_swish: H*W too large for the register-resident path (max 8192 pixels)");
+  p.Cs = best_cs;
+  p.nsplit = C / best_cs;
+  const int nv = best_nv, T = best_t;
   cudaError_t err;
   cudaStream_t st = (cudaStream_t)stream;
-  if (nv <= 1) err = launch_gn<1>(p, T, cluster, st);
-  else if (nv <= 2) err = launch_gn<2>(p, T, cluster, st);
-  else if (nv <= 4) err = launch_gn<4>(p, T, cluster, st);
-  else if (nv <= 8) err = launch_gn<8>(p, T, cluster, st);
-  else err = launch_gn<16>(p, T, cluster, st);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(groupnorm_swish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(groupnorm_swish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(groupnorm_swish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(groupnorm_swish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(groupnorm_swish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_done = true;
+  }
+  if (nv <= 1) err = launch_gn<1>(p, T, st);
+  else if (nv <= 2) err = launch_gn<2>(p, T, st);
+  else if (nv <= 4) err = launch_gn<4>(p, T, st);
+  else if (nv <= 8) err = launch_gn<8>(p, T, st);
+  else err = launch_gn<16>(p, T, st);
   return check_cuda(err, "sd_groupnorm_swish launch");
 }
 
@@ -462,10 +473,18 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
                void* out, void* stream) {
   using namespace sdb;
   if (!x || !w_hwio || !out || Cin < 1 || Cin > 4) return fail(kErrInvalidArg, "sd_conv_in: Cin must be in [1, 4]");
+  if (Cout < 32 || Cout % 32 || Cout > 512) return fail(kErrInvalidArg, "sd_conv_in: Cout must be a multiple of 32, <= 512");
   if (B == 0) return SD_OK;
-  const size_t smem = sizeof(float) * 3 * (W + 2) * Cin;
-  const int threads = Cout < 256 ? ((Cout + 31) / 32) * 32 : 256;
-  conv_in_kernel<<<B * H, threads, smem, (cudaStream_t)stream>>>(x, H, W, Cin, w_hwio, bias, Cout, (__nv_bfloat16*)out);
+  const size_t smem = sizeof(float) * ((size_t)9 * Cin * Cout + Cout);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    if (e != cudaSuccess) return check_cuda(e, "sd_conv_in: cudaFuncSetAttribute");
+    attr_done = true;
+  }
+  const size_t total = (size_t)B * H * W * (Cout / 32);
+  conv_in_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(x, B, H, W, Cin, w_hwio, bias, Cout,
+                                                                             (__nv_bfloat16*)out);
   return check_cuda(cudaGetLastError(), "sd_conv_in launch");
 }
 

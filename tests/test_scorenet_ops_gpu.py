@@ -39,6 +39,8 @@ def _conv_ref(x, w_nk, taps, C):
     (2, 32, 32, 128, 128, 9), (3, 16, 16, 256, 256, 9), (5, 8, 8, 128, 256, 9), (9, 4, 4, 256, 256, 9),
     (2, 32, 32, 64, 16, 9), (2, 32, 32, 128, 3, 9), (4, 16, 16, 256, 768, 1), (2, 32, 32, 256, 128, 1),
     (1, 32, 32, 64, 64, 9), (16, 4, 4, 512, 256, 1), (3, 8, 8, 256, 48, 1),
+    (601, 8, 8, 64, 64, 9),     # 301 m-tiles (odd) -> dual m-tile mode with a masked tail tile
+    (40, 32, 32, 64, 128, 9),   # dual m-tile mode, 320 m-tiles
 ])
 def test_conv_gemm_single_source(cuda, B, H, W, C, N, taps):
     g = torch.Generator().manual_seed(B * 1000 + H + C + N)
@@ -97,6 +99,7 @@ def test_conv_gemm_many_tiles_persistent(cuda):
 @pytest.mark.parametrize("batch,M,N,K,shareA,shareB", [
     (1, 512, 640, 512, False, True), (1, 100, 256, 128, False, True), (6, 256, 256, 256, False, False),
     (5, 256, 256, 256, True, False), (3, 128, 64, 64, False, False), (2, 200, 40, 192, False, False),
+    (1, 128 * 299, 64, 64, False, True), (160, 256, 128, 64, False, False),   # dual m-tile mode (odd tail / batched)
 ])
 def test_batched_gemm(cuda, batch, M, N, K, shareA, shareB):
     g = torch.Generator().manual_seed(batch + M + N + K)
