@@ -116,6 +116,7 @@ typedef struct sd_gemm_src {
 
 #define SD_EPI_SWISH 1u     /* out = swish(out) after everything else */
 #define SD_EPI_OUT_F32 2u   /* `out` is fp32 instead of bf16 */
+#define SD_EPI_SOFTMAX 4u   /* internal: row softmax epilogue (sd_attention_probs) */
 
 /* out[b,h,w,n] = sum_seg sum_tap sum_c src[b,h+dh,w+dw,c] * Wt[n, k(seg,tap,c)]
  *               + bias[n] + rowbias[b, n] + residual[b,h,w,n]
@@ -140,6 +141,15 @@ int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, i
                     int batch, int M, int N, int K, const float* bias, const void* residual, unsigned flags,
                     void* out, int ldc, long long strideC, void* stream);
 
+/* Attention probabilities in one launch (cifar/models/layers.py:505-507):
+ *     P[b][i][:] = softmax_j(scale * <Q[b][i], K[b][j]>)   restricted to the diagonal block of `block` columns
+ * that row i belongs to (block = S for ordinary attention; block < S packs S/block small images into one
+ * batch entry so that low-resolution attention still fills 128-row tensor-core tiles; off-block entries are 0).
+ * Q, K: bf16 [batch][S][ld] (K-contiguous, ld >= C), P: bf16 [batch][S][S]; S multiple of 16, <= 256.  The
+ * score row never leaves tensor memory: max / sum / normalise run in the GEMM epilogue. */
+int sd_attention_probs(const void* Q, int ldq, long long strideQ, const void* Kt, int ldk, long long strideK,
+                       int batch, int S, int C, float scale, int block, void* P, void* stream);
+
 /* Row softmax P[r,:] = softmax(scale * X[r,:]); X fp32 [rows, cols] -> P bf16
  * (jax.nn.softmax at cifar/models/layers.py:507 with the C^-1/2 scale of :505). */
 int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale, void* stream);
@@ -150,6 +160,7 @@ int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale,
  * cifar/models/ddpm.py:98 (flax nn.GroupNorm defaults, normalization.py:38-39). */
 int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW,
                        const float* gamma, const float* beta, float eps, int apply_swish,
+                       float* scratch /* >= (1184+B)*2*(C0+C1) floats: per-chunk channel sums */, size_t scratch_floats,
                        void* out, void* stream);
 
 /* Single-head self-attention over HW tokens (cifar/models/layers.py:505-509):

@@ -30,13 +30,14 @@ SIGNATURES = {
     "sd_step_edm_cfg": (_I, [_V, _V, _V, _V, _V, _I, _I, _F, _F, _F, _F, _I, _F, _F, _F, _V, _V, _V, _V]),
     "sd_counter_add": (_I, [_V, _I, _V]),
     "sd_conv_gemm": (_I, [ctypes.POINTER(GemmSrc), _I, _I, _I, _I, _V, _I, _V, _V, _I, _V, _U, _V, _I, _V]),
-    "sd_groupnorm_swish": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _V]),
+    "sd_groupnorm_swish": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _SZ, _V, _V]),
     "sd_attention": (_I, [_V, _I, _I, _I, _V, _V]),
     "sd_upsample2x": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_im2col_s2": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_conv_in": (_I, [_V, _I, _I, _I, _I, _V, _V, _I, _V, _V]),
     "sd_time_embedding": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sd_batched_gemm": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _I, _V, _V, _U, _V, _I, _LL, _V]),
+    "sd_attention_probs": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _F, _I, _V, _V]),
     "sd_softmax_rows": (_I, [_V, _V, ctypes.c_long, _I, _F, _V]),
     "sd_cast_f32_to_bf16": (_I, [_V, _V, _SZ, _V]),
     "sd_cast_bf16_to_f32": (_I, [_V, _V, _SZ, _V]),

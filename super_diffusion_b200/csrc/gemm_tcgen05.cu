@@ -61,6 +61,8 @@ struct GemmParams {
   void* out;
   int out_ld;
   unsigned flags;
+  float softmax_scale;        // SD_EPI_SOFTMAX: out = softmax(scale * acc) over the row's block of softmax_block columns
+  int softmax_block;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------
@@ -340,6 +342,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           img = m / p.HW;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
+        if (p.flags & SD_EPI_SOFTMAX) {
+          // the whole score row (block_n == N <= 256 columns) sits in this thread's TMEM lane: in-thread softmax over
+          // the row's diagonal block [lo, hi) (several small images share one 128-row tile), zeros elsewhere
+          const int rl = (p.flat ? (m_tile % p.m_tiles_per_batch) : 0) * BM + row;
+          const int lo = (rl / p.softmax_block) * p.softmax_block, hi = lo + p.softmax_block;
+          float mx = -INFINITY;
+          for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t r0[16];
+            tmem_ld16(taddr + c, r0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j >= lo && c + j < hi) mx = fmaxf(mx, __uint_as_float(r0[j]));
+          }
+          float sum = 0.f;
+          for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t r0[16];
+            tmem_ld16(taddr + c, r0);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (c + j >= lo && c + j < hi) sum += expf(p.softmax_scale * (__uint_as_float(r0[j]) - mx));
+          }
+          const float inv = 1.f / sum;
+          for (int c = 0; c < p.block_n; c += 16) {
+            uint32_t r0[16];
+            tmem_ld16(taddr + c, r0);
+            tmem_wait_ld();
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c0 = c + 2 * j;
+              const float e0 = (c0 >= lo && c0 < hi) ? expf(p.softmax_scale * (__uint_as_float(r0[2 * j]) - mx)) * inv : 0.f;
+              const float e1 = (c0 + 1 >= lo && c0 + 1 < hi) ? expf(p.softmax_scale * (__uint_as_float(r0[2 * j + 1]) - mx)) * inv : 0.f;
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+              w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            if (row_ok) {
+              uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + c);
+              op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          }
+          continue;
+        }
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
@@ -415,11 +462,11 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   const int n_pad = (N + 15) / 16 * 16;
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
   // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
-  if (p.block_n > 128 && p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
+  if (!(flags & SD_EPI_SOFTMAX) && p.block_n > 128 && p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
   p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
   // narrow N: pair two m-tiles per CTA tile so the B tile is fetched once per 256 rows (same smem traffic per
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
-  p.dual = (p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
+  p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
@@ -504,9 +551,10 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
                      (cudaStream_t)stream, "sd_conv_gemm");
 }
 
-extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
-                               int batch, int M, int N, int K, const float* bias, const void* residual,
-                               unsigned flags, void* out, int ldc, long long strideC, void* stream) {
+static int batched_gemm_impl(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                            int batch, int M, int N, int K, const float* bias, const void* residual,
+                            unsigned flags, void* out, int ldc, long long strideC, void* stream,
+                            float softmax_scale, int softmax_block) {
   using namespace sdb;
   if (!A || !Bt || !out || batch < 0 || M < 1 || N < 1 || K < BK || (K % BK) != 0)
     return fail(kErrInvalidArg, "sd_batched_gemm: bad argument (K must be a multiple of 64)");
@@ -514,6 +562,13 @@ extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const 
   if (((uintptr_t)A % 16) != 0 || (lda % 8) != 0 || (strideA % 8) != 0 || (strideB % 8) != 0)
     return fail(kErrInvalidArg, "sd_batched_gemm: A must be 16-byte aligned with lda, strides multiples of 8");
   GemmParams p{};
+  p.softmax_scale = softmax_scale;
+  p.softmax_block = softmax_block;
+  if (flags & SD_EPI_SOFTMAX) {
+    if (N > MAX_BN || (N % 16) != 0 || softmax_block < 1 || (N % softmax_block) != 0 || (BM % softmax_block != 0 && softmax_block % BM != 0) ||
+        bias || residual || (flags & (SD_EPI_OUT_F32 | SD_EPI_SWISH)))
+      return fail(kErrInvalidArg, "sd_attention_probs: N must be a multiple of 16, <= 256, and a multiple of the block");
+  }
   p.flat = 1;
   p.a_batched = strideA != 0;
   p.b_batched = strideB != 0;
@@ -538,4 +593,18 @@ extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const 
   if (rc != SD_OK) return rc;
   return launch_gemm(p, N, K, Bt, ldb, strideB, p.b_batched ? batch : 1, bias, nullptr, 0, residual, flags, out, ldc,
                      (cudaStream_t)stream, "sd_batched_gemm");
+}
+
+extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                               int batch, int M, int N, int K, const float* bias, const void* residual,
+                               unsigned flags, void* out, int ldc, long long strideC, void* stream) {
+  if (flags & SD_EPI_SOFTMAX) return sdb::fail(sdb::kErrInvalidArg, "sd_batched_gemm: use sd_attention_probs for the softmax epilogue");
+  return batched_gemm_impl(A, lda, strideA, Bt, ldb, strideB, batch, M, N, K, bias, residual, flags, out, ldc, strideC,
+                           stream, 1.f, 1);
+}
+
+extern "C" int sd_attention_probs(const void* Q, int ldq, long long strideQ, const void* Kt, int ldk, long long strideK,
+                                  int batch, int S, int C, float scale, int block, void* P, void* stream) {
+  return batched_gemm_impl(Q, ldq, strideQ, Kt, ldk, strideK, batch, S, S, C, nullptr, nullptr, SD_EPI_SOFTMAX, P, S,
+                           (long long)S * S, stream, scale, block);
 }

@@ -29,77 +29,85 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 }
 
 // ---------------------------------------------------------------------------
-// GroupNorm(32) + swish over concat(x0, x1) along channels.
-// Groups are independent, so the work is split over (sample, channel block): one CTA owns all H*W pixels of
-// `Cs` consecutive channels (a whole number of groups), keeps them in registers (read once), reduces per-channel
-// partials through shared memory in a fixed order (deterministic) and writes the normalised block.  No clusters,
-// no cross-CTA traffic (measured on B200: cluster launches of memory-bound kernels cost 2-3x).
+// GroupNorm(32) + swish over concat(x0, x1) along channels, as two streaming passes:
+//   gn_stats_kernel : per (sample, pixel chunk) per-channel sum / sum-of-squares -> partial[B][nchunk][2][C]
+//   gn_apply_kernel : group mean / rstd from the partials (fixed order => deterministic), then
+//                     y = swish((x - mean) * rstd * gamma + beta) streamed with 16-byte vectors.
+// Whole pixel rows are read (fully coalesced), nothing is register- or cluster-resident, so occupancy stays high.
+// Measured alternatives on B200 (profiles/): a cluster-per-sample register-resident kernel ran at 0.6-1.6 TB/s
+// (cluster launches of memory-bound kernels cost 2-3x; one fat CTA per SM serialises load/reduce/store).
+// Algorithmic bytes: 2 reads + 1 write of the activation (the second read mostly hits L2 for the
+// chunk sizes used here).
 // ---------------------------------------------------------------------------
 struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
   int C0, C1, B, HW;
-  int Cs, nsplit;            // channels per CTA, CTAs per sample
+  int nchunk, px_per_chunk;
   const float* gamma; const float* beta;
   float eps; int apply_swish;
+  float* partial;            // [B][nchunk][2][C]
   __nv_bfloat16* out;
 };
 
-template <int NV>
-__global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_constant__ GnParams p) {
-  extern __shared__ float gn_smem[];   // [2*Cs] channel sums / sumsq, [2*32] group mean / rstd, [rows][2*Cs] partials
-  const int C = p.C0 + p.C1, Cs = p.Cs;
-  const int VC = Cs / 8;               // 16-byte vectors per pixel owned by this CTA
-  float* ch_sum = gn_smem;
-  float* ch_sq = gn_smem + Cs;
-  float* g_mean = gn_smem + 2 * Cs;
-  float* g_rstd = g_mean + 32;
-  float* part = g_rstd + 32;           // [rows_per_pass][2*Cs]
-  const int sample = blockIdx.x / p.nsplit;
-  const int c_base = (blockIdx.x - sample * p.nsplit) * Cs;
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ GnParams p) {
+  extern __shared__ float gn_smem[];   // [rows_per_pass][2*C]
+  const int C = p.C0 + p.C1, VC = C / 8;
+  const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
-  const int c0 = c_base + cv * 8;      // first of this thread's 8 channels (never straddles x0 | x1: C0 % 8 == 0)
-
+  const int c0 = cv * 8;
   const bool from0 = c0 < p.C0;
   const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0
                                    : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
   const int src_ld = from0 ? p.C0 : p.C1;
-  uint4 v[NV];
-  bool ok[NV];
+  const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+  int px = px0 + r;
+  for (; px + 3 * rows_per_pass < px1; px += 4 * rows_per_pass) {      // 4 independent 16-byte loads in flight
+    uint4 v[4];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    const int px = r + j * rows_per_pass;
-    ok[j] = px < p.HW;
-    if (ok[j]) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)px * src_ld);
+    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * src_ld);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+    }
   }
-#pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    if (!ok[j]) continue;
+  for (; px < px1; px += rows_per_pass) {
     float f[8];
-    unpack8(v[j], f);
+    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * src_ld), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
   }
-  // fixed-order (deterministic) reduction over the pixel rows
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    part[(size_t)r * 2 * Cs + cv * 8 + e] = s[e];
-    part[(size_t)r * 2 * Cs + Cs + cv * 8 + e] = q[e];
+    gn_smem[(size_t)r * 2 * C + c0 + e] = s[e];
+    gn_smem[(size_t)r * 2 * C + C + c0 + e] = q[e];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * Cs; i += blockDim.x) {
+  float* dst = p.partial + ((size_t)sample * p.nchunk + chunk) * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
     float a = 0.f;
-    for (int rr = 0; rr < rows_per_pass; ++rr) a += part[(size_t)rr * 2 * Cs + i];
-    gn_smem[i] = a;
+    for (int rr = 0; rr < rows_per_pass; ++rr) a += gn_smem[(size_t)rr * 2 * C + i];   // fixed order
+    dst[i] = a;
   }
-  __syncthreads();
-  const int cpg = C / 32;
-  const int ngroups = Cs / cpg;
-  if (threadIdx.x < ngroups) {
+}
+
+__global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ GnParams p) {
+  __shared__ float g_mean[32], g_rstd[32];
+  const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32;
+  const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
+  if (threadIdx.x < 32) {
     double sum = 0.0, sq = 0.0;
-    for (int c = 0; c < cpg; ++c) { sum += (double)ch_sum[threadIdx.x * cpg + c]; sq += (double)ch_sq[threadIdx.x * cpg + c]; }
+    const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
+    for (int k = 0; k < p.nchunk; ++k)
+      for (int c = 0; c < cpg; ++c) {
+        sum += (double)base[(size_t)k * 2 * C + threadIdx.x * cpg + c];
+        sq += (double)base[(size_t)k * 2 * C + C + threadIdx.x * cpg + c];
+      }
     const double n = (double)p.HW * cpg;
     const double mean = sum / n;
     double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
@@ -108,37 +116,49 @@ __global__ void __launch_bounds__(512) groupnorm_swish_kernel(const __grid_const
     g_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
   }
   __syncthreads();
-  float mu[8], rs[8], ga[8], be[8];
+  const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
+  const int c0 = cv * 8;
+  const bool from0 = c0 < p.C0;
+  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0
+                                   : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
+  const int src_ld = from0 ? p.C0 : p.C1;
+  float sc[8], sh[8];                       // y = x * sc + sh
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    const int cl = cv * 8 + e;
-    mu[e] = g_mean[cl / cpg];
-    rs[e] = g_rstd[cl / cpg];
-    ga[e] = p.gamma[c_base + cl];
-    be[e] = p.beta[c_base + cl];
+    const int c = c0 + e;
+    const float rs = g_rstd[c / cpg] * p.gamma[c];
+    sc[e] = rs;
+    sh[e] = p.beta[c] - g_mean[c / cpg] * rs;
   }
   __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
+  const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
+  int px = px0 + r;
+  for (; px + 3 * rows_per_pass < px1; px += 4 * rows_per_pass) {
+    uint4 v[4];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) {
-    if (!ok[j]) continue;
+    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * src_ld);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+      unpack8(v[j], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float y = fmaf(f[e], sc[e], sh[e]);
+        f[e] = p.apply_swish ? swish_f(y) : y;
+      }
+      *reinterpret_cast<uint4*>(dst + (size_t)(px + j * rows_per_pass) * C) = pack8(f);
+    }
+  }
+  for (; px < px1; px += rows_per_pass) {
     float f[8];
-    unpack8(v[j], f);
+    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * src_ld), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float y = (f[e] - mu[e]) * rs[e] * ga[e] + be[e];
+      const float y = fmaf(f[e], sc[e], sh[e]);
       f[e] = p.apply_swish ? swish_f(y) : y;
     }
-    const int px = r + j * rows_per_pass;
     *reinterpret_cast<uint4*>(dst + (size_t)px * C) = pack8(f);
   }
-}
-
-template <int NV>
-static cudaError_t launch_gn(const GnParams& p, int threads, cudaStream_t st) {
-  const int rows = threads / (p.Cs / 8);
-  const size_t smem = sizeof(float) * ((size_t)2 * p.Cs * (1 + rows) + 64);
-  groupnorm_swish_kernel<NV><<<(unsigned)(p.B * p.nsplit), threads, smem, st>>>(p);
-  return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------
@@ -250,7 +270,8 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const uint4* __restrict_
 // First conv: fp32 NHWC [B,H,W,Cin<=4] -> bf16 [B,H,W,Cout].  Weights (9*Cin x Cout fp32, <= 18 KB) sit in
 // shared memory; a thread owns one pixel x 32 output channels (its 9*Cin inputs in registers) and writes
 // 64 contiguous bytes, so a pixel's 256-byte row is covered by 4 adjacent threads (coalesced).
-__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
+template <int Cin>
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, int B, int H, int W,
                                                       const float* __restrict__ w, const float* __restrict__ bias,
                                                       int Cout, __nv_bfloat16* __restrict__ out) {
   extern __shared__ float cin_smem[];   // [9*Cin][Cout] weights, then [Cout] bias
@@ -273,6 +294,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
       for (int kw = 0; kw < 3; ++kw) {
         const int hi = ho + kh - 1, wi = wo + kw - 1;
         const bool okp = hi >= 0 && hi < H && wi >= 0 && wi < W;
+#pragma unroll
         for (int c = 0; c < Cin; ++c)
           in[(kh * 3 + kw) * 4 + c] = okp ? x[(((size_t)b * H + hi) * W + wi) * Cin + c] : 0.f;
       }
@@ -281,6 +303,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
     for (int j = 0; j < 32; ++j) acc[j] = cin_smem[K * Cout + cg0 + j];
 #pragma unroll
     for (int t = 0; t < 9; ++t)
+#pragma unroll
       for (int c = 0; c < Cin; ++c) {
         const float v = in[t * 4 + c];
         const float4* wr = reinterpret_cast<const float4*>(cin_smem + (size_t)(t * Cin + c) * Cout + cg0);
@@ -360,61 +383,39 @@ static unsigned grid_for(size_t total, int threads) {
 extern "C" {
 
 int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW, const float* gamma,
-                       const float* beta, float eps, int apply_swish, void* out, void* stream) {
+                       const float* beta, float eps, int apply_swish, float* scratch, size_t scratch_floats, void* out,
+                       void* stream) {
   using namespace sdb;
-  if (!x0 || !gamma || !beta || !out || (C1 > 0 && !x1)) return fail(kErrInvalidArg, "sd_groupnorm_swish: null pointer");
+  if (!x0 || !gamma || !beta || !out || !scratch || (C1 > 0 && !x1)) return fail(kErrInvalidArg, "sd_groupnorm_swish: null pointer");
   if (C1 < 0) C1 = 0;
   const int C = C0 + C1;
-  if (C0 < 8 || C0 % 8 || C1 % 8 || C % 32 || C > 2048) return fail(kErrInvalidArg, "sd_groupnorm_swish: channels must be multiples of 8, total a multiple of 32");
+  if (C0 < 8 || C0 % 8 || C1 % 8 || C % 32 || C > 1024) return fail(kErrInvalidArg, "sd_groupnorm_swish: channels must be multiples of 8, total a multiple of 32, <= 1024");
   if (B < 0 || HW < 1) return fail(kErrInvalidArg, "sd_groupnorm_swish: bad shape");
   if (B == 0) return SD_OK;
-  GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, 0, 0, gamma, beta, eps, apply_swish,
-             (__nv_bfloat16*)out};
-  const int cpg = C / 32;
-  // channel block per CTA: a multiple of lcm(cpg, 8) channels dividing C; threads = (Cs/8) * k pixel rows per pass.
-  // Prefer <= 8 vectors per thread (3+ CTAs resident per SM), then wide channel blocks (longer contiguous segments).
-  int unit = cpg;
-  while (unit % 8) unit += cpg;
-  static const int min_cs = [] { const char* e = getenv("SDB_GN_MIN_CS"); return e ? atoi(e) : 32; }();   // tuning knob
-  int best_cs = 0, best_t = 0, best_nv = 0;
-  long best_cost = -1;
-  for (int Cs = unit; Cs <= C; Cs += unit) {
-    if (C % Cs) continue;
-    const int VC = Cs / 8;
-    for (int k = 1; VC * k <= 512; ++k) {
-      const int T = VC * k;
-      if (T % 32) continue;
-      const int need = (HW + k - 1) / k;
-      if (need > 16) continue;
-      const int nvt = need <= 1 ? 1 : need <= 2 ? 2 : need <= 4 ? 4 : need <= 8 ? 8 : 16;
-      const size_t smem = sizeof(float) * ((size_t)2 * Cs * (1 + k) + 64);
-      if (smem > 96 * 1024) continue;
-      long cost = (nvt > 8 ? 4000 : 0) + (T < 128 ? 1500 : 0) + (T > 384 ? 300 : 0) + (long)(nvt * k - HW) * 4  // idle lanes
-                  + 2048 / Cs + (Cs < min_cs ? 1000 : 0) + (smem > 32 * 1024 ? 500 : 0);
-      if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_cs = Cs; best_t = T; best_nv = need; }
-    }
-  }
-  if (best_cost < 0) return fail(kErrUnsupported, "sd_groupnorm_swish: H*W too large for the register-resident path (max 8192 pixels)");
-  p.Cs = best_cs;
-  p.nsplit = C / best_cs;
-  const int nv = best_nv, T = best_t;
-  cudaError_t err;
+  const int VC = C / 8;
+  int k = 256 / VC;                         // pixel rows per pass; threads = VC * k, whole warps
+  while (k > 1 && (VC * k) % 32) --k;
+  if (k < 1 || (VC * k) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
+  const int T = VC * k;
+  // enough CTAs for ~8 per SM, chunks of at least 4 passes
+  int nchunk = (148 * 8 + B - 1) / B;
+  const int max_chunks = (HW + 4 * k - 1) / (4 * k);
+  if (nchunk > max_chunks) nchunk = max_chunks;
+  if (nchunk < 1) nchunk = 1;
+  if (nchunk > 64) nchunk = 64;
+  const int px_per_chunk = (HW + nchunk - 1) / nchunk;
+  nchunk = (HW + px_per_chunk - 1) / px_per_chunk;
+  if ((size_t)B * nchunk * 2 * C > scratch_floats)
+    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (1184 + B) * 2 * C floats)");
+  GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, nchunk, px_per_chunk, gamma, beta, eps,
+             apply_swish, scratch, (__nv_bfloat16*)out};
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(groupnorm_swish_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(groupnorm_swish_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(groupnorm_swish_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(groupnorm_swish_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(groupnorm_swish_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
-  if (nv <= 1) err = launch_gn<1>(p, T, st);
-  else if (nv <= 2) err = launch_gn<2>(p, T, st);
-  else if (nv <= 4) err = launch_gn<4>(p, T, st);
-  else if (nv <= 8) err = launch_gn<8>(p, T, st);
-  else err = launch_gn<16>(p, T, st);
-  return check_cuda(err, "sd_groupnorm_swish launch");
+  const size_t smem = sizeof(float) * (size_t)k * 2 * C;
+  gn_stats_kernel<<<(unsigned)(B * nchunk), T, smem, st>>>(p);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
+  gn_apply_kernel<<<(unsigned)(B * nchunk), T, 0, st>>>(p);
+  return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (apply) launch");
 }
 
 int sd_attention(const void* qkv, int B, int S, int C, void* out, void* stream) {
@@ -478,13 +479,22 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
   const size_t smem = sizeof(float) * ((size_t)9 * Cin * Cout + Cout);
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    if (e != cudaSuccess) return check_cuda(e, "sd_conv_in: cudaFuncSetAttribute");
+    cudaFuncSetAttribute(conv_in_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv_in_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
   const size_t total = (size_t)B * H * W * (Cout / 32);
-  conv_in_kernel<<<grid_for(total, 256), 256, smem, (cudaStream_t)stream>>>(x, B, H, W, Cin, w_hwio, bias, Cout,
-                                                                             (__nv_bfloat16*)out);
+  const unsigned grid = grid_for(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  __nv_bfloat16* o = (__nv_bfloat16*)out;
+  switch (Cin) {
+    case 1: conv_in_kernel<1><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
+    case 2: conv_in_kernel<2><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
+    case 3: conv_in_kernel<3><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
+    default: conv_in_kernel<4><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
+  }
   return check_cuda(cudaGetLastError(), "sd_conv_in launch");
 }
 

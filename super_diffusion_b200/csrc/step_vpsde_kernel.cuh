@@ -64,45 +64,78 @@ __device__ __forceinline__ void known_weights(const StepParams& p, int sample, f
   }
 }
 
-// Solve the AND system in fp64.  G packed upper
-// triangular: idx(i,j) for i<=j.  M == 2 uses the notebook's closed form.
+// AND weights in the cancellation-free difference form.  With d_i = s_i - s_M (i < M-1... Md = M-1 of them),
+// D_ij = <d_i, d_j>, E_i = <d_i, noise>, equalising the Ito increments R_i reduces to the
+// symmetric (M-1)x(M-1) system   2 dt b sum_j D_ij kappa_j = dt b D_ii - c E_i,   kappa_M = 1 - sum_j kappa_j.
+// For M = 2 this is the notebook's select_kappa (superposition_edu.ipynb:899-905):
+//   kappa_1 = 1/2 - c <s1-s2, noise> / (2 dt b |s1-s2|^2).
+// The differences are formed element-wise in fp32 (exact-ish, like the reference's (s1-s2)**2), so nearly equal
+// models (t ~ 1) do not lose the denominator to cancellation the way a Gram-matrix formulation does.
+// D packed upper triangular over Md: idx(i,j), i <= j.
 template <int M>
-__device__ void and_solve(const double* G /*packed*/, const double* N, double dtb, double c, double* kappa) {
-  auto g = [&](int i, int j) {
+__device__ void and_solve(const double* D, const double* E, double dtb, double c, double* kappa) {
+  constexpr int Md = M - 1;
+  auto d = [&](int i, int j) {
     if (i > j) { int t = i; i = j; j = t; }
-    return G[i * M - (i * (i - 1)) / 2 + (j - i)];
+    return D[i * Md - (i * (i - 1)) / 2 + (j - i)];
   };
   if (M == 1) { kappa[0] = 1.0; return; }
   if (M == 2) {
-    const double num = dtb * (g(0, 0) - g(1, 1)) - 2.0 * dtb * (g(0, 1) - g(1, 1)) - c * (N[0] - N[1]);
-    const double den = 2.0 * dtb * (g(0, 0) - 2.0 * g(0, 1) + g(1, 1));
-    kappa[0] = num / den;
+    kappa[0] = (dtb * D[0] - c * E[0]) / (2.0 * dtb * D[0]);
     kappa[1] = 1.0 - kappa[0];
     return;
   }
-  double A[M][M + 1];
-  for (int i = 0; i < M - 1; ++i) {
-    for (int j = 0; j < M; ++j) A[i][j] = 2.0 * dtb * (g(i, j) - g(M - 1, j));
-    A[i][M] = dtb * (g(i, i) - g(M - 1, M - 1)) - c * (N[i] - N[M - 1]);
+  double A[Md > 0 ? Md : 1][Md + 1];
+  for (int i = 0; i < Md; ++i) {
+    for (int j = 0; j < Md; ++j) A[i][j] = 2.0 * dtb * d(i, j);
+    A[i][Md] = dtb * d(i, i) - c * E[i];
   }
-  for (int j = 0; j <= M; ++j) A[M - 1][j] = 1.0;
-  for (int col = 0; col < M; ++col) {  // Gaussian elimination, partial pivoting
+  for (int col = 0; col < Md; ++col) {  // Gaussian elimination, partial pivoting
     int piv = col;
     double best = fabs(A[col][col]);
-    for (int r = col + 1; r < M; ++r)
+    for (int r = col + 1; r < Md; ++r)
       if (fabs(A[r][col]) > best) { best = fabs(A[r][col]); piv = r; }
     if (piv != col)
-      for (int j = 0; j <= M; ++j) { double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
+      for (int j = 0; j <= Md; ++j) { double t = A[col][j]; A[col][j] = A[piv][j]; A[piv][j] = t; }
     const double inv = 1.0 / A[col][col];
-    for (int r = col + 1; r < M; ++r) {
+    for (int r = col + 1; r < Md; ++r) {
       const double f = A[r][col] * inv;
-      for (int j = col; j <= M; ++j) A[r][j] -= f * A[col][j];
+      for (int j = col; j <= Md; ++j) A[r][j] -= f * A[col][j];
     }
   }
-  for (int i = M - 1; i >= 0; --i) {
-    double s = A[i][M];
-    for (int j = i + 1; j < M; ++j) s -= A[i][j] * kappa[j];
-    kappa[i] = s / A[i][i];
+  double sum = 0.0;
+  for (int i = Md - 1; i >= 0; --i) {
+    double acc = A[i][Md];
+    for (int j = i + 1; j < Md; ++j) acc -= A[i][j] * kappa[j];
+    kappa[i] = acc / A[i][i];
+  }
+  for (int i = 0; i < Md; ++i) sum += kappa[i];
+  kappa[Md] = 1.0 - sum;
+}
+
+// Ito increments under AND from the difference reductions:  R_M = [2dtb(G_MM + sum_j kappa_j F_j) + c N_M - dtb G_MM]/sigma
+// with F_j = <s_M, d_j>, and R_i = R_M + (row-i residual of the system)/sigma, which is 0 up to rounding.
+// layout of `tot`: D (Md(Md+1)/2) | E (Md) | F (Md) | G_MM | N_M
+template <int M>
+__device__ void and_increments(const double* tot, const double* kappa, double dtb, double c, double sigma, double* R) {
+  constexpr int Md = M - 1;
+  constexpr int ND = Md * (Md + 1) / 2;
+  const double* D = tot;
+  const double* E = tot + ND;
+  const double* F = tot + ND + Md;
+  const double Gmm = tot[ND + 2 * Md], Nm = tot[ND + 2 * Md + 1];
+  auto d = [&](int i, int j) {
+    if (i > j) { int t = i; i = j; j = t; }
+    return D[i * Md - (i * (i - 1)) / 2 + (j - i)];
+  };
+  double mixF = 0.0;
+  for (int j = 0; j < Md; ++j) mixF += kappa[j] * F[j];
+  const double Rm = (2.0 * dtb * (Gmm + mixF) + c * Nm - dtb * Gmm) / sigma;
+  R[Md] = Rm;
+  for (int i = 0; i < Md; ++i) {
+    double acc = 0.0;
+    for (int j = 0; j < Md; ++j) acc += kappa[j] * d(i, j);
+    R[i] = Rm + (2.0 * dtb * acc - dtb * d(i, i) + c * E[i]) / sigma;
   }
 }
 
@@ -143,7 +176,7 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
   const int u1 = min(nunits, u0 + per_cta);
   const size_t base = (size_t)sample * p.D;
 
-  constexpr int KAND = M * (M + 1) / 2 + M;
+  constexpr int KAND = (M - 1) * M / 2 + 2 * (M - 1) + 2;   // D | E | F | G_MM | N_M
   constexpr int K = AND ? KAND : M;
   float part[K];
 #pragma unroll
@@ -241,23 +274,34 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
     for (int j = 0; j < NV; ++j)
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
+        constexpr int Md = M - 1;
+        constexpr int ND = Md * (Md + 1) / 2;
+        const float sm = sv[M - 1][j][e];
+        float d[Md > 0 ? Md : 1];
+#pragma unroll
+        for (int i = 0; i < Md; ++i) d[i] = sv[i][j][e] - sm;
         int k = 0;
 #pragma unroll
-        for (int i = 0; i < M; ++i)
+        for (int i = 0; i < Md; ++i)
 #pragma unroll
-          for (int l = i; l < M; ++l) { part[k] = fmaf(sv[i][j][e], sv[l][j][e], part[k]); ++k; }
+          for (int l = i; l < Md; ++l) { part[k] = fmaf(d[i], d[l], part[k]); ++k; }
 #pragma unroll
-        for (int i = 0; i < M; ++i) part[M * (M + 1) / 2 + i] = fmaf(sv[i][j][e], ev[j][e], part[M * (M + 1) / 2 + i]);
+        for (int i = 0; i < Md; ++i) {
+          part[ND + i] = fmaf(d[i], ev[j][e], part[ND + i]);
+          part[ND + Md + i] = fmaf(sm, d[i], part[ND + Md + i]);
+        }
+        part[ND + 2 * Md] = fmaf(sm, sm, part[ND + 2 * Md]);
+        part[ND + 2 * Md + 1] = fmaf(sm, ev[j][e], part[ND + 2 * Md + 1]);
       }
     const double* tot = block_cluster_sum<K, CLUSTER>(part, scratch);
     // kappa: closed form for M <= 2 (every thread), one solver thread + smem broadcast otherwise
     double* kappa_sh = scratch + ((blockDim.x + 31) / 32 + 2) * K;
     double kappa[M];
     if (M <= 2) {
-      and_solve<M>(tot, tot + M * (M + 1) / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
+      and_solve<M>(tot, tot + (M - 1) * M / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
     } else {
       if (threadIdx.x == 0) {
-        and_solve<M>(tot, tot + M * (M + 1) / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
+        and_solve<M>(tot, tot + (M - 1) * M / 2, (double)sc.dt * (double)sc.b, (double)c, kappa);
         for (int i = 0; i < M; ++i) kappa_sh[i] = kappa[i];
       }
       __syncthreads();
@@ -273,9 +317,12 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
       float o[VEC];
 #pragma unroll
       for (int e = 0; e < VEC; ++e) {
-        float mix = 0.f;
+        // s_M + sum_j kappa_j (s_j - s_M): the reference's form (superposition_edu.ipynb:942), well conditioned
+        // for the unclipped |kappa| >> 1 that occurs while the models still agree (t ~ 1)
+        const float sm = sv[M - 1][j][e];
+        float mix = sm;
 #pragma unroll
-        for (int i = 0; i < M; ++i) mix = fmaf(w[i], sv[i][j][e], mix);
+        for (int i = 0; i < M - 1; ++i) mix = fmaf(w[i], sv[i][j][e] - sm, mix);
         o[e] = xv[j][e] + (-dta * xv[j][e] + 2.f * dtb * mix + c * ev[j][e]);
       }
       const size_t off = base + (size_t)(u0 + j * blockDim.x + threadIdx.x) * VEC;
@@ -283,18 +330,8 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
       else p.x_out[off] = o[0];
     }
     if (crank == 0 && threadIdx.x == 0) {
-      // R_i = [2 dt b sum_j kappa_j G_ij + c N_i - dt b G_ii] / sigma   (Appendix A.2 with A.1 substituted)
-      auto g = [&](int i, int j) {
-        if (i > j) { int t = i; i = j; j = t; }
-        return tot[i * M - (i * (i - 1)) / 2 + (j - i)];
-      };
-      const double dtbd = (double)sc.dt * (double)sc.b;
       double R[M];
-      for (int i = 0; i < M; ++i) {
-        double acc = 0.0;
-        for (int j = 0; j < M; ++j) acc += kappa[j] * g(i, j);
-        R[i] = (2.0 * dtbd * acc + (double)c * tot[M * (M + 1) / 2 + i] - dtbd * g(i, i)) / (double)sc.sigma;
-      }
+      and_increments<M>(tot, kappa, (double)sc.dt * (double)sc.b, (double)c, (double)sc.sigma, R);
       write_logq(p, sc, sample, M, R);
       for (int i = 0; i < M; ++i) p.weights[(size_t)sample * M + i] = w[i];
     }
@@ -313,24 +350,27 @@ __global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_cons
   float w[M];
   double R[M];
   if (p.mode == SD_MODE_AND) {
-    double G[M * (M + 1) / 2], N[M];
-    for (int k = 0; k < M * (M + 1) / 2; ++k) G[k] = 0.0;
-    for (int i = 0; i < M; ++i) N[i] = 0.0;
-    for (int d = 0; d < p.D; ++d) {
-      float s[M];
+    constexpr int Md = M - 1;
+    constexpr int ND = Md * (Md + 1) / 2;
+    double Dm[ND > 0 ? ND : 1], E[Md > 0 ? Md : 1];
+    for (int k = 0; k < ND; ++k) Dm[k] = 0.0;
+    for (int i = 0; i < Md; ++i) E[i] = 0.0;
+    for (int d_ = 0; d_ < p.D; ++d_) {
+      const float sm = p.s[M - 1][base + d_];
+      const float e = p.noise[base + d_];
+      float df[Md > 0 ? Md : 1];
 #pragma unroll
-      for (int i = 0; i < M; ++i) s[i] = p.s[i][base + d];
-      const float e = p.noise[base + d];
+      for (int i = 0; i < Md; ++i) df[i] = p.s[i][base + d_] - sm;
       int k = 0;
 #pragma unroll
-      for (int i = 0; i < M; ++i) {
+      for (int i = 0; i < Md; ++i) {
 #pragma unroll
-        for (int l = i; l < M; ++l) G[k++] += (double)(s[i] * s[l]);
-        N[i] += (double)(s[i] * e);
+        for (int l = i; l < Md; ++l) Dm[k++] += (double)df[i] * (double)df[l];
+        E[i] += (double)df[i] * (double)e;
       }
     }
     double kappa[M];
-    and_solve<M>(G, N, (double)sc.dt * (double)sc.b, (double)c, kappa);
+    and_solve<M>(Dm, E, (double)sc.dt * (double)sc.b, (double)c, kappa);
 #pragma unroll
     for (int i = 0; i < M; ++i) w[i] = (float)kappa[i];
   } else {
@@ -340,14 +380,16 @@ __global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_cons
   for (int i = 0; i < M; ++i) R[i] = 0.0;
   for (int d = 0; d < p.D; ++d) {
     float s[M];
-    float mix = 0.f;
 #pragma unroll
-    for (int i = 0; i < M; ++i) { s[i] = p.s[i][base + d]; mix = fmaf(w[i], s[i], mix); }
+    for (int i = 0; i < M; ++i) s[i] = p.s[i][base + d];
+    float mix = s[M - 1];             // s_M + sum_j kappa_j (s_j - s_M), see the AND path of the vector kernel
+#pragma unroll
+    for (int i = 0; i < M - 1; ++i) mix = fmaf(w[i], s[i] - s[M - 1], mix);
     const float xe = p.x[base + d];
     const float dx = -dta * xe + 2.f * dtb * mix + c * p.noise[base + d];
     const float q = dx + dta * xe;
 #pragma unroll
-    for (int i = 0; i < M; ++i) R[i] += (double)(s[i] * (q - dtb * s[i]));
+    for (int i = 0; i < M; ++i) R[i] += (double)s[i] * (double)(q - dtb * s[i]);
     p.x_out[base + d] = xe + dx;
   }
 #pragma unroll
@@ -359,7 +401,7 @@ __global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_cons
 
 template <int M, int NV, int VEC, bool AND>
 static cudaError_t launch_cfg(const StepParams& p, int threads, int cluster, cudaStream_t st) {
-  constexpr int K = AND ? (M * (M + 1) / 2 + M) : M;
+  constexpr int K = AND ? ((M - 1) * M / 2 + 2 * (M - 1) + 2) : M;
   const size_t smem = sizeof(double) * ((size_t)(threads / 32 + 2) * K + M);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)p.B * cluster);

@@ -161,15 +161,16 @@ class _Bound:
         B, H, W, C = x.shape
         S = H * W
         h = ops.groupnorm_swish(x, a["g"], a["be"], swish=False)
-        if S <= 64:
+        g = max(1, 128 // S)              # low resolution: pack g images per 128-row tensor-core tile
+        if S < 16 or B % g or (g * S) % 16:
             qkv = ops.conv_gemm([(h, 1)], a["w_qkv"], bias=a["b_qkv"])
             o = ops.attention_small(qkv.view(B, S, 3 * C), C)
         else:
-            qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(B, S, 2 * C)
-            vt = ops.batched_gemm(a["w_vT"], h.view(B, S, C))                       # [B, C, S] = V^T (bias deferred)
-            sc = ops.batched_gemm(qk[:, :, :C], qk[:, :, C:], out_f32=True, K=C)    # [B, S, S]
-            p = ops.softmax_rows(sc, C ** -0.5)
-            o = ops.batched_gemm(p, vt, bias=a["b_v"])                              # rows of p sum to 1 -> + b_v
+            nb, Sp = B // g, g * S
+            qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(nb, Sp, 2 * C)
+            vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))                      # [nb, C, Sp] = V^T (bias deferred)
+            p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], C ** -0.5, block=S, C=C)   # [nb, Sp, Sp], block diagonal
+            o = ops.batched_gemm(p, vt, bias=a["b_v"])                               # rows of p sum to 1 -> + b_v
         return ops.conv_gemm([(o.view(B, H, W, C), 1)], a["w_o"], bias=a["b_o"], residual=x)
 
     def __call__(self, t, x, y=None, *, sched=None, step_counter=None, out=None):

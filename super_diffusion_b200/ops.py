@@ -182,6 +182,23 @@ def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, ou
     return out
 
 
+def attention_probs(q, k, scale, block=None, out=None, C=None):
+    """P = blockdiag-softmax(scale * q k^T) in one tcgen05 launch (sd_attention_probs).  q, k: bf16 [batch, S, >=C]
+    views with unit inner stride; returns bf16 [batch, S, S]."""
+    lib = _lib.load()
+    batch, S = q.shape[0], q.shape[1]
+    C = q.shape[2] if C is None else C
+    block = S if block is None else block
+    if out is None:
+        out = torch.empty(batch, S, S, device=q.device, dtype=torch.bfloat16)
+    rc = lib.sd_attention_probs(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), batch, S, C,
+                                float(scale), int(block), _ptr(out), _stream())
+    _lib.check(rc, "sd_attention_probs")
+    if batch > 0:
+        _count()
+    return out
+
+
 def softmax_rows(x, scale, out=None):
     lib = _lib.load()
     _f32c(x, "x")
@@ -192,6 +209,17 @@ def softmax_rows(x, scale, out=None):
     _lib.check(lib.sd_softmax_rows(_ptr(x), _ptr(out), rows, cols, float(scale), _stream()), "sd_softmax_rows")
     _count()
     return out
+
+
+_gn_scratch = {}
+
+
+def _gn_scratch_for(device, floats):
+    buf = _gn_scratch.get(device)
+    if buf is None or buf.numel() < floats:
+        buf = torch.empty(max(floats, 1 << 20), device=device, dtype=torch.float32)
+        _gn_scratch[device] = buf
+    return buf
 
 
 def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
@@ -206,11 +234,14 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
         C1 = x1.shape[3]
     if out is None:
         out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
+    # per-chunk channel sums; stream-ordered reuse of one buffer per device (stats -> apply are back to back)
+    scratch = _gn_scratch_for(x0.device, (1184 + B) * 2 * (C0 + C1))
     rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
-                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(out), _stream())
+                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(scratch),
+                                scratch.numel(), _ptr(out), _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
-        _count()
+        _count(2)
     return out
 
 

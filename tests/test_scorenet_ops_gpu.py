@@ -194,3 +194,19 @@ def test_upsample_im2col_convin_temb(cuda):
         h = e @ w0.double() + b0.double()
         h = (h * torch.sigmoid(h)) @ w1.double() + b1.double() + emb_tab.double()[labels.long()]
         _close(got, h * torch.sigmoid(h), rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("nb,S,block", [(4, 256, 256), (6, 128, 64), (5, 128, 16), (3, 128, 128)])
+def test_attention_probs_fused_softmax(cuda, nb, S, block):
+    """q k^T -> scaled, block-diagonal softmax in the GEMM epilogue (scores never leave tensor memory)."""
+    C = 256
+    g = torch.Generator().manual_seed(nb + S + block)
+    qk = _bf(torch.randn(nb, S, 2 * C, generator=g)).to(cuda)
+    p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], C ** -0.5, block=block, C=C)
+    sc = torch.einsum("bsc,btc->bst", qk[:, :, :C].double(), qk[:, :, C:].double()) * C ** -0.5
+    idx = torch.arange(S, device=cuda) // block
+    mask = idx[:, None] == idx[None, :]
+    ref = torch.softmax(sc.masked_fill(~mask, float("-inf")), dim=-1)
+    assert (p.double()[:, ~mask] == 0).all()
+    _close(p, ref.cpu(), rtol=1e-2, atol=1e-4)
+    assert torch.allclose(p.float().sum(-1), torch.ones(nb, S, device=cuda), atol=2e-2)

@@ -121,6 +121,23 @@ def test_or_ties_give_uniform_weights_and_bias(cuda):
     _check(got, ref)
 
 
+@pytest.mark.parametrize("D,M", [(3072, 2), (3072, 3), (2, 2), (16384, 2)])
+def test_and_with_nearly_equal_models(cuda, D, M):
+    """t ~ 1: the models still agree (s_i = s + 1e-3 * delta_i), kappa is unclipped and large.  The difference
+    form keeps kappa to 1e-4 relative where a Gram formulation loses the denominator to cancellation."""
+    B, t, dt = 6, 0.98, 1e-3
+    g = torch.Generator().manual_seed(D + M)
+    x, eps = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+    s0 = torch.randn(B, D, generator=g)
+    s = torch.stack([s0 + 1e-3 * torch.randn(B, D, generator=g) for _ in range(M)])
+    logq = torch.zeros(B, M)
+    xo, lq, w = _run(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, cuda)
+    xr, lr, wr = _ref(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO)
+    assert ((w.double() - wr).abs() / (1 + wr.abs())).max().item() <= 1e-4, (w, wr)
+    assert torch.allclose(xo.double(), xr, rtol=1e-4, atol=1e-4)
+    assert (lq.double() - lr).abs().max().item() <= 1e-4 * (1 + lr.abs().max().item())
+
+
 def test_fixed_weights_mode(cuda):
     B, D, M = 5, 3072, 3
     x, eps, s, logq = _mk(B, D, M, seed=21, dev=cuda)
