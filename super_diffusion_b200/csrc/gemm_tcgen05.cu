@@ -24,6 +24,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <mutex>
+#include <cstdlib>
 
 namespace sdb {
 
@@ -50,6 +51,7 @@ struct GemmParams {
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
+  int swap;                   // 1 (implies dual, N == 128): operands swapped, D[cout][pixel] = W . A^T with UMMA N = 256
   long long out_batch_stride; // elements
   int h_box, tiles_per_img, imgs_per_tile;
   int M_total, HW, N_out, block_n, n_tiles, m_tiles, num_kb;
@@ -286,6 +288,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // ===================== MMA issuer =====================
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc_swap = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -298,6 +301,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+          if (p.swap) {
+            // weights (128 couts) are the M operand, the two pixel boxes (256 contiguous rows) the N operand:
+            // one 128x256x16 MMA per UMMA_K instead of two 128x128x16 (which are shared-memory-read bound)
+            const uint64_t w_desc = umma_desc_sw128(sa + b_off);
+            const uint64_t x_desc = umma_desc_sw128(sa);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(d_tmem, w_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc_swap, (kb | k) != 0);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint64_t b_desc = umma_desc_sw128(sa + b_off);
           for (int sub = 0; sub < nsub; ++sub) {
             const uint64_t a_desc = umma_desc_sw128(sa + sub * A_BYTES);
@@ -324,6 +339,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_after();
       const int row = q * 32 + lane;
       const int n_base = n_tile * p.block_n;
+      if (p.swap) {
+        // TMEM lane = output channel, column = pixel of the 256-pixel pair; a warp's 32 lanes write 32 consecutive
+        // channels of one pixel (64 contiguous bytes), so the scalar stores coalesce across the warp
+        const int co = row;
+        const float bco = p.bias ? p.bias[co] : 0.f;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+        for (int c = 0; c < 256; c += 16) {
+          uint32_t r0[16];
+          tmem_ld16(taddr + c, r0);
+          tmem_wait_ld();
+          const int m0 = (m_unit * 2 + (c >> 7)) * BM + (c & 127);
+          float rb = 0.f;
+          if (p.rowbias && m0 < p.M_total) rb = p.rowbias[(size_t)(m0 / p.HW) * p.rowbias_ld + co];   // 16 | HW: one image per chunk
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + j;
+            if (m < p.M_total) {
+              float v = __uint_as_float(r0[j]) + bco + rb;
+              const size_t off = (size_t)m * p.out_ld + co;
+              if (p.residual) v += __bfloat162float(p.residual[off]);
+              if (p.flags & SD_EPI_SWISH) v = swishf(v);
+              if (p.flags & SD_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[off] = v;
+              else reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
+            }
+          }
+        }
+      } else
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
         bool row_ok;
@@ -468,6 +510,8 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
+  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
+  p.swap = (allow_swap && p.dual && !p.flat && N == 128 && p.block_n == 128 && (p.HW % 16) == 0) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store

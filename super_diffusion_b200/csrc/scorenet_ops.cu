@@ -98,16 +98,24 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
 
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ GnParams p) {
   __shared__ float g_mean[32], g_rstd[32];
+  __shared__ float ch_tot[2 * 1024];
   const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
+  {
+    const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {     // all threads: per-channel totals, chunks in fixed order
+      float a = 0.f;
+      for (int k = 0; k < p.nchunk; ++k) a += base[(size_t)k * 2 * C + i];
+      ch_tot[i] = a;
+    }
+  }
+  __syncthreads();
   if (threadIdx.x < 32) {
     double sum = 0.0, sq = 0.0;
-    const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
-    for (int k = 0; k < p.nchunk; ++k)
-      for (int c = 0; c < cpg; ++c) {
-        sum += (double)base[(size_t)k * 2 * C + threadIdx.x * cpg + c];
-        sq += (double)base[(size_t)k * 2 * C + C + threadIdx.x * cpg + c];
-      }
+    for (int c = 0; c < cpg; ++c) {
+      sum += (double)ch_tot[threadIdx.x * cpg + c];
+      sq += (double)ch_tot[C + threadIdx.x * cpg + c];
+    }
     const double n = (double)p.HW * cpg;
     const double mean = sum / n;
     double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
@@ -280,10 +288,15 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) cin_smem[K * Cout + i] = bias ? bias[i] : 0.f;
   __syncthreads();
   const int groups = Cout / 32;
-  const size_t total = (size_t)B * H * W * groups;
+  const size_t npix = (size_t)B * H * W;
+  const size_t total = ((npix + 31) / 32) * 32 * groups;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int cg0 = (int)(i % groups) * 32;
-    size_t pix = i / groups;
+    // a warp = 32 consecutive pixels of ONE 32-channel group: weight reads are smem broadcasts (the previous
+    // pixel-major mapping had 4 channel groups per quarter-warp at a 128-byte stride = 4-way bank conflicts)
+    const size_t wi = i >> 5;
+    const int cg0 = (int)(wi % groups) * 32;
+    size_t pix = (wi / groups) * 32 + (i & 31);
+    if (pix >= npix) continue;
     const int wo = pix % W; pix /= W;
     const int ho = pix % H;
     const int b = (int)(pix / H);
@@ -397,8 +410,8 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   while (k > 1 && (VC * k) % 32) --k;
   if (k < 1 || (VC * k) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   const int T = VC * k;
-  // enough CTAs for ~8 per SM, chunks of at least 4 passes
-  int nchunk = (148 * 8 + B - 1) / B;
+  // ~32 CTAs per SM in total (several waves, small tail), chunks of at least 4 passes
+  int nchunk = (148 * 32 + B - 1) / B;
   const int max_chunks = (HW + 4 * k - 1) / (4 * k);
   if (nchunk > max_chunks) nchunk = max_chunks;
   if (nchunk < 1) nchunk = 1;
@@ -406,7 +419,7 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   const int px_per_chunk = (HW + nchunk - 1) / nchunk;
   nchunk = (HW + px_per_chunk - 1) / px_per_chunk;
   if ((size_t)B * nchunk * 2 * C > scratch_floats)
-    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (1184 + B) * 2 * C floats)");
+    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (4736 + B) * 2 * C floats)");
   GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, nchunk, px_per_chunk, gamma, beta, eps,
              apply_swish, scratch, (__nv_bfloat16*)out};
   cudaStream_t st = (cudaStream_t)stream;
@@ -485,7 +498,7 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
     cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     attr_done = true;
   }
-  const size_t total = (size_t)B * H * W * (Cout / 32);
+  const size_t total = (((size_t)B * H * W + 31) / 32) * 32 * (Cout / 32);
   const unsigned grid = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;
   __nv_bfloat16* o = (__nv_bfloat16*)out;

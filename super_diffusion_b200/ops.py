@@ -235,7 +235,7 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
     if out is None:
         out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
     # per-chunk channel sums; stream-ordered reuse of one buffer per device (stats -> apply are back to back)
-    scratch = _gn_scratch_for(x0.device, (1184 + B) * 2 * (C0 + C1))
+    scratch = _gn_scratch_for(x0.device, (4736 + B) * 2 * (C0 + C1))
     rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
                                 _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(scratch),
                                 scratch.numel(), _ptr(out), _stream())

@@ -210,3 +210,30 @@ def test_attention_probs_fused_softmax(cuda, nb, S, block):
     assert (p.double()[:, ~mask] == 0).all()
     _close(p, ref.cpu(), rtol=1e-2, atol=1e-4)
     assert torch.allclose(p.float().sum(-1), torch.ones(nb, S, device=cuda), atol=2e-2)
+
+
+def test_conv_gemm_swapped_operands_epilogue(cuda):
+    """N = 128 layers run with swapped operands (D[cout][pixel]); exercise its epilogue: multi-source K,
+    bias, per-image row bias, residual, swish, fp32 output, odd pair tail (B = 37 -> 296 m-tiles + ...)."""
+    B, H, W, Co, C0, C1 = 39, 32, 32, 128, 128, 64
+    g = torch.Generator().manual_seed(21)
+    a2 = _bf(torch.randn(B, H, W, Co, generator=g))
+    xa = _bf(torch.randn(B, H, W, C0, generator=g))
+    xb = _bf(torch.randn(B, H, W, C1, generator=g))
+    w = _bf(torch.cat([torch.randn(Co, 9 * Co, generator=g) / math.sqrt(9 * Co),
+                       torch.randn(Co, C0 + C1, generator=g) / math.sqrt(C0 + C1)], dim=1))
+    bias = torch.randn(Co, generator=g)
+    rowbias = torch.randn(B, 384, generator=g)
+    res = _bf(torch.randn(B, H, W, Co, generator=g))
+    wd = w.to(cuda).float()
+    a2d, xad, xbd = a2.to(cuda), xa.to(cuda), xb.to(cuda)
+    ref = F.conv2d(a2d.float().permute(0, 3, 1, 2), wd[:, :9 * Co].reshape(Co, 3, 3, Co).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) \
+        + torch.einsum("bhwc,nc->bhwn", torch.cat([xad, xbd], -1).float(), wd[:, 9 * Co:]) \
+        + bias.to(cuda) + rowbias.to(cuda)[:, None, None, 256:256 + Co]
+    out = ops.conv_gemm([(a2d, 9), (xad, 1), (xbd, 1)], w.to(cuda), bias=bias.to(cuda), rowbias=rowbias.to(cuda)[:, 256:256 + Co])
+    _close(out, ref.cpu())
+    ref2 = ref + res.to(cuda).float()
+    ref2 = ref2 * torch.sigmoid(ref2)
+    out2 = ops.conv_gemm([(a2d, 9), (xad, 1), (xbd, 1)], w.to(cuda), bias=bias.to(cuda), rowbias=rowbias.to(cuda)[:, 256:256 + Co],
+                         residual=res.to(cuda), swish=True, out_f32=True)
+    _close(out2, ref2.cpu(), rtol=2e-3, atol=5e-3)
