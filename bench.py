@@ -154,7 +154,8 @@ def run_b200(args):
     for m in range(M_MODELS):
         model, params = mutils.init_model(10 + m, cfg, zero_init_scale=1.0)   # random init, non-degenerate
         nets.append(model.bind(params, dev))
-    sampler = SuperDiffSampler(nets, B, mode="or", n_steps=N_STEPS, temperature=1e6, device=dev)
+    sampler = SuperDiffSampler(nets, B, mode="or", n_steps=N_STEPS, temperature=1e6, device=dev,
+                               multi_stream=not args.single_stream)
     sampler.capture()
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     x0 = torch.randn(sampler.shape, generator=g, device=dev)
@@ -342,6 +343,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU (default: BASELINE config, 512)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
+    ap.add_argument("--single-stream", action="store_true", help="run the M score-nets back to back on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -160,7 +160,7 @@ int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale,
  * cifar/models/ddpm.py:98 (flax nn.GroupNorm defaults, normalization.py:38-39). */
 int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW,
                        const float* gamma, const float* beta, float eps, int apply_swish,
-                       float* scratch /* >= (4736+B)*2*(C0+C1) floats: per-chunk channel sums */, size_t scratch_floats,
+                       float* scratch /* >= (4736+B)*2*(C0+C1)+64*B floats: per-chunk channel sums, group stats */, size_t scratch_floats,
                        void* out, void* stream);
 
 /* Single-head self-attention over HW tokens (cifar/models/layers.py:505-509):

@@ -510,7 +510,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
-  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
+  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 0; }();   // tuning knob (off: its scalar-store epilogue measured 5x slower)
   p.swap = (allow_swap && p.dual && !p.flat && N == 128 && p.block_n == 128 && (p.HW % 16) == 0) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {

@@ -46,6 +46,7 @@ struct GnParams {
   const float* gamma; const float* beta;
   float eps; int apply_swish;
   float* partial;            // [B][nchunk][2][C]
+  float* stats;              // [B][32][2] (mean, rstd)
   __nv_bfloat16* out;
 };
 
@@ -96,34 +97,30 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   }
 }
 
+// one warp per (sample): lane = group; chunks and channels summed in a fixed order -> (mean, rstd) [B][32][2]
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const __grid_constant__ GnParams p) {
+  const int C = p.C0 + p.C1, cpg = C / 32;
+  const int sample = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), g = threadIdx.x & 31;
+  if (sample >= p.B) return;
+  const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
+  double sum = 0.0, sq = 0.0;
+  for (int k = 0; k < p.nchunk; ++k)
+    for (int c = 0; c < cpg; ++c) {
+      sum += (double)base[(size_t)k * 2 * C + g * cpg + c];
+      sq += (double)base[(size_t)k * 2 * C + C + g * cpg + c];
+    }
+  const double n = (double)p.HW * cpg;
+  const double mean = sum / n;
+  double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
+  if (var < 0.0) var = 0.0;
+  p.stats[((size_t)sample * 32 + g) * 2] = (float)mean;
+  p.stats[((size_t)sample * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+}
+
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ GnParams p) {
-  __shared__ float g_mean[32], g_rstd[32];
-  __shared__ float ch_tot[2 * 1024];
   const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
-  {
-    const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {     // all threads: per-channel totals, chunks in fixed order
-      float a = 0.f;
-      for (int k = 0; k < p.nchunk; ++k) a += base[(size_t)k * 2 * C + i];
-      ch_tot[i] = a;
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    double sum = 0.0, sq = 0.0;
-    for (int c = 0; c < cpg; ++c) {
-      sum += (double)ch_tot[threadIdx.x * cpg + c];
-      sq += (double)ch_tot[C + threadIdx.x * cpg + c];
-    }
-    const double n = (double)p.HW * cpg;
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
-    if (var < 0.0) var = 0.0;
-    g_mean[threadIdx.x] = (float)mean;
-    g_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)p.eps));
-  }
-  __syncthreads();
+  const float* g_stat = p.stats + (size_t)sample * 64;
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
   const int c0 = cv * 8;
   const bool from0 = c0 < p.C0;
@@ -134,9 +131,9 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     const int c = c0 + e;
-    const float rs = g_rstd[c / cpg] * p.gamma[c];
+    const float rs = g_stat[(c / cpg) * 2 + 1] * p.gamma[c];
     sc[e] = rs;
-    sh[e] = p.beta[c] - g_mean[c / cpg] * rs;
+    sh[e] = p.beta[c] - g_stat[(c / cpg) * 2] * rs;
   }
   __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
   const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
@@ -410,23 +407,27 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   while (k > 1 && (VC * k) % 32) --k;
   if (k < 1 || (VC * k) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   const int T = VC * k;
-  // ~32 CTAs per SM in total (several waves, small tail), chunks of at least 4 passes
-  int nchunk = (148 * 32 + B - 1) / B;
+  // CTA count target (tuning knob SDB_GN_CTAS, default 148 * 12), chunks of at least 4 passes
+  static const int cta_target = [] { const char* e = getenv("SDB_GN_CTAS"); return e ? atoi(e) : 148 * 12; }();
+  int nchunk = (cta_target + B - 1) / B;
   const int max_chunks = (HW + 4 * k - 1) / (4 * k);
   if (nchunk > max_chunks) nchunk = max_chunks;
   if (nchunk < 1) nchunk = 1;
   if (nchunk > 64) nchunk = 64;
   const int px_per_chunk = (HW + nchunk - 1) / nchunk;
   nchunk = (HW + px_per_chunk - 1) / px_per_chunk;
-  if ((size_t)B * nchunk * 2 * C > scratch_floats)
-    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (4736 + B) * 2 * C floats)");
+  if ((size_t)B * nchunk * 2 * C + (size_t)B * 64 > scratch_floats)
+    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (4736 + B) * 2 * C + 64 * B floats)");
   GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, nchunk, px_per_chunk, gamma, beta, eps,
-             apply_swish, scratch, (__nv_bfloat16*)out};
+             apply_swish, scratch, scratch + (size_t)B * nchunk * 2 * C, (__nv_bfloat16*)out};
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = sizeof(float) * (size_t)k * 2 * C;
   gn_stats_kernel<<<(unsigned)(B * nchunk), T, smem, st>>>(p);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
+  gn_finalize_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(p);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (finalize) launch");
   gn_apply_kernel<<<(unsigned)(B * nchunk), T, 0, st>>>(p);
   return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (apply) launch");
 }

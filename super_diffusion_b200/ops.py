@@ -215,10 +215,13 @@ _gn_scratch = {}
 
 
 def _gn_scratch_for(device, floats):
-    buf = _gn_scratch.get(device)
+    # one buffer per (device, stream): stats -> apply are back to back on a stream, but two score-nets may run on
+    # two streams concurrently (SuperDiffSampler)
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _gn_scratch.get(key)
     if buf is None or buf.numel() < floats:
         buf = torch.empty(max(floats, 1 << 20), device=device, dtype=torch.float32)
-        _gn_scratch[device] = buf
+        _gn_scratch[key] = buf
     return buf
 
 
@@ -235,13 +238,13 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
     if out is None:
         out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
     # per-chunk channel sums; stream-ordered reuse of one buffer per device (stats -> apply are back to back)
-    scratch = _gn_scratch_for(x0.device, (4736 + B) * 2 * (C0 + C1))
+    scratch = _gn_scratch_for(x0.device, (4736 + B) * 2 * (C0 + C1) + 64 * B)
     rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
                                 _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(scratch),
                                 scratch.numel(), _ptr(out), _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
-        _count(2)
+        _count(3)
     return out
 
 

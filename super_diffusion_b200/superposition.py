@@ -124,7 +124,7 @@ class SuperDiffSampler:
     """
 
     def __init__(self, nets, batch, image_shape=(32, 32, 3), mode="or", n_steps=1000, dt=None, temperature=1e6,
-                 labels=None, device=None, use_graph=True):
+                 labels=None, device=None, use_graph=True, multi_stream=True):
         _lib.require_device()
         self.nets = list(nets)
         self.M = len(self.nets)
@@ -147,12 +147,26 @@ class SuperDiffSampler:
         self.scores = [torch.zeros(self.shape, device=dev, dtype=torch.float32) for _ in range(self.M)]
         self.labels = None if labels is None else labels.to(dev)
         self.use_graph = use_graph
+        self.multi_stream = multi_stream
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.M)] if multi_stream else []
         self.graph = None
         self.launches_per_step = None
 
     def _step_body(self):
-        for i, net in enumerate(self.nets):
-            net(None, self.x, self.labels, sched=self.sched, step_counter=self.counter, out=self.scores[i])
+        # The M score-net forwards are independent: run them on M streams (forked from / joined into the current
+        # stream, also under graph capture) so one model's memory-bound GroupNorm passes overlap the other's GEMMs.
+        cur = torch.cuda.current_stream()
+        if self.multi_stream and self.M > 1:
+            for i, net in enumerate(self.nets):
+                st = self._streams[i]
+                st.wait_stream(cur)
+                with torch.cuda.stream(st):
+                    net(None, self.x, self.labels, sched=self.sched, step_counter=self.counter, out=self.scores[i])
+            for st in self._streams:
+                cur.wait_stream(st)
+        else:
+            for i, net in enumerate(self.nets):
+                net(None, self.x, self.labels, sched=self.sched, step_counter=self.counter, out=self.scores[i])
         ops.step_vpsde(self.x, self.noise, self.scores, self.logq, 0.0, 0.0, 1.0, 0.0, self.mode, self.dlogq_mode,
                        temperature=self.temperature, x_out=self.x, weights=self.weights, sched=self.sched,
                        step_counter=self.counter)
