@@ -31,14 +31,15 @@ namespace sdb {
 constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 3;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int MAX_SEGS = 3;
 constexpr int GEMM_THREADS = 192;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int STG_BYTES = 256 * (128 * 2 + 16);   // epilogue staging: 256 rows x 128 bf16 (or 128 x 256), 16 B row padding
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
   CUtensorMap a_map[MAX_SEGS];
@@ -63,6 +64,7 @@ struct GemmParams {
   void* out;
   int out_ld;
   unsigned flags;
+  int staged;                 // bf16 output staged through shared memory and written with full-line coalesced stores
   float softmax_scale;        // SD_EPI_SOFTMAX: out = softmax(scale * acc) over the row's block of softmax_block columns
   int softmax_block;
 };
@@ -135,7 +137,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float swishf(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 // Epilogue for 16 consecutive output columns of one row.
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0, int img) {
@@ -207,10 +209,25 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
   }
 }
 
+// output row r (0..127) of m-tile `m_tile` -> validity and element offset of the row start in out / residual
+__device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int r, size_t& off) {
+  if (p.flat) {
+    const int batch = m_tile / p.m_tiles_per_batch;
+    const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + r;
+    off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
+    return rl < p.M_per_batch && m_tile < p.m_tiles;
+  }
+  const int m = m_tile * BM + r;
+  off = (size_t)m * p.out_ld;
+  return m < p.M_total;
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -339,6 +356,130 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_after();
       const int row = q * 32 + lane;
       const int n_base = n_tile * p.block_n;
+      if (p.staged) {
+        // ---- staged epilogue: TMEM -> registers -> (+bias, +row bias, +residual, swish) -> bf16 in shared memory ->
+        // full-line coalesced global stores.  The direct per-row stores of the first version issued one 16-byte L2
+        // request per lane (32 per warp instruction) and cost ~17k cycles per 128x256 tile, more than the MMAs of
+        // every K <= 2304 layer; residual tiles are likewise pre-loaded with coalesced reads.
+        const int et = threadIdx.x - 64;                               // 0..127 among the epilogue warps
+        const int vcols = min(p.block_n, p.N_out - n_base);            // multiple of 16 (staged => N_out % 16 == 0)
+        const int rows = p.swap ? 256 : BM;
+        const int ncols = p.swap ? 128 : vcols;
+        const int stride = ncols * 2 + 16;                             // bytes per staged row
+        const int cpr = ncols / 8;                                     // 16-byte chunks per row
+        const int nround = p.swap ? 1 : nsub;
+        for (int sub = 0; sub < nround; ++sub) {
+          const int m_tile0 = p.swap ? m_unit * 2 : m_unit * nsub + sub;
+          if (p.residual) {
+            for (int idx = et; idx < rows * cpr; idx += 128) {
+              const int r = idx / cpr, ch = idx - r * cpr;
+              size_t off;
+              const bool ok = row_offset(p, m_tile0 + (r >> 7), r & 127, off);
+              uint4 v = make_uint4(0, 0, 0, 0);
+              if (ok) v = *reinterpret_cast<const uint4*>(p.residual + off + n_base + ch * 8);
+              *reinterpret_cast<uint4*>(stg + (size_t)r * stride + ch * 16) = v;
+            }
+            epi_bar();
+          }
+          if (!p.swap) {
+            size_t my_off;
+            row_offset(p, m_tile0, row, my_off);
+            int img = 0;
+            if (p.rowbias) img = p.flat ? m_tile0 / p.m_tiles_per_batch : min(m_tile0 * BM + row, p.M_total - 1) / p.HW;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
+            uint8_t* my = stg + (size_t)row * stride;
+            for (int c = 0; c < vcols; c += 16) {
+              uint32_t r0[16];
+              tmem_ld16(taddr + c, r0);
+              tmem_wait_ld();
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
+              const int n0 = n_base + c;
+              if (p.bias) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+              if (p.rowbias) {
+                const float* rb = p.rowbias + (size_t)img * p.rowbias_ld + n0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                  const float4 b = *reinterpret_cast<const float4*>(rb + j);
+                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+                }
+              }
+              uint4* sp = reinterpret_cast<uint4*>(my + c * 2);
+              if (p.residual) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                  const uint4 u = sp[h];
+                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    v[h * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+                    v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+                  }
+                }
+              }
+              if (p.flags & SD_EPI_SWISH) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = swishf(v[j]);
+              }
+              uint32_t w[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+                w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              sp[0] = make_uint4(w[0], w[1], w[2], w[3]);
+              sp[1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
+          } else {
+            // swapped operands: TMEM lane = output channel, column = pixel of the 256-pixel pair
+            const int co = row;
+            const float bco = p.bias ? p.bias[co] : 0.f;
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+            for (int c = 0; c < 256; c += 16) {
+              uint32_t r0[16];
+              tmem_ld16(taddr + c, r0);
+              tmem_wait_ld();
+              float rb = 0.f;
+              if (p.rowbias) {
+                const int m0 = min((m_unit * 2 + (c >> 7)) * BM + (c & 127), p.M_total - 1);
+                rb = p.rowbias[(size_t)(m0 / p.HW) * p.rowbias_ld + co];        // 16 | HW: one image per chunk
+              }
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(stg + (size_t)(c + j) * stride) + co;
+                float v = __uint_as_float(r0[j]) + bco + rb;
+                if (p.residual) v += __bfloat162float(*sp);
+                if (p.flags & SD_EPI_SWISH) v = swishf(v);
+                *sp = __float2bfloat16_rn(v);
+              }
+            }
+          }
+          if (sub == nround - 1) {            // accumulator fully read: hand the TMEM buffer back before the copy-out
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          epi_bar();
+          for (int idx = et; idx < rows * cpr; idx += 128) {
+            const int r = idx / cpr, ch = idx - r * cpr;
+            size_t off;
+            if (row_offset(p, m_tile0 + (r >> 7), r & 127, off))
+              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + n_base + ch * 8) =
+                  *reinterpret_cast<const uint4*>(stg + (size_t)r * stride + ch * 16);
+          }
+          epi_bar();                          // staging buffer free again
+        }
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       if (p.swap) {
         // TMEM lane = output channel, column = pixel of the 256-pixel pair; a warp's 32 lanes write 32 consecutive
         // channels of one pixel (64 contiguous bytes), so the scalar stores coalesce across the warp
@@ -510,7 +651,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
-  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 0; }();   // tuning knob (off: its scalar-store epilogue measured 5x slower)
+  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
   p.swap = (allow_swap && p.dual && !p.flat && N == 128 && p.block_n == 128 && (p.HW % 16) == 0) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
@@ -530,6 +671,12 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.out = out;
   p.out_ld = out_ld;
   p.flags = flags;
+  static const int allow_staged = [] { const char* e = getenv("SDB_GEMM_STAGED"); return e ? atoi(e) : 1; }();   // tuning knob
+  p.staged = (allow_staged && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX)) && (N % 16) == 0 && (out_ld % 8) == 0 &&
+              ((uintptr_t)out % 16) == 0 && (p.out_batch_stride % 8) == 0 &&
+              (!residual || (uintptr_t)residual % 16 == 0)) ? 1 : 0;
+  if (!p.staged) p.swap = 0;
+  if (p.swap && (flags & SD_EPI_OUT_F32)) p.swap = 0;
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
   const bool vec_ok = (out_ld % out_align == 0) && ((uintptr_t)out % 16 == 0) && (!residual || ((uintptr_t)residual % 16 == 0 && out_ld % 8 == 0)) &&
                       (!bias || (uintptr_t)bias % 16 == 0) && (!rowbias || ((uintptr_t)rowbias % 16 == 0 && rowbias_ld % 4 == 0)) &&

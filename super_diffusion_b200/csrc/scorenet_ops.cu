@@ -8,7 +8,7 @@
 
 namespace sdb {
 
-__device__ __forceinline__ float swish_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float swish_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }   // MUFU ex2 + rcp
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -408,7 +408,7 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   if (k < 1 || (VC * k) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   const int T = VC * k;
   // CTA count target (tuning knob SDB_GN_CTAS, default 148 * 12), chunks of at least 4 passes
-  static const int cta_target = [] { const char* e = getenv("SDB_GN_CTAS"); return e ? atoi(e) : 148 * 12; }();
+  static const int cta_target = [] { const char* e = getenv("SDB_GN_CTAS"); return e ? atoi(e) : 148 * 4; }();
   int nchunk = (cta_target + B - 1) / B;
   const int max_chunks = (HW + 4 * k - 1) / (4 * k);
   if (nchunk > max_chunks) nchunk = max_chunks;
