@@ -38,8 +38,9 @@ constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int MAX_SEGS = 3;
 constexpr int GEMM_THREADS = 192;
-constexpr int STG_BYTES = 256 * (128 * 2 + 16);   // epilogue staging: 256 rows x 128 bf16 (or 128 x 256), 16 B row padding
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + 256 + 1024;  // + barriers + alignment slack
+constexpr int STG_BYTES = BM * (MAX_BN * 2 + 16);   // residual tile staged by coalesced loads: 128 rows x 256 bf16, 16 B row padding
+constexpr int EBIAS_FLOATS = 8 * MAX_BN;           // bias + per-image row bias table of one tile (<= 8 images per tile)
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
   CUtensorMap a_map[MAX_SEGS];
@@ -52,7 +53,6 @@ struct GemmParams {
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
-  int swap;                   // 1 (implies dual, N == 128): operands swapped, D[cout][pixel] = W . A^T with UMMA N = 256
   long long out_batch_stride; // elements
   int h_box, tiles_per_img, imgs_per_tile;
   int M_total, HW, N_out, block_n, n_tiles, m_tiles, num_kb;
@@ -64,7 +64,7 @@ struct GemmParams {
   void* out;
   int out_ld;
   unsigned flags;
-  int staged;                 // bf16 output staged through shared memory and written with full-line coalesced stores
+  int imgs_in_tile;           // images covered by one 128-row tile (row-bias table rows), 1 when HW >= 128 or flat
   float softmax_scale;        // SD_EPI_SOFTMAX: out = softmax(scale * acc) over the row's block of softmax_block columns
   int softmax_block;
 };
@@ -139,30 +139,25 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
-// Epilogue for 16 consecutive output columns of one row.
-__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0, int img) {
+// Epilogue for 16 consecutive output columns of one row.  `eb`: 16 floats of (bias + row bias) in shared memory or
+// nullptr; `res_sm`: the row's 16 residual bf16 values staged in shared memory, or nullptr (then p.residual, if any,
+// is read from global memory element-wise: ragged tails only).
+__device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0,
+                                                 const float* eb, const uint8_t* res_sm) {
   float v[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
+  if (eb) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(eb + j);
+      v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+    }
+  }
   const bool full = (n0 + 16 <= p.N_out);
   if (full) {
-    if (p.bias) {
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    }
-    if (p.rowbias) {
-      const float* rb = p.rowbias + (size_t)img * p.rowbias_ld + n0;
-#pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 b = *reinterpret_cast<const float4*>(rb + j);
-        v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-      }
-    }
-    if (p.residual) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
+    if (res_sm) {
+      const uint4* rp = reinterpret_cast<const uint4*>(res_sm);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint4 u = rp[h];
@@ -173,6 +168,9 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
           v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
         }
       }
+    } else if (p.residual) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(p.residual[row_off + n0 + j]);
     }
     if (p.flags & SD_EPI_SWISH) {
 #pragma unroll
@@ -199,8 +197,6 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
       const int n = n0 + j;
       if (n >= p.N_out) break;
       float x = v[j];
-      if (p.bias) x += p.bias[n];
-      if (p.rowbias) x += p.rowbias[(size_t)img * p.rowbias_ld + n];
       if (p.residual) x += __bfloat162float(p.residual[row_off + n]);
       if (p.flags & SD_EPI_SWISH) x = swishf(x);
       if (p.flags & SD_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[row_off + n] = x;
@@ -227,7 +223,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + STG_BYTES);
+  float* ebias = reinterpret_cast<float*>(stg + STG_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + STG_BYTES + EBIAS_FLOATS * 4);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -305,7 +302,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // ===================== MMA issuer =====================
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      const uint32_t idesc_swap = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -318,18 +314,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          if (p.swap) {
-            // weights (128 couts) are the M operand, the two pixel boxes (256 contiguous rows) the N operand:
-            // one 128x256x16 MMA per UMMA_K instead of two 128x128x16 (which are shared-memory-read bound)
-            const uint64_t w_desc = umma_desc_sw128(sa + b_off);
-            const uint64_t x_desc = umma_desc_sw128(sa);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16(d_tmem, w_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc_swap, (kb | k) != 0);
-            umma_commit(&empty_bar[stage]);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
           const uint64_t b_desc = umma_desc_sw128(sa + b_off);
           for (int sub = 0; sub < nsub; ++sub) {
             const uint64_t a_desc = umma_desc_sw128(sa + sub * A_BYTES);
@@ -356,173 +340,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_after();
       const int row = q * 32 + lane;
       const int n_base = n_tile * p.block_n;
-      if (p.staged) {
-        // ---- staged epilogue: TMEM -> registers -> (+bias, +row bias, +residual, swish) -> bf16 in shared memory ->
-        // full-line coalesced global stores.  The direct per-row stores of the first version issued one 16-byte L2
-        // request per lane (32 per warp instruction) and cost ~17k cycles per 128x256 tile, more than the MMAs of
-        // every K <= 2304 layer; residual tiles are likewise pre-loaded with coalesced reads.
-        const int et = threadIdx.x - 64;                               // 0..127 among the epilogue warps
-        const int vcols = min(p.block_n, p.N_out - n_base);            // multiple of 16 (staged => N_out % 16 == 0)
-        const int rows = p.swap ? 256 : BM;
-        const int ncols = p.swap ? 128 : vcols;
-        const int stride = ncols * 2 + 16;                             // bytes per staged row
-        const int cpr = ncols / 8;                                     // 16-byte chunks per row
-        const int nround = p.swap ? 1 : nsub;
-        for (int sub = 0; sub < nround; ++sub) {
-          const int m_tile0 = p.swap ? m_unit * 2 : m_unit * nsub + sub;
-          if (p.residual) {
-            for (int idx = et; idx < rows * cpr; idx += 128) {
-              const int r = idx / cpr, ch = idx - r * cpr;
-              size_t off;
-              const bool ok = row_offset(p, m_tile0 + (r >> 7), r & 127, off);
-              uint4 v = make_uint4(0, 0, 0, 0);
-              if (ok) v = *reinterpret_cast<const uint4*>(p.residual + off + n_base + ch * 8);
-              *reinterpret_cast<uint4*>(stg + (size_t)r * stride + ch * 16) = v;
-            }
-            epi_bar();
-          }
-          if (!p.swap) {
-            size_t my_off;
-            row_offset(p, m_tile0, row, my_off);
-            int img = 0;
-            if (p.rowbias) img = p.flat ? m_tile0 / p.m_tiles_per_batch : min(m_tile0 * BM + row, p.M_total - 1) / p.HW;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
-            uint8_t* my = stg + (size_t)row * stride;
-            for (int c = 0; c < vcols; c += 16) {
-              uint32_t r0[16];
-              tmem_ld16(taddr + c, r0);
-              tmem_wait_ld();
-              float v[16];
-#pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r0[j]);
-              const int n0 = n_base + c;
-              if (p.bias) {
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(p.bias + n0 + j);
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-              }
-              if (p.rowbias) {
-                const float* rb = p.rowbias + (size_t)img * p.rowbias_ld + n0;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) {
-                  const float4 b = *reinterpret_cast<const float4*>(rb + j);
-                  v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
-                }
-              }
-              uint4* sp = reinterpret_cast<uint4*>(my + c * 2);
-              if (p.residual) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                  const uint4 u = sp[h];
-                  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int j = 0; j < 4; ++j) {
-                    v[h * 8 + 2 * j] += __uint_as_float(w[j] << 16);
-                    v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
-                  }
-                }
-              }
-              if (p.flags & SD_EPI_SWISH) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = swishf(v[j]);
-              }
-              uint32_t w[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-                w[j] = *reinterpret_cast<const uint32_t*>(&h2);
-              }
-              sp[0] = make_uint4(w[0], w[1], w[2], w[3]);
-              sp[1] = make_uint4(w[4], w[5], w[6], w[7]);
-            }
-          } else {
-            // swapped operands: TMEM lane = output channel, column = pixel of the 256-pixel pair
-            const int co = row;
-            const float bco = p.bias ? p.bias[co] : 0.f;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
-            for (int c = 0; c < 256; c += 16) {
-              uint32_t r0[16];
-              tmem_ld16(taddr + c, r0);
-              tmem_wait_ld();
-              float rb = 0.f;
-              if (p.rowbias) {
-                const int m0 = min((m_unit * 2 + (c >> 7)) * BM + (c & 127), p.M_total - 1);
-                rb = p.rowbias[(size_t)(m0 / p.HW) * p.rowbias_ld + co];        // 16 | HW: one image per chunk
-              }
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16* sp = reinterpret_cast<__nv_bfloat16*>(stg + (size_t)(c + j) * stride) + co;
-                float v = __uint_as_float(r0[j]) + bco + rb;
-                if (p.residual) v += __bfloat162float(*sp);
-                if (p.flags & SD_EPI_SWISH) v = swishf(v);
-                *sp = __float2bfloat16_rn(v);
-              }
-            }
-          }
-          if (sub == nround - 1) {            // accumulator fully read: hand the TMEM buffer back before the copy-out
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-          }
-          epi_bar();
-          for (int idx = et; idx < rows * cpr; idx += 128) {
-            const int r = idx / cpr, ch = idx - r * cpr;
-            size_t off;
-            if (row_offset(p, m_tile0 + (r >> 7), r & 127, off))
-              *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + off + n_base + ch * 8) =
-                  *reinterpret_cast<const uint4*>(stg + (size_t)r * stride + ch * 16);
-          }
-          epi_bar();                          // staging buffer free again
-        }
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-        continue;
-      }
-      if (p.swap) {
-        // TMEM lane = output channel, column = pixel of the 256-pixel pair; a warp's 32 lanes write 32 consecutive
-        // channels of one pixel (64 contiguous bytes), so the scalar stores coalesce across the warp
-        const int co = row;
-        const float bco = p.bias ? p.bias[co] : 0.f;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
-        for (int c = 0; c < 256; c += 16) {
-          uint32_t r0[16];
-          tmem_ld16(taddr + c, r0);
-          tmem_wait_ld();
-          const int m0 = (m_unit * 2 + (c >> 7)) * BM + (c & 127);
-          float rb = 0.f;
-          if (p.rowbias && m0 < p.M_total) rb = p.rowbias[(size_t)(m0 / p.HW) * p.rowbias_ld + co];   // 16 | HW: one image per chunk
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + j;
-            if (m < p.M_total) {
-              float v = __uint_as_float(r0[j]) + bco + rb;
-              const size_t off = (size_t)m * p.out_ld + co;
-              if (p.residual) v += __bfloat162float(p.residual[off]);
-              if (p.flags & SD_EPI_SWISH) v = swishf(v);
-              if (p.flags & SD_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[off] = v;
-              else reinterpret_cast<__nv_bfloat16*>(p.out)[off] = __float2bfloat16_rn(v);
-            }
-          }
-        }
-      } else
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
         bool row_ok;
         size_t row_off;
-        int img;
         if (p.flat) {
           const int batch = m_tile / p.m_tiles_per_batch;
           const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + row;
           row_ok = rl < p.M_per_batch && m_tile < p.m_tiles;
           row_off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
-          img = batch;
         } else {
           const int m = m_tile * BM + row;
           row_ok = m < p.M_total;
           row_off = (size_t)m * p.out_ld;
-          img = m / p.HW;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
         if (p.flags & SD_EPI_SOFTMAX) {
@@ -570,6 +400,59 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           }
           continue;
         }
+        // ---- phase 0: cooperative, latency-tolerant loads.  The first version read bias / row bias / residual from
+        // global memory per 16-column chunk; with one epilogue warp per scheduler the L2 latency was fully exposed
+        // (ncu: 35-45 % of the kernel's stall samples) and a 128x256 tile cost ~17k cycles, more than its MMAs for
+        // K <= 2304.  Now: (bias + row bias) go into a small smem table, the residual tile is staged
+        // with coalesced 16-byte loads (all in flight before ONE named barrier), and phase 1 only touches TMEM + smem.
+        const int et = threadIdx.x - 64;                                   // 0..127 among the epilogue warps
+        const bool use_tab = p.bias != nullptr || p.rowbias != nullptr;
+        float* eb = ebias;
+        const int vcols = min(p.block_n, p.N_out - n_base);
+        if (use_tab) {
+          const int img0 = p.flat ? m_tile / p.m_tiles_per_batch : (m_tile * BM) / p.HW;
+          const int img_last = p.flat ? img0 : (p.M_total - 1) / p.HW;
+          for (int k = 0; k < p.imgs_in_tile; ++k) {
+            const int im = min(img0 + k, img_last);
+            for (int n = et; n < p.block_n; n += 128) {
+              float v = 0.f;
+              if (n < vcols) {
+                if (p.bias) v = p.bias[n_base + n];
+                if (p.rowbias) v += p.rowbias[(size_t)im * p.rowbias_ld + n_base + n];
+              }
+              eb[k * MAX_BN + n] = v;
+            }
+          }
+        }
+        const bool res_staged = p.residual != nullptr && (vcols % 8) == 0;
+        const int stride = p.block_n * 2 + 16;                             // bytes per staged residual row
+        if (res_staged) {
+          const int cpr = vcols / 8;                                        // 16-byte chunks per row
+          const int total = BM * cpr;
+          for (int idx0 = et; idx0 < total; idx0 += 4 * 128) {
+            uint4 v[4];
+            int rr[4], cc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = idx0 + u * 128;
+              v[u] = make_uint4(0, 0, 0, 0);
+              rr[u] = -1;
+              if (idx < total) {
+                rr[u] = idx / cpr;
+                cc[u] = idx - rr[u] * cpr;
+                size_t off;
+                if (row_offset(p, m_tile, rr[u], off)) v[u] = *reinterpret_cast<const uint4*>(p.residual + off + n_base + cc[u] * 8);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (rr[u] >= 0) *reinterpret_cast<uint4*>(stg + (size_t)rr[u] * stride + cc[u] * 16) = v[u];
+          }
+        }
+        if (use_tab || res_staged) epi_bar();
+        // ---- phase 1: this thread's row
+        const float* eb_row = eb + ((p.imgs_in_tile > 1) ? (row / p.HW) * MAX_BN : 0);
+        const uint8_t* res_row = stg + (size_t)row * stride;
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
@@ -577,10 +460,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (second) tmem_ld16(taddr + c + 16, r1);
           tmem_wait_ld();
           if (row_ok) {
-            if (n_base + c < p.N_out) epilogue_store16(p, r0, row_off, n_base + c, img);
-            if (second && n_base + c + 16 < p.N_out) epilogue_store16(p, r1, row_off, n_base + c + 16, img);
+            if (c < vcols) epilogue_store16(p, r0, row_off, n_base + c, use_tab ? eb_row + c : nullptr, res_staged ? res_row + c * 2 : nullptr);
+            if (second && c + 16 < vcols) epilogue_store16(p, r1, row_off, n_base + c + 16, use_tab ? eb_row + c + 16 : nullptr, res_staged ? res_row + (c + 16) * 2 : nullptr);
           }
         }
+        if (use_tab || res_staged) epi_bar();   // table / staging are rewritten by the next (sub-)tile
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -651,8 +535,6 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
-  static const int allow_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
-  p.swap = (allow_swap && p.dual && !p.flat && N == 128 && p.block_n == 128 && (p.HW % 16) == 0) ? 1 : 0;
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
@@ -671,12 +553,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.out = out;
   p.out_ld = out_ld;
   p.flags = flags;
-  static const int allow_staged = [] { const char* e = getenv("SDB_GEMM_STAGED"); return e ? atoi(e) : 1; }();   // tuning knob
-  p.staged = (allow_staged && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX)) && (N % 16) == 0 && (out_ld % 8) == 0 &&
-              ((uintptr_t)out % 16) == 0 && (p.out_batch_stride % 8) == 0 &&
-              (!residual || (uintptr_t)residual % 16 == 0)) ? 1 : 0;
-  if (!p.staged) p.swap = 0;
-  if (p.swap && (flags & SD_EPI_OUT_F32)) p.swap = 0;
+  p.imgs_in_tile = (!p.flat && p.HW < BM) ? BM / p.HW : 1;
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
   const bool vec_ok = (out_ld % out_align == 0) && ((uintptr_t)out % 16 == 0) && (!residual || ((uintptr_t)residual % 16 == 0 && out_ld % 8 == 0)) &&
                       (!bias || (uintptr_t)bias % 16 == 0) && (!rowbias || ((uintptr_t)rowbias % 16 == 0 && rowbias_ld % 4 == 0)) &&
@@ -706,6 +583,7 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
   if (B == 0) return SD_OK;
   GemmParams p{};
   if (W > BM || (BM % W) != 0) return fail(kErrUnsupported, "sd_conv_gemm: W must divide 128");
+  if (H * W < 16) return fail(kErrUnsupported, "sd_conv_gemm: images smaller than 16 pixels are not supported (row-bias table holds 8 images per tile)");
   const int h_box = (H * W >= BM) ? BM / W : H;
   if ((H % h_box) != 0 || (BM % (W * h_box)) != 0)
     return fail(kErrUnsupported, "sd_conv_gemm: H*W must divide or be a multiple of 128 in whole rows");
