@@ -129,7 +129,11 @@ typedef struct sd_gemm_src {
 int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W,
                  const void* Wt, int N, const float* bias,
                  const float* rowbias, int rowbias_ld,
-                 const void* residual, unsigned flags, void* out, int out_ld, void* stream);
+                 const void* residual, unsigned flags, void* out, int out_ld,
+                 float* stats_out /* optional fp32 [B*H*W/128][2][N]: per 128-pixel tile, per output channel sum and
+                                     sum of squares of `out` (feeds sd_groupnorm_swish, saving its statistics pass);
+                                     needs H*W % 128 == 0 and N % 16 == 0 */,
+                 void* stream);
 
 /* Batched "NT" GEMM on the same tcgen05 kernel:
  *     out[b][m][n] = sum_k A[b][m][k] * Bt[b][n][k] + bias[n] + residual[b][m][n]
@@ -160,8 +164,10 @@ int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale,
  * cifar/models/ddpm.py:98 (flax nn.GroupNorm defaults, normalization.py:38-39). */
 int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW,
                        const float* gamma, const float* beta, float eps, int apply_swish,
-                       float* scratch /* >= (4736+B)*2*(C0+C1)+64*B floats: per-chunk channel sums, group stats */, size_t scratch_floats,
-                       void* out, void* stream);
+                       const float* stats0 /* optional [B][nchunk0][2][C0] channel sums from sd_conv_gemm's stats_out */, int nchunk0,
+                       const float* stats1 /* same for x1, [B][nchunk1][2][C1] */, int nchunk1,
+                       float* scratch /* >= 2*(4736+B)*(C0+C1) + 64*B floats: channel sums of sources without stats, group stats */,
+                       size_t scratch_floats, void* out, void* stream);
 
 /* Single-head self-attention over HW tokens (cifar/models/layers.py:505-509):
  * out = softmax_{HW}(q k^T * C^-1/2) v.  qkv: bf16 [B, S, 3C] (q | k | v

@@ -39,7 +39,7 @@ constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int MAX_SEGS = 3;
 constexpr int GEMM_THREADS = 192;
 constexpr int STG_BYTES = BM * (MAX_BN * 2 + 16);   // residual tile staged by coalesced loads: 128 rows x 256 bf16, 16 B row padding
-constexpr int EBIAS_FLOATS = 8 * MAX_BN;           // bias + per-image row bias table of one tile (<= 8 images per tile)
+constexpr int EBIAS_FLOATS = 9 * MAX_BN;           // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
@@ -60,6 +60,7 @@ struct GemmParams {
   const float* rowbias;
   int rowbias_ld;
   const __nv_bfloat16* residual;
+  float* stats_out;           // optional [m_tiles][2][N_out]: per-tile column sum / sum of squares of the output
   int res_ld;
   void* out;
   int out_ld;
@@ -143,8 +144,7 @@ __device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.f + __
 // nullptr; `res_sm`: the row's 16 residual bf16 values staged in shared memory, or nullptr (then p.residual, if any,
 // is read from global memory element-wise: ragged tails only).
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0,
-                                                 const float* eb, const uint8_t* res_sm) {
-  float v[16];
+                                                 const float* eb, const uint8_t* res_sm, float (&v)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   if (eb) {
@@ -203,6 +203,26 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
       else reinterpret_cast<__nv_bfloat16*>(p.out)[row_off + n] = __float2bfloat16_rn(x);
     }
   }
+}
+
+// Column sums over the 32 rows held by a warp: in = 16 values per lane (one row, 16 columns).  Reduce-scatter
+// butterfly over (v, v*v): 31 shuffles instead of 160; on return lane L holds the warp total of
+// column (L & 15) -- the plain sum for L < 16, the sum of squares for L >= 16.  Fixed order => deterministic.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float s[32];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { s[j] = v[j]; s[16 + j] = v[j] * v[j]; }
+#pragma unroll
+  for (int step = 16, half = 16; step >= 1; step >>= 1, half >>= 1) {
+    const bool upper = (lane & step) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = upper ? s[i] : s[i + half];
+      const float keep = upper ? s[i + half] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return s[0];
 }
 
 // output row r (0..127) of m-tile `m_tile` -> validity and element offset of the row start in out / residual
@@ -453,18 +473,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // ---- phase 1: this thread's row
         const float* eb_row = eb + ((p.imgs_in_tile > 1) ? (row / p.HW) * MAX_BN : 0);
         const uint8_t* res_row = stg + (size_t)row * stride;
+        const bool do_stats = p.stats_out != nullptr;         // host guarantees one image per tile and N_out % 16 == 0
+        float* wstat = ebias + MAX_BN;                          // [4 warps][2][MAX_BN]
         for (int c = 0; c < p.block_n; c += 32) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
           const bool second = (c + 16 < p.block_n);
           if (second) tmem_ld16(taddr + c + 16, r1);
           tmem_wait_ld();
+          float v0[16], v1[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
           if (row_ok) {
-            if (c < vcols) epilogue_store16(p, r0, row_off, n_base + c, use_tab ? eb_row + c : nullptr, res_staged ? res_row + c * 2 : nullptr);
-            if (second && c + 16 < vcols) epilogue_store16(p, r1, row_off, n_base + c + 16, use_tab ? eb_row + c + 16 : nullptr, res_staged ? res_row + (c + 16) * 2 : nullptr);
+            if (c < vcols) epilogue_store16(p, r0, row_off, n_base + c, use_tab ? eb_row + c : nullptr, res_staged ? res_row + c * 2 : nullptr, v0);
+            if (second && c + 16 < vcols) epilogue_store16(p, r1, row_off, n_base + c + 16, use_tab ? eb_row + c + 16 : nullptr, res_staged ? res_row + (c + 16) * 2 : nullptr, v1);
+          }
+          if (do_stats) {
+            if (c < vcols) wstat[(q * 2 + (lane >> 4)) * MAX_BN + c + (lane & 15)] = warp_colsum16(v0, lane);
+            if (second && c + 16 < vcols) wstat[(q * 2 + (lane >> 4)) * MAX_BN + c + 16 + (lane & 15)] = warp_colsum16(v1, lane);
           }
         }
-        if (use_tab || res_staged) epi_bar();   // table / staging are rewritten by the next (sub-)tile
+        if (do_stats) {
+          epi_bar();
+          if (m_tile < p.m_tiles)
+            for (int i = et; i < 2 * vcols; i += 128) {
+              const int which = i >= vcols ? 1 : 0, n = i - which * vcols;
+              const float t = wstat[(0 * 2 + which) * MAX_BN + n] + wstat[(1 * 2 + which) * MAX_BN + n] +
+                              wstat[(2 * 2 + which) * MAX_BN + n] + wstat[(3 * 2 + which) * MAX_BN + n];
+              p.stats_out[((size_t)m_tile * 2 + which) * p.N_out + n_base + n] = t;
+            }
+        }
+        if (use_tab || res_staged || do_stats) epi_bar();   // table / staging / partials are rewritten by the next (sub-)tile
       }
       tcgen05_fence_before();
       __syncwarp();
@@ -525,7 +564,7 @@ static int num_sms() {
 
 static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, long long strideB, int nbatchB,
                        const float* bias, const float* rowbias, int rowbias_ld, const void* residual, unsigned flags,
-                       void* out, int out_ld, cudaStream_t st, const char* who) {
+                       void* out, int out_ld, cudaStream_t st, const char* who, float* stats_out = nullptr) {
   const int n_pad = (N + 15) / 16 * 16;
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
   // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
@@ -554,6 +593,9 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.out_ld = out_ld;
   p.flags = flags;
   p.imgs_in_tile = (!p.flat && p.HW < BM) ? BM / p.HW : 1;
+  p.stats_out = stats_out;
+  if (stats_out && (p.flat || (p.HW % BM) != 0 || (N % 16) != 0 || (flags & SD_EPI_SOFTMAX)))
+    return fail(kErrInvalidArg, std::string(who) + ": stats_out needs a conv-mode GEMM with H*W a multiple of 128 and N a multiple of 16");
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
   const bool vec_ok = (out_ld % out_align == 0) && ((uintptr_t)out % 16 == 0) && (!residual || ((uintptr_t)residual % 16 == 0 && out_ld % 8 == 0)) &&
                       (!bias || (uintptr_t)bias % 16 == 0) && (!rowbias || ((uintptr_t)rowbias % 16 == 0 && rowbias_ld % 4 == 0)) &&
@@ -576,7 +618,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
 
 extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
                             const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
-                            unsigned flags, void* out, int out_ld, void* stream) {
+                            unsigned flags, void* out, int out_ld, float* stats_out, void* stream) {
   using namespace sdb;
   if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, "sd_conv_gemm: 1..3 sources required");
   if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, "sd_conv_gemm: bad argument");
@@ -617,7 +659,7 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
   p.m_tiles = (p.M_total + BM - 1) / BM;
   p.m_tiles_per_batch = 1;
   return launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
-                     (cudaStream_t)stream, "sd_conv_gemm");
+                     (cudaStream_t)stream, "sd_conv_gemm", stats_out);
 }
 
 static int batched_gemm_impl(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,

@@ -39,27 +39,31 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // Algorithmic bytes: 2 reads + 1 write of the activation (the second read mostly hits L2 for the
 // chunk sizes used here).
 // ---------------------------------------------------------------------------
+struct GnStatsParams {
+  const __nv_bfloat16* x;    // [B][HW][C]
+  int C, B, HW, nchunk, px_per_chunk;
+  float* partial;            // [B][nchunk][2][C]
+};
+
 struct GnParams {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
   int C0, C1, B, HW;
-  int nchunk, px_per_chunk;
+  int nchunk, px_per_chunk;  // apply-pass chunking
   const float* gamma; const float* beta;
   float eps; int apply_swish;
-  float* partial;            // [B][nchunk][2][C]
+  const float* part0; int nch0;   // per-source channel partials [B][nch][2][Csrc]
+  const float* part1; int nch1;
   float* stats;              // [B][32][2] (mean, rstd)
   __nv_bfloat16* out;
 };
 
-__global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ GnParams p) {
+__global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ GnStatsParams p) {
   extern __shared__ float gn_smem[];   // [rows_per_pass][2*C]
-  const int C = p.C0 + p.C1, VC = C / 8;
+  const int C = p.C, VC = C / 8;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
   const int c0 = cv * 8;
-  const bool from0 = c0 < p.C0;
-  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0
-                                   : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
-  const int src_ld = from0 ? p.C0 : p.C1;
+  const __nv_bfloat16* src = p.x + (size_t)sample * p.HW * C + c0;
   const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
   float s[8], q[8];
 #pragma unroll
@@ -68,7 +72,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   for (; px + 3 * rows_per_pass < px1; px += 4 * rows_per_pass) {      // 4 independent 16-byte loads in flight
     uint4 v[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * src_ld);
+    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * C);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float f[8];
@@ -79,7 +83,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   }
   for (; px < px1; px += rows_per_pass) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * src_ld), f);
+    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * C), f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
   }
@@ -102,13 +106,16 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const __grid_constant_
   const int C = p.C0 + p.C1, cpg = C / 32;
   const int sample = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), g = threadIdx.x & 31;
   if (sample >= p.B) return;
-  const float* base = p.partial + (size_t)sample * p.nchunk * 2 * C;
   double sum = 0.0, sq = 0.0;
-  for (int k = 0; k < p.nchunk; ++k)
-    for (int c = 0; c < cpg; ++c) {
-      sum += (double)base[(size_t)k * 2 * C + g * cpg + c];
-      sq += (double)base[(size_t)k * 2 * C + C + g * cpg + c];
+  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {            // a group may straddle the x0 | x1 boundary
+    const bool in0 = c < p.C0;
+    const int Cs = in0 ? p.C0 : p.C1, cl = in0 ? c : c - p.C0, nch = in0 ? p.nch0 : p.nch1;
+    const float* base = (in0 ? p.part0 : p.part1) + (size_t)sample * nch * 2 * Cs;
+    for (int k = 0; k < nch; ++k) {
+      sum += (double)base[(size_t)k * 2 * Cs + cl];
+      sq += (double)base[(size_t)k * 2 * Cs + Cs + cl];
     }
+  }
   const double n = (double)p.HW * cpg;
   const double mean = sum / n;
   double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
@@ -393,7 +400,8 @@ static unsigned grid_for(size_t total, int threads) {
 extern "C" {
 
 int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, int HW, const float* gamma,
-                       const float* beta, float eps, int apply_swish, float* scratch, size_t scratch_floats, void* out,
+                       const float* beta, float eps, int apply_swish, const float* stats0, int nchunk0,
+                       const float* stats1, int nchunk1, float* scratch, size_t scratch_floats, void* out,
                        void* stream) {
   using namespace sdb;
   if (!x0 || !gamma || !beta || !out || !scratch || (C1 > 0 && !x1)) return fail(kErrInvalidArg, "sd_groupnorm_swish: null pointer");
@@ -401,34 +409,64 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   const int C = C0 + C1;
   if (C0 < 8 || C0 % 8 || C1 % 8 || C % 32 || C > 1024) return fail(kErrInvalidArg, "sd_groupnorm_swish: channels must be multiples of 8, total a multiple of 32, <= 1024");
   if (B < 0 || HW < 1) return fail(kErrInvalidArg, "sd_groupnorm_swish: bad shape");
+  if ((stats0 && nchunk0 < 1) || (stats1 && nchunk1 < 1)) return fail(kErrInvalidArg, "sd_groupnorm_swish: stats need nchunk >= 1");
   if (B == 0) return SD_OK;
-  const int VC = C / 8;
-  int k = 256 / VC;                         // pixel rows per pass; threads = VC * k, whole warps
-  while (k > 1 && (VC * k) % 32) --k;
-  if (k < 1 || (VC * k) % 32) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
-  const int T = VC * k;
-  // CTA count target (tuning knob SDB_GN_CTAS, default 148 * 12), chunks of at least 4 passes
-  static const int cta_target = [] { const char* e = getenv("SDB_GN_CTAS"); return e ? atoi(e) : 148 * 4; }();
-  int nchunk = (cta_target + B - 1) / B;
-  const int max_chunks = (HW + 4 * k - 1) / (4 * k);
-  if (nchunk > max_chunks) nchunk = max_chunks;
-  if (nchunk < 1) nchunk = 1;
-  if (nchunk > 64) nchunk = 64;
-  const int px_per_chunk = (HW + nchunk - 1) / nchunk;
-  nchunk = (HW + px_per_chunk - 1) / px_per_chunk;
-  if ((size_t)B * nchunk * 2 * C + (size_t)B * 64 > scratch_floats)
-    return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small (need (4736 + B) * 2 * C + 64 * B floats)");
-  GnParams p{(const __nv_bfloat16*)x0, (const __nv_bfloat16*)x1, C0, C1, B, HW, nchunk, px_per_chunk, gamma, beta, eps,
-             apply_swish, scratch, scratch + (size_t)B * nchunk * 2 * C, (__nv_bfloat16*)out};
+  static const int cta_target = [] { const char* e = getenv("SDB_GN_CTAS"); return e ? atoi(e) : 148 * 4; }();   // tuning knob
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smem = sizeof(float) * (size_t)k * 2 * C;
-  gn_stats_kernel<<<(unsigned)(B * nchunk), T, smem, st>>>(p);
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
+  auto threads_for = [](int Cc, int& k) {          // threads = (Cc/8) * k pixel rows per pass, whole warps, <= 256
+    const int VC = Cc / 8;
+    k = 256 / VC;
+    if (k < 1) k = 1;
+    while (k > 1 && (VC * k) % 32) --k;
+    return VC * k;
+  };
+  auto chunks_for = [&](int k, int& px_per_chunk) {
+    int nchunk = (cta_target + B - 1) / B;
+    const int max_chunks = (HW + 4 * k - 1) / (4 * k);
+    if (nchunk > max_chunks) nchunk = max_chunks;
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 64) nchunk = 64;
+    px_per_chunk = (HW + nchunk - 1) / nchunk;
+    return (HW + px_per_chunk - 1) / px_per_chunk;
+  };
+  GnParams p{};
+  p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1;
+  p.C0 = C0; p.C1 = C1; p.B = B; p.HW = HW;
+  p.gamma = gamma; p.beta = beta; p.eps = eps; p.apply_swish = apply_swish;
+  p.out = (__nv_bfloat16*)out;
+  size_t used = 0;
+  // statistics pass only for the sources whose producer did not already emit per-tile channel sums
+  for (int srcI = 0; srcI < 2; ++srcI) {
+    const int Cs = srcI == 0 ? C0 : C1;
+    if (Cs == 0) { if (srcI == 1) { p.part1 = scratch; p.nch1 = 0; } continue; }
+    const float* given = srcI == 0 ? stats0 : stats1;
+    if (given) {
+      if (srcI == 0) { p.part0 = given; p.nch0 = nchunk0; } else { p.part1 = given; p.nch1 = nchunk1; }
+      continue;
+    }
+    int k;
+    const int T = threads_for(Cs, k);
+    if (T % 32 || T > 256) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
+    GnStatsParams sp{srcI == 0 ? p.x0 : p.x1, Cs, B, HW, 0, 0, scratch + used};
+    sp.nchunk = chunks_for(k, sp.px_per_chunk);
+    const size_t need = (size_t)B * sp.nchunk * 2 * Cs;
+    if (used + need > scratch_floats) return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small");
+    used += need;
+    if (srcI == 0) { p.part0 = sp.partial; p.nch0 = sp.nchunk; } else { p.part1 = sp.partial; p.nch1 = sp.nchunk; }
+    gn_stats_kernel<<<(unsigned)(B * sp.nchunk), T, sizeof(float) * (size_t)k * 2 * Cs, st>>>(sp);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
+  }
+  if (used + (size_t)B * 64 > scratch_floats) return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small");
+  p.stats = scratch + used;
+  int k;
+  const int T = threads_for(C, k);
+  if (T % 32 || T > 256) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
+  p.nchunk = chunks_for(k, p.px_per_chunk);
   gn_finalize_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(p);
-  err = cudaGetLastError();
+  cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (finalize) launch");
-  gn_apply_kernel<<<(unsigned)(B * nchunk), T, 0, st>>>(p);
+  gn_apply_kernel<<<(unsigned)(B * p.nchunk), T, 0, st>>>(p);
   return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (apply) launch");
 }
 

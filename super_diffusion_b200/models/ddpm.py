@@ -150,11 +150,11 @@ class _Bound:
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
         a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1)
-        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]])
+        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True)
         a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"])
         if r["nin"]:
-            return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"])
-        return ops.conv_gemm([(a2, 9)], r["w2"], bias=r["b2"], residual=x0)
+            return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True)
+        return ops.conv_gemm([(a2, 9)], r["w2"], bias=r["b2"], residual=x0, want_stats=True)
 
     def _attn(self, x, i):
         a = self.attn[i]
@@ -171,7 +171,7 @@ class _Bound:
             vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))                      # [nb, C, Sp] = V^T (bias deferred)
             p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], C ** -0.5, block=S, C=C)   # [nb, Sp, Sp], block diagonal
             o = ops.batched_gemm(p, vt, bias=a["b_v"])                               # rows of p sum to 1 -> + b_v
-        return ops.conv_gemm([(o.view(B, H, W, C), 1)], a["w_o"], bias=a["b_o"], residual=x)
+        return ops.conv_gemm([(o.view(B, H, W, C), 1)], a["w_o"], bias=a["b_o"], residual=x, want_stats=True)
 
     def __call__(self, t, x, y=None, *, sched=None, step_counter=None, out=None):
         """t: (B,1,1,1)/(B,)/scalar tensor or float; x: (B,H,W,C) fp32 NHWC on the device."""
@@ -208,7 +208,7 @@ class _Bound:
                 hs.append(h)
             elif kind == "downsample":
                 d = self.down[op[1]]
-                h = ops.conv_gemm([(ops.im2col_s2(hs[-1]), 1)], d["w"], bias=d["b"])
+                h = ops.conv_gemm([(ops.im2col_s2(hs[-1]), 1)], d["w"], bias=d["b"], want_stats=True)
                 hs.append(h)
             elif kind == "mid":
                 h = self._res([hs[-1]], op[1], rowbias)
@@ -220,7 +220,7 @@ class _Bound:
                 h = self._attn(h, op[1])
             elif kind == "upsample":
                 u = self.up[op[1]]
-                h = ops.conv_gemm([(ops.upsample2x(h), 9)], u["w"], bias=u["b"])
+                h = ops.conv_gemm([(ops.upsample2x(h), 9)], u["w"], bias=u["b"], want_stats=True)
         assert not hs
         a = ops.groupnorm_swish(h, self.out_g, self.out_be)
         return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)

@@ -121,9 +121,11 @@ def _bf16c(t, name):
 
 
 def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False, out_f32=False, out=None,
-              n_out=None):
+              n_out=None, want_stats=False):
     """Implicit GEMM over NHWC bf16 sources (sd_conv_gemm).  srcs: list of
-    (tensor [B,H,W,C], taps) with taps in {1, 9}; weight: bf16 [N, K]."""
+    (tensor [B,H,W,C], taps) with taps in {1, 9}; weight: bf16 [N, K].  want_stats: also emit per-128-pixel-tile
+    channel sums of the output (attached as ``out.gn_stats = (tensor [B, HW/128, 2, N], HW/128)``) so a following
+    groupnorm_swish skips its statistics pass; silently ignored where the layout does not allow it."""
     lib = _lib.load()
     x0 = srcs[0][0]
     B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
@@ -147,11 +149,16 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     rb_ld = rowbias.stride(0) if rowbias is not None else 0
     if residual is not None:
         _bf16c(residual, "residual")
+    stats = None
+    if want_stats and (H * W) % 128 == 0 and N % 16 == 0 and not out_f32 and B > 0:
+        stats = torch.empty(B, (H * W) // 128, 2, N, device=x0.device, dtype=torch.float32)
     rc = lib.sd_conv_gemm(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld,
-                          _ptr(residual), flags, _ptr(out), out.shape[-1], _stream())
+                          _ptr(residual), flags, _ptr(out), out.shape[-1], _ptr(stats), _stream())
     _lib.check(rc, "sd_conv_gemm")
     if B > 0:
         _count()
+    if stats is not None:
+        out.gn_stats = (stats, (H * W) // 128)
     return out
 
 
@@ -226,6 +233,8 @@ def _gn_scratch_for(device, floats):
 
 
 def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
+    """GroupNorm(32) + swish over concat(x0, x1) (sd_groupnorm_swish).  Sources carrying ``gn_stats`` (set by
+    conv_gemm(want_stats=True)) skip the statistics pass."""
     lib = _lib.load()
     _bf16c(x0, "x0")
     B = x0.shape[0]
@@ -237,14 +246,16 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
         C1 = x1.shape[3]
     if out is None:
         out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
-    # per-chunk channel sums; stream-ordered reuse of one buffer per device (stats -> apply are back to back)
+    st0, n0 = getattr(x0, "gn_stats", (None, 0))
+    st1, n1 = getattr(x1, "gn_stats", (None, 0)) if x1 is not None else (None, 0)
+    # channel sums of sources without stats + group stats; stream-ordered reuse of one buffer per (device, stream)
     scratch = _gn_scratch_for(x0.device, (4736 + B) * 2 * (C0 + C1) + 64 * B)
     rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
-                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(scratch),
-                                scratch.numel(), _ptr(out), _stream())
+                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(st0), int(n0),
+                                _ptr(st1), int(n1), _ptr(scratch), scratch.numel(), _ptr(out), _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
-        _count(3)
+        _count(2 + (st0 is None) + (x1 is not None and st1 is None))
     return out
 
 

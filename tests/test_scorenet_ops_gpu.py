@@ -237,3 +237,32 @@ def test_conv_gemm_swapped_operands_epilogue(cuda):
     out2 = ops.conv_gemm([(a2d, 9), (xad, 1), (xbd, 1)], w.to(cuda), bias=bias.to(cuda), rowbias=rowbias.to(cuda)[:, 256:256 + Co],
                          residual=res.to(cuda), swish=True, out_f32=True)
     _close(out2, ref2.cpu(), rtol=2e-3, atol=5e-3)
+
+
+@pytest.mark.parametrize("B,H,C,N,taps", [(40, 32, 64, 128, 9), (6, 16, 128, 256, 9), (3, 32, 128, 128, 1)])
+def test_groupnorm_from_gemm_emitted_statistics(cuda, B, H, C, N, taps):
+    """conv_gemm(want_stats=True) emits per-tile channel sums in its epilogue; GroupNorm fed with them (no statistics
+    pass) equals GroupNorm that measures the tensor itself, also for a concat of one source with and one without stats."""
+    g = torch.Generator().manual_seed(B + H + N)
+    x = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    w = _bf(torch.randn(N, taps * C, generator=g) / math.sqrt(taps * C)).to(cuda)
+    bias = torch.randn(N, generator=g).to(cuda)
+    res = _bf(torch.randn(B, H, H, N, generator=g)).to(cuda)
+    y = ops.conv_gemm([(x, taps)], w, bias=bias, residual=res, want_stats=True)
+    assert hasattr(y, "gn_stats") and y.gn_stats[0].shape == (B, H * H // 128, 2, N)
+    st = y.gn_stats[0]
+    yf = y.float().reshape(B, H * H // 128, 128, N)
+    assert torch.allclose(st[:, :, 0], yf.sum(2), rtol=2e-2, atol=0.5)          # sums of the (bf16-rounded) output
+    assert torch.allclose(st[:, :, 1], (yf * yf).sum(2), rtol=2e-2, atol=0.5)
+    gamma = (1 + 0.1 * torch.randn(N, generator=g)).to(cuda)
+    beta = (0.1 * torch.randn(N, generator=g)).to(cuda)
+    a = ops.groupnorm_swish(y, gamma, beta)
+    y_plain = y.clone()                                   # same data, no gn_stats attribute
+    b = ops.groupnorm_swish(y_plain, gamma, beta)
+    assert (a.float() - b.float()).abs().max().item() <= 3e-2
+    skip = _bf(torch.randn(B, H, H, 64, generator=g)).to(cuda)
+    g2 = (1 + 0.1 * torch.randn(N + 64, generator=g)).to(cuda)
+    b2 = (0.1 * torch.randn(N + 64, generator=g)).to(cuda)
+    a2 = ops.groupnorm_swish(y, g2, b2, x1=skip)
+    r2 = ops.groupnorm_swish(y_plain, g2, b2, x1=skip)
+    assert (a2.float() - r2.float()).abs().max().item() <= 3e-2
