@@ -135,6 +135,15 @@ int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W
                                      needs H*W % 128 == 0 and N % 16 == 0 */,
                  void* stream);
 
+/* Nearest-neighbour x2 upsample followed by a 3x3 SAME conv (cifar/models/layers.py:514-523), fused and reduced:
+ * output pixel (2i+a, 2j+b) only sees a 2x2 neighbourhood of the low-resolution input, so the layer is four
+ * 2x2-tap implicit GEMMs (one per phase (a, b)) over x [B,H,W,C] with pre-summed weights -- 16/36 of the FLOPs of
+ * convolving the upsampled tensor, and the upsampled tensor is never materialised.
+ * Wt4: bf16 [4 phases][N][4 taps * C] (tap = r*2+c over source offsets (a-1+r, b-1+c)); out: bf16 [B,2H,2W,N];
+ * stats_out (optional, H*W % 128 == 0): fp32 [B][4*H*W/128][2][N] channel sums for sd_groupnorm_swish. */
+int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const void* Wt4, int N, const float* bias,
+                   unsigned flags, void* out, float* stats_out, void* stream);
+
 /* Batched "NT" GEMM on the same tcgen05 kernel:
  *     out[b][m][n] = sum_k A[b][m][k] * Bt[b][n][k] + bias[n] + residual[b][m][n]
  * A: bf16 [batch][M][lda], Bt: bf16 [batch][N][ldb] (both K-contiguous); a batch

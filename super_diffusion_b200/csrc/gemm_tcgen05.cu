@@ -37,7 +37,9 @@ constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int MAX_SEGS = 3;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, each takes alternate 32-column groups
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int STG_BYTES = BM * (MAX_BN * 2 + 16);   // residual tile staged by coalesced loads: 128 rows x 256 bf16, 16 B row padding
 constexpr int EBIAS_FLOATS = 9 * MAX_BN;           // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials
 constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
@@ -65,6 +67,9 @@ struct GemmParams {
   void* out;
   int out_ld;
   unsigned flags;
+  int up_phase;               // -1, or a*2+b: this launch computes output pixels (2i+a, 2j+b) of a fused nearest-x2 upsample + 3x3 conv
+  int img_H, img_W;           // source image size (conv mode)
+  int stats_tpi_total, stats_slot0;   // stats_out slot = img * stats_tpi_total + stats_slot0 + tile-in-image
   int imgs_in_tile;           // images covered by one 128-row tile (row-bias table rows), 1 when HW >= 128 or flat
   float softmax_scale;        // SD_EPI_SOFTMAX: out = softmax(scale * acc) over the row's block of softmax_block columns
   int softmax_block;
@@ -234,10 +239,16 @@ __device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int 
     return rl < p.M_per_batch && m_tile < p.m_tiles;
   }
   const int m = m_tile * BM + r;
-  off = (size_t)m * p.out_ld;
+  if (p.up_phase >= 0) {      // low-res pixel (img, i, j) -> output pixel (2i+a, 2j+b) of the 2H x 2W image
+    const int img = m / p.HW, rem = m - img * p.HW;
+    const int i = rem / p.img_W, j = rem - i * p.img_W;
+    off = ((size_t)(img * 2 * p.img_H + 2 * i + (p.up_phase >> 1)) * (2 * p.img_W) + 2 * j + (p.up_phase & 1)) * (size_t)p.out_ld;
+  } else {
+    off = (size_t)m * p.out_ld;
+  }
   return m < p.M_total;
 }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }   // the 4 epilogue warps
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }   // the epilogue warps only
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -307,6 +318,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           const int cb = local - tap * p.seg_cblocks[seg];
           int dh = 0, dw = 0;
           if (p.seg_taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+          else if (p.seg_taps[seg] == 4) { dh = (p.up_phase >> 1) - 1 + (tap >> 1); dw = (p.up_phase & 1) - 1 + (tap & 1); }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
@@ -350,8 +362,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int q = warp & 3;                        // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;             // which alternate 32-column groups this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -362,20 +375,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       const int n_base = n_tile * p.block_n;
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
-        bool row_ok;
         size_t row_off;
-        if (p.flat) {
-          const int batch = m_tile / p.m_tiles_per_batch;
-          const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + row;
-          row_ok = rl < p.M_per_batch && m_tile < p.m_tiles;
-          row_off = (size_t)batch * (size_t)p.out_batch_stride + (size_t)rl * p.out_ld;
-        } else {
-          const int m = m_tile * BM + row;
-          row_ok = m < p.M_total;
-          row_off = (size_t)m * p.out_ld;
-        }
+        const bool row_ok = row_offset(p, m_tile, row, row_off);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
         if (p.flags & SD_EPI_SOFTMAX) {
+          if (chalf != 0) continue;                 // one thread needs the whole row: the second warp of the pair idles
           // the whole score row (block_n == N <= 256 columns) sits in this thread's TMEM lane: in-thread softmax over
           // the row's diagonal block [lo, hi) (several small images share one 128-row tile), zeros elsewhere
           const int rl = (p.flat ? (m_tile % p.m_tiles_per_batch) : 0) * BM + row;
@@ -425,7 +429,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // (ncu: 35-45 % of the kernel's stall samples) and a 128x256 tile cost ~17k cycles, more than its MMAs for
         // K <= 2304.  Now: (bias + row bias) go into a small smem table, the residual tile is staged
         // with coalesced 16-byte loads (all in flight before ONE named barrier), and phase 1 only touches TMEM + smem.
-        const int et = threadIdx.x - 64;                                   // 0..127 among the epilogue warps
+        const int et = threadIdx.x - 64;                                   // 0..EPI_THREADS-1 among the epilogue warps
         const bool use_tab = p.bias != nullptr || p.rowbias != nullptr;
         float* eb = ebias;
         const int vcols = min(p.block_n, p.N_out - n_base);
@@ -434,7 +438,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           const int img_last = p.flat ? img0 : (p.M_total - 1) / p.HW;
           for (int k = 0; k < p.imgs_in_tile; ++k) {
             const int im = min(img0 + k, img_last);
-            for (int n = et; n < p.block_n; n += 128) {
+            for (int n = et; n < p.block_n; n += EPI_THREADS) {
               float v = 0.f;
               if (n < vcols) {
                 if (p.bias) v = p.bias[n_base + n];
@@ -449,12 +453,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (res_staged) {
           const int cpr = vcols / 8;                                        // 16-byte chunks per row
           const int total = BM * cpr;
-          for (int idx0 = et; idx0 < total; idx0 += 4 * 128) {
+          for (int idx0 = et; idx0 < total; idx0 += 4 * EPI_THREADS) {
             uint4 v[4];
             int rr[4], cc[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-              const int idx = idx0 + u * 128;
+              const int idx = idx0 + u * EPI_THREADS;
               v[u] = make_uint4(0, 0, 0, 0);
               rr[u] = -1;
               if (idx < total) {
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const uint8_t* res_row = stg + (size_t)row * stride;
         const bool do_stats = p.stats_out != nullptr;         // host guarantees one image per tile and N_out % 16 == 0
         float* wstat = ebias + MAX_BN;                          // [4 warps][2][MAX_BN]
-        for (int c = 0; c < p.block_n; c += 32) {
+        for (int c = chalf * 32; c < p.block_n; c += 64) {
           uint32_t r0[16], r1[16];
           tmem_ld16(taddr + c, r0);
           const bool second = (c + 16 < p.block_n);
@@ -496,11 +500,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (do_stats) {
           epi_bar();
           if (m_tile < p.m_tiles)
-            for (int i = et; i < 2 * vcols; i += 128) {
+            for (int i = et; i < 2 * vcols; i += EPI_THREADS) {
               const int which = i >= vcols ? 1 : 0, n = i - which * vcols;
               const float t = wstat[(0 * 2 + which) * MAX_BN + n] + wstat[(1 * 2 + which) * MAX_BN + n] +
                               wstat[(2 * 2 + which) * MAX_BN + n] + wstat[(3 * 2 + which) * MAX_BN + n];
-              p.stats_out[((size_t)m_tile * 2 + which) * p.N_out + n_base + n] = t;
+              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + p.stats_slot0 + (m_tile % p.tiles_per_img);
+              p.stats_out[(slot * 2 + which) * p.N_out + n_base + n] = t;
             }
         }
         if (use_tab || res_staged || do_stats) epi_bar();   // table / staging / partials are rewritten by the next (sub-)tile
@@ -616,30 +621,36 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
 
 }  // namespace sdb
 
-extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
-                            const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
-                            unsigned flags, void* out, int out_ld, float* stats_out, void* stream) {
+static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
+                          const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
+                          unsigned flags, void* out, int out_ld, float* stats_out, void* stream, int up_phase,
+                          int stats_tpi_total, int stats_slot0, const char* who) {
   using namespace sdb;
-  if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, "sd_conv_gemm: 1..3 sources required");
-  if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, "sd_conv_gemm: bad argument");
+  if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, std::string(who) + ": 1..3 sources required");
+  if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, std::string(who) + ": bad argument");
   if (B == 0) return SD_OK;
   GemmParams p{};
-  if (W > BM || (BM % W) != 0) return fail(kErrUnsupported, "sd_conv_gemm: W must divide 128");
-  if (H * W < 16) return fail(kErrUnsupported, "sd_conv_gemm: images smaller than 16 pixels are not supported (row-bias table holds 8 images per tile)");
+  if (W > BM || (BM % W) != 0) return fail(kErrUnsupported, std::string(who) + ": W must divide 128");
+  if (H * W < 16) return fail(kErrUnsupported, std::string(who) + ": images smaller than 16 pixels are not supported (row-bias table holds 8 images per tile)");
   const int h_box = (H * W >= BM) ? BM / W : H;
   if ((H % h_box) != 0 || (BM % (W * h_box)) != 0)
-    return fail(kErrUnsupported, "sd_conv_gemm: H*W must divide or be a multiple of 128 in whole rows");
+    return fail(kErrUnsupported, std::string(who) + ": H*W must divide or be a multiple of 128 in whole rows");
   p.h_box = h_box;
   p.tiles_per_img = (H * W >= BM) ? (H * W) / BM : 1;
   p.imgs_per_tile = (H * W >= BM) ? 1 : BM / (H * W);
   p.flat = 0;
+  p.up_phase = up_phase;
+  p.img_H = H;
+  p.img_W = W;
+  p.stats_tpi_total = stats_tpi_total > 0 ? stats_tpi_total : p.tiles_per_img;
+  p.stats_slot0 = stats_slot0;
   int kb = 0;
   long K = 0;
   for (int s = 0; s < num_srcs; ++s) {
     const sd_gemm_src& src = srcs[s];
-    if (!src.ptr || src.C < BK || (src.C % BK) != 0) return fail(kErrInvalidArg, "sd_conv_gemm: source channels must be a multiple of 64");
-    if (!(src.taps == 1 || src.taps == 9)) return fail(kErrInvalidArg, "sd_conv_gemm: taps must be 1 or 9");
-    if (((uintptr_t)src.ptr % 16) != 0) return fail(kErrInvalidArg, "sd_conv_gemm: source must be 16-byte aligned");
+    if (!src.ptr || src.C < BK || (src.C % BK) != 0) return fail(kErrInvalidArg, std::string(who) + ": source channels must be a multiple of 64");
+    if (!(src.taps == 1 || src.taps == 9 || (src.taps == 4 && up_phase >= 0))) return fail(kErrInvalidArg, std::string(who) + ": taps must be 1 or 9");
+    if (((uintptr_t)src.ptr % 16) != 0) return fail(kErrInvalidArg, std::string(who) + ": source must be 16-byte aligned");
     p.seg_taps[s] = src.taps;
     p.seg_cblocks[s] = src.C / BK;
     kb += src.taps * (src.C / BK);
@@ -659,7 +670,31 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
   p.m_tiles = (p.M_total + BM - 1) / BM;
   p.m_tiles_per_batch = 1;
   return launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
-                     (cudaStream_t)stream, "sd_conv_gemm", stats_out);
+                     (cudaStream_t)stream, who, stats_out);
+}
+
+extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
+                            const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
+                            unsigned flags, void* out, int out_ld, float* stats_out, void* stream) {
+  return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
+                        stats_out, stream, -1, 0, 0, "sd_conv_gemm");
+}
+
+extern "C" int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const void* Wt4, int N, const float* bias,
+                              unsigned flags, void* out, float* stats_out, void* stream) {
+  using namespace sdb;
+  if (!x || !Wt4 || !out) return fail(kErrInvalidArg, "sd_upconv_gemm: null pointer");
+  if (flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX)) return fail(kErrInvalidArg, "sd_upconv_gemm: bf16 output only");
+  if (stats_out && ((H * W) % BM) != 0) return fail(kErrInvalidArg, "sd_upconv_gemm: stats_out needs H*W % 128 == 0");
+  const int tpi = (H * W >= BM) ? (H * W) / BM : 1;
+  sd_gemm_src src{x, C, 4};
+  for (int ph = 0; ph < 4; ++ph) {
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(Wt4) + (size_t)ph * N * 4 * C;
+    int rc = conv_gemm_impl(&src, 1, B, H, W, w, N, bias, nullptr, 0, nullptr, flags, out, N, stats_out, stream, ph,
+                            4 * tpi, ph * tpi, "sd_upconv_gemm");
+    if (rc != SD_OK) return rc;
+  }
+  return SD_OK;
 }
 
 static int batched_gemm_impl(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,

@@ -129,7 +129,7 @@ class _Bound:
                 self.plan.append(("attn", add_attn(c)))
             if lvl != 0:
                 blk = P[f"Upsample_{counters['up']}"]["Conv_0"]
-                self.up.append(dict(w=self._dev(_conv_w(blk), bf), b=self._dev(blk["bias"])))
+                self.up.append(dict(w4=self._dev(ops.upconv_weights(blk["kernel"]), bf), b=self._dev(blk["bias"])))
                 self.plan.append(("upsample", len(self.up) - 1))
                 counters["up"] += 1
                 size *= 2
@@ -220,7 +220,7 @@ class _Bound:
                 h = self._attn(h, op[1])
             elif kind == "upsample":
                 u = self.up[op[1]]
-                h = ops.conv_gemm([(ops.upsample2x(h), 9)], u["w"], bias=u["b"], want_stats=True)
+                h = ops.upconv_gemm(h, u["w4"], bias=u["b"], want_stats=True)
         assert not hs
         a = ops.groupnorm_swish(h, self.out_g, self.out_be)
         return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)

@@ -162,6 +162,43 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     return out
 
 
+def upconv_weights(kernel_hwio):
+    """Flax HWIO [3,3,C,N] kernel of the conv that follows a nearest x2 upsample -> fp32 [4, N, 4*C] phase weights:
+    for output phase (a, b) the 3x3 taps that land on the same low-resolution source pixel are pre-summed."""
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}      # phase -> taps hitting source offset (phase-1), (phase)
+    out = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for r in (0, 1):
+                for c in (0, 1):
+                    w = sum(kernel_hwio[kh, kw] for kh in rows[a][r] for kw in rows[b][c])    # [C, N]
+                    taps.append(w.T)                                                            # [N, C]
+            out.append(torch.cat(taps, dim=1))                                                  # [N, 4C]
+    return torch.stack(out)
+
+
+def upconv_gemm(x, w4, bias=None, out=None, want_stats=False):
+    """Fused nearest-x2 upsample + 3x3 conv as four 2x2-tap implicit GEMMs (sd_upconv_gemm).
+    x: bf16 [B,H,W,C]; w4: bf16 [4, N, 4C] from upconv_weights()."""
+    lib = _lib.load()
+    _bf16c(x, "x"); _bf16c(w4, "w4")
+    B, H, W, C = x.shape
+    N = w4.shape[1]
+    if out is None:
+        out = torch.empty(B, 2 * H, 2 * W, N, device=x.device, dtype=torch.bfloat16)
+    stats = None
+    if want_stats and (H * W) % 128 == 0 and N % 16 == 0 and B > 0:
+        stats = torch.empty(B, 4 * (H * W) // 128, 2, N, device=x.device, dtype=torch.float32)
+    rc = lib.sd_upconv_gemm(_ptr(x), B, H, W, C, _ptr(w4), N, _ptr(bias), 0, _ptr(out), _ptr(stats), _stream())
+    _lib.check(rc, "sd_upconv_gemm")
+    if B > 0:
+        _count(4)
+    if stats is not None:
+        out.gn_stats = (stats, 4 * (H * W) // 128)
+    return out
+
+
 def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None):
     """out[b] = A[b] @ Bt[b]^T (sd_batched_gemm).  A: bf16 [batch, M, >=K] or [M, K]
     (shared), Bt: bf16 [batch, N, >=K] or [N, K] (shared); row strides may exceed K."""

@@ -259,10 +259,34 @@ def test_groupnorm_from_gemm_emitted_statistics(cuda, B, H, C, N, taps):
     a = ops.groupnorm_swish(y, gamma, beta)
     y_plain = y.clone()                                   # same data, no gn_stats attribute
     b = ops.groupnorm_swish(y_plain, gamma, beta)
-    assert (a.float() - b.float()).abs().max().item() <= 3e-2
+    assert (a.float() - b.float()).abs().max().item() <= 6.5e-2      # at most one bf16 ulp at |y| < 8
     skip = _bf(torch.randn(B, H, H, 64, generator=g)).to(cuda)
     g2 = (1 + 0.1 * torch.randn(N + 64, generator=g)).to(cuda)
     b2 = (0.1 * torch.randn(N + 64, generator=g)).to(cuda)
     a2 = ops.groupnorm_swish(y, g2, b2, x1=skip)
     r2 = ops.groupnorm_swish(y_plain, g2, b2, x1=skip)
-    assert (a2.float() - r2.float()).abs().max().item() <= 3e-2
+    assert (a2.float() - r2.float()).abs().max().item() <= 6.5e-2
+
+
+@pytest.mark.parametrize("B,H,C,N", [(3, 16, 128, 256), (5, 8, 256, 256), (9, 4, 64, 64), (40, 16, 64, 128)])
+def test_upconv_gemm_equals_upsample_then_conv(cuda, B, H, C, N):
+    """Nearest x2 upsample + 3x3 SAME conv (cifar/models/layers.py:514-523) as four 2x2-tap phase GEMMs."""
+    g = torch.Generator().manual_seed(B + H + C + N)
+    x = _bf(torch.randn(B, H, H, C, generator=g))
+    k = torch.randn(3, 3, C, N, generator=g) / math.sqrt(9 * C)          # Flax HWIO
+    bias = torch.randn(N, generator=g)
+    w4 = ops.upconv_weights(k)
+    assert w4.shape == (4, N, 4 * C)
+    out = ops.upconv_gemm(x.to(cuda), w4.bfloat16().to(cuda), bias=bias.to(cuda), want_stats=True)
+    up = x.double().repeat_interleave(2, 1).repeat_interleave(2, 2)
+    ref = F.conv2d(up.permute(0, 3, 1, 2), k.double().permute(3, 2, 0, 1), bias.double(), padding=1).permute(0, 2, 3, 1)
+    assert out.shape == (B, 2 * H, 2 * H, N)
+    _close(out, ref, rtol=1.5e-2)
+    if (H * H) % 128 == 0:
+        st, n = out.gn_stats
+        assert n == 4 * H * H // 128
+        assert torch.allclose(st[:, :, 0].sum(1), out.float().sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
+        gamma, beta = torch.ones(N, device=cuda), torch.zeros(N, device=cuda)
+        a = ops.groupnorm_swish(out, gamma, beta)
+        b = ops.groupnorm_swish(out.clone(), gamma, beta)
+        assert (a.float() - b.float()).abs().max().item() <= 6.5e-2
