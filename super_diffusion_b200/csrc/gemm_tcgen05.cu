@@ -54,6 +54,7 @@ struct GemmParams {
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
+  int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile, share the B tile via TMA multicast
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   long long out_batch_stride; // elements
   int h_box, tiles_per_img, imgs_per_tile;
@@ -116,6 +117,24 @@ __device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, void* dst, u
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+// multicast variant: the box lands at the same CTA-relative offset in every CTA of `mask` and signals each one's mbarrier
+__device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -263,7 +282,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_units = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
-  const int total_tiles = m_units * p.n_tiles;
+  // tiles are handed out per cluster: group g = (m_group, n_tile); CTA `crank` of the cluster takes m-unit m_group * cluster + crank
+  // (units past the end are processed as all-zero tiles so that every CTA keeps feeding its slice of the shared B tile)
+  const int csize = p.cluster;
+  const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / csize, num_clusters = gridDim.x / csize;
+  const int total_tiles = ((m_units + csize - 1) / csize) * p.n_tiles;       // tile groups
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int nsub = p.dual ? 2 : 1;
   const uint32_t b_off = p.dual ? 2 * A_BYTES : A_BYTES;
 
@@ -274,7 +299,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], csize); }
       for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -285,6 +310,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();      // peers' mbarriers are initialised before any multicast / remote commit targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_sh;
 
@@ -294,8 +320,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+        const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
         int c1[2], c2[2], c3[2], bz = 0;
         for (int sub = 0; sub < nsub; ++sub) {
           const int m_tile = m_unit * nsub + sub;     // may be == m_tiles for an odd tail: TMA zero-fills, epilogue masks
@@ -324,7 +350,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           for (int sub = 0; sub < nsub; ++sub)
             tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
-          tma_load_3d(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
+          if (csize == 1) {
+            tma_load_3d(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
+          } else {      // this CTA fetches its 1/csize slice of the B tile for the whole cluster
+            const int rows_per = p.block_n / csize;
+            tma_load_3d_mcast(&p.b_map, sa + b_off + (size_t)crank * rows_per * (BK * 2), &full_bar[stage], kb * BK,
+                              n_tile * p.block_n + crank * rows_per, bz, cmask);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -338,7 +370,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
@@ -353,7 +385,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom
               umma_bf16(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+          if (csize == 1) umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
+          else umma_commit_mcast(&empty_bar[stage], cmask);        // ... in every CTA of the cluster (their TMA writes land here too)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
@@ -367,8 +400,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int chalf = (warp - 2) >> 2;             // which alternate 32-column groups this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_unit = tile / p.n_tiles, n_tile = tile - m_unit * p.n_tiles;
+    for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
+      const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int row = q * 32 + lane;
@@ -519,6 +552,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (csize > 1) cluster_sync_all();      // no CTA exits while a peer may still multicast into its smem or signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
@@ -579,12 +613,22 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
+  // thread-block clusters: consecutive m-units share the B tile (weights) through TMA multicast, which cuts the
+  // L2->SM traffic per MMA (ncu: the single-CTA kernel saturates ~11 TB/s of L2 read throughput at 57-73 % tensor activity).
+  // Cluster size 2 tiles the 148 SMs exactly; 4 strands 16 SMs but halves the B traffic again.
+  static const int want_cluster = [] { const char* e = getenv("SDB_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();   // tuning knob
+  {
+    const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
+    int c = want_cluster;
+    while (c > 1 && (p.block_n % (8 * c) != 0 || m_units_h * p.n_tiles < 2 * num_sms() || p.b_batched)) c >>= 1;
+    p.cluster = c < 1 ? 1 : c;
+  }
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)nbatchB};
     cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)(nbatchB > 1 ? strideB : (long long)N * ldb) * 2};
-    cuuint32_t box[3] = {BK, (cuuint32_t)p.block_n, 1};
+    cuuint32_t box[3] = {BK, (cuuint32_t)(p.block_n / p.cluster), 1};
     int rc = encode_map(&p.b_map, Wt, 3, dims, strides, box);
     if (rc != SD_OK) return rc;
   }
@@ -613,10 +657,25 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
-  const int total = (p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles) * p.n_tiles;
-  const int grid = total < num_sms() ? total : num_sms();
-  gemm_tcgen05_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(p);
-  return check_cuda(cudaGetLastError(), who);
+  const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
+  const int groups = ((m_units_h + p.cluster - 1) / p.cluster) * p.n_tiles;
+  const int max_clusters = num_sms() / p.cluster;
+  const int grid = (groups < max_clusters ? groups : max_clusters) * p.cluster;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = GEMM_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (p.cluster > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+  }
+  return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p), who);
 }
 
 }  // namespace sdb
