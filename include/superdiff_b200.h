@@ -135,6 +135,13 @@ int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W
                                      needs H*W % 128 == 0 and N % 16 == 0 */,
                  void* stream);
 
+/* 3x3 stride-2 SAME conv of the Downsample block (cifar/models/layers.py:526-537; flax pads (0,1) on even sizes):
+ * out[b,ho,wo,n] = sum_{kh,kw,c} x[b, 2ho+kh, 2wo+kw, c] * Wt[n, (kh*3+kw)*C + c] + bias[n], x = 0 outside.
+ * The stride lives in the TMA descriptor (element strides 2 along w and h), so no im2col buffer is materialised.
+ * x: bf16 [B,H_in,W_in,C]; out: bf16 [B,H_in/2,W_in/2,N]; stats_out as in sd_conv_gemm (output geometry). */
+int sd_conv_gemm_s2(const void* x, int B, int H_in, int W_in, int C, const void* Wt, int N, const float* bias,
+                    unsigned flags, void* out, float* stats_out, void* stream);
+
 /* Nearest-neighbour x2 upsample followed by a 3x3 SAME conv (cifar/models/layers.py:514-523), fused and reduced:
  * output pixel (2i+a, 2j+b) only sees a 2x2 neighbourhood of the low-resolution input, so the layer is four
  * 2x2-tap implicit GEMMs (one per phase (a, b)) over x [B,H,W,C] with pre-summed weights -- 16/36 of the FLOPs of

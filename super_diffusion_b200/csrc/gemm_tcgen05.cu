@@ -68,6 +68,8 @@ struct GemmParams {
   void* out;
   int out_ld;
   unsigned flags;
+  int stride2;                // 1: 3x3 stride-2 SAME conv (pad (0,1)): taps read input pixel (2*ho + kh, 2*wo + kw) through a TMA map
+                              //    with element strides (1,2,2,1); the tile geometry (h_box, ...) is that of the OUTPUT image
   int up_phase;               // -1, or a*2+b: this launch computes output pixels (2i+a, 2j+b) of a fused nearest-x2 upsample + 3x3 conv
   int img_H, img_W;           // source image size (conv mode)
   int stats_tpi_total, stats_slot0;   // stats_out slot = img * stats_tpi_total + stats_slot0 + tile-in-image
@@ -348,8 +350,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          for (int sub = 0; sub < nsub; ++sub)
-            tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
+          for (int sub = 0; sub < nsub; ++sub) {
+            if (p.stride2)   // input coordinates of output row c2 / column 0 for tap (kh, kw): (2*c2 + kh, kw); index H / W is OOB -> 0
+              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tap % 3, 2 * c2[sub] + tap / 3, c3[sub]);
+            else
+              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
+          }
           if (csize == 1) {
             tma_load_3d(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
           } else {      // this CTA fetches its 1/csize slice of the B tile for the whole cluster
@@ -578,10 +584,11 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 static int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                      const cuuint32_t* box) {
+                      const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(kErrCuda, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -613,10 +620,12 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
   p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
-  // thread-block clusters: consecutive m-units share the B tile (weights) through TMA multicast, which cuts the
-  // L2->SM traffic per MMA (ncu: the single-CTA kernel saturates ~11 TB/s of L2 read throughput at 57-73 % tensor activity).
-  // Cluster size 2 tiles the 148 SMs exactly; 4 strands 16 SMs but halves the B traffic again.
-  static const int want_cluster = [] { const char* e = getenv("SDB_GEMM_CLUSTER"); return e ? atoi(e) : 2; }();   // tuning knob
+  // thread-block clusters (optional): consecutive m-units share the B tile (weights) through TMA multicast.  Built to
+  // cut the L2->SM traffic per MMA (the kernel moves ~44-54 B/clk/SM of TMA traffic at 57-73 % tensor activity, the
+  // practical L2->SM ceiling), but measured on B200 it does not: cluster 2 is 2 % slower and cluster 4 45 % slower than
+  // independent CTAs (multicast at cluster size <= 4 does not reduce L2 reads, and lock-stepped CTAs lose slack),
+  // so the default is 1.  Parity-tested (tests/test_scorenet_ops_gpu.py with SDB_GEMM_CLUSTER=2).
+  static const int want_cluster = [] { const char* e = getenv("SDB_GEMM_CLUSTER"); return e ? atoi(e) : 1; }();   // tuning knob, default off (see below)
   {
     const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
     int c = want_cluster;
@@ -683,7 +692,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
 static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
                           const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
                           unsigned flags, void* out, int out_ld, float* stats_out, void* stream, int up_phase,
-                          int stats_tpi_total, int stats_slot0, const char* who) {
+                          int stats_tpi_total, int stats_slot0, const char* who, int stride2 = 0) {
   using namespace sdb;
   if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, std::string(who) + ": 1..3 sources required");
   if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, std::string(who) + ": bad argument");
@@ -699,6 +708,7 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.imgs_per_tile = (H * W >= BM) ? 1 : BM / (H * W);
   p.flat = 0;
   p.up_phase = up_phase;
+  p.stride2 = stride2;
   p.img_H = H;
   p.img_W = W;
   p.stats_tpi_total = stats_tpi_total > 0 ? stats_tpi_total : p.tiles_per_img;
@@ -715,10 +725,20 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
     kb += src.taps * (src.C / BK);
     p.seg_kb_end[s] = kb;
     K += (long)src.taps * src.C;
-    cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-    cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * W, (cuuint64_t)src.C * 2 * W * H};
-    cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)p.h_box, (cuuint32_t)p.imgs_per_tile};
-    int rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box);
+    int rc;
+    if (stride2) {
+      // the source is the (2H x 2W) input; to load N elements at element stride 2 the box extent is 2N
+      cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)(2 * W), (cuuint64_t)(2 * H), (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * (2 * W), (cuuint64_t)src.C * 2 * (2 * W) * (2 * H)};
+      cuuint32_t box[4] = {BK, (cuuint32_t)(2 * W), (cuuint32_t)(2 * p.h_box), (cuuint32_t)p.imgs_per_tile};
+      cuuint32_t estr[4] = {1, 2, 2, 1};
+      rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box, estr);
+    } else {
+      cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * W, (cuuint64_t)src.C * 2 * W * H};
+      cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)p.h_box, (cuuint32_t)p.imgs_per_tile};
+      rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box);
+    }
     if (rc != SD_OK) return rc;
   }
   for (int s = num_srcs; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
@@ -737,6 +757,15 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
                             unsigned flags, void* out, int out_ld, float* stats_out, void* stream) {
   return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
                         stats_out, stream, -1, 0, 0, "sd_conv_gemm");
+}
+
+extern "C" int sd_conv_gemm_s2(const void* x, int B, int H_in, int W_in, int C, const void* Wt, int N, const float* bias,
+                               unsigned flags, void* out, float* stats_out, void* stream) {
+  using namespace sdb;
+  if (!x || (H_in % 2) || (W_in % 2)) return fail(kErrInvalidArg, "sd_conv_gemm_s2: even input size required");
+  sd_gemm_src src{x, C, 9};
+  return conv_gemm_impl(&src, 1, B, H_in / 2, W_in / 2, Wt, N, bias, nullptr, 0, nullptr, flags, out, N, stats_out, stream,
+                        -1, 0, 0, "sd_conv_gemm_s2", 1);
 }
 
 extern "C" int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const void* Wt4, int N, const float* bias,

@@ -208,7 +208,7 @@ class _Bound:
                 hs.append(h)
             elif kind == "downsample":
                 d = self.down[op[1]]
-                h = ops.conv_gemm([(ops.im2col_s2(hs[-1]), 1)], d["w"], bias=d["b"], want_stats=True)
+                h = ops.conv_gemm_s2(hs[-1], d["w"], bias=d["b"], want_stats=True)
                 hs.append(h)
             elif kind == "mid":
                 h = self._res([hs[-1]], op[1], rowbias)

@@ -162,6 +162,28 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     return out
 
 
+def conv_gemm_s2(x, weight, bias=None, out=None, want_stats=False):
+    """3x3 stride-2 SAME conv (flax pad (0,1)) with the stride in the TMA descriptor (sd_conv_gemm_s2).
+    x: bf16 [B,H,W,C]; weight: bf16 [N, 9C]."""
+    lib = _lib.load()
+    _bf16c(x, "x"); _bf16c(weight, "weight")
+    B, H, W, C = x.shape
+    N = weight.shape[0]
+    Ho, Wo = H // 2, W // 2
+    if out is None:
+        out = torch.empty(B, Ho, Wo, N, device=x.device, dtype=torch.bfloat16)
+    stats = None
+    if want_stats and (Ho * Wo) % 128 == 0 and N % 16 == 0 and B > 0:
+        stats = torch.empty(B, (Ho * Wo) // 128, 2, N, device=x.device, dtype=torch.float32)
+    rc = lib.sd_conv_gemm_s2(_ptr(x), B, H, W, C, _ptr(weight), N, _ptr(bias), 0, _ptr(out), _ptr(stats), _stream())
+    _lib.check(rc, "sd_conv_gemm_s2")
+    if B > 0:
+        _count()
+    if stats is not None:
+        out.gn_stats = (stats, (Ho * Wo) // 128)
+    return out
+
+
 def upconv_weights(kernel_hwio):
     """Flax HWIO [3,3,C,N] kernel of the conv that follows a nearest x2 upsample -> fp32 [4, N, 4*C] phase weights:
     for output phase (a, b) the 3x3 taps that land on the same low-resolution source pixel are pre-summed."""

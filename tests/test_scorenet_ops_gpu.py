@@ -290,3 +290,20 @@ def test_upconv_gemm_equals_upsample_then_conv(cuda, B, H, C, N):
         a = ops.groupnorm_swish(out, gamma, beta)
         b = ops.groupnorm_swish(out.clone(), gamma, beta)
         assert (a.float() - b.float()).abs().max().item() <= 6.5e-2
+
+
+@pytest.mark.parametrize("B,H,C,N", [(3, 32, 128, 128), (5, 16, 256, 256), (9, 8, 256, 256), (40, 32, 64, 64)])
+def test_conv_gemm_stride2_tma(cuda, B, H, C, N):
+    """Downsample conv (cifar/models/layers.py:533): 3x3, stride 2, SAME => pad (0,1); stride carried by the TMA descriptor.
+    Also equals the explicit im2col gather + 1x1 GEMM path."""
+    g = torch.Generator().manual_seed(B + H + C)
+    x = _bf(torch.randn(B, H, H, C, generator=g))
+    w = _bf(torch.randn(N, 9 * C, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(N, generator=g)
+    out = ops.conv_gemm_s2(x.to(cuda), w.to(cuda), bias=bias.to(cuda), want_stats=True)
+    xp = F.pad(x.double().permute(0, 3, 1, 2), (0, 1, 0, 1))
+    ref = F.conv2d(xp, w.double().reshape(N, 3, 3, C).permute(0, 3, 1, 2), bias.double(), stride=2).permute(0, 2, 3, 1)
+    assert out.shape == (B, H // 2, H // 2, N)
+    _close(out, ref)
+    alt = ops.conv_gemm([(ops.im2col_s2(x.to(cuda)), 1)], w.to(cuda), bias=bias.to(cuda))
+    assert torch.equal(out, alt)
