@@ -93,3 +93,14 @@ def test_product_fails_loudly_without_gpu():
     model, params = mutils.init_model(0, cfg)
     with pytest.raises(Exception):
         mutils.get_model_fn(model, params)(torch.zeros(1, 1, 1, 1), torch.zeros(1, 32, 32, 3), None)
+
+
+def test_uint8_conversion_matches_reference_formula():
+    """cifar/run_lib.py:244-245 + cifar/datasets.py:32-35: x*0.5+0.5, clip(x*255, 0, 255), truncating cast."""
+    from super_diffusion_b200 import run_lib
+    cfg = vpsde.get_config()
+    x = torch.tensor([-3.0, -1.0, -0.5, 0.0, 0.5, 0.999, 1.0, 7.0])
+    out = run_lib.to_uint8(x, cfg)
+    ref = np.clip((x.numpy() * 0.5 + 0.5) * 255.0, 0.0, 255.0).astype(np.uint8)
+    assert np.array_equal(out.numpy(), ref)
+    assert run_lib.get_image_scaler(cfg)(torch.tensor(0.75)).item() == 0.5

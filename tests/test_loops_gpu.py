@@ -2,6 +2,7 @@
 on identical inputs and noise (north_star: samples and log-density trajectories within rel 1e-3
 in fp32, kappa / mixing weights within 1e-4)."""
 import math
+import os
 
 import pytest
 import torch
@@ -219,3 +220,40 @@ def test_sd_latent_loop_against_cpu_oracle(cuda):
         assert _rel(llg.cpu(), ll) <= 1e-3, method
         krs = torch.stack(kr)
         assert (traj["kappa"][1:].cpu().double() - krs).abs().max().item() <= 1e-4 * (1 + krs.abs().max().item()), method
+
+
+def test_cifar_sampler_and_mode_and_three_models(cuda):
+    """BASELINE config 3 shape of work at a tiny batch: SuperDiff-AND on CIFAR tensors through the graph sampler
+    (log-density increments equalised across models, weights sum to 1), and an M = 3 OR run."""
+    cfg, models, states, _ = _two_models(cuda)
+    nets = [m.bind(s.params_ema, cuda) for m, s in zip(models, states)]
+    B, n = 8, 4
+    g = torch.Generator(device=cuda).manual_seed(3)
+    x0 = torch.randn(B, 32, 32, 3, generator=g, device=cuda)
+    noise = torch.randn(n, B, 32, 32, 3, generator=g, device=cuda)
+    smp = SuperDiffSampler(nets, B, mode="and", n_steps=n, dt=5e-3, device=cuda)
+    x, lq, w = smp.sample(x0=x0, noise=noise)
+    assert torch.isfinite(x).all() and torch.isfinite(lq).all()
+    assert torch.allclose(w.sum(1), torch.ones(B, device=cuda), atol=1e-5)
+    assert (lq[:, 0] - lq[:, 1]).abs().max().item() <= 1e-3 * (1 + lq.abs().max().item())
+    model3, p3 = mutils.init_model(12, cfg, zero_init_scale=1.0)
+    nets3 = nets + [model3.bind(p3, cuda)]
+    smp3 = SuperDiffSampler(nets3, B, mode="or", n_steps=n, dt=5e-3, temperature=1e6, device=cuda)
+    x3, lq3, w3 = smp3.sample(x0=x0, noise=noise)
+    assert w3.shape == (B, 3) and torch.allclose(w3.sum(1), torch.ones(B, device=cuda), atol=1e-5)
+    assert (lq3.max(dim=1).values == 0).all()
+
+
+def test_sample_driver_writes_reference_npz_format(cuda, tmp_path):
+    """run_lib.evaluate_joint_samples: samples_{i}.npz with uint8 `samples` [B,32,32,3] and `num_steps` (cifar/run_lib.py:244-251)."""
+    import numpy as np
+    from super_diffusion_b200 import run_lib
+    cfg = vpsde.get_config()
+    cfg.eval.batch_size = 4
+    cfg.eval.num_samples = 8
+    params = [mutils.init_model(s, cfg, zero_init_scale=1.0)[1] for s in (1, 2)]
+    d = run_lib.evaluate_joint_samples(cfg, str(tmp_path), "eval", params, stoch=True, dt=0.25, device=cuda)
+    files = sorted(os.listdir(d))
+    assert files == ["samples_0.npz", "samples_1.npz"]
+    z = np.load(os.path.join(d, files[0]))
+    assert z["samples"].dtype == np.uint8 and z["samples"].shape == (4, 32, 32, 3) and int(z["num_steps"]) == 4
