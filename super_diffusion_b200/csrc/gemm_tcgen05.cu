@@ -31,7 +31,7 @@ namespace sdb {
 constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 4;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
@@ -40,9 +40,8 @@ constexpr int MAX_SEGS = 3;
 constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, each takes alternate 32-column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
-constexpr int STG_BYTES = BM * (MAX_BN * 2 + 16);   // residual tile staged by coalesced loads: 128 rows x 256 bf16, 16 B row padding
 constexpr int EBIAS_FLOATS = 9 * MAX_BN;           // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + STG_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
+constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
   CUtensorMap a_map[MAX_SEGS];
@@ -167,10 +166,10 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 __device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.f + __expf(-v)); }
 
 // Epilogue for 16 consecutive output columns of one row.  `eb`: 16 floats of (bias + row bias) in shared memory or
-// nullptr; `res_sm`: the row's 16 residual bf16 values staged in shared memory, or nullptr (then p.residual, if any,
-// is read from global memory element-wise: ragged tails only).
+// nullptr.  p.residual (generic API) is read straight from global memory; the score-net itself adds its residuals
+// inside the MMA as an identity-weight K segment, so its epilogues never touch global memory for inputs.
 __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint32_t (&acc)[16], size_t row_off, int n0,
-                                                 const float* eb, const uint8_t* res_sm, float (&v)[16]) {
+                                                 const float* eb, float (&v)[16]) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(acc[j]);
   if (eb) {
@@ -182,8 +181,8 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
   }
   const bool full = (n0 + 16 <= p.N_out);
   if (full) {
-    if (res_sm) {
-      const uint4* rp = reinterpret_cast<const uint4*>(res_sm);
+    if (p.residual) {
+      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const uint4 u = rp[h];
@@ -194,9 +193,6 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
           v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
         }
       }
-    } else if (p.residual) {
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(p.residual[row_off + n0 + j]);
     }
     if (p.flags & SD_EPI_SWISH) {
 #pragma unroll
@@ -274,9 +270,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* stg = smem + (size_t)STAGES * STAGE_BYTES;
-  float* ebias = reinterpret_cast<float*>(stg + STG_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + STG_BYTES + EBIAS_FLOATS * 4);
+  float* ebias = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + EBIAS_FLOATS * 4);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
@@ -466,8 +461,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // ---- phase 0: cooperative, latency-tolerant loads.  The first version read bias / row bias / residual from
         // global memory per 16-column chunk; with one epilogue warp per scheduler the L2 latency was fully exposed
         // (ncu: 35-45 % of the kernel's stall samples) and a 128x256 tile cost ~17k cycles, more than its MMAs for
-        // K <= 2304.  Now: (bias + row bias) go into a small smem table, the residual tile is staged
-        // with coalesced 16-byte loads (all in flight before ONE named barrier), and phase 1 only touches TMEM + smem.
+        // K <= 2304.  Now: (bias + row bias) go into a small smem table (one named barrier) and phase 1 only touches
+        // TMEM + smem; residual adds of the score-net ride the MMA as an identity-weight K segment fed by TMA.
         const int et = threadIdx.x - 64;                                   // 0..EPI_THREADS-1 among the epilogue warps
         const bool use_tab = p.bias != nullptr || p.rowbias != nullptr;
         float* eb = ebias;
@@ -487,35 +482,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
           }
         }
-        const bool res_staged = p.residual != nullptr && (vcols % 8) == 0;
-        const int stride = p.block_n * 2 + 16;                             // bytes per staged residual row
-        if (res_staged) {
-          const int cpr = vcols / 8;                                        // 16-byte chunks per row
-          const int total = BM * cpr;
-          for (int idx0 = et; idx0 < total; idx0 += 4 * EPI_THREADS) {
-            uint4 v[4];
-            int rr[4], cc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = idx0 + u * EPI_THREADS;
-              v[u] = make_uint4(0, 0, 0, 0);
-              rr[u] = -1;
-              if (idx < total) {
-                rr[u] = idx / cpr;
-                cc[u] = idx - rr[u] * cpr;
-                size_t off;
-                if (row_offset(p, m_tile, rr[u], off)) v[u] = *reinterpret_cast<const uint4*>(p.residual + off + n_base + cc[u] * 8);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (rr[u] >= 0) *reinterpret_cast<uint4*>(stg + (size_t)rr[u] * stride + cc[u] * 16) = v[u];
-          }
-        }
-        if (use_tab || res_staged) epi_bar();
+        if (use_tab) epi_bar();
         // ---- phase 1: this thread's row
         const float* eb_row = eb + ((p.imgs_in_tile > 1) ? (row / p.HW) * MAX_BN : 0);
-        const uint8_t* res_row = stg + (size_t)row * stride;
         const bool do_stats = p.stats_out != nullptr;         // host guarantees one image per tile and N_out % 16 == 0
         float* wstat = ebias + MAX_BN;                          // [4 warps][2][MAX_BN]
         for (int c = chalf * 32; c < p.block_n; c += 64) {
@@ -528,8 +497,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 16; ++j) { v0[j] = 0.f; v1[j] = 0.f; }
           if (row_ok) {
-            if (c < vcols) epilogue_store16(p, r0, row_off, n_base + c, use_tab ? eb_row + c : nullptr, res_staged ? res_row + c * 2 : nullptr, v0);
-            if (second && c + 16 < vcols) epilogue_store16(p, r1, row_off, n_base + c + 16, use_tab ? eb_row + c + 16 : nullptr, res_staged ? res_row + (c + 16) * 2 : nullptr, v1);
+            if (c < vcols) epilogue_store16(p, r0, row_off, n_base + c, use_tab ? eb_row + c : nullptr, v0);
+            if (second && c + 16 < vcols) epilogue_store16(p, r1, row_off, n_base + c + 16, use_tab ? eb_row + c + 16 : nullptr, v1);
           }
           if (do_stats) {
             if (c < vcols) wstat[(q * 2 + (lane >> 4)) * MAX_BN + c + (lane & 15)] = warp_colsum16(v0, lane);
@@ -547,7 +516,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               p.stats_out[(slot * 2 + which) * p.N_out + n_base + n] = t;
             }
         }
-        if (use_tab || res_staged || do_stats) epi_bar();   // table / staging / partials are rewritten by the next (sub-)tile
+        if (use_tab || do_stats) epi_bar();   // table / partials are rewritten by the next (sub-)tile
       }
       tcgen05_fence_before();
       __syncwarp();

@@ -31,7 +31,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // ---------------------------------------------------------------------------
 // GroupNorm(32) + swish over concat(x0, x1) along channels, as two streaming passes:
 //   gn_stats_kernel : per (sample, pixel chunk) per-channel sum / sum-of-squares -> partial[B][nchunk][2][C]
-//   gn_apply_kernel : group mean / rstd from the partials (fixed order => deterministic), then
+//   gn_apply_kernel : group mean / rstd from the partials in its prologue (fixed order => deterministic), then
 //                     y = swish((x - mean) * rstd * gamma + beta) streamed with 16-byte vectors.
 // Whole pixel rows are read (fully coalesced), nothing is register- or cluster-resident, so occupancy stays high.
 // Measured alternatives on B200 (profiles/): a cluster-per-sample register-resident kernel ran at 0.6-1.6 TB/s
@@ -53,7 +53,6 @@ struct GnParams {
   float eps; int apply_swish;
   const float* part0; int nch0;   // per-source channel partials [B][nch][2][Csrc]
   const float* part1; int nch1;
-  float* stats;              // [B][32][2] (mean, rstd)
   __nv_bfloat16* out;
 };
 
@@ -101,33 +100,37 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   }
 }
 
-// one warp per (sample): lane = group; chunks and channels summed in a fixed order -> (mean, rstd) [B][32][2]
-__global__ void __launch_bounds__(128) gn_finalize_kernel(const __grid_constant__ GnParams p) {
-  const int C = p.C0 + p.C1, cpg = C / 32;
-  const int sample = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), g = threadIdx.x & 31;
-  if (sample >= p.B) return;
-  double sum = 0.0, sq = 0.0;
-  for (int c = g * cpg; c < (g + 1) * cpg; ++c) {            // a group may straddle the x0 | x1 boundary
-    const bool in0 = c < p.C0;
-    const int Cs = in0 ? p.C0 : p.C1, cl = in0 ? c : c - p.C0, nch = in0 ? p.nch0 : p.nch1;
-    const float* base = (in0 ? p.part0 : p.part1) + (size_t)sample * nch * 2 * Cs;
-    for (int k = 0; k < nch; ++k) {
-      sum += (double)base[(size_t)k * 2 * Cs + cl];
-      sq += (double)base[(size_t)k * 2 * Cs + Cs + cl];
-    }
-  }
-  const double n = (double)p.HW * cpg;
-  const double mean = sum / n;
-  double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
-  if (var < 0.0) var = 0.0;
-  p.stats[((size_t)sample * 32 + g) * 2] = (float)mean;
-  p.stats[((size_t)sample * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
-}
-
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ GnParams p) {
+  __shared__ float ch_tot[2 * 1024];
+  __shared__ float g_stat[64];
   const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
-  const float* g_stat = p.stats + (size_t)sample * 64;
+  // prologue: every CTA rebuilds its sample's group statistics from the per-chunk channel sums (a few KB from L2;
+  // chunks and channels are summed in a fixed order, so all CTAs of a sample -- and every run -- get identical bits)
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int which = i >= C ? 1 : 0, c = i - which * C;   // a group may straddle the x0 | x1 boundary: per channel
+    const bool in0 = c < p.C0;
+    const int Cs = in0 ? p.C0 : p.C1, cl = in0 ? c : c - p.C0, nch = in0 ? p.nch0 : p.nch1;
+    const float* base = (in0 ? p.part0 : p.part1) + (size_t)sample * nch * 2 * Cs + which * Cs + cl;
+    float a = 0.f;
+    for (int k = 0; k < nch; ++k) a += base[(size_t)k * 2 * Cs];
+    ch_tot[i] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double sum = 0.0, sq = 0.0;
+    for (int c = 0; c < cpg; ++c) {
+      sum += (double)ch_tot[threadIdx.x * cpg + c];
+      sq += (double)ch_tot[C + threadIdx.x * cpg + c];
+    }
+    const double n = (double)p.HW * cpg;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
+    if (var < 0.0) var = 0.0;
+    g_stat[threadIdx.x * 2] = (float)mean;
+    g_stat[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
   const int c0 = cv * 8;
   const bool from0 = c0 < p.C0;
@@ -457,15 +460,10 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
   }
-  if (used + (size_t)B * 64 > scratch_floats) return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small");
-  p.stats = scratch + used;
   int k;
   const int T = threads_for(C, k);
   if (T % 32 || T > 256) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   p.nchunk = chunks_for(k, p.px_per_chunk);
-  gn_finalize_kernel<<<(unsigned)((B + 3) / 4), 128, 0, st>>>(p);
-  cudaError_t err = cudaGetLastError();
-  if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (finalize) launch");
   gn_apply_kernel<<<(unsigned)(B * p.nchunk), T, 0, st>>>(p);
   return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (apply) launch");
 }

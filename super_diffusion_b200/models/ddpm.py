@@ -76,6 +76,8 @@ class _Bound:
             if nin:
                 w2 = torch.cat([w2, blk["NIN_0"]["W"].T], dim=1)
                 b2 = b2 + blk["NIN_0"]["b"]
+            else:   # x + h (layers.py:565): the residual rides the MMA as an identity-weight 1x1 segment (exact in bf16)
+                w2 = torch.cat([w2, torch.eye(cout)], dim=1)
             dense_w.append(blk["Dense_0"]["kernel"].T)                       # [cout, 4nf]
             dense_b.append(blk["Dense_0"]["bias"] + blk["Conv_0"]["bias"])   # conv1 bias folded into the row bias
             r = dict(g1=self._dev(blk["GroupNorm_0"]["scale"]), be1=self._dev(blk["GroupNorm_0"]["bias"]),
@@ -95,7 +97,7 @@ class _Bound:
                      w_qkv=self._dev(torch.cat([wq.T, wk.T, wv.T], 0), bf), b_qkv=self._dev(torch.cat([bq, bk, bv])),
                      w_qk=self._dev(torch.cat([wq.T, wk.T], 0), bf), b_qk=self._dev(torch.cat([bq, bk])),
                      w_vT=self._dev(wv.T, bf), b_v=self._dev(bv),
-                     w_o=self._dev(wo.T, bf), b_o=self._dev(bo), c=c)
+                     w_o=self._dev(torch.cat([wo.T, torch.eye(c)], dim=1), bf), b_o=self._dev(bo), c=c)   # + x (layers.py:511)
             self.attn.append(a)
             counters["attn"] += 1
             return len(self.attn) - 1
@@ -152,9 +154,8 @@ class _Bound:
         a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1)
         h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True)
         a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"])
-        if r["nin"]:
-            return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True)
-        return ops.conv_gemm([(a2, 9)], r["w2"], bias=r["b2"], residual=x0, want_stats=True)
+        # NIN shortcut (C_in != C_out) or identity residual: both are extra 1-tap K segments of the same GEMM
+        return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True)
 
     def _attn(self, x, i):
         a = self.attn[i]
@@ -171,7 +172,7 @@ class _Bound:
             vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))                      # [nb, C, Sp] = V^T (bias deferred)
             p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], C ** -0.5, block=S, C=C)   # [nb, Sp, Sp], block diagonal
             o = ops.batched_gemm(p, vt, bias=a["b_v"])                               # rows of p sum to 1 -> + b_v
-        return ops.conv_gemm([(o.view(B, H, W, C), 1)], a["w_o"], bias=a["b_o"], residual=x, want_stats=True)
+        return ops.conv_gemm([(o.view(B, H, W, C), 1), (x, 1)], a["w_o"], bias=a["b_o"], want_stats=True)
 
     def __call__(self, t, x, y=None, *, sched=None, step_counter=None, out=None):
         """t: (B,1,1,1)/(B,)/scalar tensor or float; x: (B,H,W,C) fp32 NHWC on the device."""

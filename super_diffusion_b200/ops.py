@@ -314,7 +314,7 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
                                 _ptr(st1), int(n1), _ptr(scratch), scratch.numel(), _ptr(out), _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
-        _count(2 + (st0 is None) + (x1 is not None and st1 is None))
+        _count(1 + (st0 is None) + (x1 is not None and st1 is None))
     return out
 
 
