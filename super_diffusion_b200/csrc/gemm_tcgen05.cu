@@ -53,6 +53,8 @@ struct GemmParams {
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
+  int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
+                              //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
   int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile, share the B tile via TMA multicast
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   long long out_batch_stride; // elements
@@ -128,6 +130,36 @@ __device__ __forceinline__ void tma_load_3d_mcast(const CUtensorMap* map, void* 
 __device__ __forceinline__ void umma_commit_mcast(uint64_t* bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// cta_group::2 variants ------------------------------------------------------------------------------------
+// TMA load whose completion is signalled on the LEADER CTA's mbarrier (same offset, rank-0 window: peer bit cleared)
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {     // arrive on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_rank(uint64_t* bar, uint32_t rank) {   // arrive on the same barrier in CTA `rank`
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -296,14 +328,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], csize); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], EPI_WARPS); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 1 : csize); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], p.pair ? 2 * EPI_WARPS : EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     // whole TMEM (512 columns): two 256-column fp32 accumulators; 1 CTA / SM by construction (smem)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (p.pair) {   // both CTAs of the pair issue the 2-SM allocation from the same warp, same smem destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -316,7 +353,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
+      // pair mode: only the leader arms its full barrier, with the bytes of BOTH CTAs (each: own A tile + half of the B tile)
+      const uint32_t tx_bytes = p.pair ? 2u * (A_BYTES + (uint32_t)(p.block_n / 2) * BK * 2)
+                                       : (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
         int c1[2], c2[2], c3[2], bz = 0;
@@ -343,8 +382,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (p.seg_taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
           else if (p.seg_taps[seg] == 4) { dh = (p.up_phase >> 1) - 1 + (tap >> 1); dw = (p.up_phase & 1) - 1 + (tap & 1); }
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+          if (p.pair) {
+            if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
+            if (p.stride2)
+              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, tap % 3, 2 * c2[0] + tap / 3, c3[0]);
+            else
+              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, c1[0] + dw, c2[0] + dh, c3[0]);
+            const int rows_per = p.block_n / 2;      // this CTA's half of the weight tile (N rows), same smem offset in both CTAs
+            tma_load_3d_pair(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n + crank * rows_per, bz);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int sub = 0; sub < nsub; ++sub) {
             if (p.stride2)   // input coordinates of output row c2 / column 0 for tap (kh, kw): (2*c2 + kh, kw); index H / W is OOB -> 0
               tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tap % 3, 2 * c2[sub] + tap / 3, c3[sub]);
@@ -363,10 +413,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && !(p.pair && crank != 0)) {
+      // ===================== MMA issuer (pair mode: the leader CTA issues for both SMs) =====================
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)((p.pair ? 2 * BM : BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -380,6 +431,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint64_t b_desc = umma_desc_sw128(sa + b_off);
+          if (p.pair) {
+            const uint64_t a_desc = umma_desc_sw128(sa);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            umma_commit_pair(&empty_bar[stage]);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           for (int sub = 0; sub < nsub; ++sub) {
             const uint64_t a_desc = umma_desc_sw128(sa + sub * A_BYTES);
 #pragma unroll
@@ -390,7 +450,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           else umma_commit_mcast(&empty_bar[stage], cmask);        // ... in every CTA of the cluster (their TMA writes land here too)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);              // accumulator complete -> epilogue
+        if (p.pair) umma_commit_pair(&tmem_full[acc]);   // each CTA's epilogue drains its own 128 TMEM lanes
+        else umma_commit(&tmem_full[acc]);               // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -520,7 +581,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (p.pair) mbar_arrive_rank(&tmem_empty[acc], 0);     // the leader's MMA warp waits for both CTAs' epilogues
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -530,7 +594,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (csize > 1) cluster_sync_all();      // no CTA exits while a peer may still multicast into its smem or signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -600,13 +665,21 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     int c = want_cluster;
     while (c > 1 && (p.block_n % (8 * c) != 0 || m_units_h * p.n_tiles < 2 * num_sms() || p.b_batched)) c >>= 1;
     p.cluster = c < 1 ? 1 : c;
+    // cta_group::2 pairs for wide tiles: halves the weight bytes each SM has to receive per K-block
+    static const int want_pair = [] { const char* e = getenv("SDB_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // tuning knob
+    p.pair = 0;
+    if (want_pair && !p.dual && p.block_n == MAX_BN && !p.b_batched && !(flags & SD_EPI_SOFTMAX) &&
+        p.m_tiles * p.n_tiles >= 2 * num_sms()) {
+      p.pair = 1;
+      p.cluster = 2;
+    }
   }
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)nbatchB};
     cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)(nbatchB > 1 ? strideB : (long long)N * ldb) * 2};
-    cuuint32_t box[3] = {BK, (cuuint32_t)(p.block_n / p.cluster), 1};
+    cuuint32_t box[3] = {BK, (cuuint32_t)(p.block_n / p.cluster), 1};   // multicast slice or pair half
     int rc = encode_map(&p.b_map, Wt, 3, dims, strides, box);
     if (rc != SD_OK) return rc;
   }

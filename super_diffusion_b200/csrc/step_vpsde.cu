@@ -63,7 +63,7 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
     int best_t = 256, best_nv = nv_cap, best_c = 8;
     long best_cost = -1;
     for (int c = 1; c <= 8; c *= 2)
-      for (int t = 64; t <= 256; t *= 2)
+      for (int t = 64; t <= 256; t += 32)
         for (int n = 1; n <= nv_cap; ++n) {
           const long cap = (long)c * t * n;
           if (is_and && cap < nunits) continue;            // AND needs the sample resident
@@ -72,9 +72,18 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
           const long ctas = (long)B * c;
           // measured on B200 (tools/time_forward.py): one CTA per sample beats cluster splits at every
           // batch size that fills the chip, so clusters are only for residency (AND, large D) or tiny batches
-          long cost = waste * 4 + (c > 1 ? 2000L * c : 0) + rounds * 16;
+          long cost = waste * 4 + (c > 1 ? 2000L * c : 0) + rounds * 16 + n;
           if (ctas < 148) cost += (148 - ctas) * 50;
           if (t < 128) cost += 32;
+          // wave quantisation: estimated registers/thread = 4 per float4 held + 28; a second, nearly empty wave
+          // (e.g. 512 CTAs on 444 resident slots) costs more than slightly fatter threads
+          const long regs = 4L * (M + 2) * n + 28 + (is_and ? 16 : 0);
+          long occ = 65536 / (regs * t);
+          if (occ > 2048 / t) occ = 2048 / t;
+          if (occ < 1) occ = 1;
+          const long slots = 148 * occ;
+          const long waves = (ctas + slots - 1) / slots;
+          if (waves <= 3) cost += (waves * slots - ctas) * 2;     // idle CTA slots in the last wave
           if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_t = t; best_nv = n; best_c = c; }
         }
     if (best_cost < 0)

@@ -74,7 +74,7 @@ for (Bs, M, mode) in [(512, 2, ops.MODE_OR), (8192, 2, ops.MODE_AND), (8192, 2, 
     bytes_ = 4 * Bs * D * (M + 3)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     res = []
-    for shape in [None, (256, 3, 1), (128, 3, 2), (128, 2, 4), (192, 1, 4), (96, 1, 8), (256, 1, 4), (64, 3, 4), (128, 1, 8), (256, 2, 2)]:
+    for shape in [None, (256, 3, 1), (192, 4, 1), (192, 2, 1), (128, 2, 1), (128, 3, 1), (256, 1, 1), (128, 3, 2), (128, 2, 4), (192, 1, 4), (96, 1, 8), (256, 1, 4), (64, 3, 4), (128, 1, 8), (256, 2, 2)]:
         def f():
             ops.step_vpsde(xs, ns, sc, lq, -5.0, 5.0, 0.5, 1e-3, mode, ops.DLOGQ_CIFAR_MAXSUB if mode == ops.MODE_OR else ops.DLOGQ_ITO,
                            temperature=1e6, x_out=xo, weights=w, launch_shape=shape)
