@@ -299,6 +299,9 @@ __device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int 
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }   // the epilogue warps only
 
+// PAIR = true is a separate instantiation: a kernel that contains cta_group::2 instructions can only be launched as
+// a cluster of 2 ("cluster misconfiguration" otherwise), so the single-CTA kernel must not contain them.
+template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -328,13 +331,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], p.pair ? 1 : csize); }
-      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], p.pair ? 2 * EPI_WARPS : EPI_WARPS); }
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : csize); }
+      for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
     // whole TMEM (512 columns): two 256-column fp32 accumulators; 1 CTA / SM by construction (smem)
-    if (p.pair) {   // both CTAs of the pair issue the 2-SM allocation from the same warp, same smem destination offset
+    if constexpr (PAIR) {   // both CTAs of the pair issue the 2-SM allocation from the same warp, same smem destination offset
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
@@ -354,7 +357,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       int stage = 0;
       uint32_t phase = 0;
       // pair mode: only the leader arms its full barrier, with the bytes of BOTH CTAs (each: own A tile + half of the B tile)
-      const uint32_t tx_bytes = p.pair ? 2u * (A_BYTES + (uint32_t)(p.block_n / 2) * BK * 2)
+      const uint32_t tx_bytes = PAIR ? 2u * (A_BYTES + (uint32_t)(p.block_n / 2) * BK * 2)
                                        : (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           else if (p.seg_taps[seg] == 4) { dh = (p.up_phase >> 1) - 1 + (tap >> 1); dw = (p.up_phase & 1) - 1 + (tap & 1); }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          if (p.pair) {
+          if constexpr (PAIR) {
             if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
             if (p.stride2)
               tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, tap % 3, 2 * c2[0] + tap / 3, c3[0]);
@@ -413,11 +416,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && !(p.pair && crank != 0)) {
+    if (lane == 0 && !(PAIR && crank != 0)) {
       // ===================== MMA issuer (pair mode: the leader CTA issues for both SMs) =====================
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)((p.pair ? 2 * BM : BM) >> 4) << 24);
+                             ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -431,7 +434,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
           const uint64_t b_desc = umma_desc_sw128(sa + b_off);
-          if (p.pair) {
+          if constexpr (PAIR) {
             const uint64_t a_desc = umma_desc_sw128(sa);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k)
@@ -450,8 +453,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           else umma_commit_mcast(&empty_bar[stage], cmask);        // ... in every CTA of the cluster (their TMA writes land here too)
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (p.pair) umma_commit_pair(&tmem_full[acc]);   // each CTA's epilogue drains its own 128 TMEM lanes
-        else umma_commit(&tmem_full[acc]);               // accumulator complete -> epilogue
+        if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);   // each CTA's epilogue drains its own 128 TMEM lanes
+        else umma_commit(&tmem_full[acc]);                        // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (p.pair) mbar_arrive_rank(&tmem_empty[acc], 0);     // the leader's MMA warp waits for both CTAs' epilogues
+        if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);     // the leader's MMA warp waits for both CTAs' epilogues
         else mbar_arrive(&tmem_empty[acc]);
       }
       acc ^= 1;
@@ -594,7 +597,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (csize > 1) cluster_sync_all();      // no CTA exits while a peer may still multicast into its smem or signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
-    if (p.pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
@@ -705,7 +708,9 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
   const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
@@ -726,7 +731,8 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     cfg.attrs = attr;
     cfg.numAttrs = 1;
   }
-  return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel, p), who);
+  if (p.pair) return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p), who);
+  return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p), who);
 }
 
 }  // namespace sdb
