@@ -219,6 +219,12 @@ def run_b200(args):
     # ---- fused step kernel alone, L2 flushed between launches ----
     step_us, step_bytes = _step_kernel_time(sampler, ops, torch, noise_dev[0])
     step_gbs = step_bytes / (step_us * 1e-6) / 1e9
+    # the same kernel at BASELINE config 3's single-GPU size (B = 8192, AND with the per-sample kappa solve, and OR)
+    big = {}
+    if rank == 0:
+        for name, md in (("and", ops.MODE_AND), ("or", ops.MODE_OR)):
+            us, by = _step_kernel_time(sampler, ops, torch, None, B=8192, mode=md)
+            big[name] = {"us_per_launch": us, "achieved": by / (us * 1e-6) / 1e9, "frac": by / (us * 1e-6) / 1e9 / hbm_peak}
 
     if rank != 0:
         if world > 1:
@@ -250,6 +256,9 @@ def run_b200(args):
                           "traffic": None, "kernel": "step_vpsde_kernel", "us_per_launch": step_us,
                           "bytes_per_launch": step_bytes, "peak_kind": f"{peak_kind} copy bandwidth",
                           "note": "4*B*D*(M+3) algorithmic bytes; standalone launches with a 256 MB L2 flush between them"},
+        "roofline_step_b8192": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "bytes_per_launch": 4 * 8192 * D * (M_MODELS + 3),
+                                "and": big.get("and"), "or": big.get("or"),
+                                "note": "same fused step kernel at BASELINE config 3's single-GPU batch (8192), L2 flushed"},
         "scorenet_tflops_whole_step": fwd_tf,
         "gather_ms": gather_ms,
     }
@@ -312,13 +321,15 @@ def _instrumented_step(sampler, ops, torch):
     return gemm_ms, gemm_flop, other_ms
 
 
-def _step_kernel_time(sampler, ops, torch, noise):
-    B, M = sampler.B, sampler.M
+def _step_kernel_time(sampler, ops, torch, noise, B=None, mode=None):
+    B = sampler.B if B is None else B
+    M = sampler.M
+    mode = ops.MODE_OR if mode is None else mode
     flush = torch.empty(64 * 1024 * 1024, device=sampler.device, dtype=torch.float32)   # 256 MB > 126 MB L2
     x = torch.randn(B, D, device=sampler.device)
     xo = torch.empty_like(x)
     sc = [torch.randn(B, D, device=sampler.device) for _ in range(M)]
-    nz = noise.reshape(B, D)
+    nz = noise.reshape(-1, D) if noise is not None and noise.numel() == B * D else torch.randn(B, D, device=sampler.device)
     lq = torch.zeros(B, M, device=sampler.device)
     w = torch.zeros(B, M, device=sampler.device)
     ts = []
@@ -326,7 +337,8 @@ def _step_kernel_time(sampler, ops, torch, noise):
         flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6,
+        ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, mode,
+                       ops.DLOGQ_CIFAR_MAXSUB if mode == ops.MODE_OR else ops.DLOGQ_ITO, temperature=1e6,
                        x_out=xo, weights=w)
         e.record()
         torch.cuda.synchronize()

@@ -31,7 +31,8 @@ namespace sdb {
 constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int RING_BYTES = 4 * (BM * BK * 2 + 256 * BK * 2);   // 192 KB operand ring, cut into 4..8 stages of the size a launch needs
+constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
@@ -41,7 +42,7 @@ constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, e
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
 constexpr int EBIAS_FLOATS = 9 * MAX_BN;           // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials
-constexpr size_t GEMM_SMEM = (size_t)STAGES * STAGE_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
+constexpr size_t GEMM_SMEM = (size_t)RING_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
   CUtensorMap a_map[MAX_SEGS];
@@ -53,6 +54,7 @@ struct GemmParams {
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
+  int num_stages, stage_bytes; // operand ring geometry: stage_bytes = A bytes + B bytes of one K-block (1 KB multiple)
   int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
                               //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
   int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile, share the B tile via TMA multicast
@@ -305,10 +307,12 @@ template <bool PAIR>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  float* ebias = reinterpret_cast<float*>(smem + (size_t)STAGES * STAGE_BYTES);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES * STAGE_BYTES + EBIAS_FLOATS * 4);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;   // [2]
+  float* ebias = reinterpret_cast<float*>(smem + (size_t)RING_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)RING_BYTES + EBIAS_FLOATS * 4);
+  uint64_t* empty_bar = full_bar + MAX_STAGES;
+  uint64_t* tmem_full = empty_bar + MAX_STAGES;   // [2]
+  const int STAGES = p.num_stages;               // ring depth / stage size chosen per launch (deeper when stages are small)
+  const int STAGE_BYTES = p.stage_bytes;
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -676,6 +680,20 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
       p.pair = 1;
       p.cluster = 2;
     }
+  }
+  {
+    // one stage = the A tile(s) + the B rows this CTA receives per K-block; a deeper ring hides more TMA latency
+    const int a_bytes = (p.dual ? 2 : 1) * A_BYTES;
+    const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
+    int sb = a_bytes + b_rows * BK * 2;
+    sb = (sb + 1023) / 1024 * 1024;
+    int ns = RING_BYTES / sb;
+    if (ns > MAX_STAGES) ns = MAX_STAGES;
+    static const int max_stages_env = [] { const char* e = getenv("SDB_GEMM_STAGES"); return e ? atoi(e) : MAX_STAGES; }();   // tuning knob
+    if (ns > max_stages_env) ns = max_stages_env;
+    if (ns < 2) ns = 2;
+    p.stage_bytes = sb;
+    p.num_stages = ns;
   }
   if (((uintptr_t)Wt % 16) != 0 || (ldb % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": B operand must be 16-byte aligned with ld % 8 == 0");
   {
