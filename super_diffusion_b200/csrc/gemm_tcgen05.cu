@@ -14,11 +14,12 @@
 // UMMA operand layout, and is consumed by tcgen05.mma (M=128, N<=256, K=16)
 // with the fp32 accumulator in tensor memory.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
-// MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld -> bias /
-// time-embedding / residual / swish -> global).  Persistent over output tiles,
-// 4-stage smem ring, two TMEM accumulators so the epilogue of tile i overlaps
-// the MMAs of tile i+1.
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld -> bias /
+// time-embedding / swish / GroupNorm statistics -> global).  Persistent over
+// output tiles, a 192 KB smem ring cut into 4..8 stages, two TMEM accumulators
+// so the epilogue of tile i overlaps the MMAs of tile i+1.  Wide (N = 256)
+// layers run as cta_group::2 pairs (kernel<PAIR = true>).
 #include "common.cuh"
 #include "../../include/superdiff_b200.h"
 #include <cuda.h>
@@ -94,19 +95,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // Bounded wait: a protocol bug must end in a trap (launch failure), never in a hung GPU.
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;        // fast path: no clock reads
   const long long t0 = clock64();
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    if (done) return;
-    if (clock64() - t0 > 4000000000LL) __trap();   // ~2 s
-  }
+  while (!mbar_try_wait(addr, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s: a protocol bug ends in a launch failure, never a hung GPU
 }
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, void* dst, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -379,32 +382,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             c3[sub] = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
           }
         }
-        int seg = 0, seg_start = 0;
+        // (segment, tap row, tap column, channel block) advance as counters: this single thread issues every TMA of the
+        // CTA, and ncu showed it busy (never waiting for a free slot) while the MMA warp waited for data -- the
+        // div/mod chain of the first version cost more per K-block than the MMAs it feeds
+        int seg = 0, th = 0, tw = 0, cb = 0;
+        int tside = p.seg_taps[0] == 9 ? 3 : (p.seg_taps[0] == 4 ? 2 : 1);
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          while (kb >= p.seg_kb_end[seg]) { seg_start = p.seg_kb_end[seg]; ++seg; }
-          const int local = kb - seg_start;
-          const int tap = local / p.seg_cblocks[seg];
-          const int cb = local - tap * p.seg_cblocks[seg];
           int dh = 0, dw = 0;
-          if (p.seg_taps[seg] == 9) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-          else if (p.seg_taps[seg] == 4) { dh = (p.up_phase >> 1) - 1 + (tap >> 1); dw = (p.up_phase & 1) - 1 + (tap & 1); }
+          if (tside == 3) { dh = th - 1; dw = tw - 1; }
+          else if (tside == 2) { dh = (p.up_phase >> 1) - 1 + th; dw = (p.up_phase & 1) - 1 + tw; }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
           if constexpr (PAIR) {
             if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
             if (p.stride2)
-              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, tap % 3, 2 * c2[0] + tap / 3, c3[0]);
+              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, tw, 2 * c2[0] + th, c3[0]);
             else
               tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, c1[0] + dw, c2[0] + dh, c3[0]);
             const int rows_per = p.block_n / 2;      // this CTA's half of the weight tile (N rows), same smem offset in both CTAs
             tma_load_3d_pair(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n + crank * rows_per, bz);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (++cb == p.seg_cblocks[seg]) {
+              cb = 0;
+              if (++tw == tside) { tw = 0; if (++th == tside) { th = 0; ++seg; if (seg < p.nseg) tside = p.seg_taps[seg] == 9 ? 3 : (p.seg_taps[seg] == 4 ? 2 : 1); } }
+            }
             continue;
           }
           mbar_expect_tx(&full_bar[stage], tx_bytes);
           for (int sub = 0; sub < nsub; ++sub) {
             if (p.stride2)   // input coordinates of output row c2 / column 0 for tap (kh, kw): (2*c2 + kh, kw); index H / W is OOB -> 0
-              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tap % 3, 2 * c2[sub] + tap / 3, c3[sub]);
+              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tw, 2 * c2[sub] + th, c3[sub]);
             else
               tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
           }
@@ -416,6 +423,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                               n_tile * p.block_n + crank * rows_per, bz, cmask);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++cb == p.seg_cblocks[seg]) {
+            cb = 0;
+            if (++tw == tside) { tw = 0; if (++th == tside) { th = 0; ++seg; if (seg < p.nseg) tside = p.seg_taps[seg] == 9 ? 3 : (p.seg_taps[seg] == 4 ? 2 : 1); } }
+          }
+
         }
       }
     }
