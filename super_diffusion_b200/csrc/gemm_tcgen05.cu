@@ -32,7 +32,7 @@ namespace sdb {
 constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int RING_BYTES = 4 * (BM * BK * 2 + 256 * BK * 2);   // 192 KB operand ring, cut into 4..8 stages of the size a launch needs
+constexpr int RING_BYTES = 216 * 1024;     // operand ring, cut into 2..8 slots of the size a launch needs (48 KB K-blocks: 4)
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
@@ -55,6 +55,11 @@ struct GemmParams {
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
+  const void* slab_src;       // host-only: segment-0 source for the slab tensor map (nullptr = not a slab candidate)
+  int slab_C, slab_B;
+  int slab;                   // 1: segment 0 (3x3, stride 1) is fed as activation slabs shared by the three vertical taps
+  int slab_bytes, a_region_bytes;   // bytes of one slab; bytes reserved for A at the start of a ring slot
+  CUtensorMap a_slab_map;     // segment-0 map with a (64, W, hb+2, 1) box
   int num_stages, stage_bytes; // operand ring geometry: stage_bytes = A bytes + B bytes of one K-block (1 KB multiple)
   int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
                               //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
@@ -314,8 +319,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)RING_BYTES + EBIAS_FLOATS * 4);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;   // [2]
-  const int STAGES = p.num_stages;               // ring depth / stage size chosen per launch (deeper when stages are small)
-  const int STAGE_BYTES = p.stage_bytes;
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
@@ -329,7 +332,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int total_tiles = ((m_units + csize - 1) / csize) * p.n_tiles;       // tile groups
   const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   const int nsub = p.dual ? 2 : 1;
-  const uint32_t b_off = p.dual ? 2 * A_BYTES : A_BYTES;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s)
@@ -338,7 +340,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : csize); }
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : csize); }
       for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -358,14 +360,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_sh;
 
+  // ---- K loop as a sequence of "steps", one smem ring slot each -------------------------------------------------
+  //  plain step: one 64-channel K-block of one filter tap: A tile(s) + one B tile                      (1 MMA group)
+  //  slab step (p.slab, segment 0 = 3x3 stride-1 conv): for one (channel block, kw) the CTA loads the activation rows
+  //    h0-1 .. h0+hb ONCE (hb+2 image rows, shifted by kw-1 along w; out-of-image rows/columns are zero-filled) plus
+  //    the three weight tiles kh = 0,1,2; the three vertical taps are the same rows read at smem offsets of
+  //    kh * (row pitch) -- whole 1024-byte swizzle atoms because a pixel row is W * 128 B                (3 MMA groups)
+  //    => the activation bytes an SM must receive drop from 9 to 3*(hb+2)/hb tiles per channel block; the kernel is
+  //    bound by the ~48 B/clk an SM can take in from L2 (measured), not by the MMA rate.
+  const int STAGES = p.num_stages;               // ring depth / slot size chosen per launch
+  const int STAGE_BYTES = p.stage_bytes;
+  const uint32_t b_off = (uint32_t)p.a_region_bytes;          // B tile(s) follow the A region inside a slot
+  const uint32_t b_cta_bytes = (uint32_t)(PAIR ? p.block_n / 2 : p.block_n) * BK * 2;   // B bytes landing in THIS CTA per weight tile
+  const uint32_t b_tile_bytes = b_cta_bytes;                  // pitch of the (up to three) B tiles inside a slot
+  const uint32_t row_pitch = (uint32_t)p.img_W * BK * 2;      // one image row of a 64-channel block in smem
+
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      // pair mode: only the leader arms its full barrier, with the bytes of BOTH CTAs (each: own A tile + half of the B tile)
-      const uint32_t tx_bytes = PAIR ? 2u * (A_BYTES + (uint32_t)(p.block_n / 2) * BK * 2)
-                                       : (uint32_t)nsub * A_BYTES + (uint32_t)p.block_n * BK * 2;
+      auto load_b = [&](uint8_t* dst, uint64_t* bar, int kcol, int n_tile, int bz) {
+        if constexpr (PAIR) {
+          tma_load_3d_pair(&p.b_map, dst, bar, kcol, n_tile * p.block_n + crank * (p.block_n / 2), bz);
+        } else if (csize == 1) {
+          tma_load_3d(&p.b_map, dst, bar, kcol, n_tile * p.block_n, bz);
+        } else {      // this CTA fetches its 1/csize slice of the B tile for the whole cluster
+          const int rows_per = p.block_n / csize;
+          tma_load_3d_mcast(&p.b_map, dst + (size_t)crank * rows_per * (BK * 2), bar, kcol, n_tile * p.block_n + crank * rows_per, bz, cmask);
+        }
+      };
+      auto load_a = [&](const CUtensorMap* map, uint8_t* dst, uint64_t* bar, int c0, int cw, int ch, int cimg) {
+        if constexpr (PAIR) tma_load_4d_pair(map, dst, bar, c0, cw, ch, cimg);
+        else tma_load_4d(map, dst, bar, c0, cw, ch, cimg);
+      };
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
         const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
         int c1[2], c2[2], c3[2], bz = 0;
@@ -382,52 +410,48 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             c3[sub] = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
           }
         }
-        // (segment, tap row, tap column, channel block) advance as counters: this single thread issues every TMA of the
-        // CTA, and ncu showed it busy (never waiting for a free slot) while the MMA warp waited for data -- the
-        // div/mod chain of the first version cost more per K-block than the MMAs it feeds
-        int seg = 0, th = 0, tw = 0, cb = 0;
-        int tside = p.seg_taps[0] == 9 ? 3 : (p.seg_taps[0] == 4 ? 2 : 1);
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          int dh = 0, dw = 0;
-          if (tside == 3) { dh = th - 1; dw = tw - 1; }
-          else if (tside == 2) { dh = (p.up_phase >> 1) - 1 + th; dw = (p.up_phase & 1) - 1 + tw; }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
-          if constexpr (PAIR) {
-            if (crank == 0) mbar_expect_tx(&full_bar[stage], tx_bytes);
-            if (p.stride2)
-              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, tw, 2 * c2[0] + th, c3[0]);
-            else
-              tma_load_4d_pair(&p.a_map[seg], sa, &full_bar[stage], cb * BK, c1[0] + dw, c2[0] + dh, c3[0]);
-            const int rows_per = p.block_n / 2;      // this CTA's half of the weight tile (N rows), same smem offset in both CTAs
-            tma_load_3d_pair(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n + crank * rows_per, bz);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            if (++cb == p.seg_cblocks[seg]) {
-              cb = 0;
-              if (++tw == tside) { tw = 0; if (++th == tside) { th = 0; ++seg; if (seg < p.nseg) tside = p.seg_taps[seg] == 9 ? 3 : (p.seg_taps[seg] == 4 ? 2 : 1); } }
-            }
-            continue;
+        int kb_base = 0;                                // K-block index (weight column / 64) where the segment starts
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const int cblocks = p.seg_cblocks[seg], taps = p.seg_taps[seg];
+          if (p.slab && seg == 0) {
+            const uint32_t tx = (PAIR ? 2u : 1u) * ((uint32_t)p.slab_bytes + 3u * b_cta_bytes);
+            for (int cb = 0; cb < cblocks; ++cb)
+              for (int kw = 0; kw < 3; ++kw) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                load_a(&p.a_slab_map, sa, &full_bar[stage], cb * BK, kw - 1, c2[0] - 1, c3[0]);
+                for (int kh = 0; kh < 3; ++kh)
+                  load_b(sa + b_off + kh * b_tile_bytes, &full_bar[stage], (kb_base + (kh * 3 + kw) * cblocks + cb) * BK, n_tile, bz);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+              }
+          } else {
+            // (tap row, tap column, channel block) advance as counters, no div/mod: this single thread issues every TMA
+            // of the CTA, and ncu showed it busy while the MMA warp waited for data with the div/mod chain of the first version
+            const int tside = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
+            const uint32_t tx = PAIR ? 2u * (A_BYTES + b_cta_bytes) : (uint32_t)nsub * A_BYTES + b_cta_bytes;
+            int kb = kb_base;
+            for (int th = 0; th < tside; ++th)
+              for (int tw = 0; tw < tside; ++tw) {
+                int dh = 0, dw = 0;
+                if (tside == 3) { dh = th - 1; dw = tw - 1; }
+                else if (tside == 2) { dh = (p.up_phase >> 1) - 1 + th; dw = (p.up_phase & 1) - 1 + tw; }
+                for (int cb = 0; cb < cblocks; ++cb, ++kb) {
+                  mbar_wait(&empty_bar[stage], phase ^ 1);
+                  uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
+                  if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], tx);
+                  for (int sub = 0; sub < nsub; ++sub) {
+                    if (p.stride2)   // input coordinates of output row c2 / column 0 for tap (kh, kw): (2*c2 + kh, kw); index H / W is OOB -> 0
+                      load_a(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tw, 2 * c2[sub] + th, c3[sub]);
+                    else
+                      load_a(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
+                  }
+                  load_b(sa + b_off, &full_bar[stage], kb * BK, n_tile, bz);
+                  if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+              }
           }
-          mbar_expect_tx(&full_bar[stage], tx_bytes);
-          for (int sub = 0; sub < nsub; ++sub) {
-            if (p.stride2)   // input coordinates of output row c2 / column 0 for tap (kh, kw): (2*c2 + kh, kw); index H / W is OOB -> 0
-              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, tw, 2 * c2[sub] + th, c3[sub]);
-            else
-              tma_load_4d(&p.a_map[seg], sa + sub * A_BYTES, &full_bar[stage], cb * BK, c1[sub] + dw, c2[sub] + dh, c3[sub]);
-          }
-          if (csize == 1) {
-            tma_load_3d(&p.b_map, sa + b_off, &full_bar[stage], kb * BK, n_tile * p.block_n, bz);
-          } else {      // this CTA fetches its 1/csize slice of the B tile for the whole cluster
-            const int rows_per = p.block_n / csize;
-            tma_load_3d_mcast(&p.b_map, sa + b_off + (size_t)crank * rows_per * (BK * 2), &full_bar[stage], kb * BK,
-                              n_tile * p.block_n + crank * rows_per, bz, cmask);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          if (++cb == p.seg_cblocks[seg]) {
-            cb = 0;
-            if (++tw == tside) { tw = 0; if (++th == tside) { th = 0; ++seg; if (seg < p.nseg) tside = p.seg_taps[seg] == 9 ? 3 : (p.seg_taps[seg] == 4 ? 2 : 1); } }
-          }
-
+          kb_base += taps * cblocks;
         }
       }
     }
@@ -445,29 +469,35 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
-          const uint64_t b_desc = umma_desc_sw128(sa + b_off);
-          if constexpr (PAIR) {
-            const uint64_t a_desc = umma_desc_sw128(sa);
+        uint32_t accumulate = 0;
+        for (int seg = 0; seg < p.nseg; ++seg) {
+          const bool slab = p.slab && seg == 0;
+          const int nsteps = slab ? p.seg_cblocks[seg] * 3 : p.seg_taps[seg] * p.seg_cblocks[seg];
+          const int groups = slab ? 3 : 1;
+          for (int st = 0; st < nsteps; ++st) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
+            for (int g = 0; g < groups; ++g) {
+              const uint64_t b_desc = umma_desc_sw128(sa + b_off + (uint32_t)g * b_tile_bytes);
+              for (int sub = 0; sub < nsub; ++sub) {
+                // slab: vertical tap g of sub-tile `sub` = the slab rows starting (g + sub * h_box) image rows in
+                const uint32_t a_addr = slab ? sa + (uint32_t)(g + sub * p.h_box) * row_pitch : sa + (uint32_t)sub * A_BYTES;
+                const uint64_t a_desc = umma_desc_sw128(a_addr);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)
-              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-            umma_commit_pair(&empty_bar[stage]);
+                for (int k = 0; k < BK / UMMA_K; ++k) {   // +32 B per UMMA_K inside the swizzle atom
+                  if constexpr (PAIR) umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                  else umma_bf16(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                }
+              }
+              accumulate = 1;
+            }
+            // frees the smem slot once these MMAs retire (in every CTA whose TMA writes land here)
+            if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
+            else if (csize == 1) umma_commit(&empty_bar[stage]);
+            else umma_commit_mcast(&empty_bar[stage], cmask);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
           }
-          for (int sub = 0; sub < nsub; ++sub) {
-            const uint64_t a_desc = umma_desc_sw128(sa + sub * A_BYTES);
-#pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per UMMA_K inside the swizzle atom
-              umma_bf16(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
-          }
-          if (csize == 1) umma_commit(&empty_bar[stage]);          // frees the smem slot once these MMAs retire
-          else umma_commit_mcast(&empty_bar[stage], cmask);        // ... in every CTA of the cluster (their TMA writes land here too)
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if constexpr (PAIR) umma_commit_pair(&tmem_full[acc]);   // each CTA's epilogue drains its own 128 TMEM lanes
         else umma_commit(&tmem_full[acc]);                        // accumulator complete -> epilogue
@@ -694,10 +724,32 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     }
   }
   {
-    // one stage = the A tile(s) + the B rows this CTA receives per K-block; a deeper ring hides more TMA latency
-    const int a_bytes = (p.dual ? 2 : 1) * A_BYTES;
-    const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
-    int sb = a_bytes + b_rows * BK * 2;
+    // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
+    const int nsub_h = p.dual ? 2 : 1;
+    const int b_cta = (p.pair ? p.block_n / 2 : p.block_n) * BK * 2;
+    static const int want_slab = [] { const char* e = getenv("SDB_GEMM_SLAB"); return e ? atoi(e) : 1; }();   // tuning knob
+    p.slab = 0;
+    p.a_region_bytes = nsub_h * A_BYTES;
+    int groups = 1;
+    if (want_slab && p.slab_src && (p.dual || p.pair) && (p.cluster == 1 || p.pair) && p.imgs_per_tile == 1 &&
+        (nsub_h == 1 || (p.tiles_per_img % 2) == 0)) {
+      const int hb = nsub_h * p.h_box;
+      const int slab_bytes = (hb + 2) * p.img_W * BK * 2;
+      int a_region = slab_bytes > nsub_h * A_BYTES ? slab_bytes : nsub_h * A_BYTES;
+      a_region = (a_region + 1023) / 1024 * 1024;
+      if (2 * (a_region + 3 * b_cta) <= RING_BYTES && hb + 2 <= 256) {
+        cuuint64_t dims[4] = {(cuuint64_t)p.slab_C, (cuuint64_t)p.img_W, (cuuint64_t)p.img_H, (cuuint64_t)p.slab_B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.slab_C * 2, (cuuint64_t)p.slab_C * 2 * p.img_W, (cuuint64_t)p.slab_C * 2 * p.img_W * p.img_H};
+        cuuint32_t box[4] = {BK, (cuuint32_t)p.img_W, (cuuint32_t)(hb + 2), 1};
+        int rc = encode_map(&p.a_slab_map, p.slab_src, 4, dims, strides, box);
+        if (rc != SD_OK) return rc;
+        p.slab = 1;
+        p.slab_bytes = slab_bytes;
+        p.a_region_bytes = a_region;
+        groups = 3;
+      }
+    }
+    int sb = p.a_region_bytes + groups * b_cta;
     sb = (sb + 1023) / 1024 * 1024;
     int ns = RING_BYTES / sb;
     if (ns > MAX_STAGES) ns = MAX_STAGES;
@@ -822,6 +874,7 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   for (int s = num_srcs; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
   p.nseg = num_srcs;
   p.num_kb = kb;
+  if (srcs[0].taps == 9 && !stride2 && up_phase < 0) { p.slab_src = srcs[0].ptr; p.slab_C = srcs[0].C; p.slab_B = B; }
   p.M_total = B * H * W;
   p.HW = H * W;
   p.m_tiles = (p.M_total + BM - 1) / BM;

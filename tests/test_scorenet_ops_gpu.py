@@ -307,3 +307,31 @@ def test_conv_gemm_stride2_tma(cuda, B, H, C, N):
     _close(out, ref)
     alt = ops.conv_gemm([(ops.im2col_s2(x.to(cuda)), 1)], w.to(cuda), bias=bias.to(cuda))
     assert torch.equal(out, alt)
+
+
+def test_conv_gemm_pair_slab_multisegment(cuda):
+    """Wide (N = 256) layer large enough for the cta_group::2 pair kernel with activation slabs (three vertical taps
+    share one TMA load), followed by 1-tap segments (NIN shortcut over a concat), row bias and emitted GN statistics."""
+    B, H, W, Co, C0, C1 = 152, 16, 16, 256, 128, 64
+    g = torch.Generator().manual_seed(31)
+    a2 = _bf(torch.randn(B, H, W, Co, generator=g)).to(cuda)
+    xa = _bf(torch.randn(B, H, W, C0, generator=g)).to(cuda)
+    xb = _bf(torch.randn(B, H, W, C1, generator=g)).to(cuda)
+    w = _bf(torch.cat([torch.randn(Co, 9 * Co, generator=g) / math.sqrt(9 * Co),
+                       torch.randn(Co, C0 + C1, generator=g) / math.sqrt(C0 + C1)], dim=1)).to(cuda)
+    bias = torch.randn(Co, generator=g).to(cuda)
+    rowbias = torch.randn(B, 512, generator=g).to(cuda)
+    out = ops.conv_gemm([(a2, 9), (xa, 1), (xb, 1)], w, bias=bias, rowbias=rowbias[:, 256:256 + Co], want_stats=True)
+    wf = w.float()
+    ref = F.conv2d(a2.float().permute(0, 3, 1, 2), wf[:, :9 * Co].reshape(Co, 3, 3, Co).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) \
+        + torch.einsum("bhwc,nc->bhwn", torch.cat([xa, xb], -1).float(), wf[:, 9 * Co:]) + bias + rowbias[:, None, None, 256:256 + Co]
+    _close(out, ref.cpu())
+    st = out.gn_stats[0]
+    assert torch.allclose(st[:, :, 0].sum(1), out.float().sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
+    # odd number of m-tiles (pair tail) and a different channel count
+    B2 = 149
+    x = _bf(torch.randn(B2, H, W, 64, generator=g)).to(cuda)
+    w2 = _bf(torch.randn(256, 9 * 64, generator=g) / math.sqrt(9 * 64)).to(cuda)
+    out2 = ops.conv_gemm([(x, 9)], w2)
+    ref2 = F.conv2d(x.float().permute(0, 3, 1, 2), w2.float().reshape(256, 3, 3, 64).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    _close(out2, ref2.cpu())
