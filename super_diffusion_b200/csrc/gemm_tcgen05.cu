@@ -523,49 +523,71 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const bool row_ok = row_offset(p, m_tile, row, row_off);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
         if (p.flags & SD_EPI_SOFTMAX) {
-          if (chalf != 0) continue;                 // one thread needs the whole row: the second warp of the pair idles
-          // the whole score row (block_n == N <= 256 columns) sits in this thread's TMEM lane: in-thread softmax over
-          // the row's diagonal block [lo, hi) (several small images share one 128-row tile), zeros elsewhere
+          // the whole score row (block_n == N <= 256 columns) sits in one TMEM lane: softmax over the row's diagonal block
+          // [lo, hi) (several small images share one 128-row tile), zeros elsewhere.  The two warps of a lane quarter take
+          // alternate 32-column groups and exchange the row max / row sum through shared memory (two named barriers).
           const int rl = (p.flat ? (m_tile % p.m_tiles_per_batch) : 0) * BM + row;
           const int lo = (rl / p.softmax_block) * p.softmax_block, hi = lo + p.softmax_block;
+          const float sl2 = p.softmax_scale * 1.4426950408889634f;       // exp(s*x) = exp2(s*log2(e)*x): one FFMA + MUFU.EX2
+          float* xch = ebias;                                             // [128 rows][2 halves]
           float mx = -INFINITY;
-          for (int c = 0; c < p.block_n; c += 16) {
-            uint32_t r0[16];
+          for (int c = chalf * 32; c < p.block_n; c += 64) {
+            uint32_t r0[16], r1[16];
             tmem_ld16(taddr + c, r0);
+            tmem_ld16(taddr + c + 16, r1);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
+            for (int j = 0; j < 16; ++j) {
               if (c + j >= lo && c + j < hi) mx = fmaxf(mx, __uint_as_float(r0[j]));
+              if (c + 16 + j >= lo && c + 16 + j < hi) mx = fmaxf(mx, __uint_as_float(r1[j]));
+            }
           }
+          xch[row * 2 + chalf] = mx;
+          epi_bar();
+          mx = fmaxf(xch[row * 2], xch[row * 2 + 1]);
+          epi_bar();
+          const float mxs = mx * sl2;
           float sum = 0.f;
-          for (int c = 0; c < p.block_n; c += 16) {
-            uint32_t r0[16];
+          for (int c = chalf * 32; c < p.block_n; c += 64) {
+            uint32_t r0[16], r1[16];
             tmem_ld16(taddr + c, r0);
+            tmem_ld16(taddr + c + 16, r1);
             tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-              if (c + j >= lo && c + j < hi) sum += expf(p.softmax_scale * (__uint_as_float(r0[j]) - mx));
+            for (int j = 0; j < 16; ++j) {
+              if (c + j >= lo && c + j < hi) sum += exp2f(fmaf(__uint_as_float(r0[j]), sl2, -mxs));
+              if (c + 16 + j >= lo && c + 16 + j < hi) sum += exp2f(fmaf(__uint_as_float(r1[j]), sl2, -mxs));
+            }
           }
-          const float inv = 1.f / sum;
-          for (int c = 0; c < p.block_n; c += 16) {
-            uint32_t r0[16];
+          xch[row * 2 + chalf] = sum;
+          epi_bar();
+          const float inv = 1.f / (xch[row * 2] + xch[row * 2 + 1]);
+          for (int c = chalf * 32; c < p.block_n; c += 64) {
+            uint32_t r0[16], r1[16];
             tmem_ld16(taddr + c, r0);
+            tmem_ld16(taddr + c + 16, r1);
             tmem_wait_ld();
-            uint32_t w[8];
+            uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const int c0 = c + 2 * j;
-              const float e0 = (c0 >= lo && c0 < hi) ? expf(p.softmax_scale * (__uint_as_float(r0[2 * j]) - mx)) * inv : 0.f;
-              const float e1 = (c0 + 1 >= lo && c0 + 1 < hi) ? expf(p.softmax_scale * (__uint_as_float(r0[2 * j + 1]) - mx)) * inv : 0.f;
-              const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-              w[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              const int c0 = c + 2 * j, c1 = c + 16 + 2 * j;
+              const float e0 = (c0 >= lo && c0 < hi) ? exp2f(fmaf(__uint_as_float(r0[2 * j]), sl2, -mxs)) * inv : 0.f;
+              const float e1 = (c0 + 1 >= lo && c0 + 1 < hi) ? exp2f(fmaf(__uint_as_float(r0[2 * j + 1]), sl2, -mxs)) * inv : 0.f;
+              const float e2 = (c1 >= lo && c1 < hi) ? exp2f(fmaf(__uint_as_float(r1[2 * j]), sl2, -mxs)) * inv : 0.f;
+              const float e3 = (c1 + 1 >= lo && c1 + 1 < hi) ? exp2f(fmaf(__uint_as_float(r1[2 * j + 1]), sl2, -mxs)) * inv : 0.f;
+              const __nv_bfloat162 ha = __floats2bfloat162_rn(e0, e1), hb = __floats2bfloat162_rn(e2, e3);
+              w[j] = *reinterpret_cast<const uint32_t*>(&ha);
+              w[8 + j] = *reinterpret_cast<const uint32_t*>(&hb);
             }
             if (row_ok) {
               uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + c);
               op[0] = make_uint4(w[0], w[1], w[2], w[3]);
               op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+              op[2] = make_uint4(w[8], w[9], w[10], w[11]);
+              op[3] = make_uint4(w[12], w[13], w[14], w[15]);
             }
           }
+          epi_bar();                                  // the exchange area is reused by the next tile
           continue;
         }
         // ---- phase 0: cooperative, latency-tolerant loads.  The first version read bias / row bias / residual from
@@ -930,7 +952,7 @@ static int batched_gemm_impl(const void* A, int lda, long long strideA, const vo
   p.softmax_scale = softmax_scale;
   p.softmax_block = softmax_block;
   if (flags & SD_EPI_SOFTMAX) {
-    if (N > MAX_BN || (N % 16) != 0 || softmax_block < 1 || (N % softmax_block) != 0 || (BM % softmax_block != 0 && softmax_block % BM != 0) ||
+    if (N > MAX_BN || (N % 32) != 0 || softmax_block < 1 || (N % softmax_block) != 0 || (BM % softmax_block != 0 && softmax_block % BM != 0) ||
         bias || residual || (flags & (SD_EPI_OUT_F32 | SD_EPI_SWISH)))
       return fail(kErrInvalidArg, "sd_attention_probs: N must be a multiple of 16, <= 256, and a multiple of the block");
   }

@@ -1,4 +1,5 @@
-"""Small driver for `ncu --set full`: one launch each of the kernels that matter (after a warm-up pass)."""
+"""Small driver for `ncu --set full`: one launch each of the kernels that matter (after a warm-up pass).
+Matched kernels per pass (regex step_vpsde|gn_|gemm_tcgen05): 2 + 2 + 5 = 9."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import math, torch
@@ -17,21 +18,27 @@ def run_all():
     ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, x_out=xo, weights=w)
     ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_AND, ops.DLOGQ_ITO, x_out=xo, weights=w)
     del x, nz, sc, xo
-    # GroupNorm at the largest activation
+    # GroupNorm at the largest activation (stats pass + apply pass; producer-emitted stats skip the first)
     a = torch.randn(B, 32, 32, 128, device=dev).bfloat16()
     g = torch.ones(128, device=dev); b = torch.zeros(128, device=dev)
     ops.groupnorm_swish(a, g, b)
-    # implicit GEMM: 3x3 conv 128->128 at 32x32 (N = 128) and 256->256 at 16x16 (N = 256)
+    # implicit GEMM: 3x3 conv 128->128 at 32x32 (N = 128: paired m-tiles + activation slabs), with row bias + GN stats
     w1 = (torch.randn(128, 9 * 128, device=dev) / math.sqrt(9 * 128)).bfloat16()
-    ops.conv_gemm([(a, 9)], w1)
+    rb = torch.randn(B, 128, device=dev)
+    ops.conv_gemm([(a, 9)], w1, rowbias=rb, want_stats=True)
+    # 3x3 conv 256->256 at 16x16 + identity residual segment (N = 256: cta_group::2 pair + slabs)
     a2 = torch.randn(B, 16, 16, 256, device=dev).bfloat16()
-    w2 = (torch.randn(256, 9 * 256, device=dev) / math.sqrt(9 * 256)).bfloat16()
-    ops.conv_gemm([(a2, 9)], w2)
-    # short-K GEMM with residual (attention out-projection shape)
-    w3 = (torch.randn(256, 256, device=dev) / 16).bfloat16()
-    ops.conv_gemm([(a2, 1)], w3, residual=a2)
+    w2 = torch.cat([torch.randn(256, 9 * 256, device=dev) / math.sqrt(9 * 256), torch.eye(256, device=dev)], 1).bfloat16()
+    ops.conv_gemm([(a2, 9), (a2, 1)], w2, bias=torch.zeros(256, device=dev), want_stats=True)
+    # short-K GEMM (attention q,k projection shape) and the fused attention-probability GEMM
+    w3 = (torch.randn(512, 256, device=dev) / 16).bfloat16()
+    qk = ops.conv_gemm([(a2, 1)], w3).view(B, 256, 512)
+    ops.attention_probs(qk[:, :, :256], qk[:, :, 256:], 256 ** -0.5, block=256, C=256)
+    # low-resolution layer (4x4, few tiles)
+    a4 = torch.randn(B, 4, 4, 256, device=dev).bfloat16()
+    ops.conv_gemm([(a4, 9)], w2[:, :9 * 256].contiguous())
     torch.cuda.synchronize()
 
-run_all()   # warm-up (ncu skips these with -s)
+run_all()   # warm-up (ncu skips these with -s 9)
 run_all()
 print("profile driver done")
