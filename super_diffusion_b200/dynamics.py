@@ -48,10 +48,16 @@ def _scores(nets, t, x, labels):
     return [net(tt, x, labels) for net in nets]
 
 
-def _make(nets, mode, dlogq_mode, temperature, n_models):
+def _make(nets, mode, dlogq_mode, temperature, n_models, ode=False):
     def step(t, x, logq, args, x_out=None, weights=None):
         dt = float(args["dt"])
         scores = _scores(nets, t, x, args.get("labels"))
+        if ode:
+            # probability-flow form -dt*(a x - b s) (cifar/dynamics.py:52,165): the kernel's drift is
+            # -dt*(a x - 2 b' s), so b' = b/2; the diffusion term is switched off with zero noise.
+            return ops.step_vpsde(x, torch.zeros_like(x), scores, logq, sde.dlog_alphadt(t), 0.5 * sde.beta(t),
+                                  sde.sigma(t), dt, mode, dlogq_mode, temperature=temperature, x_out=x_out,
+                                  weights=weights)
         noise = _noise_for(args, t, x)
         return ops.step_vpsde(x, noise, scores, logq, sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t), dt,
                               mode, dlogq_mode, temperature=temperature, x_out=x_out, weights=weights)
@@ -86,10 +92,7 @@ def get_joint_and_vf(key, models, states):
 def get_avg_vf(key, models, states, stoch=True):
     """Averaged vector field (cifar/dynamics.py:140-173); with one model this is the plain
     reverse SDE used by evaluate_fid (cifar/run_lib.py:145).  dlogq = 0 (:171)."""
-    if not stoch:
-        raise NotImplementedError("the deterministic (probability-flow ODE) variant is SURVEY.md §8(f) row N1, "
-                                  "outside the stochastic hot path")
-    return _make(_nets(models, states), ops.MODE_AVG, ops.DLOGQ_NONE, 1.0, len(models))
+    return _make(_nets(models, states), ops.MODE_AVG, ops.DLOGQ_NONE, 1.0, len(models), ode=not stoch)
 
 
 def get_vpsde(config, model, train):
@@ -109,7 +112,9 @@ def get_vpsde(config, model, train):
         raise NotImplementedError("training (DSM loss) is outside the sampling path")
 
     def vector_field(t, data, args):
-        raise NotImplementedError("the single-model probability-flow ODE field (cifar/dynamics.py:48-54) is "
-                                  "SURVEY.md §8(f) row N1")
+        # cifar/dynamics.py:48-54: dx = -dt*(a x - b s) with the raw (non-EMA) parameters, dlogq = zeros (B, 1)
+        net = mutils.get_model_fn(model, args["state"].model_params, train=False)
+        vf = _make([net], ops.MODE_AVG, ops.DLOGQ_NONE, 1.0, 1, ode=True)
+        return vf(t, (data[0], None), args)
 
     return q_t, loss, vector_field

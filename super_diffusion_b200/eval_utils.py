@@ -30,8 +30,12 @@ def get_generator(models, config, vector_field, train=False, dt=None, device=Non
         g.manual_seed(seed)
         return torch.randn(shape, generator=g, device=device, dtype=torch.float32), seed
 
-    def artifact_generator(key, labels, state=None):
+    def artifact_generator(key, labels, state=None, x0=None, noise=None):
+        """``x0`` / ``noise`` ([n, *shape]) override the draws made from ``key`` (parity tests feed the
+        reference's recorded draws); the reference signature is (key, labels)."""
         x, seed = _x0(key)
+        if x0 is not None:
+            x = x0.to(device, torch.float32).reshape(shape).clone()
         t = 1.0
         n = int(t / step_dt)
         logq = torch.zeros(shape[0], n_models, device=device, dtype=torch.float32)
@@ -39,7 +43,9 @@ def get_generator(models, config, vector_field, train=False, dt=None, device=Non
         if state is not None:
             args["state"] = state
         fast = getattr(vector_field, "step", None)
-        for _ in range(n):
+        for i in range(n):
+            if noise is not None:
+                args["noise"] = noise[i].to(device, torch.float32).reshape(shape).contiguous()
             if fast is not None:
                 x, logq, _ = fast(t, x, logq, args, x_out=x)
             else:
