@@ -65,6 +65,8 @@ struct GemmParams {
                               //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
   int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile, share the B tile via TMA multicast
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
+  int swap;                   // 1 (dual, conv mode, N = 128): operands swapped inside the MMA -- D^T[128 channels x 256 pixels] =
+                              //    W[128 x K] * X^T: ONE M=128, N=256 instruction per K step instead of two N=128 ones (see launch_gemm)
   long long out_batch_stride; // elements
   int h_box, tiles_per_img, imgs_per_tile;
   int M_total, HW, N_out, block_n, n_tiles, m_tiles, num_kb;
@@ -429,7 +431,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             // (tap row, tap column, channel block) advance as counters, no div/mod: this single thread issues every TMA
             // of the CTA, and ncu showed it busy while the MMA warp waited for data with the div/mod chain of the first version
             const int tside = taps == 9 ? 3 : (taps == 4 ? 2 : 1);
-            const uint32_t tx = PAIR ? 2u * (A_BYTES + b_cta_bytes) : (uint32_t)nsub * A_BYTES + b_cta_bytes;
+            const uint32_t tx = (PAIR ? 2u : 1u) * ((uint32_t)nsub * A_BYTES + b_cta_bytes);
             int kb = kb_base;
             for (int th = 0; th < tside; ++th)
               for (int tw = 0; tw < tside; ++tw) {
@@ -461,6 +463,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       // instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), K-major both, N>>3 @17, M>>4 @24
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)((PAIR ? 2 * BM : BM) >> 4) << 24);
+      const uint32_t idesc_swap = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(2 * BM >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -480,13 +483,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             const uint32_t sa = smem_u32(smem + (size_t)stage * STAGE_BYTES);
             for (int g = 0; g < groups; ++g) {
               const uint64_t b_desc = umma_desc_sw128(sa + b_off + (uint32_t)g * b_tile_bytes);
+              if (p.swap) {
+                // weights are the M = 128 operand, the two adjacent pixel tiles (contiguous in the slot: 256 rows) the N = 256 one
+                const uint64_t x_desc = umma_desc_sw128(slab ? sa + (uint32_t)g * row_pitch : sa);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k)
+                  umma_bf16(d_tmem, b_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc_swap, accumulate | (uint32_t)k);
+                accumulate = 1;
+                continue;
+              }
               for (int sub = 0; sub < nsub; ++sub) {
                 // slab: vertical tap g of sub-tile `sub` = the slab rows starting (g + sub * h_box) image rows in
                 const uint32_t a_addr = slab ? sa + (uint32_t)(g + sub * p.h_box) * row_pitch : sa + (uint32_t)sub * A_BYTES;
                 const uint64_t a_desc = umma_desc_sw128(a_addr);
 #pragma unroll
                 for (int k = 0; k < BK / UMMA_K; ++k) {   // +32 B per UMMA_K inside the swizzle atom
-                  if constexpr (PAIR) umma_bf16_pair(d_tmem, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                  if constexpr (PAIR) umma_bf16_pair(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
                   else umma_bf16(d_tmem + (uint32_t)sub * 128u, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
                 }
               }
@@ -517,6 +529,78 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       tcgen05_fence_after();
       const int row = q * 32 + lane;
       const int n_base = n_tile * p.block_n;
+      if (p.swap) {
+        // ---- swapped tile: TMEM lane = output channel, column = pixel (256 pixels = the unit's two m-tiles, one image).
+        // bias / time-embedding bias are one register per thread, GroupNorm channel sums are thread-local running sums
+        // (no shuffles); a lane-pair exchange packs adjacent channels so every store instruction writes two 64-byte
+        // runs of the NHWC row (even lanes pixel P, odd lanes pixel P + 1).
+        const int et = threadIdx.x - 64;
+        const int ch = n_base + row;
+        const bool ch_ok = ch < p.N_out;
+        const int m_tile0 = m_unit * 2;
+        const size_t pix0 = (size_t)m_tile0 * BM;
+        float bv = 0.f;
+        if (ch_ok) {
+          if (p.bias) bv = p.bias[ch];
+          if (p.rowbias) bv += p.rowbias[(size_t)min((int)(pix0 / p.HW), (p.M_total - 1) / p.HW) * p.rowbias_ld + ch];
+        }
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
+        float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
+        const bool odd = (lane & 1) != 0;
+        __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + (ch & ~1);
+        const bool pair_ok = (ch | 1) < p.N_out;
+        for (int c = chalf * 32; c < 2 * BM; c += 64) {
+          uint32_t r[2][16];
+          tmem_ld16(taddr + c, r[0]);
+          tmem_ld16(taddr + c + 16, r[1]);
+          tmem_wait_ld();
+          const int sub = c >> 7;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = __uint_as_float(r[h][j]) + bv;
+              if (p.flags & SD_EPI_SWISH) x = swishf(x);
+              v[j] = x;
+              ssum[sub] += x;
+              ssq[sub] = fmaf(x, x, ssq[sub]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) {
+              const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
+              const __nv_bfloat162 h2 = odd ? __floats2bfloat162_rn(recv, v[j + 1]) : __floats2bfloat162_rn(v[j], recv);
+              const size_t pix = pix0 + (size_t)(c + h * 16 + j + (odd ? 1 : 0));
+              if (pair_ok && pix < (size_t)p.M_total)
+                *reinterpret_cast<__nv_bfloat162*>(obase + pix * (size_t)p.out_ld) = h2;
+            }
+          }
+        }
+        if (p.stats_out) {
+          float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
+          wstat[((chalf * 2 + 0) * 2 + 0) * BM + row] = ssum[0];
+          wstat[((chalf * 2 + 0) * 2 + 1) * BM + row] = ssq[0];
+          wstat[((chalf * 2 + 1) * 2 + 0) * BM + row] = ssum[1];
+          wstat[((chalf * 2 + 1) * 2 + 1) * BM + row] = ssq[1];
+          epi_bar();
+          for (int i = et; i < 4 * BM; i += EPI_THREADS) {
+            const int sub = i / (2 * BM), which = (i / BM) & 1, n = i & (BM - 1);
+            const int m_tile = m_tile0 + sub;
+            if (m_tile < p.m_tiles && n_base + n < p.N_out) {
+              const float t = wstat[((0 * 2 + sub) * 2 + which) * BM + n] + wstat[((1 * 2 + sub) * 2 + which) * BM + n];
+              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + p.stats_slot0 + (m_tile % p.tiles_per_img);
+              p.stats_out[(slot * 2 + which) * p.N_out + n_base + n] = t;
+            }
+          }
+          epi_bar();
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
         size_t row_off;
@@ -745,6 +829,15 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
       p.cluster = 2;
     }
   }
+  // N = 128 conv layers (all 32x32 layers of the score-net): as two 128 x 128 x 16 instructions per K step (dual) the tensor
+  // pipe ran at 45-60 % -- every 64-clk instruction re-reads its 4 KB A tile AND the 4 KB weight tile from shared memory
+  // (128 B/clk, the whole SM port, shared with the TMA writes).  Swapped, the weights are the M = 128 operand and the 256
+  // pixels the N = 256 operand: one 128-clk instruction per K step, 12 KB of operand reads (96 B/clk) -- the shape the
+  // N = 256 layers already run at 85-95 % of peak with.  The accumulator is then [channel][pixel]; see the epilogue.
+  static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
+  p.swap = (want_swap && p.dual && !p.pair && p.cluster == 1 && !p.flat && p.up_phase < 0 && !p.stride2 && N == 128 &&
+            p.imgs_per_tile == 1 && (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX)) && !residual &&
+            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0) ? 1 : 0;
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
     const int nsub_h = p.dual ? 2 : 1;

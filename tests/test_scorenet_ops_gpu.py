@@ -335,3 +335,36 @@ def test_conv_gemm_pair_slab_multisegment(cuda):
     out2 = ops.conv_gemm([(x, 9)], w2)
     ref2 = F.conv2d(x.float().permute(0, 3, 1, 2), w2.float().reshape(256, 3, 3, 64).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
     _close(out2, ref2.cpu())
+
+
+def test_conv_gemm_swapped_n128(cuda):
+    """N = 128 conv layers with >= 2*148 tiles run operand-swapped (weights = M operand, 256 pixels = N operand, accumulator
+    [channel][pixel]): activation slabs, 1-tap segments, bias + row bias, thread-local GN statistics, lane-pair packed stores."""
+    B, H, W, Co, C0, C1 = 40, 32, 32, 128, 128, 64
+    g = torch.Generator().manual_seed(47)
+    a2 = _bf(torch.randn(B, H, W, Co, generator=g)).to(cuda)
+    xa = _bf(torch.randn(B, H, W, C0, generator=g)).to(cuda)
+    xb = _bf(torch.randn(B, H, W, C1, generator=g)).to(cuda)
+    w = _bf(torch.cat([torch.randn(Co, 9 * Co, generator=g) / math.sqrt(9 * Co),
+                       torch.randn(Co, C0 + C1, generator=g) / math.sqrt(C0 + C1)], dim=1)).to(cuda)
+    bias = torch.randn(Co, generator=g).to(cuda)
+    rowbias = torch.randn(B, 512, generator=g).to(cuda)
+    out = ops.conv_gemm([(a2, 9), (xa, 1), (xb, 1)], w, bias=bias, rowbias=rowbias[:, 256:256 + Co], want_stats=True)
+    wf = w.float()
+    ref = F.conv2d(a2.float().permute(0, 3, 1, 2), wf[:, :9 * Co].reshape(Co, 3, 3, Co).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) \
+        + torch.einsum("bhwc,nc->bhwn", torch.cat([xa, xb], -1).float(), wf[:, 9 * Co:]) + bias + rowbias[:, None, None, 256:256 + Co]
+    _close(out, ref.cpu())
+    st, nt = out.gn_stats
+    assert nt == 8 and st.shape == (B, 8, 2, Co)
+    tiles = out.float().reshape(B, 8, 128, Co)
+    assert torch.allclose(st[:, :, 0], tiles.sum(2), rtol=2e-2, atol=0.5)
+    assert torch.allclose(st[:, :, 1], (tiles ** 2).sum(2), rtol=2e-2, atol=0.5)
+    # swish epilogue, no bias, 16x16 images (2 m-tiles per image = one unit per image), 1-tap only
+    x = _bf(torch.randn(301, 16, 16, 64, generator=g)).to(cuda)
+    w2 = _bf(torch.randn(128, 9 * 64, generator=g) / math.sqrt(9 * 64)).to(cuda)
+    out2 = ops.conv_gemm([(x, 9)], w2, swish=True)
+    ref2 = F.conv2d(x.float().permute(0, 3, 1, 2), w2.float().reshape(128, 3, 3, 64).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    _close(out2, (ref2 * torch.sigmoid(ref2)).cpu())
+    w3 = _bf(torch.randn(128, 64, generator=g) / 8).to(cuda)
+    out3 = ops.conv_gemm([(x, 1)], w3, bias=bias)
+    _close(out3, (torch.einsum("bhwc,nc->bhwn", x.float(), w3.float()) + bias).cpu())
