@@ -545,43 +545,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           if (p.rowbias) bv += p.rowbias[(size_t)min((int)(pix0 / p.HW), (p.M_total - 1) / p.HW) * p.rowbias_ld + ch];
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN;
-        float ssum[2] = {0.f, 0.f}, ssq[2] = {0.f, 0.f};
         const bool odd = (lane & 1) != 0;
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + (ch & ~1);
         const bool pair_ok = (ch | 1) < p.N_out;
-        for (int c = chalf * 32; c < 2 * BM; c += 64) {
-          uint32_t r[2][16];
-          tmem_ld16(taddr + c, r[0]);
-          tmem_ld16(taddr + c + 16, r[1]);
-          tmem_wait_ld();
-          const int sub = c >> 7;
+        const bool do_stats = p.stats_out != nullptr;
+        float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
+        float ssum = 0.f, ssq = 0.f;
+        if (!(p.flags & 0x100u)) {      // 0x100: timing probe (tools/gemm_probe.py) -- release the accumulator without draining it
+          // four 32-column groups per warp (columns chalf*32 + it*64); groups 0,1 belong to the unit's first m-tile, 2,3 to
+          // the second.  Rolled on purpose: unrolled, the epilogue was ~4000 instructions (64 KB of SASS) and ncu showed 17 %
+          // of all stall samples as instruction-cache misses (stall_no_inst).
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            const int c = chalf * 32 + it * 64;
+            uint32_t r[2][16];
+            tmem_ld16(taddr + c, r[0]);
+            tmem_ld16(taddr + c + 16, r[1]);
+            tmem_wait_ld();
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float v[16];
+            for (int h = 0; h < 2; ++h) {
+              float v[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float x = __uint_as_float(r[h][j]) + bv;
-              if (p.flags & SD_EPI_SWISH) x = swishf(x);
-              v[j] = x;
-              ssum[sub] += x;
-              ssq[sub] = fmaf(x, x, ssq[sub]);
+              for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(r[h][j]) + bv;
+                v[j] = x;
+                ssum += x;
+                ssq = fmaf(x, x, ssq);
+              }
+              __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+              const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;    // tiles are whole (HW % 256 == 0)
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
+                const __nv_bfloat162 h2 = odd ? __floats2bfloat162_rn(recv, v[j + 1]) : __floats2bfloat162_rn(v[j], recv);
+                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = h2;
+              }
             }
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) {
-              const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
-              const __nv_bfloat162 h2 = odd ? __floats2bfloat162_rn(recv, v[j + 1]) : __floats2bfloat162_rn(v[j], recv);
-              const size_t pix = pix0 + (size_t)(c + h * 16 + j + (odd ? 1 : 0));
-              if (pair_ok && pix < (size_t)p.M_total)
-                *reinterpret_cast<__nv_bfloat162*>(obase + pix * (size_t)p.out_ld) = h2;
+            if (do_stats && (it & 1)) {
+              const int sub = it >> 1;
+              wstat[((chalf * 2 + sub) * 2 + 0) * BM + row] = ssum;
+              wstat[((chalf * 2 + sub) * 2 + 1) * BM + row] = ssq;
+              ssum = 0.f; ssq = 0.f;
             }
           }
         }
-        if (p.stats_out) {
-          float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
-          wstat[((chalf * 2 + 0) * 2 + 0) * BM + row] = ssum[0];
-          wstat[((chalf * 2 + 0) * 2 + 1) * BM + row] = ssq[0];
-          wstat[((chalf * 2 + 1) * 2 + 0) * BM + row] = ssum[1];
-          wstat[((chalf * 2 + 1) * 2 + 1) * BM + row] = ssq[1];
+        if (do_stats) {
           epi_bar();
           for (int i = et; i < 4 * BM; i += EPI_THREADS) {
             const int sub = i / (2 * BM), which = (i / BM) & 1, n = i & (BM - 1);
@@ -836,7 +844,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // N = 256 layers already run at 85-95 % of peak with.  The accumulator is then [channel][pixel]; see the epilogue.
   static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
   p.swap = (want_swap && p.dual && !p.pair && p.cluster == 1 && !p.flat && p.up_phase < 0 && !p.stride2 && N == 128 &&
-            p.imgs_per_tile == 1 && (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX)) && !residual &&
+            p.imgs_per_tile == 1 && (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
             (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0) ? 1 : 0;
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot

@@ -8,7 +8,15 @@
 
 namespace sdb {
 
-__device__ __forceinline__ float swish_f(float v) { return __fdividef(v, 1.f + __expf(-v)); }   // MUFU ex2 + rcp
+// swish(v) = v * sigmoid(v) = h + h * tanh(h), h = v / 2: ONE MUFU op (tanh.approx, max rel. error 2^-11, below the bf16
+// rounding of the result) instead of ex2 + rcp -- the GroupNorm apply pass needs ~1.5 T elements/s to stream at HBM rate,
+// and two MUFU ops per element is 70 % of the chip's 16 / clk / SM
+__device__ __forceinline__ float swish_f(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
@@ -173,6 +181,74 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
       f[e] = p.apply_swish ? swish_f(y) : y;
     }
     *reinterpret_cast<uint4*>(dst + (size_t)px * C) = pack8(f);
+  }
+}
+
+// Small activations (H*W*C <= 32768 elements per sample: the 8x8 and 4x4 levels): one CTA per sample, the whole sample
+// register-resident -> ONE kernel, one read and one write (the streaming form needs a statistics launch + an apply
+// launch and re-reads the tensor; at 4-33 MB per tensor that was 22-41 us per GroupNorm, launch-latency bound).
+// Requires C/8 to divide 256 and C/32 to be a multiple of 8 (C = 256, 512), so a thread's 8 channels sit in one group.
+template <int NV>
+__global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ GnParams p) {
+  __shared__ float part[256 * 2];
+  __shared__ float g_stat[64];
+  const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32, vpg = cpg / 8;   // vectors per group
+  const int sample = blockIdx.x, tid = threadIdx.x;
+  const int cv = tid % VC, r = tid / VC, rows_per_pass = 256 / VC;
+  const int c0 = cv * 8;
+  const bool from0 = c0 < p.C0;
+  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0 : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
+  const int src_ld = from0 ? p.C0 : p.C1;
+  uint4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(r + j * rows_per_pass) * src_ld);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float f[8];
+    unpack8(v[j], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s += f[e]; q = fmaf(f[e], f[e], q); }
+  }
+  part[tid * 2] = s;
+  part[tid * 2 + 1] = q;
+  __syncthreads();
+  if (tid < 32) {        // group tid: vectors [tid*vpg, (tid+1)*vpg) of every pixel row, fixed order
+    double sum = 0.0, sq = 0.0;
+    for (int rr = 0; rr < rows_per_pass; ++rr)
+      for (int k = 0; k < vpg; ++k) {
+        const int t = rr * VC + tid * vpg + k;
+        sum += (double)part[t * 2];
+        sq += (double)part[t * 2 + 1];
+      }
+    const double n = (double)p.HW * cpg;
+    const double mean = sum / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    g_stat[tid * 2] = (float)mean;
+    g_stat[tid * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+  }
+  __syncthreads();
+  const int grp = c0 / cpg;
+  const float mean = g_stat[grp * 2], rstd = g_stat[grp * 2 + 1];
+  float sc[8], sh[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float rs = rstd * p.gamma[c0 + e];
+    sc[e] = rs;
+    sh[e] = p.beta[c0 + e] - mean * rs;
+  }
+  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    float f[8];
+    unpack8(v[j], f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float y = fmaf(f[e], sc[e], sh[e]);
+      f[e] = p.apply_swish ? swish_f(y) : y;
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)(r + j * rows_per_pass) * C) = pack8(f);
   }
 }
 
@@ -437,6 +513,19 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   p.C0 = C0; p.C1 = C1; p.B = B; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.apply_swish = apply_swish;
   p.out = (__nv_bfloat16*)out;
+  if (!stats0 && !stats1 && (C == 256 || C == 512) && ((size_t)HW * C / 8) % 256 == 0) {
+    const size_t nv = (size_t)HW * C / 8 / 256;
+    void (*kern)(const GnParams) = nullptr;
+    if (nv == 1) kern = gn_small_kernel<1>;
+    else if (nv == 2) kern = gn_small_kernel<2>;
+    else if (nv == 4) kern = gn_small_kernel<4>;
+    else if (nv == 8) kern = gn_small_kernel<8>;
+    else if (nv == 16) kern = gn_small_kernel<16>;
+    if (kern) {
+      kern<<<(unsigned)B, 256, 0, st>>>(p);
+      return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (small) launch");
+    }
+  }
   size_t used = 0;
   // statistics pass only for the sources whose producer did not already emit per-tile channel sums
   for (int srcI = 0; srcI < 2; ++srcI) {

@@ -314,7 +314,9 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
                                 _ptr(st1), int(n1), _ptr(scratch), scratch.numel(), _ptr(out), _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
-        _count(1 + (st0 is None) + (x1 is not None and st1 is None))
+        C, nv = C0 + C1, HW * (C0 + C1) // 8
+        small = st0 is None and st1 is None and C in (256, 512) and nv % 256 == 0 and nv // 256 in (1, 2, 4, 8, 16)
+        _count(1 if small else 1 + (st0 is None) + (x1 is not None and st1 is None))
     return out
 
 

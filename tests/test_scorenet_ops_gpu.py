@@ -126,7 +126,9 @@ def test_batched_gemm_strided_qkv_views(cuda):
 
 @pytest.mark.parametrize("B,H,C0,C1,swish", [(3, 32, 128, 0, True), (2, 32, 256, 128, True), (2, 16, 256, 256, True),
                                             (5, 8, 256, 0, False), (9, 4, 256, 256, True), (2, 32, 128, 128, True),
-                                            (2, 16, 128, 0, True), (1, 16, 256, 128, True)])
+                                            (2, 16, 128, 0, True), (1, 16, 256, 128, True),
+                                            # single-kernel register-resident form (8x8 / 4x4 levels, C = 256 / 512)
+                                            (7, 8, 256, 0, True), (5, 8, 256, 256, True), (6, 4, 256, 0, True), (3, 8, 512, 0, True)])
 def test_groupnorm_swish(cuda, B, H, C0, C1, swish):
     g = torch.Generator().manual_seed(B + H + C0 + C1)
     x0 = _bf(1.5 * torch.randn(B, H, H, C0, generator=g) + 0.3)
