@@ -812,6 +812,15 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
   // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
   if (!(flags & SD_EPI_SOFTMAX) && p.block_n > 128 && p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
+  // 1x1 layers (NIN, attention projections; K = 256..512) are bound by the epilogue and the output write, not by the MMAs:
+  // run them as N = 128 column blocks so they take the operand-swapped path below (64-byte store runs, thread-local GN sums)
+  static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
+  bool all_1tap = !p.flat;
+  for (int sgi = 0; sgi < p.nseg; ++sgi) all_1tap = all_1tap && p.seg_taps[sgi] == 1;
+  const bool swap_epi_ok = want_swap && !p.flat && p.up_phase < 0 && !p.stride2 && (N % 128) == 0 && p.imgs_per_tile == 1 &&
+                           (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
+                           (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0;
+  if (swap_epi_ok && all_1tap && N > 128) p.block_n = 128;
   p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
   // narrow N: pair two m-tiles per CTA tile so the B tile is fetched once per 256 rows (same smem traffic per
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
@@ -842,10 +851,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // (128 B/clk, the whole SM port, shared with the TMA writes).  Swapped, the weights are the M = 128 operand and the 256
   // pixels the N = 256 operand: one 128-clk instruction per K step, 12 KB of operand reads (96 B/clk) -- the shape the
   // N = 256 layers already run at 85-95 % of peak with.  The accumulator is then [channel][pixel]; see the epilogue.
-  static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
-  p.swap = (want_swap && p.dual && !p.pair && p.cluster == 1 && !p.flat && p.up_phase < 0 && !p.stride2 && N == 128 &&
-            p.imgs_per_tile == 1 && (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
-            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0) ? 1 : 0;
+  p.swap = (swap_epi_ok && p.dual && !p.pair && p.cluster == 1 && p.block_n == 128) ? 1 : 0;
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
     const int nsub_h = p.dual ? 2 : 1;

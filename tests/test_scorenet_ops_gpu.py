@@ -370,3 +370,25 @@ def test_conv_gemm_swapped_n128(cuda):
     w3 = _bf(torch.randn(128, 64, generator=g) / 8).to(cuda)
     out3 = ops.conv_gemm([(x, 1)], w3, bias=bias)
     _close(out3, (torch.einsum("bhwc,nc->bhwn", x.float(), w3.float()) + bias).cpu())
+
+
+def test_conv_gemm_swapped_1x1_multi_ntile(cuda):
+    """1x1 layers with N = 256 / 512 run as N = 128 column blocks through the operand-swapped path (n_tiles > 1):
+    attention q,k projection (bias) and out-projection + identity residual segment with GN statistics."""
+    B, H, C = 160, 16, 256
+    g = torch.Generator().manual_seed(53)
+    h = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    x = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    wqk = _bf(torch.randn(2 * C, C, generator=g) / 16).to(cuda)
+    bqk = torch.randn(2 * C, generator=g).to(cuda)
+    qk = ops.conv_gemm([(h, 1)], wqk, bias=bqk)
+    _close(qk, (torch.einsum("bhwc,nc->bhwn", h.float(), wqk.float()) + bqk).cpu())
+    wo = _bf(torch.cat([torch.randn(C, C, generator=g) / 16, torch.eye(C)], dim=1)).to(cuda)
+    bo = torch.randn(C, generator=g).to(cuda)
+    out = ops.conv_gemm([(h, 1), (x, 1)], wo, bias=bo, want_stats=True)
+    ref = torch.einsum("bhwc,nc->bhwn", torch.cat([h, x], -1).float(), wo.float()) + bo
+    _close(out, ref.cpu())
+    st, nt = out.gn_stats
+    tiles = out.float().reshape(B, nt, 128, C)
+    assert torch.allclose(st[:, :, 0], tiles.sum(2), rtol=2e-2, atol=0.5)
+    assert torch.allclose(st[:, :, 1], (tiles ** 2).sum(2), rtol=2e-2, atol=0.5)
