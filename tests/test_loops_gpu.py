@@ -257,3 +257,24 @@ def test_sample_driver_writes_reference_npz_format(cuda, tmp_path):
     assert files == ["samples_0.npz", "samples_1.npz"]
     z = np.load(os.path.join(d, files[0]))
     assert z["samples"].dtype == np.uint8 and z["samples"].shape == (4, 32, 32, 3) and int(z["num_steps"]) == 4
+
+
+def test_cli_joint_eval_from_exported_checkpoints(cuda, tmp_path):
+    """python -m super_diffusion_b200.main --mode eval_joint_fid_stoch --chkpts a.npz,b.msgpack (cifar/main.py:33-35 ->
+    run_lib.evaluate_joint_fid) and --mode eval_fid (deterministic single-model path, run_lib.evaluate_fid :129-167)."""
+    import numpy as np
+    from super_diffusion_b200 import checkpoint, main as cli
+    cfg = vpsde.get_config()
+    pa = mutils.init_model(1, cfg, zero_init_scale=1.0)[1]
+    pb = mutils.init_model(2, cfg, zero_init_scale=1.0)[1]
+    checkpoint.save_npz(tmp_path / "a.npz", pa)
+    (tmp_path / "b.msgpack").write_bytes(checkpoint.to_msgpack_bytes(pb))
+    d = cli.launch(["--config", "vpsde", "--workdir", str(tmp_path), "--mode", "eval_joint_fid_stoch", "--chkpts",
+                    f"{tmp_path / 'a.npz'}, {tmp_path / 'b.msgpack'}", "--batch_size", "4", "--num_batches", "1", "--dt", "0.25"])
+    assert d.endswith(os.path.join("eval", "samples_stoch"))
+    z = np.load(os.path.join(d, "samples_0.npz"))
+    assert z["samples"].dtype == np.uint8 and z["samples"].shape == (4, 32, 32, 3) and int(z["num_steps"]) == 4
+    checkpoint.save_npz(tmp_path / "params_ema.npz", pa)
+    d2 = cli.launch(["--config", "vpsde", "--workdir", str(tmp_path), "--mode", "eval_fid", "--batch_size", "4", "--num_batches", "1",
+                     "--dt", "0.25"])
+    assert d2.endswith(os.path.join("eval", "samples")) and os.path.exists(os.path.join(d2, "samples_0.npz"))
