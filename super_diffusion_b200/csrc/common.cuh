@@ -4,6 +4,7 @@
 #include <cooperative_groups.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 
 namespace sdb {
 
@@ -33,6 +34,26 @@ __device__ __forceinline__ float ld_stream1(const float* p) {
 }
 __device__ __forceinline__ void st4(float* p, const float4& v) {
   asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// ---- programmatic dependent launch ---------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor on the
+// stream is still draining: everything before pdl_wait() (barrier init, TMEM allocation, descriptor prefetch, smem
+// carve-up) overlaps the predecessor's tail; pdl_wait() returns once the predecessor grid has completed and its
+// memory is visible.  pdl_launch_dependents() lets the *next* kernel begin the same way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();   // SDB_PDL=1 (default off, see capi.cu)
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  if (pdl_enabled()) { cfg.attrs = attr; cfg.numAttrs = 1; }
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -361,6 +361,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   if (csize > 1) cluster_sync_all();      // peers' mbarriers are initialised before any multicast / remote commit targets them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_sh;
+  // programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the
+  // previous kernel's tail; its outputs (our A operand / bias tables) are visible after this point
+  pdl_wait();
+  pdl_launch_dependents();
 
   // ---- K loop as a sequence of "steps", one smem ring slot each -------------------------------------------------
   //  plain step: one 64-channel K-block of one filter tap: A tile(s) + one B tile                      (1 MMA group)
@@ -933,15 +937,21 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
   if (p.cluster > 1) {
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = p.cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = p.cluster;
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
   }
+  if (pdl_enabled()) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  if (nattr) { cfg.attrs = attr; cfg.numAttrs = nattr; }
   if (p.pair) return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p), who);
   return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p), who);
 }

@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   const int c0 = cv * 8;
   const __nv_bfloat16* src = p.x + (size_t)sample * p.HW * C + c0;
   const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
+  pdl_wait();
+  pdl_launch_dependents();
   float s[8], q[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
@@ -113,6 +115,8 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
   __shared__ float g_stat[64];
   const int C = p.C0 + p.C1, VC = C / 8, cpg = C / 32;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
+  pdl_wait();
+  pdl_launch_dependents();
   // prologue: every CTA rebuilds its sample's group statistics from the per-chunk channel sums (a few KB from L2;
   // chunks and channels are summed in a fixed order, so all CTAs of a sample -- and every run -- get identical bits)
   for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
@@ -199,6 +203,8 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ G
   const bool from0 = c0 < p.C0;
   const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0 : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
   const int src_ld = from0 ? p.C0 : p.C1;
+  pdl_wait();
+  pdl_launch_dependents();
   uint4 v[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(r + j * rows_per_pass) * src_ld);
@@ -522,8 +528,7 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
     else if (nv == 8) kern = gn_small_kernel<8>;
     else if (nv == 16) kern = gn_small_kernel<16>;
     if (kern) {
-      kern<<<(unsigned)B, 256, 0, st>>>(p);
-      return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (small) launch");
+      return check_cuda(launch_pdl(kern, dim3((unsigned)B), dim3(256), 0, st, p), "sd_groupnorm_swish (small) launch");
     }
   }
   size_t used = 0;
@@ -545,16 +550,14 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
     if (used + need > scratch_floats) return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small");
     used += need;
     if (srcI == 0) { p.part0 = sp.partial; p.nch0 = sp.nchunk; } else { p.part1 = sp.partial; p.nch1 = sp.nchunk; }
-    gn_stats_kernel<<<(unsigned)(B * sp.nchunk), T, sizeof(float) * (size_t)k * 2 * Cs, st>>>(sp);
-    cudaError_t err = cudaGetLastError();
+    cudaError_t err = launch_pdl(gn_stats_kernel, dim3((unsigned)(B * sp.nchunk)), dim3(T), sizeof(float) * (size_t)k * 2 * Cs, st, sp);
     if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
   }
   int k;
   const int T = threads_for(C, k);
   if (T % 32 || T > 256) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   p.nchunk = chunks_for(k, p.px_per_chunk);
-  gn_apply_kernel<<<(unsigned)(B * p.nchunk), T, 0, st>>>(p);
-  return check_cuda(cudaGetLastError(), "sd_groupnorm_swish (apply) launch");
+  return check_cuda(launch_pdl(gn_apply_kernel, dim3((unsigned)(B * p.nchunk)), dim3(T), 0, st, p), "sd_groupnorm_swish (apply) launch");
 }
 
 int sd_attention(const void* qkv, int B, int S, int C, void* out, void* stream) {
