@@ -82,6 +82,22 @@ int sd_step_vpsde_ex(const float* x, const float* noise, const float* const* sco
                      float* logq, float* x_out, float* weights, void* stream,
                      int threads, int vec_per_thread, int cluster);
 
+/* Deterministic (probability-flow ODE) SuperDiff step with a caller-supplied divergence term -- the body of
+ * get_joint_vf.joint_vf after the jax.jvp calls (reference cifar/dynamics.py:87-96), get_avg_vf(stoch=False) (:165-167)
+ * and get_vpsde's vector_field (:48-54):
+ *     w = softmax(T*logq) | 1/M | fixed;   dx = -dt*(a*x - b*sum_i w_i s_i);   x_out = x + dx
+ *     dlogq_i = dlogq_add[b][i] + sum_d s_i/sigma_eps * (dx + dt*(a*x - b*s_i));  CIFAR_MAXSUB subtracts the row max (:95)
+ * with sigma_eps = t + 1e-3 (:85) and dlogq_add = dt*div_i = -dt*b*<jvp_i, eps_i> (:86,:93; see sd_rowdot).
+ * No noise tensor is read: 4*B*D*(M+2) bytes.  sched rows are (a, b, sigma_eps, dt).  SD_MODE_AND is rejected. */
+int sd_step_vpsde_ode(const float* x, const float* const* scores_host, int M, int B, int D,
+                      float a_t, float b_t, float sigma_eps, float dt, const float* sched, const int* step_counter,
+                      int mode, int dlogq_mode, float temperature, const float* logp_bias,
+                      const float* dlogq_add /* [B][M] or NULL */, float* logq, float* x_out, float* weights, void* stream);
+
+/* out[b*out_stride] = scale * <a[b,:], b[b,:]> over D fp32 elements (fp64 reduction): the Hutchinson contraction
+ * (jvp_val*eps).sum((1,2,3)) of cifar/dynamics.py:86 written straight into column i of the [B][M] dlogq_add array. */
+int sd_rowdot(const float* a, const float* b, int B, int D, float scale, float* out, int out_stride, void* stream);
+
 /* Fused EDM-sigma SuperDiff step on Stable-Diffusion latents with
  * classifier-free guidance.  Replaces applications/images/clip_eval.py:395-413
  * (methods "and", "or") and :417-424 ("avg"):
@@ -184,6 +200,18 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
                        const float* stats1 /* same for x1, [B][nchunk1][2][C1] */, int nchunk1,
                        float* scratch /* >= 2*(4736+B)*(C0+C1) + 64*B floats: channel sums of sources without stats, group stats */,
                        size_t scratch_floats, void* out, void* stream);
+
+/* Forward-mode derivative of sd_groupnorm_swish: given the primal sources and their tangents (same layouts) writes
+ * out = act(GN(x)) and dout = d/dh act(GN(x + h*dx)) at h = 0, both bf16 [B,HW,C0+C1]:
+ *     xhat = (x-mean)*rstd,  du = rstd*gamma*(dx - mean_g(dx) - xhat*mean_g(xhat*dx)),  dout = swish'(u)*du.
+ * One link of jax.jvp through cifar/models/ddpm.py (reference cifar/dynamics.py:84).  scratch >= 4*B*64*(C0+C1) floats. */
+int sd_groupnorm_swish_jvp(const void* x0, const void* dx0, int C0, const void* x1, const void* dx1, int C1, int B, int HW,
+                           const float* gamma, const float* beta, float eps, int apply_swish, float* scratch,
+                           size_t scratch_floats, void* out, void* dout, void* stream);
+
+/* JVP of a row softmax from its output: dP = P * (dS - sum_k P_k dS_k) with dS = scale*(dS1 + dS2) (dS2 may be NULL).
+ * P: bf16 [rows][cols], dS1/dS2: fp32, dP: bf16 (attention tangent, cifar/models/layers.py:505-509). */
+int sd_softmax_jvp(const void* P, const float* dS1, const float* dS2, float scale, void* dP, long rows, int cols, void* stream);
 
 /* Single-head self-attention over HW tokens (cifar/models/layers.py:505-509):
  * out = softmax_{HW}(q k^T * C^-1/2) v.  qkv: bf16 [B, S, 3C] (q | k | v

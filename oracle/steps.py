@@ -55,6 +55,25 @@ def or_step_cifar_literal(x, logq, sscores, eps, t, dt, temperature=1e6):
     return dx, dlogq, weights
 
 
+def ode_step_cifar_literal(x, logq, sscores, jvps, probes, t, dt, temperature=1e6):
+    """cifar/dynamics.py:87-96 (get_joint_vf.joint_vf) after the M (score, jvp) evaluations: ``jvps[i]`` = J_i eps_i,
+    ``probes[i]`` = eps_i (Rademacher, :83).  Returns (dx, dlogq (B, M), weights)."""
+    a = S.dlog_alphadt(t)
+    b = S.beta(t)
+    M = sscores.shape[0]
+    red = tuple(range(2, sscores.dim()))
+    vfs = a * x[None] - b * sscores                                        # :85
+    dlogdx = sscores / (t + 1e-3)                                          # :85
+    div = -b * (jvps * probes).reshape(M, x.shape[0], -1).sum(-1)          # :86
+    weights = torch.softmax(temperature * logq, dim=-1)                    # :88
+    w = weights.T.reshape(M, -1, *([1] * (x.dim() - 1)))
+    dx = -dt * (w * vfs).sum(0)                                            # :89
+    dlogq = -(-dt) * div + (dlogdx * (dx[None] - (-dt) * vfs)).sum(red)    # :90
+    dlogq = dlogq.T                                                        # :91
+    dlogq = dlogq - dlogq.max(dim=1, keepdim=True).values                  # :92
+    return dx, dlogq, weights
+
+
 def avg_step_cifar_literal(x, sscores, eps, t, dt, stoch=True):
     """cifar/dynamics.py:155-171 (get_avg_vf.joint_vf).  dlogq is zeros."""
     a = S.dlog_alphadt(t)

@@ -17,15 +17,18 @@ namespace sdb {
 static int step_vpsde_impl(const float* x, const float* noise, const float* const* scores, int M, int B, int D,
                            float a_t, float b_t, float sigma_t, float dt, const float* sched, const int* step_counter,
                            int mode, int dlogq_mode, float temperature, const float* logp_bias, float ito_scale,
-                           float* logq, float* x_out, float* weights, void* stream, int threads, int nv, int cluster) {
+                           float* logq, float* x_out, float* weights, void* stream, int threads, int nv, int cluster,
+                           float mix_scale = 2.f, const float* dlogq_add = nullptr, bool ode = false) {
   if (M < 1 || M > SD_MAX_MODELS) return fail(kErrInvalidArg, "sd_step_vpsde: M must be in [1, 8]");
   if (B < 0 || D < 1) return fail(kErrInvalidArg, "sd_step_vpsde: B >= 0 and D >= 1 required");
   if (mode < SD_MODE_OR || mode > SD_MODE_FIXED) return fail(kErrInvalidArg, "sd_step_vpsde: unknown mode");
   if (dlogq_mode < SD_DLOGQ_CIFAR_MAXSUB || dlogq_mode > SD_DLOGQ_NONE)
     return fail(kErrInvalidArg, "sd_step_vpsde: unknown dlogq_mode");
   if (B == 0) return SD_OK;  // empty batch: nothing to launch (pointers may be null)
-  if (!x || !noise || !scores || !x_out || !weights || (!logq && (mode == SD_MODE_OR || dlogq_mode != SD_DLOGQ_NONE)))
+  if (!x || (!noise && !ode) || !scores || !x_out || !weights || (!logq && (mode == SD_MODE_OR || dlogq_mode != SD_DLOGQ_NONE)))
     return fail(kErrInvalidArg, "sd_step_vpsde: null pointer argument");
+  if (ode && mode == SD_MODE_AND)
+    return fail(kErrUnsupported, "sd_step_vpsde_ode: the AND weights are defined by the noise of the stochastic step (superposition_edu.ipynb:899-905)");
   StepParams p{};
   p.x = x; p.noise = noise;
   for (int i = 0; i < M; ++i) {
@@ -37,6 +40,7 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
   p.M = M; p.B = B; p.D = D;
   p.a = a_t; p.b = b_t; p.sigma = sigma_t; p.dt = dt;
   p.mode = mode; p.dlogq_mode = dlogq_mode; p.temperature = temperature; p.ito_scale = ito_scale;
+  p.mix_scale = mix_scale; p.dlogq_add = dlogq_add;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t err;
 
@@ -51,7 +55,7 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
   }
 
   // vector width: float4 when every base pointer is 16B aligned and D % 4 == 0
-  bool aligned = (D % 4 == 0) && (((uintptr_t)x | (uintptr_t)noise | (uintptr_t)x_out) % 16 == 0);
+  bool aligned = (D % 4 == 0) && (((uintptr_t)x | (uintptr_t)(noise ? noise : x) | (uintptr_t)x_out) % 16 == 0);
   for (int i = 0; i < M; ++i) aligned = aligned && ((uintptr_t)scores[i] % 16 == 0);
   const int vec = aligned ? 4 : 1;
   const int nunits = D / vec;
@@ -126,6 +130,15 @@ int sd_step_vpsde_ex(const float* x, const float* noise, const float* const* sco
   return sdb::step_vpsde_impl(x, noise, scores_host, M, B, D, a_t, b_t, sigma_t, dt, sched, step_counter, mode,
                               dlogq_mode, temperature, logp_bias, ito_scale, logq, x_out, weights, stream, threads,
                               vec_per_thread, cluster);
+}
+
+int sd_step_vpsde_ode(const float* x, const float* const* scores_host, int M, int B, int D,
+                      float a_t, float b_t, float sigma_eps, float dt, const float* sched, const int* step_counter,
+                      int mode, int dlogq_mode, float temperature, const float* logp_bias, const float* dlogq_add,
+                      float* logq, float* x_out, float* weights, void* stream) {
+  return sdb::step_vpsde_impl(x, nullptr, scores_host, M, B, D, a_t, b_t, sigma_eps, dt, sched, step_counter, mode,
+                              dlogq_mode, temperature, logp_bias, 0.f, logq, x_out, weights, stream, 0, 0, 0, 1.f,
+                              dlogq_add, true);
 }
 
 int sd_counter_add(int* counter, int delta, void* stream) {

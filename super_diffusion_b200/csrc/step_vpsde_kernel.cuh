@@ -142,6 +142,9 @@ __device__ void and_increments(const double* tot, const double* kappa, double dt
 __device__ __forceinline__ void write_logq(const StepParams& p, const StepScalars& sc, int sample, int M,
                                            const double* R /* already divided by sigma */) {
   if (p.dlogq_mode == SD_DLOGQ_NONE) return;
+  double Ra[SD_MAX_MODELS];
+  for (int i = 0; i < M; ++i) Ra[i] = R[i] + (p.dlogq_add ? (double)p.dlogq_add[(size_t)sample * M + i] : 0.0);
+  R = Ra;
   double sub = 0.0;
   if (p.dlogq_mode == SD_DLOGQ_CIFAR_MAXSUB) {
     sub = -R[0];
@@ -169,7 +172,8 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
   const int sample = blockIdx.x / csize;
   const StepScalars sc = load_scalars(p);
   const float dta = sc.dt * sc.a, dtb = sc.dt * sc.b;
-  const float c = sqrtf(2.f * sc.sigma * sc.b * sc.dt);
+  const float c = p.noise ? sqrtf(2.f * sc.sigma * sc.b * sc.dt) : 0.f;     // no noise tensor: deterministic (ODE) step
+  const float mixc = p.mix_scale * dtb;
   const int nunits = p.D / VEC;                                   // float4 (or scalar) units per sample
   const int per_cta = (nunits + csize - 1) / csize;
   const int u0 = crank * per_cta;
@@ -197,12 +201,13 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
           const size_t off = base + (size_t)u * VEC;
           if constexpr (VEC == 4) {
             ldv4(xv[j], p.x + off);
-            ldv4(ev[j], p.noise + off);
+            if (p.noise) ldv4(ev[j], p.noise + off);
+            else { ev[j][0] = 0.f; ev[j][1] = 0.f; ev[j][2] = 0.f; ev[j][3] = 0.f; }
 #pragma unroll
             for (int i = 0; i < M; ++i) ldv4(sv[i][j], p.s[i] + off);
           } else {
             xv[j][0] = ld_stream1(p.x + off);
-            ev[j][0] = ld_stream1(p.noise + off);
+            ev[j][0] = p.noise ? ld_stream1(p.noise + off) : 0.f;
 #pragma unroll
             for (int i = 0; i < M; ++i) sv[i][j][0] = ld_stream1(p.s[i] + off);
           }
@@ -218,7 +223,7 @@ __global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__
 #pragma unroll
           for (int i = 0; i < M; ++i) mix = fmaf(w[i], sv[i][j][e], mix);
           const float xe = xv[j][e];
-          const float dx = -dta * xe + 2.f * dtb * mix + c * ev[j][e];
+          const float dx = -dta * xe + mixc * mix + c * ev[j][e];
           o[e] = xe + dx;
           const float q = dx + dta * xe;                // dx + dt*a*x
 #pragma unroll
@@ -345,7 +350,8 @@ __global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_cons
   if (sample >= p.B) return;
   const StepScalars sc = load_scalars(p);
   const float dta = sc.dt * sc.a, dtb = sc.dt * sc.b;
-  const float c = sqrtf(2.f * sc.sigma * sc.b * sc.dt);
+  const float c = p.noise ? sqrtf(2.f * sc.sigma * sc.b * sc.dt) : 0.f;
+  const float mixc = p.mix_scale * dtb;
   const size_t base = (size_t)sample * p.D;
   float w[M];
   double R[M];
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(128) step_vpsde_small_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < M - 1; ++i) mix = fmaf(w[i], s[i] - s[M - 1], mix);
     const float xe = p.x[base + d];
-    const float dx = -dta * xe + 2.f * dtb * mix + c * p.noise[base + d];
+    const float dx = -dta * xe + mixc * mix + (p.noise ? c * p.noise[base + d] : 0.f);
     const float q = dx + dta * xe;
 #pragma unroll
     for (int i = 0; i < M; ++i) R[i] += (double)s[i] * (double)(q - dtb * s[i]);

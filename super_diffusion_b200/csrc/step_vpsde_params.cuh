@@ -18,6 +18,8 @@ struct StepParams {
   float a, b, sigma, dt;
   int mode, dlogq_mode;
   float temperature, ito_scale;
+  float mix_scale;            // dx = -dt*a*x + mix_scale*dt*b*mix + c*noise: 2 for the reverse SDE, 1 for the probability-flow ODE
+  const float* dlogq_add;     // optional [B][M], added to the per-model increment before the max-subtraction (ODE: dt * div_i)
 };
 
 }  // namespace sdb

@@ -53,11 +53,9 @@ def _make(nets, mode, dlogq_mode, temperature, n_models, ode=False):
         dt = float(args["dt"])
         scores = _scores(nets, t, x, args.get("labels"))
         if ode:
-            # probability-flow form -dt*(a x - b s) (cifar/dynamics.py:52,165): the kernel's drift is
-            # -dt*(a x - 2 b' s), so b' = b/2; the diffusion term is switched off with zero noise.
-            return ops.step_vpsde(x, torch.zeros_like(x), scores, logq, sde.dlog_alphadt(t), 0.5 * sde.beta(t),
-                                  sde.sigma(t), dt, mode, dlogq_mode, temperature=temperature, x_out=x_out,
-                                  weights=weights)
+            # probability-flow form -dt*(a x - b s) (cifar/dynamics.py:52,165): the noise-free kernel entry
+            return ops.step_vpsde_ode(x, scores, logq, sde.dlog_alphadt(t), sde.beta(t), float(t) + 1e-3, dt, mode,
+                                      dlogq_mode, temperature=temperature, x_out=x_out, weights=weights)
         noise = _noise_for(args, t, x)
         return ops.step_vpsde(x, noise, scores, logq, sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t), dt,
                               mode, dlogq_mode, temperature=temperature, x_out=x_out, weights=weights)
@@ -79,6 +77,51 @@ def get_joint_stoch_vf(key, models, states, temperature=1e6):
     """SuperDiff-OR, stochastic (cifar/dynamics.py:100-137).  ``temperature`` is the
     reference's hard-coded 1e6 (:124)."""
     return _make(_nets(models, states), ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature, len(models))
+
+
+def _probe_for(args, t, x, i):
+    probes = args.get("probes") if isinstance(args, dict) else None
+    if probes is not None:
+        return probes[i]
+    g = torch.Generator(device=x.device)
+    g.manual_seed(((_seed_of(args["key"]) * 1_000_003 + int(round(float(t) * 10_000))) * 31 + i + 1) % (2 ** 63 - 1))
+    return (torch.randint(0, 2, x.shape, generator=g, device=x.device, dtype=torch.int32) * 2 - 1).to(torch.float32)
+
+
+def get_joint_vf(key, models, states, temperature=1e6):
+    """SuperDiff-OR along the probability-flow ODE with Hutchinson divergence estimates (cifar/dynamics.py:59-97).
+
+    Per model: a Rademacher probe eps_i (:83; ``args['probes']`` -- a list of M tensors -- overrides the draw made from
+    (key, t, i)), (s_i, J_i eps_i) by forward-mode differentiation of the score model (:84), div_i = -b <J_i eps_i, eps_i>
+    (:86); then one fused kernel: w = softmax(1e6 logq) (:88), dx = -dt sum_i w_i (a x - b s_i) (:89) and
+    dlogq_i = dt div_i + sum s_i/(t + 1e-3) * (dx + dt (a x - b s_i)), minus the row max (:90-95)."""
+    jvps = [mutils.get_model_jvp_fn(models[i], states[i].params_ema) for i in range(len(models))]
+    M = len(models)
+
+    def step(t, x, logq, args, x_out=None, weights=None):
+        dt = float(args["dt"])
+        tt = torch.full((1,), float(t), device=x.device, dtype=torch.float32)
+        add = torch.empty(x.shape[0], M, device=x.device, dtype=torch.float32)
+        scores = []
+        for i, f in enumerate(jvps):
+            eps = _probe_for(args, t, x, i).contiguous()
+            s, js = f(tt, x, args.get("labels"), eps)
+            scores.append(s.contiguous())
+            ops.rowdot(js.contiguous(), eps, scale=-dt * sde.beta(t), out=add, column=i)      # dt * div_i
+        return ops.step_vpsde_ode(x, scores, logq, sde.dlog_alphadt(t), sde.beta(t), float(t) + 1e-3, dt, ops.MODE_OR,
+                                  ops.DLOGQ_CIFAR_MAXSUB, temperature=temperature, dlogq_add=add, x_out=x_out, weights=weights)
+
+    def joint_vf(t, data, args):
+        x, logq = data
+        if logq is None or logq.shape[-1] != M:
+            logq = torch.zeros(x.shape[0], M, device=x.device, dtype=torch.float32)
+        lq = logq.clone()
+        x_next, lq, _ = step(t, x, lq, args)
+        return x_next - x, lq - logq
+
+    joint_vf.step = step
+    joint_vf.num_models = M
+    return joint_vf
 
 
 def get_joint_and_vf(key, models, states):

@@ -180,24 +180,7 @@ class _Bound:
         B = x.shape[0]
         if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise ValueError("x must be a contiguous float32 CUDA tensor (NHWC)")
-        labels = None
-        if self.class_emb is not None:
-            if y is None:
-                raise ValueError("conditioned score-net needs labels")
-            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
-        if sched is not None:
-            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
-                                     sched=sched, step_counter=step_counter, class_emb=self.class_emb, labels=labels)
-        else:
-            if not torch.is_tensor(t):
-                t = torch.full((1,), float(t), device=x.device, dtype=torch.float32)
-            t = t.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
-            stride = 0 if t.numel() == 1 else 1
-            if stride and t.numel() != B:
-                raise ValueError("t must have one entry per sample")
-            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
-                                     t=t, t_stride=stride, class_emb=self.class_emb, labels=labels)
-        rowbias = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0]    # [B, sum cout]
+        rowbias = self._rowbias(t, x, y, sched, step_counter)
         h = ops.conv_in(x, self.conv_in_w, self.conv_in_b)
         hs = [h]
         for op in self.plan:
@@ -225,6 +208,107 @@ class _Bound:
         assert not hs
         a = ops.groupnorm_swish(h, self.out_g, self.out_be)
         return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)
+
+    def _rowbias(self, t, x, y, sched, step_counter):
+        """Time embedding (ddpm.py:64-68) -> the per-sample bias of every ResBlock's Dense(temb) (layers.py:556): [B, sum cout]."""
+        B = x.shape[0]
+        labels = None
+        if self.class_emb is not None:
+            if y is None:
+                raise ValueError("conditioned score-net needs labels")
+            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
+        if sched is not None:
+            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
+                                     sched=sched, step_counter=step_counter, class_emb=self.class_emb, labels=labels)
+        else:
+            if not torch.is_tensor(t):
+                t = torch.full((1,), float(t), device=x.device, dtype=torch.float32)
+            t = t.to(device=x.device, dtype=torch.float32).reshape(-1).contiguous()
+            stride = 0 if t.numel() == 1 else 1
+            if stride and t.numel() != B:
+                raise ValueError("t must have one entry per sample")
+            act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
+                                     t=t, t_stride=stride, class_emb=self.class_emb, labels=labels)
+        return ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0]    # [B, sum cout]
+
+    # -- forward-mode derivative (Hutchinson probes of the deterministic sampler, cifar/dynamics.py:84) -------------
+    def _res_jvp(self, srcs, dsrcs, i, rowbias):
+        r = self.res[i]
+        two = len(srcs) > 1
+        a1, da1 = ops.groupnorm_swish_jvp(srcs[0], dsrcs[0], r["g1"], r["be1"], x1=srcs[1] if two else None,
+                                          dx1=dsrcs[1] if two else None)
+        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]])
+        dh1 = ops.conv_gemm([(da1, 9)], r["w1"])                     # the time-embedding bias does not depend on x
+        a2, da2 = ops.groupnorm_swish_jvp(h1, dh1, r["g2"], r["be2"])
+        out = ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"])
+        dout = ops.conv_gemm([(da2, 9)] + [(d, 1) for d in dsrcs], r["w2"])
+        return out, dout
+
+    def _attn_jvp(self, x, dx, i):
+        a = self.attn[i]
+        B, H, W, C = x.shape
+        S = H * W
+        g = max(1, 128 // S)
+        if S < 16 or B % g or (g * S) % 16:
+            raise NotImplementedError(f"score-net JVP needs the batch to pack into 128-row attention tiles (B % {g} == 0)")
+        h, dh = ops.groupnorm_swish_jvp(x, dx, a["g"], a["be"], swish=False)
+        nb, Sp = B // g, g * S
+        scale = C ** -0.5
+        qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(nb, Sp, 2 * C)
+        dqk = ops.conv_gemm([(dh, 1)], a["w_qk"]).view(nb, Sp, 2 * C)
+        vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))
+        dvt = ops.batched_gemm(a["w_vT"], dh.view(nb, Sp, C))
+        p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], scale, block=S, C=C)
+        ds1 = ops.batched_gemm(dqk[:, :, :C], qk[:, :, C:], out_f32=True, K=C)       # dq k^T
+        ds2 = ops.batched_gemm(qk[:, :, :C], dqk[:, :, C:], out_f32=True, K=C)       # q dk^T
+        dp = ops.softmax_jvp(p, ds1, ds2, scale)       # off-block entries of a packed tile: p = 0 -> dp = 0
+        o = ops.batched_gemm(p, vt, bias=a["b_v"])
+        do = ops.batched_gemm(p, dvt, residual=ops.batched_gemm(dp, vt))             # dP V + P dV
+        out = ops.conv_gemm([(o.view(B, H, W, C), 1), (x, 1)], a["w_o"], bias=a["b_o"])
+        dout = ops.conv_gemm([(do.view(B, H, W, C), 1), (dx, 1)], a["w_o"])
+        return out, dout
+
+    def jvp(self, t, x, y, v, *, sched=None, step_counter=None, out=None, jvp_out=None):
+        """(score(x), d/dh score(x + h v)|_0): what jax.jvp(sdlogdx_fn, (x,), (eps,)) returns at cifar/dynamics.py:84.
+        Linear layers reuse the tcgen05 GEMMs on the tangent stream (no bias); GroupNorm+swish and the attention softmax
+        have tangent kernels (csrc/scorenet_jvp.cu).  Tangents travel in bf16 like the activations."""
+        _lib.require_device()
+        for name, ten in (("x", x), ("v", v)):
+            if not (ten.is_cuda and ten.dtype == torch.float32 and ten.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous float32 CUDA tensor (NHWC)")
+        if v.shape != x.shape:
+            raise ValueError("tangent must have the shape of x")
+        rowbias = self._rowbias(t, x, y, sched, step_counter)
+        h, dh = ops.conv_in(x, self.conv_in_w, self.conv_in_b), ops.conv_in(v, self.conv_in_w, None)
+        hs = [(h, dh)]
+        for op in self.plan:
+            kind = op[0]
+            if kind == "down_block":
+                h, dh = self._res_jvp([hs[-1][0]], [hs[-1][1]], op[1], rowbias)
+                if op[2] is not None:
+                    h, dh = self._attn_jvp(h, dh, op[2])
+                hs.append((h, dh))
+            elif kind == "downsample":
+                d = self.down[op[1]]
+                h, dh = ops.conv_gemm_s2(hs[-1][0], d["w"], bias=d["b"]), ops.conv_gemm_s2(hs[-1][1], d["w"])
+                hs.append((h, dh))
+            elif kind == "mid":
+                h, dh = self._res_jvp([hs[-1][0]], [hs[-1][1]], op[1], rowbias)
+                h, dh = self._attn_jvp(h, dh, op[2])
+                h, dh = self._res_jvp([h], [dh], op[3], rowbias)
+            elif kind == "up_block":
+                sk, dsk = hs.pop()
+                h, dh = self._res_jvp([h, sk], [dh, dsk], op[1], rowbias)
+            elif kind == "attn":
+                h, dh = self._attn_jvp(h, dh, op[1])
+            elif kind == "upsample":
+                u = self.up[op[1]]
+                h, dh = ops.upconv_gemm(h, u["w4"], bias=u["b"]), ops.upconv_gemm(dh, u["w4"])
+        assert not hs
+        a, da = ops.groupnorm_swish_jvp(h, dh, self.out_g, self.out_be)
+        score = ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)
+        tangent = ops.conv_gemm([(da, 9)], self.out_w, out_f32=True, n_out=self.n_img, out=jvp_out)
+        return score, tangent
 
 
 @utils.register_model(name="score-net")

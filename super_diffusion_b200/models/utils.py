@@ -198,3 +198,16 @@ def get_model_fn(model, params, train=False):
         return bound(t, x, y)
 
     return model_fn
+
+
+def get_model_jvp_fn(model, params):
+    """``jvp_fn(t, x, y, v) -> (model_fn(t, x, y), d/dh model_fn(t, x + h v, y)|_0)`` -- the pair jax.jvp returns at
+    cifar/dynamics.py:84.  The B200 score-net has tangent kernels (``_Bound.jvp``); any other bound model that is a
+    differentiable PyTorch callable goes through ``torch.func.jvp``."""
+    bound = model.bind(params)
+    if hasattr(bound, "jvp"):
+        return lambda t, x, y, v: bound.jvp(t, x, y, v)
+
+    def jvp_fn(t, x, y, v):
+        return torch.func.jvp(lambda _x: bound(t, _x, y), (x,), (v,))
+    return jvp_fn

@@ -78,6 +78,59 @@ def step_vpsde(x, noise, scores, logq, a, b, sigma, dt, mode, dlogq_mode, temper
     return x_out, logq, weights
 
 
+def step_vpsde_ode(x, scores, logq, a, b, sigma_eps, dt, mode, dlogq_mode, temperature=1.0, logp_bias=None,
+                   dlogq_add=None, x_out=None, weights=None, sched=None, step_counter=None):
+    """Deterministic SuperDiff / averaged / single-model ODE step (sd_step_vpsde_ode): no noise tensor, drift
+    -dt*(a x - b s_mix), optional per-(sample, model) additive term ``dlogq_add`` (B, M) = dt * divergence estimate."""
+    lib = _lib.load()
+    if isinstance(scores, torch.Tensor):
+        scores = list(scores.unbind(0))
+    M, B = len(scores), x.shape[0]
+    D = x[0].numel()
+    _f32c(x, "x")
+    for i, s in enumerate(scores):
+        _f32c(s, f"scores[{i}]")
+        if s.shape != x.shape:
+            raise ValueError("score shape mismatch")
+    if logq is not None:
+        _f32c(logq, "logq")
+        if logq.shape != (B, M):
+            raise ValueError("logq must be (B, M)")
+    if dlogq_add is not None and (_f32c(dlogq_add, "dlogq_add").shape != (B, M)):
+        raise ValueError("dlogq_add must be (B, M)")
+    if x_out is None:
+        x_out = torch.empty_like(x)
+    if weights is None:
+        weights = torch.empty(B, M, device=x.device, dtype=torch.float32)
+    mode = MODES[mode] if isinstance(mode, str) else mode
+    dlogq_mode = DLOGQ_MODES[dlogq_mode] if isinstance(dlogq_mode, str) else dlogq_mode
+    sp = (ctypes.c_void_p * M)(*[s.data_ptr() for s in scores])
+    rc = lib.sd_step_vpsde_ode(_ptr(x), sp, M, B, D, float(a), float(b), float(sigma_eps), float(dt), _ptr(sched),
+                               _ptr(step_counter), int(mode), int(dlogq_mode), float(temperature), _ptr(logp_bias),
+                               _ptr(dlogq_add), _ptr(logq), _ptr(x_out), _ptr(weights), _stream())
+    _lib.check(rc, "sd_step_vpsde_ode")
+    if B > 0:
+        _count()
+    return x_out, logq, weights
+
+
+def rowdot(a, b, scale=1.0, out=None, column=0):
+    """out[:, column] = scale * sum over all but the first axis of a*b (sd_rowdot); out: (B, M) fp32 or None -> (B,)."""
+    lib = _lib.load()
+    _f32c(a, "a"); _f32c(b, "b")
+    B, D = a.shape[0], a[0].numel()
+    if out is None:
+        out = torch.empty(B, device=a.device, dtype=torch.float32)
+        ptr, stride = out.data_ptr(), 1
+    else:
+        _f32c(out, "out")
+        ptr, stride = out.data_ptr() + 4 * column, out.shape[1]
+    _lib.check(lib.sd_rowdot(_ptr(a), _ptr(b), B, D, float(scale), ctypes.c_void_p(ptr), stride, _stream()), "sd_rowdot")
+    if B > 0:
+        _count()
+    return out
+
+
 def step_edm_cfg(latents, z, v_obj, v_bg, v_unc, ll, sigma, dsigma, mode, guidance=7.5, lift_term=0.0,
                  temperature=1.0, logp=0.0, kappa_fixed=0.5, latents_out=None, kappa_out=None):
     """Fused EDM/CFG SuperDiff step on SD latents (sd_step_edm_cfg).  ll: (B, 2)
@@ -318,6 +371,42 @@ def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
         small = st0 is None and st1 is None and C in (256, 512) and nv % 256 == 0 and nv // 256 in (1, 2, 4, 8, 16)
         _count(1 if small else 1 + (st0 is None) + (x1 is not None and st1 is None))
     return out
+
+
+def groupnorm_swish_jvp(x0, dx0, gamma, beta, x1=None, dx1=None, eps=1e-6, swish=True):
+    """(out, dout) = JVP of GroupNorm(32)+swish over concat(x0, x1) in direction concat(dx0, dx1) (sd_groupnorm_swish_jvp)."""
+    lib = _lib.load()
+    _bf16c(x0, "x0"); _bf16c(dx0, "dx0")
+    B, HW, C0 = x0.shape[0], x0.shape[1] * x0.shape[2], x0.shape[3]
+    C1 = 0
+    if x1 is not None:
+        _bf16c(x1, "x1"); _bf16c(dx1, "dx1")
+        C1 = x1.shape[3]
+    out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
+    dout = torch.empty_like(out)
+    scratch = _gn_scratch_for(x0.device, 4 * max(B, 1) * 64 * (C0 + C1))
+    rc = lib.sd_groupnorm_swish_jvp(_ptr(x0), _ptr(dx0), C0, _ptr(x1), _ptr(dx1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
+                                    _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(scratch), scratch.numel(),
+                                    _ptr(out), _ptr(dout), _stream())
+    _lib.check(rc, "sd_groupnorm_swish_jvp")
+    if B > 0:
+        _count(2)
+    return out, dout
+
+
+def softmax_jvp(P, dS1, dS2, scale):
+    """dP = P * (dS - rowsum(P * dS)), dS = scale * (dS1 + dS2) (sd_softmax_jvp); P bf16, dS fp32, same shape."""
+    lib = _lib.load()
+    _bf16c(P, "P"); _f32c(dS1, "dS1")
+    if dS2 is not None:
+        _f32c(dS2, "dS2")
+    cols = P.shape[-1]
+    rows = P.numel() // cols
+    dP = torch.empty_like(P)
+    _lib.check(lib.sd_softmax_jvp(_ptr(P), _ptr(dS1), _ptr(dS2), float(scale), _ptr(dP), rows, cols, _stream()), "sd_softmax_jvp")
+    if rows > 0:
+        _count()
+    return dP
 
 
 def attention_small(qkv, C, out=None):

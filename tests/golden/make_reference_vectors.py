@@ -8,6 +8,7 @@ CPU-PyTorch API shims of tests/golden/ref_shims/ (README there) and the referenc
 *unmodified from where they lie* under /root/reference:
 
     cifar/dynamics.py            get_joint_stoch_vf, get_avg_vf, get_vpsde          -> ref_cifar_steps.npz
+    cifar/dynamics.py            get_joint_vf (ODE + Hutchinson probes)             -> ref_cifar_ode.npz
     cifar/eval_utils.py          get_generator.artifact_generator (the loop)        -> ref_cifar_loop.npz
     cifar/models/{ddpm,layers,normalization,utils}.py + configs/sm/cifar/vpsde*.py   -> ref_scorenet.npz
     notebooks/superposition_edu.ipynb  code cells (get_stoch_dll, select_kappa, the OR / AND loops)
@@ -127,6 +128,41 @@ def cifar_steps(jax, dynamics):
         assert np.array_equal(f4(eps).astype(np.float64), eps)
         out[name] = dict(kind=kind, t=t, dt=dt, x=f4(x), logq=f4(logq), labels=labels, scores=f4(np.stack(tables)), eps=f4(eps),
                          dx=np.asarray(dx), dlogq=np.asarray(dlogq))
+    return out
+
+
+class NonlinModel:
+    """Smooth non-linear score stand-in with a non-diagonal Jacobian (tests re-implement it in torch):
+    s = -t (x - alpha mu)/var + 0.3 sin(1.7 x + phi) + 0.2 x * roll(x, 1, axis=2)."""
+
+    def apply(self, variables, t, x, y, train=False, mutable=False):
+        p = variables["params"]
+        alpha = np.exp(-0.5 * t * 0.1 - 0.25 * t ** 2 * 19.9)
+        var = alpha ** 2 * 0.25 + t ** 2
+        return -t * (x - alpha * p["mu"]) / var + 0.3 * np.sin(1.7 * x + p["phi"]) + 0.2 * x * np.roll(x, 1, axis=2)
+
+
+def cifar_ode_steps(jax, dynamics):
+    """cifar/dynamics.py:59-97 get_joint_vf (deterministic SuperDiff-OR with Hutchinson probes)."""
+    jax.config.update("jax_enable_x64", True)
+    from jax import random as jr
+    out = {}
+    rng = np.random.default_rng(77)
+    for name, M, B, t, dt in (("ode_m2", 2, 3, 0.55, 5e-3), ("ode_m3", 3, 2, 0.08, 1e-2)):
+        shape = (B, 8, 8, 3)
+        x = f32r(rng.standard_normal(shape))
+        logq = f32r(1e-6 * rng.standard_normal((B, M)))
+        mus = [f32r(0.6 * rng.standard_normal((1, 8, 8, 3))) for _ in range(M)]
+        phis = [float(np.float32(rng.uniform(0, 3))) for _ in range(M)]
+        models = [NonlinModel() for _ in range(M)]
+        states = [St({"mu": mus[i], "phi": phis[i]}) for i in range(M)]
+        vf = dynamics.get_joint_vf(0, models, states)
+        jr.DRAWS.clear(); jr.LOG.clear()
+        dx, dlogq = vf(t, (x, logq), {"key": 3, "labels": np.arange(B) % 10, "dt": dt})
+        assert [k for k, *_ in jr.LOG] == ["randint"] * M
+        probes = np.stack([d.astype(np.float32) * 2 - 1 for d in jr.DRAWS])
+        out[name] = dict(t=t, dt=dt, x=x.astype(np.float32), logq=logq.astype(np.float32), mus=np.stack(mus).astype(np.float32),
+                         phis=np.asarray(phis), probes=probes, dx=np.asarray(dx), dlogq=np.asarray(dlogq))
     return out
 
 
@@ -464,6 +500,7 @@ def main():
     if "cifar" in which:
         save("ref_cifar_steps.npz", cifar_steps(jax, dynamics))
         save("ref_cifar_loop.npz", cifar_loop(jax, dynamics, eval_utils))
+        save("ref_cifar_ode.npz", cifar_ode_steps(jax, dynamics))
     if "scorenet" in which:
         save("ref_scorenet.npz", scorenet(jax, mutils_ref))
     if "toy" in which:

@@ -53,3 +53,14 @@ def grad(fn):
         return asjarr(g.numpy().astype(t.dtype))
 
     return dfn
+
+
+def jvp(fn, primals, tangents):
+    """(fn(x), d/dh fn(x + h v)|_0) by central differences in float64 (h = 1e-6): exact to ~1e-10 for the smooth
+    stand-in score models of the fixtures; jax.jvp itself is third-party (restated, not pinned)."""
+    (x,), (v,) = primals, tangents
+    x64, v64 = _np.asarray(x, dtype=_np.float64), _np.asarray(v, dtype=_np.float64)
+    h = 1e-6
+    out = fn(asjarr(_np.asarray(x)))
+    d = (_np.asarray(fn(asjarr(x64 + h * v64)), dtype=_np.float64) - _np.asarray(fn(asjarr(x64 - h * v64)), dtype=_np.float64)) / (2 * h)
+    return out, asjarr(d.astype(_np.asarray(out).dtype))

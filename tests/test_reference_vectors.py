@@ -76,6 +76,19 @@ class TableModelTorch:
         return lambda t, x, y: params["table"]
 
 
+def nonlin_score(mu, phi, t, x):
+    """NonlinModel of make_reference_vectors.py in torch."""
+    t = float(t)
+    alpha = math.exp(-0.5 * t * 0.1 - 0.25 * t ** 2 * 19.9)
+    var = alpha ** 2 * 0.25 + t ** 2
+    return -t * (x - alpha * mu) / var + 0.3 * torch.sin(1.7 * x + phi) + 0.2 * x * torch.roll(x, 1, dims=2)
+
+
+class NonlinModelTorch:
+    def bind(self, params, device=None):
+        return lambda t, x, y: nonlin_score(params["mu"].to(x.device, x.dtype), params["phi"], float(torch.as_tensor(t).reshape(-1)[0]), x)
+
+
 def sd_unet_stub(x_in, t, phase):
     return 0.8 * x_in * math.cos(phase) + torch.sin(1.3 * x_in + phase + 1e-3 * float(t))
 
@@ -102,6 +115,23 @@ def test_oracle_matches_reference_cifar_steps():
         else:
             dx, dlogq = O.single_ode_step_cifar_literal(x, s[0], t, dt)
             assert _rel(dx, c["dx"]) < 1e-13 and np.array_equal(dlogq.numpy(), c["dlogq"]), name
+
+
+def test_oracle_matches_reference_cifar_ode():
+    """get_joint_vf (cifar/dynamics.py:59-97): scores and J eps from torch.func.jvp of the same stand-in models."""
+    for name, c in _load("ref_cifar_ode.npz").items():
+        t, dt = float(c["t"]), float(c["dt"])
+        x, logq = _t(c["x"], torch.float64), _t(c["logq"], torch.float64)
+        M = c["mus"].shape[0]
+        ss, js = [], []
+        for i in range(M):
+            f = lambda _x, i=i: nonlin_score(_t(c["mus"][i], torch.float64), float(c["phis"][i]), t, _x)
+            s_i, j_i = torch.func.jvp(f, (x,), (_t(c["probes"][i], torch.float64),))
+            ss.append(s_i); js.append(j_i)
+        dx, dlogq, _ = O.ode_step_cifar_literal(x, logq, torch.stack(ss), torch.stack(js), _t(c["probes"], torch.float64), t, dt)
+        assert _rel(dx, c["dx"]) < 1e-12, name
+        # the fixture's jax.jvp stand-in is a central difference (h = 1e-6): ~1e-9 relative on the divergence term
+        assert np.abs(dlogq.numpy() - c["dlogq"]).max() < 1e-7 * (1 + np.abs(c["dlogq"]).max()), name
 
 
 def _oracle_cifar_loop(c):
@@ -265,6 +295,23 @@ def test_cuda_matches_reference_cifar_steps(cuda):
                                      ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6)
             w_ref = torch.softmax(1e6 * _t(c["logq"], torch.float64), dim=-1).numpy()
             assert np.abs(w.cpu().numpy() - w_ref).max() <= 1e-4, name
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_cifar_ode(cuda):
+    """dynamics.get_joint_vf over sd_rowdot + sd_step_vpsde_ode, torch.func.jvp for the caller-supplied models."""
+    from super_diffusion_b200 import dynamics
+    from super_diffusion_b200.models.utils import State
+    for name, c in _load("ref_cifar_ode.npz").items():
+        t, dt = float(c["t"]), float(c["dt"])
+        x, logq = _t(c["x"]).to(cuda), _t(c["logq"]).to(cuda)
+        M = c["mus"].shape[0]
+        models = [NonlinModelTorch() for _ in range(M)]
+        states = [State(params_ema={"mu": _t(c["mus"][i]).to(cuda), "phi": float(c["phis"][i])}) for i in range(M)]
+        vf = dynamics.get_joint_vf(0, models, states)
+        dx, dlogq = vf(t, (x, logq), {"key": 3, "labels": None, "dt": dt, "probes": [_t(p).to(cuda) for p in c["probes"]]})
+        assert np.abs(dx.cpu().numpy() - c["dx"]).max() <= 1e-3 * np.abs(c["dx"]).max() + 4e-6, name
+        assert np.abs(dlogq.cpu().numpy() - c["dlogq"]).max() <= 1e-3 * np.abs(c["dlogq"]).max(), name
 
 
 @pytest.mark.gpu

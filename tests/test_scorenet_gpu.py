@@ -74,3 +74,34 @@ def test_forward_batch_independence_and_schedule_table(cuda):
     counter = torch.ones(1, dtype=torch.int32, device=cuda)
     viat = net(None, x, sched=table, step_counter=counter)
     assert torch.allclose(full, viat, rtol=0, atol=1e-6 + 1e-3 * full.abs().max().item())
+
+
+def test_scorenet_jvp_matches_autodiff_of_oracle(cuda):
+    """_Bound.jvp (tangent GEMMs + GroupNorm/swish and softmax tangent kernels) against torch.func.jvp of the fp64 oracle
+    score-net on the same parameters: the pair jax.jvp returns at cifar/dynamics.py:84.  bf16 tangents: rel-RMS <= 3e-2."""
+    cfg = vpsde.get_config()
+    gen = torch.Generator().manual_seed(11)
+    model, params = mutils.init_model(gen, cfg, zero_init_scale=1.0)
+    params = mutils.perturb_params(params, gen)
+    B = 8                                    # 4x4 attention packs 8 images per 128-row tile
+    x = torch.randn(B, 32, 32, 3, generator=gen)
+    v = (torch.randint(0, 2, (B, 32, 32, 3), generator=gen) * 2 - 1).float()
+    t = torch.full((B,), 0.4)
+    p64 = OS.params_to(params, dtype=torch.float64)
+    ref_s, ref_j = torch.func.jvp(lambda _x: OS.scorenet_apply(p64, cfg, t.double(), _x), (x.double(),), (v.double(),))
+    bound = model.bind(params, cuda)
+    s, j = bound.jvp(t.to(cuda), x.to(cuda), None, v.to(cuda))
+    torch.cuda.synchronize()
+    s0 = bound(t.to(cuda), x.to(cuda), None)   # the plain forward (different GroupNorm kernels: bf16-level differences only)
+    assert (s - s0).abs().max().item() <= 4e-2 * s0.abs().max().item()
+    rms = lambda a, b: ((a.double().cpu() - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt()).item()
+    assert rms(s, ref_s) <= 2e-2, rms(s, ref_s)
+    assert rms(j, ref_j) <= 3e-2, rms(j, ref_j)
+    # the Hutchinson contraction itself (cifar/dynamics.py:86): <J v, v> per sample
+    from super_diffusion_b200 import ops
+    d = ops.rowdot(j, v.to(cuda)).cpu().double()
+    d_ref = (ref_j * v.double()).reshape(B, -1).sum(1)
+    # bf16 tangents: the error of the contraction is a random walk over 3072 terms, |J v| * sqrt(D) * 2^-8-ish, not relative to
+    # the (partly cancelling) sum itself
+    scale = ref_j.reshape(B, -1).norm(dim=1)
+    assert ((d - d_ref).abs() / scale).max().item() <= 1e-1, (d.tolist(), d_ref.tolist(), scale.tolist())   # ~3 sigma of |J v| * 3e-2
