@@ -44,7 +44,7 @@ def _peaks():
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index):
         self.index = index
@@ -73,8 +73,16 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower() == "active"})
+        def _num(r, i):
+            try:
+                return float(r[i])
+            except (IndexError, ValueError):
+                return None
+        pw = [v for v in (_num(r, 6) for r in self.rows) if v is not None]
+        pl = [v for v in (_num(r, 7) for r in self.rows) if v is not None]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": statistics.median(pw) if pw else None,
+                "power_limit_w": max(pl) if pl else None}
 
 
 def _cpu_oracle_step(batch, threads):
@@ -255,10 +263,10 @@ def run_b200(args):
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                           "traffic": None, "kernel": "step_vpsde_kernel", "us_per_launch": step_us,
                           "bytes_per_launch": step_bytes, "peak_kind": f"{peak_kind} copy bandwidth",
-                          "note": "4*B*D*(M+3) algorithmic bytes; standalone launches with a 256 MB L2 flush between them"},
+                          "note": "4*B*D*(M+3) algorithmic bytes / average launch duration over round-robin input sets totalling > 2x the 126 MB L2 (every launch reads HBM), launches captured in one CUDA graph; at this batch (31 MB per launch) the kernel is ramp-bound, see roofline_step_b8192"},
         "roofline_step_b8192": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "bytes_per_launch": 4 * 8192 * D * (M_MODELS + 3),
                                 "and": big.get("and"), "or": big.get("or"),
-                                "note": "same fused step kernel at BASELINE config 3's single-GPU batch (8192), L2 flushed"},
+                                "note": "same fused step kernel at BASELINE config 3's single-GPU batch (8192): 503 MB per launch, input sets rotate so nothing is L2-resident"},
         "scorenet_tflops_whole_step": fwd_tf,
         "gather_ms": gather_ms,
     }
@@ -322,29 +330,50 @@ def _instrumented_step(sampler, ops, torch):
 
 
 def _step_kernel_time(sampler, ops, torch, noise, B=None, mode=None):
+    """Average launch duration of the fused step kernel with cold inputs: R independent input sets, together larger than
+    twice the 126 MB L2, visited round-robin, so every launch reads its operands from HBM ("inputs larger than L2"); the
+    R*k launches are captured in one CUDA graph and timed with events on the launching stream (no host launch latency and
+    no event overhead inside the per-launch figure)."""
     B = sampler.B if B is None else B
     M = sampler.M
+    dev = sampler.device
     mode = ops.MODE_OR if mode is None else mode
-    flush = torch.empty(64 * 1024 * 1024, device=sampler.device, dtype=torch.float32)   # 256 MB > 126 MB L2
-    x = torch.randn(B, D, device=sampler.device)
-    xo = torch.empty_like(x)
-    sc = [torch.randn(B, D, device=sampler.device) for _ in range(M)]
-    nz = noise.reshape(-1, D) if noise is not None and noise.numel() == B * D else torch.randn(B, D, device=sampler.device)
-    lq = torch.zeros(B, M, device=sampler.device)
-    w = torch.zeros(B, M, device=sampler.device)
+    set_bytes = 4 * B * D * (M + 3)
+    R = max(2, -(-2 * 126 * 1024 * 1024 // set_bytes) + 1)
+    sets = []
+    for _ in range(R):
+        sets.append(dict(x=torch.randn(B, D, device=dev), xo=torch.empty(B, D, device=dev),
+                         sc=[torch.randn(B, D, device=dev) for _ in range(M)], nz=torch.randn(B, D, device=dev),
+                         lq=torch.zeros(B, M, device=dev), w=torch.zeros(B, M, device=dev)))
+    dmode = ops.DLOGQ_CIFAR_MAXSUB if mode == ops.MODE_OR else ops.DLOGQ_ITO
+
+    def one(st):
+        ops.step_vpsde(st["x"], st["nz"], st["sc"], st["lq"], -5.0, 5.0, 0.5, 1e-3, mode, dmode, temperature=1e6,
+                       x_out=st["xo"], weights=st["w"])
+    for st in sets:
+        one(st)
+    torch.cuda.synchronize()
+    reps = max(1, 48 // R)
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one(sets[0])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            for st in sets:
+                one(st)
     ts = []
-    for i in range(13):
-        flush.zero_()
+    for i in range(6):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, mode,
-                       ops.DLOGQ_CIFAR_MAXSUB if mode == ops.MODE_OR else ops.DLOGQ_ITO, temperature=1e6,
-                       x_out=xo, weights=w)
+        g.replay()
         e.record()
         torch.cuda.synchronize()
-        if i >= 3:
-            ts.append(s.elapsed_time(e) * 1e3)
-    return statistics.median(ts), 4 * B * D * (M + 3)
+        if i >= 2:
+            ts.append(s.elapsed_time(e) * 1e3 / (reps * R))
+    return statistics.median(ts), set_bytes
 
 
 def main():

@@ -65,3 +65,45 @@ def loop_toy(score_fns, x0, noise, mode, n_steps=1000, dt=1e-3, accumulate="floa
     if record:
         return x, ll, {k: torch.stack(v) for k, v in traj.items()}
     return x, ll, None
+
+
+def loop_toy_ode(score_fns, x0, probes, mode, n_steps=1000, dt=1e-3, accumulate="float32", record=False):
+    """notebooks/superposition_edu.ipynb ODE cells, restated: ``vector_field`` (:242-247: probe eps, (s, <J eps, eps>) by
+    forward-mode differentiation), ``get_dll`` / ``get_kappa`` (:397-409) and the loops :426-447 (mode 'and'),
+    :520-541 ('avg', kappa = 0.5), :633-656 ('or', kappa from the running log-densities).  ``probes[i]`` is the
+    +-1 draw of step i, shared by both models (same ikey).  Dtype follows x0."""
+    ts = S.time_grid(n_steps, dt, accumulate)
+    x = x0.clone()
+    B, ndim = x.shape
+    ll = torch.zeros(B, 2, dtype=x.dtype)
+    traj = {"ll": [ll.clone()], "kappa": [], "x": [x.clone()]}
+    for i in range(n_steps):
+        t = float(ts[i])
+        a, b, sig = S.dlog_alphadt(t), S.beta(t), S.sigma(t)
+        tt = torch.full((B, 1), t, dtype=x.dtype)
+        eps = probes[i].to(x.dtype)
+        out = [torch.func.jvp(lambda _x, f=f: f(tt, _x), (x,), (eps,)) for f in score_fns]
+        s1, s2 = out[0][0], out[1][0]
+        div1, div2 = (out[0][1] * eps).sum(1, keepdim=True), (out[1][1] * eps).sum(1, keepdim=True)
+        if mode == "and":
+            kappa = sig * (div1 - div2) + (s1 * (s1 - s2)).sum(1, keepdim=True)           # get_kappa
+            kappa = kappa / ((s1 - s2) ** 2).sum(1, keepdim=True)
+        elif mode == "or":
+            mx = torch.maximum(ll[:, 0], ll[:, 1])
+            e1, e2 = torch.exp(ll[:, 0] - mx), torch.exp(ll[:, 1] - mx)
+            kappa = (e1 / (e1 + e2))[:, None]
+        else:
+            kappa = torch.full((B, 1), 0.5, dtype=x.dtype)
+        dxdt = a * x - b * (s2 + kappa * (s1 - s2))
+
+        def get_dll(s, div):
+            v = a * x - b * s
+            dlldt = -a * ndim + b * div
+            return dlldt - ((s / sig) * (v - dxdt)).sum(1, keepdim=True)
+        ll = torch.stack([ll[:, 0] - dt * get_dll(s1, div1).squeeze(1), ll[:, 1] - dt * get_dll(s2, div2).squeeze(1)], dim=1)
+        x = x - dt * dxdt
+        if record:
+            traj["ll"].append(ll.clone()); traj["kappa"].append(kappa[:, 0].clone()); traj["x"].append(x.clone())
+    if record:
+        return x, ll, {k: torch.stack(v) for k, v in traj.items()}
+    return x, ll, None

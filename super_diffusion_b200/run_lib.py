@@ -38,9 +38,8 @@ def evaluate_joint_samples(config, workdir, eval_folder, params_list, stoch=True
     """Generate ``config.eval.num_samples`` SuperDiff samples from the models whose parameter trees are in
     ``params_list`` (the reference restores them from orbax checkpoints, :207-210) and write
     ``<workdir>/<eval_folder>/samples_stoch/samples_{i}.npz``.  Returns the sample directory."""
-    if not stoch and mode != "avg":
-        raise NotImplementedError("deterministic (ODE) SuperDiff with the Hutchinson divergence (cifar/dynamics.py:59-97) is "
-                                  "SURVEY.md §8(f) row N1")
+    if not stoch and mode == "and":
+        raise NotImplementedError("SuperDiff-AND is defined by the noise of the stochastic step (superposition_edu.ipynb:899-905)")
     models, states = [], []
     for params in params_list:
         model = mutils.get_model(config.model.name)(config=config)
@@ -49,7 +48,9 @@ def evaluate_joint_samples(config, workdir, eval_folder, params_list, stoch=True
     sample_dir = os.path.join(workdir, eval_folder, "samples_stoch" if stoch else "samples")      # :214-217
     os.makedirs(sample_dir, exist_ok=True)
     key = int(config.seed)
-    if mode == "or":
+    if mode == "or" and not stoch:
+        vector_field = dynamics.get_joint_vf(key, models, states)                 # :224-225 (ODE + Hutchinson divergence)
+    elif mode == "or":
         vector_field = dynamics.get_joint_stoch_vf(key, models, states)           # :222-223
     elif mode == "and":
         vector_field = dynamics.get_joint_and_vf(key, models, states)

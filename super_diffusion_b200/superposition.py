@@ -84,6 +84,56 @@ def superdiff_and(score_fns, x0, n_steps=1000, dt=1e-3, noise=None, seed=0, ito_
                        accumulate, record)
 
 
+def superdiff_ode(score_fns, x0, mode="and", n_steps=1000, dt=1e-3, probes=None, seed=0, accumulate="float32", record=False):
+    """Deterministic SuperDiff on the probability-flow ODE with Hutchinson divergence estimates -- the notebook's ODE cells
+    (superposition_edu.ipynb: ``vector_field`` :242-247, ``get_dll`` / ``get_kappa`` :397-409, loops :426-447 (AND),
+    :520-541 (kappa = 0.5), :633-656 (OR)), two caller-supplied differentiable score models.
+
+    Per step: one Rademacher probe eps shared by both models (the notebook passes the same ``ikey`` to both calls);
+    (s_k, J_k eps) by ``torch.func.jvp``; div_k = <J_k eps, eps>;
+      and: kappa = [sigma (div_1 - div_2) + <s_1, s_1 - s_2>] / |s_1 - s_2|^2          (get_kappa)
+      or:  kappa = softmax(ll)[0];      avg: kappa = 1/2
+    dx = -dt (a x - b (s_2 + kappa (s_1 - s_2)));  ll_k += dt a ndim - dt b div_k + sum s_k/sigma (dx + dt (a x - b s_k))  (get_dll).
+    ``probes``: [n_steps, *x0.shape] tensor of +-1 or None (drawn from ``seed``).  Returns (x, ll (B,2), kappa, traj)."""
+    _lib.require_device()
+    if len(score_fns) != 2:
+        raise ValueError("the notebook's ODE superposition is defined for two models")
+    x = x0.clone().contiguous()
+    B, dev = x.shape[0], x.device
+    D = x[0].numel()
+    ll = torch.zeros(B, 2, device=dev, dtype=torch.float32)
+    w = torch.full((B, 2), 0.5, device=dev, dtype=torch.float32)
+    add = torch.empty(B, 2, device=dev, dtype=torch.float32)
+    ts = sde.time_grid(n_steps, dt, accumulate)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    kmode = {"and": ops.MODE_FIXED, "or": ops.MODE_OR, "avg": ops.MODE_AVG}[mode]
+    traj = {"ll": [ll.clone()], "kappa": [], "x": [x.clone()]} if record else None
+    for i in range(n_steps):
+        t = float(ts[i])
+        a, b, sig = sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t)
+        eps = (probes[i].to(dev, torch.float32) if probes is not None else
+               (torch.randint(0, 2, x.shape, generator=g, device=dev, dtype=torch.int32) * 2 - 1).to(torch.float32)).contiguous()
+        tt = torch.full((B, 1), t, device=dev, dtype=torch.float32)
+        scores, divs = [], []
+        for k, f in enumerate(score_fns):
+            s_k, j_k = torch.func.jvp(lambda _x: f(tt, _x), (x,), (eps,))
+            scores.append(s_k.contiguous())
+            divs.append(ops.rowdot(j_k.contiguous(), eps))
+            add[:, k] = dt * a * D - dt * b * divs[k]
+        if mode == "and":
+            d = (scores[0] - scores[1]).contiguous()
+            kappa = (sig * (divs[0] - divs[1]) + ops.rowdot(scores[0], d)) / ops.rowdot(d, d)
+            w[:, 0] = kappa
+            w[:, 1] = 1.0 - kappa
+        ops.step_vpsde_ode(x, scores, ll, a, b, sig, dt, kmode, ops.DLOGQ_ITO, temperature=1.0, dlogq_add=add, x_out=x, weights=w)
+        if record:
+            traj["ll"].append(ll.clone()); traj["kappa"].append(w[:, 0].clone()); traj["x"].append(x.clone())
+    if record:
+        traj = {k: torch.stack(v) for k, v in traj.items()}
+    return x, ll, w[:, 0].clone(), traj
+
+
 def sd_superdiff(get_vel, latents0, method="and", num_inference_steps=50, guidance_scale=7.5, lift=0.0, T=1.0,
                  logp=0.0, kappa_avg=0.5, noise=None, seed=1, record=False):
     """Stable-Diffusion latent SuperDiff (clip_eval.py:348-415).  ``get_vel(t, sigma, latents, which)`` with

@@ -344,6 +344,33 @@ def toy(jax):
                 d["kappa"] = np.stack(kappas)[::50]
             out[f"toy_{loop_name}_{mode}"] = d
             print(f"toy_{loop_name}_{mode}", "x rms", float(np.sqrt((x_gen[:, -1] ** 2).mean())), "t_final", d["t_final"])
+    # ---- deterministic (ODE) cells: vector_field (jvp + Rademacher probe), get_dll / get_kappa, the three loops ----
+    jax.config.update("jax_enable_x64", True)
+    import jax.numpy as jnp
+    from functools import partial
+    vf_cell = cell("def vector_field(key,t,x,state)")
+    dll_cell = cell("def get_dll")
+    loops = {"and": cell("kappa = get_kappa("), "avg": cell("x_gen_avg = jnp.copy(x_gen)"), "or": cell("max_ll = jnp.maximum")}
+    for mode, src in loops.items():
+        ns = dict(jax=jax, jnp=jnp, np=np, random=jr, trange=lambda n: range(n), partial=partial,
+                  state_up=mixture_state("up"), state_down=mixture_state("down"))
+        exec(defs, ns); exec(vf_cell, ns); exec(dll_cell, ns)
+        ns["key"] = jr.PRNGKey({"and": 11, "avg": 12, "or": 13}[mode])
+        ns["x_t"] = jnp.zeros((512, 2))
+        jr.LOG.clear(); jr.DRAWS.clear()
+        exec(src, ns)
+        n = ns["n"]
+        kinds = [k for k, *_ in jr.LOG]
+        # draw 0: x0 (normal); per step the same ikey feeds vector_field twice (one randint each)
+        assert kinds == ["normal"] + ["randint"] * (2 * n), (kinds[:4], len(kinds))
+        keys = [k for _, k, _ in jr.LOG]
+        assert keys[1::2] == keys[2::2]
+        x_gen = np.asarray(ns["x_gen"])
+        ll1, ll2 = np.asarray(ns["ll_1"]), np.asarray(ns["ll_2"])
+        out[f"toy_ode_{mode}"] = dict(x0_key=keys[0], step_keys=np.asarray(keys[1::2], dtype=np.int64), n=n, dt=float(ns["dt"]),
+                                      bs=int(ns["bs"]), x0=x_gen[:, 0, :], x_final=x_gen[:, -1, :], x_quarters=x_gen[:, ::250, :],
+                                      ll=np.stack([ll1[:, ::50], ll2[:, ::50]], -1))
+        print(f"toy_ode_{mode}", "x rms", float(np.sqrt((x_gen[:, -1] ** 2).mean())), "ll range", float(ll1.min()), float(ll1.max()))
     # single calls of the two estimators on random fp64 inputs
     jax.config.update("jax_enable_x64", True)
     import jax.numpy as jnp

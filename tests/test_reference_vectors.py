@@ -235,6 +235,26 @@ def test_oracle_matches_reference_toy():
     assert abs(float(z["toy_or_f32"]["t_final"]) - (S.time_grid(1001, 1e-3, "float32")[-1])) < 1e-9
 
 
+def ref_probe(key, shape):
+    """The +-1 probe behind the shim's jax.random.randint(key, shape, 0, 2).astype(float)*2 - 1."""
+    return (np.random.default_rng(int(key)).integers(0, 2, tuple(shape)).astype(np.float32) * 2 - 1)
+
+
+def test_oracle_matches_reference_toy_ode():
+    """The notebook's deterministic cells (vector_field / get_dll / get_kappa and the AND, kappa = 1/2 and OR loops)."""
+    z = _load("ref_toy.npz")
+    fns = [toy.mixture_sscore("up"), toy.mixture_sscore("down")]
+    for mode in ("and", "avg", "or"):
+        c = z[f"toy_ode_{mode}"]
+        n, dt, B = int(c["n"]), float(c["dt"]), int(c["bs"])
+        x0 = _t(c["x0"], torch.float64)
+        probes = torch.stack([_t(ref_probe(k, (B, 2))) for k in c["step_keys"]])
+        xf, ll, tr = toy.loop_toy_ode(fns, x0, probes, mode, n, dt, accumulate="float64", record=True)
+        # the fixture's jax.jvp stand-in is a central difference (h = 1e-6)
+        assert _rel(tr["x"][::250].permute(1, 0, 2), c["x_quarters"]) < 1e-6, (mode, _rel(tr["x"][::250].permute(1, 0, 2), c["x_quarters"]))
+        assert _rel(tr["ll"][::50].permute(1, 0, 2), c["ll"]) < 1e-6, (mode, _rel(tr["ll"][::50].permute(1, 0, 2), c["ll"]))
+
+
 def test_oracle_matches_reference_sd():
     for name, c in _load("ref_sd.npz").items():
         method, N = str(c["method"]), int(c["N"])
@@ -372,6 +392,24 @@ def test_cuda_matches_reference_toy(cuda):
         # and against the fp64 run of the same cells (time accumulated in fp64 there: F10 drift shows up at ~1e-2)
         c64 = z[f"toy_{mode}_f64"]
         assert _rel(x.cpu().numpy(), c64["x_final"]) <= 5e-2, mode
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_toy_ode(cuda):
+    """superposition.superdiff_ode (torch.func.jvp + sd_rowdot + sd_step_vpsde_ode) vs the notebook's ODE cells, 1000 steps."""
+    from super_diffusion_b200.superposition import superdiff_ode
+    z = _load("ref_toy.npz")
+    fns = [toy.mixture_sscore("up"), toy.mixture_sscore("down")]
+    for mode in ("and", "avg", "or"):
+        c = z[f"toy_ode_{mode}"]
+        n, dt, B = int(c["n"]), float(c["dt"]), int(c["bs"])
+        probes = torch.stack([_t(ref_probe(k, (B, 2))) for k in c["step_keys"]]).to(cuda)
+        x, ll, kappa, traj = superdiff_ode(fns, _t(c["x0"]).float().to(cuda), mode=mode, n_steps=n, dt=dt, probes=probes,
+                                           accumulate="float64", record=True)
+        torch.cuda.synchronize()
+        ex = _rel(traj["x"][::250].permute(1, 0, 2).cpu().numpy(), c["x_quarters"])
+        el = _rel(traj["ll"][::50].permute(1, 0, 2).cpu().numpy(), c["ll"])
+        assert ex <= 1e-3 and el <= 1e-3, (mode, ex, el)
 
 
 @pytest.mark.gpu
