@@ -113,6 +113,16 @@ int sd_step_edm_cfg(const float* latents, const float* z, const float* v_obj, co
                     float temperature, float logp, float kappa_fixed,
                     float* ll, float* latents_out, float* kappa_out, void* stream);
 
+/* Deterministic AND on SD latents (method "and_ode", applications/images/clip_eval.py:377-391):
+ *     kappa = [sigma (dlog_o - dlog_b) + <v_o - v_b, v_o + v_b> + lift_term - <v_o - v_b, v_u + g (v_b - v_u)>] / (g |v_o - v_b|^2)
+ *     vf = v_u + g ((v_b - v_u) + kappa (v_o - v_b));   latents_out = latents + dsigma * vf
+ *     ll_k += dsigma * (dlog_k + <v_k, v_k - vf> / sigma)
+ * dlog: [B][2] = (dlog_obj, dlog_bg) = -<eps, J eps> Hutchinson estimates of get_vel(..., get_div=True) (:97-103; see
+ * sd_rowdot); lift_term = lift/dsigma*sigma/num_inference_steps (:383).  4*B*D*5 bytes. */
+int sd_step_edm_ode(const float* latents, const float* v_obj, const float* v_bg, const float* v_unc, const float* dlog,
+                    int B, int D, float sigma, float dsigma, float guidance, float lift_term,
+                    float* ll /* [B][2] in/out */, float* latents_out, float* kappa_out /* [B] */, void* stream);
+
 /* In-graph helper: *counter += delta (single thread).  Lets a captured graph
  * advance the row of `sched` it reads. */
 int sd_counter_add(int* counter, int delta, void* stream);

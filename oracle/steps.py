@@ -206,6 +206,23 @@ def sd_step_literal(latents, z, v_obj, v_bg, v_unc, ll, sigma, dsigma, method,
     return dx, torch.stack([l_obj, l_bg], dim=1), kappa
 
 
+def sd_and_ode_step_literal(latents, v_obj, v_bg, v_unc, dlog_obj, dlog_bg, ll, sigma, dsigma, guidance_scale=7.5, lift=0.0,
+                            num_inference_steps=50):
+    """applications/images/clip_eval.py:383-390 (method "and_ode") after the three get_vel calls: dlog_* are the Hutchinson
+    divergences -(eps * jvp).sum (:103).  Returns (dx, ll_next (B,2), kappa (B,))."""
+    red = tuple(range(1, latents.dim()))
+    g = guidance_scale
+    kappa = sigma * (dlog_obj - dlog_bg) + ((v_obj - v_bg) * (v_obj + v_bg)).sum(red) + lift / dsigma * sigma / num_inference_steps  # :383
+    kappa = kappa - ((v_obj - v_bg) * (v_unc + g * (v_bg - v_unc))).sum(red)                                     # :384
+    kappa = kappa / (g * ((v_obj - v_bg) ** 2).sum(red))                                                          # :385
+    k = kappa.reshape(-1, *([1] * (latents.dim() - 1)))
+    vf = v_unc + g * ((v_bg - v_unc) + k * (v_obj - v_bg))                                                        # :387
+    dx = dsigma * vf                                                                                              # :388
+    l_obj = ll[:, 0] + dsigma * (dlog_obj - ((-v_obj / sigma) * (v_obj - vf)).sum(red))                           # :389
+    l_bg = ll[:, 1] + dsigma * (dlog_bg - ((-v_bg / sigma) * (v_bg - vf)).sum(red))                               # :390
+    return dx, torch.stack([l_obj, l_bg], dim=1), kappa
+
+
 # ---------------------------------------------------------------------------
 # Gram-reduction restatement (SURVEY.md Appendix A) -- what the kernels compute
 # ---------------------------------------------------------------------------

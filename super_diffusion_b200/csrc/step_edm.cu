@@ -18,7 +18,10 @@ struct EdmParams {
   int B, D;
   float sigma, dsigma, g, lift_term, temperature, logp, kappa_fixed;
   int mode;
+  const float* dlog;     // SD_EDM_MODE_AND_ODE: [B][2] = (dlog_obj, dlog_bg), the Hutchinson divergence estimates (clip_eval.py:103)
 };
+
+constexpr int SD_EDM_MODE_AND_ODE = 100;   // internal: deterministic AND (clip_eval.py:377-391), reached through sd_step_edm_ode
 
 // reductions (all per sample):
 //  0 dd=<d,d>  1 bd=<base,d>  2 zd=<z,d>  3 oo=<vo,vo>  4 bb=<vb,vb>  5 ob=<vo,base>  6 od=<vo,d>  7 oz=<vo,z>
@@ -37,7 +40,8 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
   const int per_cta = (nunits + csize - 1) / csize;
   const int u0 = crank * per_cta, u1 = min(nunits, u0 + per_cta);
   const size_t base_off = (size_t)sample * p.D;
-  const float cn = sqrtf(2.f * fabsf(p.dsigma) * p.sigma);
+  const bool ode = p.mode == SD_EDM_MODE_AND_ODE;
+  const float cn = ode ? 0.f : sqrtf(2.f * fabsf(p.dsigma) * p.sigma);
 
   float4 x[NV], z[NV], d[NV], bs[NV], vo[NV];
   bool ok[NV];
@@ -52,7 +56,7 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
     if (ok[j]) {
       const size_t off = base_off + (size_t)u * 4;
       x[j] = ld_stream4(p.x + off);
-      z[j] = ld_stream4(p.z + off);
+      if (p.z) z[j] = ld_stream4(p.z + off);
       vo[j] = ld_stream4(p.vo + off);
       const float4 vb = ld_stream4(p.vb + off);
       const float4 vu = ld_stream4(p.vu + off);
@@ -84,7 +88,11 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
   const double DD = t[0], BD = t[1], ZD = t[2], OO = t[3], BB = t[4], OB = t[5], OD = t[6], OZ = t[7];
   const double ds = p.dsigma, sg = p.sigma, g = p.g;
   double kappa;
-  if (p.mode == SD_MODE_AND) {
+  if (ode) {
+    // clip_eval.py:383-385: kappa = [sigma (dlog_o - dlog_b) + <d, vo + vb> + lift/dsigma*sigma/N - <d, base>] / (g <d,d>)
+    const double dl = (double)p.dlog[2 * sample] - (double)p.dlog[2 * sample + 1];
+    kappa = (sg * dl + (OO - BB) + (double)p.lift_term - BD) / (g * DD);
+  } else if (p.mode == SD_MODE_AND) {
     // clip_eval.py:398-400 with dx_ind = 2 dsigma base + cn z
     const double num = fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term;
     kappa = num / (2.0 * ds * g * DD);
@@ -98,7 +106,7 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
     kappa = (double)p.kappa_fixed;
   }
   const float kf = (float)kappa;
-  const float two_ds = 2.f * p.dsigma;
+  const float two_ds = ode ? p.dsigma : 2.f * p.dsigma;      // ODE: latents += dsigma * vf (clip_eval.py:388)
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     if (!ok[j]) continue;
@@ -110,7 +118,13 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
     o.w = x[j].w + (two_ds * (bs[j].w + p.g * kf * d[j].w) + cn * z[j].w);
     st4(p.x_out + base_off + (size_t)(u0 + j * blockDim.x + threadIdx.x) * 4, o);
   }
-  if (crank == 0 && threadIdx.x == 0) {
+  if (crank == 0 && threadIdx.x == 0 && ode) {
+    // clip_eval.py:389-390: ll_k += dsigma (dlog_k - sum (-v_k/sigma)(v_k - vf)),  <vo,vf> = OB + g k OD, <d,vf> = BD + g k DD
+    const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);
+    p.ll[2 * sample] = p.ll[2 * sample] + (float)(ds * ((double)p.dlog[2 * sample] + (OO - o_vf) / sg));
+    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(ds * ((double)p.dlog[2 * sample + 1] + (BB - b_vf) / sg));
+    p.kappa_out[sample] = kf;
+  } else if (crank == 0 && threadIdx.x == 0) {
     // <vo,dx> = 2ds(OB + g k OD) + cn OZ ; <vb,dx> = <vo,dx> - <d,dx>, <d,dx> = 2ds(BD + g k DD) + cn ZD
     const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
     const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
@@ -144,24 +158,24 @@ static cudaError_t launch_edm(const EdmParams& p, int threads, int cluster, cuda
 
 }  // namespace sdb
 
-extern "C" int sd_step_edm_cfg(const float* latents, const float* z, const float* v_obj, const float* v_bg,
-                               const float* v_unc, int B, int D, float sigma, float dsigma, float guidance,
-                               float lift_term, int mode, float temperature, float logp, float kappa_fixed, float* ll,
-                               float* latents_out, float* kappa_out, void* stream) {
+static int step_edm_impl(const float* latents, const float* z, const float* v_obj, const float* v_bg,
+                         const float* v_unc, int B, int D, float sigma, float dsigma, float guidance,
+                         float lift_term, int mode, float temperature, float logp, float kappa_fixed, float* ll,
+                         float* latents_out, float* kappa_out, const float* dlog, void* stream) {
   using namespace sdb;
+  const bool ode = mode == SD_EDM_MODE_AND_ODE;
   if (B == 0) return SD_OK;
-  if (!latents || !z || !v_obj || !v_bg || !v_unc || !ll || !latents_out || !kappa_out)
+  if (!latents || (!z && !ode) || !v_obj || !v_bg || !v_unc || !ll || !latents_out || !kappa_out || (ode && !dlog))
     return fail(kErrInvalidArg, "sd_step_edm_cfg: null pointer argument");
   if (B < 0 || D < 4 || D % 4) return fail(kErrInvalidArg, "sd_step_edm_cfg: D must be a positive multiple of 4");
-  if (!(mode == SD_MODE_AND || mode == SD_MODE_OR || mode == SD_MODE_AVG))
+  if (!(mode == SD_MODE_AND || mode == SD_MODE_OR || mode == SD_MODE_AVG || ode))
     return fail(kErrInvalidArg, "sd_step_edm_cfg: mode must be AND, OR or AVG");
   if (!(sigma > 0.f)) return fail(kErrInvalidArg, "sd_step_edm_cfg: sigma must be > 0");
-  if ((((uintptr_t)latents | (uintptr_t)z | (uintptr_t)v_obj | (uintptr_t)v_bg | (uintptr_t)v_unc |
+  if ((((uintptr_t)latents | (uintptr_t)(z ? z : latents) | (uintptr_t)v_obj | (uintptr_t)v_bg | (uintptr_t)v_unc |
         (uintptr_t)latents_out) % 16) != 0)
     return fail(kErrInvalidArg, "sd_step_edm_cfg: tensors must be 16-byte aligned");
-  if (B == 0) return SD_OK;
   EdmParams p{latents, z, v_obj, v_bg, v_unc, ll, latents_out, kappa_out, B, D,
-              sigma, dsigma, guidance, lift_term, temperature, logp, kappa_fixed, mode};
+              sigma, dsigma, guidance, lift_term, temperature, logp, kappa_fixed, mode, dlog};
   const int nunits = D / 4;
   // smallest (cluster, threads, NV <= 2) that keeps the sample resident; prefer more CTAs when B is small
   int best_c = 0, best_t = 0, best_nv = 0;
@@ -181,4 +195,21 @@ extern "C" int sd_step_edm_cfg(const float* latents, const float* z, const float
   cudaError_t err = best_nv == 1 ? launch_edm<1>(p, best_t, best_c, (cudaStream_t)stream)
                                  : launch_edm<2>(p, best_t, best_c, (cudaStream_t)stream);
   return check_cuda(err, "sd_step_edm_cfg launch");
+}
+
+extern "C" int sd_step_edm_cfg(const float* latents, const float* z, const float* v_obj, const float* v_bg,
+                               const float* v_unc, int B, int D, float sigma, float dsigma, float guidance,
+                               float lift_term, int mode, float temperature, float logp, float kappa_fixed, float* ll,
+                               float* latents_out, float* kappa_out, void* stream) {
+  if (!(mode == SD_MODE_AND || mode == SD_MODE_OR || mode == SD_MODE_AVG))
+    return sdb::fail(sdb::kErrInvalidArg, "sd_step_edm_cfg: mode must be AND, OR or AVG");
+  return step_edm_impl(latents, z, v_obj, v_bg, v_unc, B, D, sigma, dsigma, guidance, lift_term, mode, temperature, logp,
+                       kappa_fixed, ll, latents_out, kappa_out, nullptr, stream);
+}
+
+extern "C" int sd_step_edm_ode(const float* latents, const float* v_obj, const float* v_bg, const float* v_unc,
+                               const float* dlog, int B, int D, float sigma, float dsigma, float guidance,
+                               float lift_term, float* ll, float* latents_out, float* kappa_out, void* stream) {
+  return step_edm_impl(latents, nullptr, v_obj, v_bg, v_unc, B, D, sigma, dsigma, guidance, lift_term,
+                       sdb::SD_EDM_MODE_AND_ODE, 1.f, 0.f, 0.5f, ll, latents_out, kappa_out, dlog, stream);
 }

@@ -156,6 +156,27 @@ def step_edm_cfg(latents, z, v_obj, v_bg, v_unc, ll, sigma, dsigma, mode, guidan
     return latents_out, ll, kappa_out
 
 
+def step_edm_ode(latents, v_obj, v_bg, v_unc, dlog, ll, sigma, dsigma, guidance=7.5, lift_term=0.0, latents_out=None,
+                 kappa_out=None):
+    """Deterministic AND step on SD latents (sd_step_edm_ode).  dlog: (B, 2) Hutchinson divergences; ll: (B, 2) in place."""
+    lib = _lib.load()
+    B, D = latents.shape[0], latents[0].numel()
+    for n, t in (("latents", latents), ("v_obj", v_obj), ("v_bg", v_bg), ("v_unc", v_unc), ("dlog", dlog), ("ll", ll)):
+        _f32c(t, n)
+    if dlog.shape != (B, 2) or ll.shape != (B, 2):
+        raise ValueError("dlog and ll must be (B, 2)")
+    if latents_out is None:
+        latents_out = torch.empty_like(latents)
+    if kappa_out is None:
+        kappa_out = torch.empty(B, device=latents.device, dtype=torch.float32)
+    rc = lib.sd_step_edm_ode(_ptr(latents), _ptr(v_obj), _ptr(v_bg), _ptr(v_unc), _ptr(dlog), B, D, float(sigma), float(dsigma),
+                             float(guidance), float(lift_term), _ptr(ll), _ptr(latents_out), _ptr(kappa_out), _stream())
+    _lib.check(rc, "sd_step_edm_ode")
+    if B > 0:
+        _count()
+    return latents_out, ll, kappa_out
+
+
 def counter_add(counter, delta=1):
     _lib.check(_lib.load().sd_counter_add(_ptr(counter), int(delta), _stream()), "sd_counter_add")
     _count()

@@ -141,6 +141,8 @@ def sd_superdiff(get_vel, latents0, method="and", num_inference_steps=50, guidan
     :89-105); ``latents0`` is the unit-variance draw of :329-333 and is scaled by init_noise_sigma (:340).
     Returns (latents, ll (B,2), kappa trajectory or last kappa, traj)."""
     _lib.require_device()
+    if method == "and_ode":
+        return _sd_and_ode(get_vel, latents0, num_inference_steps, guidance_scale, lift, noise, seed, record)
     mode = {"and": ops.MODE_AND, "or": ops.MODE_OR, "avg": ops.MODE_AVG}[method]
     sigmas, timesteps, init_sigma = sde.edm_sigmas(num_inference_steps)
     x = (latents0 * init_sigma).contiguous()
@@ -158,6 +160,38 @@ def sd_superdiff(get_vel, latents0, method="and", num_inference_steps=50, guidan
         ops.step_edm_cfg(x, nz(i), v_obj, v_bg, v_unc, ll, sigma, dsigma, mode, guidance=guidance_scale,
                          lift_term=sigma * lift / num_inference_steps, temperature=T, logp=logp,
                          kappa_fixed=kappa_avg, latents_out=x, kappa_out=kappa)
+        if record:
+            traj["ll"].append(ll.clone()); traj["kappa"].append(kappa.clone())
+    if record:
+        traj = {k: torch.stack(v) for k, v in traj.items()}
+    return x, ll, kappa, traj
+
+
+def _sd_and_ode(get_vel, latents0, num_inference_steps, guidance_scale, lift, probes, seed, record):
+    """clip_eval.py:377-391 (method "and_ode"): Rademacher probe per step (:379), (vel_k, dlog_k) by forward-mode
+    differentiation of the caller's velocity function (:97-103), fused kappa / latent / log-likelihood update."""
+    sigmas, timesteps, init_sigma = sde.edm_sigmas(num_inference_steps)
+    x = (latents0 * init_sigma).contiguous()
+    B, dev = x.shape[0], x.device
+    ll = torch.ones(B, 2, device=dev, dtype=torch.float32)
+    kappa = torch.full((B,), 0.5, device=dev, dtype=torch.float32)
+    dlog = torch.empty(B, 2, device=dev, dtype=torch.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    traj = {"ll": [ll.clone()], "kappa": [kappa.clone()]} if record else None
+    for i in range(num_inference_steps):
+        sigma, dsigma = float(sigmas[i]), float(sigmas[i + 1] - sigmas[i])
+        t = float(timesteps[i])
+        eps = (probes[i].to(dev, torch.float32) if probes is not None else
+               (torch.randint(0, 2, x.shape, generator=g, device=dev, dtype=torch.int32) * 2 - 1).to(torch.float32)).contiguous()
+        vels = []
+        for k, which in enumerate(("obj", "bg")):
+            v, jv = torch.func.jvp(lambda _x, which=which: get_vel(t, sigma, _x, which), (x,), (eps,))
+            vels.append(v.contiguous())
+            ops.rowdot(jv.contiguous(), eps, scale=-1.0, out=dlog, column=k)          # div = -(eps * jvp).sum  (:103)
+        v_unc = get_vel(t, sigma, x, "uncond").contiguous()
+        ops.step_edm_ode(x, vels[0], vels[1], v_unc, dlog, ll, sigma, dsigma, guidance=guidance_scale,
+                         lift_term=lift / dsigma * sigma / num_inference_steps, latents_out=x, kappa_out=kappa)
         if record:
             traj["ll"].append(ll.clone()); traj["kappa"].append(kappa.clone())
     if record:

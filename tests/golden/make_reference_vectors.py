@@ -458,12 +458,12 @@ def sd(oracle_sigmas):
     ce.tqdm = lambda it, **kw: it
     real_manual_seed = torch.cuda.manual_seed
     out = {}
-    for method, T, logp in (("and", 1.0, 0.0), ("or", 2.0, 0.1), ("avg", 1.0, 0.0)):
+    for method, T, logp in (("and", 1.0, 0.0), ("or", 2.0, 0.1), ("avg", 1.0, 0.0), ("and_ode", 1.0, 0.0)):
         N, B = 12, 3
         args = types.SimpleNamespace(method=method, batch_size=B, num_inference_steps=N, seed=1, height=64, width=64,
                                      T=T, logp=logp, guidance_scale=7.5, obj="a cat", bg="a dog")
-        zs, vels = [], []
-        real_randn_like, real_get_vel = torch.randn_like, ce.get_vel
+        zs, vels, divs, probes = [], [], [], []
+        real_randn_like, real_get_vel, real_randint_like = torch.randn_like, ce.get_vel, torch.randint_like
         g = torch.Generator().manual_seed(77)
 
         def randn_like(x, g=g, zs=zs):
@@ -471,13 +471,19 @@ def sd(oracle_sigmas):
             zs.append(z.clone())
             return z
 
-        def get_vel(t, sigma, latents, embeddings, *a, vels=vels, **kw):
+        def get_vel(t, sigma, latents, embeddings, *a, vels=vels, divs=divs, **kw):
             v, d = real_get_vel(t, sigma, latents, embeddings, *a, **kw)
             vels.append(v.clone())
+            divs.append(d.clone())
             return v, d
 
+        def randint_like(x, high, dtype=None, g=g, probes=probes):
+            r = torch.randint(0, high, x.shape, generator=g).to(dtype or x.dtype)
+            probes.append((r * 2 - 1).clone())
+            return r
+
         lat_hist = []
-        torch.randn_like, ce.get_vel = randn_like, get_vel
+        torch.randn_like, ce.get_vel, torch.randint_like = randn_like, get_vel, randint_like
         torch.cuda.manual_seed = lambda s: torch.Generator().manual_seed(s)
         try:
             try:
@@ -490,14 +496,28 @@ def sd(oracle_sigmas):
                         loc = tb.tb_frame.f_locals
                     tb = tb.tb_next
         finally:
-            torch.randn_like, ce.get_vel = real_randn_like, real_get_vel
+            torch.randn_like, ce.get_vel, torch.randint_like = real_randn_like, real_get_vel, real_randint_like
             torch.cuda.manual_seed = real_manual_seed
         assert loc is not None
         kappa = loc["kappa"]
         kappa = kappa if torch.is_tensor(kappa) else torch.full((N + 1, B), float(kappa))
+        sig = loc["scheduler"].sigmas if "scheduler" in loc else ce.scheduler.sigmas
+        if method == "and_ode":
+            # call order: vel_obj, vel_uncond (:354-355), then vel_obj+div, vel_bg+div, vel_uncond (:380-382)
+            vel = torch.stack(vels).reshape(N, 5, B, 4, 8, 8)
+            dv = torch.stack(divs).reshape(N, 5, B)
+            out["sd_and_ode"] = dict(method=method, guidance=7.5, N=N, sigmas=sig.numpy(), timesteps=ce.scheduler.timesteps.numpy(),
+                                     latents0=(loc["latents_og"] * ce.scheduler.init_noise_sigma).numpy(),
+                                     probes=torch.stack(probes).numpy().astype(np.float32), v_obj=vel[:, 2].numpy(), v_bg=vel[:, 3].numpy(),
+                                     v_unc=vel[:, 4].numpy(), dlog_obj=dv[:, 2].numpy(), dlog_bg=dv[:, 3].numpy(),
+                                     ll_obj=loc["ll_obj"].numpy(), ll_bg=loc["ll_bg"].numpy(), kappa=kappa.numpy(),
+                                     latents=loc["latents"].numpy(),
+                                     emb_phase=np.array([float(e.mean()) for e in (loc["obj_embeddings"][:1], loc["uncond_embeddings"][:1],
+                                                                                     loc["bg_embeddings"][:1])]))
+            print("sd and_ode latents rms", float(loc["latents"].pow(2).mean().sqrt()), "kappa[-1]", kappa[-1].numpy())
+            continue
         # call order inside the loop: vel_obj, vel_uncond, vel_bg  (clip_eval.py:354-355,394)
         vel = torch.stack(vels).reshape(N, 3, B, 4, 8, 8)
-        sig = loc["scheduler"].sigmas if "scheduler" in loc else ce.scheduler.sigmas
         out[f"sd_{method}"] = dict(method=method, T=T, logp=logp, guidance=7.5, N=N, sigmas=sig.numpy(),
                                    timesteps=ce.scheduler.timesteps.numpy(),
                                    latents0=(loc["latents_og"] * ce.scheduler.init_noise_sigma).numpy(),

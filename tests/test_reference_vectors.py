@@ -255,8 +255,37 @@ def test_oracle_matches_reference_toy_ode():
         assert _rel(tr["ll"][::50].permute(1, 0, 2), c["ll"]) < 1e-6, (mode, _rel(tr["ll"][::50].permute(1, 0, 2), c["ll"]))
 
 
+def test_oracle_matches_reference_sd_and_ode():
+    """clip_eval.py:377-391 (method "and_ode"): teacher-forced on the recorded velocities / divergences, and closed-loop with
+    torch.func.jvp through the same UNet stand-in."""
+    c = _load("ref_sd.npz")["sd_and_ode"]
+    N = int(c["N"])
+    sig, ts, _ = S.edm_sigmas(N)
+    lat = _t(c["latents0"])
+    ll = torch.ones(lat.shape[0], 2, dtype=torch.float64)
+    ph = c["emb_phase"]
+    for i in range(N):
+        sigma, dsigma = float(sig[i]), float(sig[i + 1]) - float(sig[i])
+        eps = _t(c["probes"][i], torch.float64)
+        f = lambda _x, p: sd_unet_stub(_x / ((sigma ** 2 + 1) ** 0.5), ts[i], p)
+        vo, jo = torch.func.jvp(lambda _x: f(_x, ph[0]), (lat,), (eps,))
+        vb, jb = torch.func.jvp(lambda _x: f(_x, ph[2]), (lat,), (eps,))
+        vu = f(lat, ph[1])
+        dlo, dlb = -(eps * jo).sum((1, 2, 3)), -(eps * jb).sum((1, 2, 3))
+        assert _rel(vo, c["v_obj"][i]) < 1e-10 and _rel(dlo, c["dlog_obj"][i]) < 1e-10 and _rel(dlb, c["dlog_bg"][i]) < 1e-10
+        dx, ll, kappa = O.sd_and_ode_step_literal(lat, vo, vb, vu, dlo, dlb, ll, sigma, dsigma, guidance_scale=float(c["guidance"]),
+                                                  num_inference_steps=N)
+        lat = lat + dx
+        assert np.abs(kappa.numpy() - c["kappa"][i + 1]).max() < 1e-10 * (1 + np.abs(c["kappa"][i + 1]).max()), i
+        assert np.abs(ll[:, 0].numpy() - c["ll_obj"][i + 1]).max() < 1e-9 * (1 + np.abs(c["ll_obj"][i + 1]).max()), i
+        assert np.abs(ll[:, 1].numpy() - c["ll_bg"][i + 1]).max() < 1e-9 * (1 + np.abs(c["ll_bg"][i + 1]).max()), i
+    assert _rel(lat, c["latents"]) < 1e-10
+
+
 def test_oracle_matches_reference_sd():
     for name, c in _load("ref_sd.npz").items():
+        if name == "sd_and_ode":
+            continue
         method, N = str(c["method"]), int(c["N"])
         sig, ts, init = S.edm_sigmas(N)
         assert np.array_equal(sig.astype(np.float64), c["sigmas"])
@@ -418,6 +447,8 @@ def test_cuda_matches_reference_sd(cuda):
     from super_diffusion_b200 import ops
     from super_diffusion_b200.superposition import sd_superdiff
     for name, c in _load("ref_sd.npz").items():
+        if name == "sd_and_ode":
+            continue
         method, N = str(c["method"]), int(c["N"])
         mode = {"and": ops.MODE_AND, "or": ops.MODE_OR, "avg": ops.MODE_AVG}[method]
         sig = c["sigmas"]
@@ -454,3 +485,41 @@ def test_cuda_matches_reference_sd(cuda):
         assert _rel(x.cpu().numpy(), c["latents"]) <= 2e-3, (name, _rel(x.cpu().numpy(), c["latents"]))
         ref_ll = np.stack([c["ll_obj"][-1], c["ll_bg"][-1]], 1)
         assert np.abs(ll.cpu().numpy() - ref_ll).max() <= 2e-3 * np.abs(ref_ll).max(), name
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_sd_and_ode(cuda):
+    """sd_step_edm_ode teacher-forced on the reference's recorded tensors, then sd_superdiff(method="and_ode") closed loop."""
+    from super_diffusion_b200 import ops
+    from super_diffusion_b200.superposition import sd_superdiff
+    c = _load("ref_sd.npz")["sd_and_ode"]
+    N = int(c["N"])
+    sig = c["sigmas"]
+    f = lambda a: _t(np.asarray(a)).float().to(cuda).contiguous()
+    lat = _t(c["latents0"], torch.float64)
+    for i in range(N):
+        sigma, dsigma = float(sig[i]), float(sig[i + 1] - sig[i])
+        vo, vb, vu = (_t(c[k][i], torch.float64) for k in ("v_obj", "v_bg", "v_unc"))
+        dlo, dlb = _t(c["dlog_obj"][i], torch.float64), _t(c["dlog_bg"][i], torch.float64)
+        ll_in = torch.stack([_t(c["ll_obj"][i]), _t(c["ll_bg"][i])], 1)
+        lo, ll, kap = ops.step_edm_ode(f(lat), f(vo), f(vb), f(vu), f(torch.stack([dlo, dlb], 1)), f(ll_in), sigma, dsigma,
+                                       guidance=float(c["guidance"]), lift_term=0.0)
+        dxr, _, _ = O.sd_and_ode_step_literal(lat, vo, vb, vu, dlo, dlb, ll_in, sigma, dsigma, guidance_scale=float(c["guidance"]),
+                                              num_inference_steps=N)
+        lat = lat + dxr
+        assert np.abs(kap.cpu().numpy() - c["kappa"][i + 1]).max() <= 1e-4 * (1 + np.abs(c["kappa"][i + 1]).max()), i
+        ref_ll = np.stack([c["ll_obj"][i + 1], c["ll_bg"][i + 1]], 1)
+        assert np.abs(ll.cpu().numpy() - ref_ll).max() <= 1e-3 * np.abs(ref_ll).max(), i
+        assert _rel(lo.cpu().numpy(), lat.numpy()) <= 1e-3, i
+    ph = {"obj": float(c["emb_phase"][0]), "uncond": float(c["emb_phase"][1]), "bg": float(c["emb_phase"][2])}
+
+    def get_vel(t, sigma, latents, which):
+        return sd_unet_stub(latents / ((sigma ** 2 + 1) ** 0.5), t, ph[which])
+
+    init = float(np.max(sig))
+    x, ll, kappa, _ = sd_superdiff(get_vel, (_t(c["latents0"]) / init).float().to(cuda), method="and_ode", num_inference_steps=N,
+                                   guidance_scale=float(c["guidance"]), noise=_t(c["probes"]).to(cuda))
+    torch.cuda.synchronize()
+    assert _rel(x.cpu().numpy(), c["latents"]) <= 2e-3, _rel(x.cpu().numpy(), c["latents"])
+    ref_ll = np.stack([c["ll_obj"][-1], c["ll_bg"][-1]], 1)
+    assert np.abs(ll.cpu().numpy() - ref_ll).max() <= 2e-3 * np.abs(ref_ll).max()
