@@ -1,5 +1,5 @@
 """Small driver for `ncu --set full`: one launch each of the kernels that matter (after a warm-up pass).
-Matched kernels per pass (regex step_vpsde|gn_|gemm_tcgen05): 2 + 2 + 5 = 9."""
+Matched kernels per pass (regex step_vpsde|gn_|gemm_tcgen05): 3 + 3 + 5 = 11 (ncu: -s 11 -c 11)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import math, torch
@@ -17,11 +17,15 @@ def run_all():
     lq = torch.zeros(Bs, M, device=dev); w = torch.zeros(Bs, M, device=dev); xo = torch.empty_like(x)
     ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, x_out=xo, weights=w)
     ops.step_vpsde(x, nz, sc, lq, -5.0, 5.0, 0.5, 1e-3, ops.MODE_AND, ops.DLOGQ_ITO, x_out=xo, weights=w)
+    add = torch.zeros(Bs, M, device=dev)
+    ops.step_vpsde_ode(x, sc, lq, -5.0, 5.0, 0.501, 1e-3, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, dlogq_add=add, x_out=xo, weights=w)
     del x, nz, sc, xo
     # GroupNorm at the largest activation (stats pass + apply pass; producer-emitted stats skip the first)
     a = torch.randn(B, 32, 32, 128, device=dev).bfloat16()
     g = torch.ones(128, device=dev); b = torch.zeros(128, device=dev)
     ops.groupnorm_swish(a, g, b)
+    a8 = torch.randn(B, 8, 8, 256, device=dev).bfloat16()
+    ops.groupnorm_swish(a8, torch.ones(256, device=dev), torch.zeros(256, device=dev))     # single-kernel register-resident form
     # implicit GEMM: 3x3 conv 128->128 at 32x32 (N = 128: paired m-tiles + activation slabs), with row bias + GN stats
     w1 = (torch.randn(128, 9 * 128, device=dev) / math.sqrt(9 * 128)).bfloat16()
     rb = torch.randn(B, 128, device=dev)
@@ -39,6 +43,6 @@ def run_all():
     ops.conv_gemm([(a4, 9)], w2[:, :9 * 256].contiguous())
     torch.cuda.synchronize()
 
-run_all()   # warm-up (ncu skips these with -s 9)
+run_all()   # warm-up (ncu skips these with -s 11)
 run_all()
 print("profile driver done")
