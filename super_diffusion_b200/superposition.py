@@ -235,6 +235,14 @@ class SuperDiffSampler:
         self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.M)] if multi_stream else []
         self.graph = None
         self.launches_per_step = None
+        # host-noise pipeline: the next step's noise crosses PCIe on a copy stream into one of two staging buffers while the
+        # current step computes; step() then only does a device-to-device copy into the buffer the captured graph reads
+        self._copy_stream = None
+        self._stage = None
+        self._stage_ready = None      # per staging buffer: H2D finished
+        self._stage_free = None       # per staging buffer: the D2D that consumed it finished
+        self._stage_next = 0
+        self._staged = None
 
     def _step_body(self):
         # The M score-net forwards are independent: run them on M streams (forked from / joined into the current
@@ -278,10 +286,36 @@ class SuperDiffSampler:
         if x0 is not None:
             self.x.copy_(x0)
 
+    def prefetch(self, noise_host):
+        """Start the host -> device copy of a later step's noise (pinned host tensor) on the copy stream; the next
+        ``step()`` without a ``noise`` argument consumes it.  Call right after ``step()`` so the transfer overlaps compute."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._stage = [torch.empty_like(self.noise) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event() for _ in range(2)]
+            self._stage_free = [None, None]
+        k = self._stage_next
+        self._stage_next ^= 1
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[k] is not None:
+                self._copy_stream.wait_event(self._stage_free[k])
+            self._stage[k].copy_(noise_host, non_blocking=True)
+            self._stage_ready[k].record(self._copy_stream)
+        self._staged = k
+
     def step(self, noise=None):
-        """One Euler-Maruyama timestep at the schedule row the device counter points to."""
+        """One Euler-Maruyama timestep at the schedule row the device counter points to.  ``noise``: device or host tensor
+        copied on the current stream; None: use the buffer filled by ``prefetch()`` (or whatever ``self.noise`` holds)."""
         if noise is not None:
             self.noise.copy_(noise, non_blocking=True)
+        elif self._staged is not None:
+            k, self._staged = self._staged, None
+            cur = torch.cuda.current_stream()
+            cur.wait_event(self._stage_ready[k])
+            self.noise.copy_(self._stage[k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._stage_free[k] = ev
         if self.launches_per_step is None:
             self.capture()
         if self.graph is not None:
@@ -298,6 +332,16 @@ class SuperDiffSampler:
         if x0 is None:
             x0 = torch.randn(self.shape, generator=g, device=self.device, dtype=torch.float32)
         self.reset(x0)
+        host_noise = torch.is_tensor(noise) and not noise.is_cuda and noise.is_pinned()
+        if host_noise:      # pipelined: noise[i+1] crosses PCIe while step i computes
+            if noise.shape[0] < self.n_steps:
+                raise ValueError("noise tensor has fewer steps than n_steps")
+            self.prefetch(noise[0])
+            for i in range(self.n_steps):
+                self.step()
+                if i + 1 < self.n_steps:
+                    self.prefetch(noise[i + 1])
+            return self.x, self.logq, self.weights
         nz = _noise_iter(noise, self.n_steps, self.shape, self.device, seed + 1)
         for i in range(self.n_steps):
             self.step(nz(i))

@@ -236,6 +236,11 @@ def test_cifar_sampler_and_mode_and_three_models(cuda):
     assert torch.isfinite(x).all() and torch.isfinite(lq).all()
     assert torch.allclose(w.sum(1), torch.ones(B, device=cuda), atol=1e-5)
     assert (lq[:, 0] - lq[:, 1]).abs().max().item() <= 1e-3 * (1 + lq.abs().max().item())
+    # pinned host noise: the pipelined path (copy stream + staging buffers) gives bit-identical results
+    x_dev, lq_dev = x.clone(), lq.clone()
+    x_h, lq_h, _ = smp.sample(x0=x0, noise=noise.cpu().pin_memory())
+    torch.cuda.synchronize()
+    assert torch.equal(x_h, x_dev) and torch.equal(lq_h, lq_dev)
     model3, p3 = mutils.init_model(12, cfg, zero_init_scale=1.0)
     nets3 = nets + [model3.bind(p3, cuda)]
     smp3 = SuperDiffSampler(nets3, B, mode="or", n_steps=n, dt=5e-3, temperature=1e6, device=cuda)
