@@ -63,7 +63,13 @@ def launch(argv=None):
         out = run_lib.evaluate_joint_fid(config, args.workdir, args.eval_folder, chk, stoch, num_batches=args.num_batches, dt=args.dt)
     else:
         out = run_lib.evaluate_fid(config, args.workdir, args.eval_folder, stoch, num_batches=args.num_batches, dt=args.dt)
-    print(out)
+    if torch.distributed.is_initialized():
+        torch.distributed.barrier()
+        if torch.distributed.get_rank() == 0:
+            print(out)
+        torch.distributed.destroy_process_group()
+    else:
+        print(out)
     return out
 
 
