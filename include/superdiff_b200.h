@@ -237,6 +237,11 @@ int sd_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* st
  * out[b,ho,wo, tap*C + c] = x[b, 2ho+kh, 2wo+kw, c] (0 outside). bf16. */
 int sd_im2col_s2(const void* x, int B, int H, int W, int C, void* out, void* stream);
 
+/* Operand gather for the first conv (cifar/models/ddpm.py:71) on the tensor cores: out[pixel] = 64 bf16 =
+ * [hi(9*Cin) | lo(9*Cin) | zeros], hi = bf16(v), lo = bf16(v - hi) of the zero-padded 3x3xCin fp32 neighbourhood (Cin <= 3).
+ * The conv is then sd_conv_gemm with one 1-tap source of 64 channels against weights [w | w | 0] (bf16 [Cout, 64]). */
+int sd_im2col_in(const float* x, int B, int H, int W, int Cin, void* out /* bf16 [B,H,W,64] */, void* stream);
+
 /* First conv (cifar/models/ddpm.py:71): fp32 NHWC [B,H,W,Cin<=4] -> bf16
  * [B,H,W,Cout], 3x3 SAME, fp32 weights [3,3,Cin,Cout] (Flax HWIO) + bias. */
 int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio, const float* bias,

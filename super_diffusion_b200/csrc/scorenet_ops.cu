@@ -427,6 +427,40 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// First conv on the tensor cores: gather the 3x3xCin (<= 27) fp32 neighbourhood of every pixel into one 64-wide bf16 K-block,
+// split as hi = bf16(v), lo = bf16(v - hi) so the fp32 input keeps ~16 mantissa bits:  row = [hi(9*Cin) | lo(9*Cin) | 0...].
+// The conv is then a 1-tap implicit GEMM with K = 64 against [w | w | 0] (sd_conv_gemm: bias, GroupNorm statistics for free).
+__global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const size_t npix = (size_t)B * H * W;
+  const int K = 9 * Cin;
+  for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
+    size_t q = pix;
+    const int wo = q % W; q /= W;
+    const int ho = q % H;
+    const int b = (int)(q / H);
+    __nv_bfloat16 row[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) row[i] = __float2bfloat16_rn(0.f);
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) {
+        const int hi = ho + kh - 1, wi = wo + kw - 1;
+        if (hi < 0 || hi >= H || wi < 0 || wi >= W) continue;
+        const float* src = x + (((size_t)b * H + hi) * W + wi) * Cin;
+        for (int c = 0; c < Cin; ++c) {
+          const float v = src[c];
+          const __nv_bfloat16 h16 = __float2bfloat16_rn(v);
+          row[(kh * 3 + kw) * Cin + c] = h16;
+          row[K + (kh * 3 + kw) * Cin + c] = __float2bfloat16_rn(v - __bfloat162float(h16));
+        }
+      }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+    const uint4* r4 = reinterpret_cast<const uint4*>(row);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dst[i] = r4[i];
+  }
+}
+
 // temb = Dense1(swish(Dense0(sinusoidal(t))))  for n_t distinct times -> fp32 scratch [n_t, 4nf]
 __global__ void __launch_bounds__(512) temb_dense_kernel(const float* __restrict__ t_dev, int t_stride,
                                                          const float* __restrict__ sched, const int* __restrict__ step_counter,
@@ -638,6 +672,16 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
     default: conv_in_kernel<4><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
   }
   return check_cuda(cudaGetLastError(), "sd_conv_in launch");
+}
+
+int sd_im2col_in(const float* x, int B, int H, int W, int Cin, void* out, void* stream) {
+  using namespace sdb;
+  if (!x || !out || B < 0 || H < 1 || W < 1 || Cin < 1 || 18 * Cin > 64)
+    return fail(kErrInvalidArg, "sd_im2col_in: 1 <= Cin <= 3 required (hi/lo split of 9*Cin values must fit one 64-wide K-block)");
+  if (B == 0) return SD_OK;
+  const size_t npix = (size_t)B * H * W;
+  im2col_in_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cin, (__nv_bfloat16*)out);
+  return check_cuda(cudaGetLastError(), "sd_im2col_in launch");
 }
 
 int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, const int* step_counter, int B, int nf,

@@ -466,6 +466,27 @@ def im2col_s2(x, out=None):
     return out
 
 
+def im2col_in(x, out=None):
+    """fp32 NHWC [B,H,W,Cin<=3] -> bf16 [B,H,W,64] hi/lo-split 3x3 neighbourhoods (sd_im2col_in)."""
+    lib = _lib.load()
+    _f32c(x, "x")
+    B, H, W, Cin = x.shape
+    if out is None:
+        out = torch.empty(B, H, W, 64, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_im2col_in(_ptr(x), B, H, W, Cin, _ptr(out), _stream()), "sd_im2col_in")
+    if B > 0:
+        _count()
+    return out
+
+
+def conv_in_weights(w_hwio):
+    """Flax HWIO [3,3,Cin,Cout] fp32 -> fp32 [Cout, 64] = [w | w | 0] matching im2col_in's [hi | lo | 0] rows."""
+    cout = w_hwio.shape[-1]
+    w = w_hwio.reshape(-1, cout).T                       # [Cout, 9*Cin], (kh, kw, c) order
+    pad = torch.zeros(cout, 64 - 2 * w.shape[1], dtype=w.dtype, device=w.device)
+    return torch.cat([w, w, pad], dim=1)
+
+
 def conv_in(x, w_hwio, bias, out=None):
     lib = _lib.load()
     _f32c(x, "x")

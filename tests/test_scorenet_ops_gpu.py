@@ -392,3 +392,29 @@ def test_conv_gemm_swapped_1x1_multi_ntile(cuda):
     tiles = out.float().reshape(B, nt, 128, C)
     assert torch.allclose(st[:, :, 0], tiles.sum(2), rtol=2e-2, atol=0.5)
     assert torch.allclose(st[:, :, 1], (tiles ** 2).sum(2), rtol=2e-2, atol=0.5)
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout", [(3, 32, 3, 128), (40, 32, 3, 128), (5, 16, 1, 64)])
+def test_conv_in_tensor_core_form(cuda, B, H, Cin, Cout):
+    """First conv as im2col_in (hi/lo split of the fp32 input, one 64-wide K-block) + 1-tap implicit GEMM, with bias and the
+    GroupNorm channel sums of the output; the fp32 input keeps ~16 mantissa bits, the weights are bf16 like every other layer."""
+    g = torch.Generator().manual_seed(B + H + Cin)
+    x = torch.randn(B, H, H, Cin, generator=g) * 3.0
+    w = torch.randn(3, 3, Cin, Cout, generator=g) / math.sqrt(9 * Cin)
+    bias = torch.randn(Cout, generator=g)
+    w64 = ops.conv_in_weights(w)
+    assert w64.shape == (Cout, 64)
+    a = ops.im2col_in(x.to(cuda))
+    # the gather itself: hi + lo reproduces the fp32 neighbourhood to 2^-16 relative
+    xp = F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1))
+    nb = torch.stack([xp[:, :, kh:kh + H, kw:kw + H] for kh in range(3) for kw in range(3)], dim=1)   # [B, 9, Cin, H, H]
+    nb = nb.permute(0, 3, 4, 1, 2).reshape(B, H, H, 9 * Cin)
+    af = a.float().cpu()
+    assert torch.allclose(af[..., :9 * Cin] + af[..., 9 * Cin:18 * Cin], nb, rtol=2e-5, atol=1e-6)
+    assert (af[..., 18 * Cin:] == 0).all()
+    out = ops.conv_gemm([(a, 1)], _bf(w64).to(cuda), bias=bias.to(cuda), want_stats=(H * H) % 128 == 0)
+    wb = _bf(w).float()
+    ref = F.conv2d(x.permute(0, 3, 1, 2).double(), wb.permute(3, 2, 0, 1).double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    _close(out, ref)
+    old = ops.conv_in(x.to(cuda), w.to(cuda), bias.to(cuda))
+    _close(old, ref, rtol=2e-2)

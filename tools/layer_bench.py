@@ -27,7 +27,7 @@ net(0.5, x, out=out)
 torch.cuda.synchronize()
 
 NAMES = ["conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs", "groupnorm_swish", "attention_small",
-         "softmax_rows", "upsample2x", "im2col_s2", "conv_in", "time_embedding", "cast_bf16"]
+         "softmax_rows", "upsample2x", "im2col_s2", "im2col_in", "conv_in", "time_embedding", "cast_bf16"]
 calls = []
 orig = {}
 
