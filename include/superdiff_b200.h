@@ -187,6 +187,13 @@ int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, i
                     int batch, int M, int N, int K, const float* bias, const void* residual, unsigned flags,
                     void* out, int ldc, long long strideC, void* stream);
 
+/* sd_batched_gemm that also emits per-128-row-tile channel sums of its output (as sd_conv_gemm's stats_out):
+ * stats_out fp32 [batch][M/128][2][N]; needs M % 128 == 0 and N % 16 == 0.  Used for the fused attention tail
+ * out = P (V Wo) + (b_v Wo + b_o) + x, whose output feeds the next GroupNorm (cifar/models/layers.py:509-511). */
+int sd_batched_gemm_stats(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                          int batch, int M, int N, int K, const float* bias, const void* residual, unsigned flags,
+                          void* out, int ldc, long long strideC, float* stats_out, void* stream);
+
 /* Attention probabilities in one launch (cifar/models/layers.py:505-507):
  *     P[b][i][:] = softmax_j(scale * <Q[b][i], K[b][j]>)   restricted to the diagonal block of `block` columns
  * that row i belongs to (block = S for ordinary attention; block < S packs S/block small images into one

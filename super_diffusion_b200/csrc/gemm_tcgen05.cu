@@ -912,8 +912,8 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.flags = flags;
   p.imgs_in_tile = (!p.flat && p.HW < BM) ? BM / p.HW : 1;
   p.stats_out = stats_out;
-  if (stats_out && (p.flat || (p.HW % BM) != 0 || (N % 16) != 0 || (flags & SD_EPI_SOFTMAX)))
-    return fail(kErrInvalidArg, std::string(who) + ": stats_out needs a conv-mode GEMM with H*W a multiple of 128 and N a multiple of 16");
+  if (stats_out && ((p.flat ? (p.M_per_batch % BM) != 0 : (p.HW % BM) != 0) || (N % 16) != 0 || (flags & SD_EPI_SOFTMAX)))
+    return fail(kErrInvalidArg, std::string(who) + ": stats_out needs whole 128-row tiles per image / batch entry and N a multiple of 16");
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
   const bool vec_ok = (out_ld % out_align == 0) && ((uintptr_t)out % 16 == 0) && (!residual || ((uintptr_t)residual % 16 == 0 && out_ld % 8 == 0)) &&
                       (!bias || (uintptr_t)bias % 16 == 0) && (!rowbias || ((uintptr_t)rowbias % 16 == 0 && rowbias_ld % 4 == 0)) &&
@@ -1058,7 +1058,7 @@ extern "C" int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const v
 static int batched_gemm_impl(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
                             int batch, int M, int N, int K, const float* bias, const void* residual,
                             unsigned flags, void* out, int ldc, long long strideC, void* stream,
-                            float softmax_scale, int softmax_block) {
+                            float softmax_scale, int softmax_block, float* stats_out = nullptr) {
   using namespace sdb;
   if (!A || !Bt || !out || batch < 0 || M < 1 || N < 1 || K < BK || (K % BK) != 0)
     return fail(kErrInvalidArg, "sd_batched_gemm: bad argument (K must be a multiple of 64)");
@@ -1079,6 +1079,11 @@ static int batched_gemm_impl(const void* A, int lda, long long strideA, const vo
   p.M_per_batch = M;
   p.m_tiles_per_batch = (M + BM - 1) / BM;
   p.m_tiles = p.m_tiles_per_batch * batch;
+  p.tiles_per_img = p.m_tiles_per_batch;          // stats_out slot = batch * tiles + tile-in-batch
+  p.stats_tpi_total = p.m_tiles_per_batch;
+  p.stats_slot0 = 0;
+  p.imgs_per_tile = 1;
+  p.up_phase = -1;
   p.out_batch_stride = strideC;
   p.nseg = 1;
   p.seg_taps[0] = 1;
@@ -1096,7 +1101,15 @@ static int batched_gemm_impl(const void* A, int lda, long long strideA, const vo
   int rc = encode_map(&p.a_map[0], A, 4, dims, strides, box);
   if (rc != SD_OK) return rc;
   return launch_gemm(p, N, K, Bt, ldb, strideB, p.b_batched ? batch : 1, bias, nullptr, 0, residual, flags, out, ldc,
-                     (cudaStream_t)stream, "sd_batched_gemm");
+                     (cudaStream_t)stream, "sd_batched_gemm", stats_out);
+}
+
+extern "C" int sd_batched_gemm_stats(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,
+                                     int batch, int M, int N, int K, const float* bias, const void* residual,
+                                     unsigned flags, void* out, int ldc, long long strideC, float* stats_out, void* stream) {
+  if (flags & SD_EPI_SOFTMAX) return sdb::fail(sdb::kErrInvalidArg, "sd_batched_gemm_stats: no softmax epilogue");
+  return batched_gemm_impl(A, lda, strideA, Bt, ldb, strideB, batch, M, N, K, bias, residual, flags, out, ldc, strideC,
+                           stream, 1.f, 1, stats_out);
 }
 
 extern "C" int sd_batched_gemm(const void* A, int lda, long long strideA, const void* Bt, int ldb, long long strideB,

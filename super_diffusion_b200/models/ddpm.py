@@ -96,10 +96,18 @@ class _Bound:
             blk = P[f"AttnBlock_{counters['attn']}"]
             wq, wk, wv, wo = (blk[f"NIN_{i}"]["W"] for i in range(4))
             bq, bk, bv, bo = (blk[f"NIN_{i}"]["b"] for i in range(4))
+            # Folded projections (exact algebra, evaluated in fp64 at bind time; layers.py:500-511):
+            #   q k^T = (h Wq + bq)(h Wk + bk)^T = (h Wq Wk^T + (Wk bq)^T) h^T + [terms constant along a row, which the row
+            #           softmax cancels]                  ->  q' = NIN(h; Wq Wk^T, Wk bq), keys = h itself (no k projection)
+            #   NIN_3(P v) + x = P (h Wv Wo) + (bv Wo + bo) + x   (rows of P sum to 1)   -> V' = h (Wv Wo), no out projection
+            wq64, wk64, wv64, wo64 = (w.double() for w in (wq, wk, wv, wo))
+            w_q2 = (wq64 @ wk64.T).T.float()                      # GEMM weight layout [out, in]
+            b_q2 = (wk64 @ bq.double()).float()
+            w_vo = (wv64 @ wo64).float()                          # [C_in, C_out]
+            b_vo = (bv.double() @ wo64 + bo.double()).float()
             a = dict(g=self._dev(blk["GroupNorm_0"]["scale"]), be=self._dev(blk["GroupNorm_0"]["bias"]),
                      w_qkv=self._dev(torch.cat([wq.T, wk.T, wv.T], 0), bf), b_qkv=self._dev(torch.cat([bq, bk, bv])),
-                     w_qk=self._dev(torch.cat([wq.T, wk.T], 0), bf), b_qk=self._dev(torch.cat([bq, bk])),
-                     w_vT=self._dev(wv.T, bf), b_v=self._dev(bv),
+                     w_q2=self._dev(w_q2, bf), b_q2=self._dev(b_q2), w_voT=self._dev(w_vo.T, bf), b_vo=self._dev(b_vo),
                      w_o=self._dev(torch.cat([wo.T, torch.eye(c)], dim=1), bf), b_o=self._dev(bo), c=c)   # + x (layers.py:511)
             self.attn.append(a)
             counters["attn"] += 1
@@ -169,13 +177,17 @@ class _Bound:
         if S < 16 or B % g or (g * S) % 16:
             qkv = ops.conv_gemm([(h, 1)], a["w_qkv"], bias=a["b_qkv"])
             o = ops.attention_small(qkv.view(B, S, 3 * C), C)
-        else:
-            nb, Sp = B // g, g * S
-            qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(nb, Sp, 2 * C)
-            vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))                      # [nb, C, Sp] = V^T (bias deferred)
-            p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], C ** -0.5, block=S, C=C)   # [nb, Sp, Sp], block diagonal
-            o = ops.batched_gemm(p, vt, bias=a["b_v"])                               # rows of p sum to 1 -> + b_v
-        return ops.conv_gemm([(o.view(B, H, W, C), 1), (x, 1)], a["w_o"], bias=a["b_o"], want_stats=True)
+            return ops.conv_gemm([(o.view(B, H, W, C), 1), (x, 1)], a["w_o"], bias=a["b_o"], want_stats=True)
+        nb, Sp = B // g, g * S
+        hb = h.view(nb, Sp, C)
+        q2 = ops.conv_gemm([(h, 1)], a["w_q2"], bias=a["b_q2"]).view(nb, Sp, C)      # q' = h Wq Wk^T + Wk bq
+        vt = ops.batched_gemm(a["w_voT"], hb)                                        # [nb, C, Sp] = (h Wv Wo)^T
+        p = ops.attention_probs(q2, hb, C ** -0.5, block=S, C=C)                     # [nb, Sp, Sp], block diagonal; keys = h
+        out = ops.batched_gemm(p, vt, bias=a["b_vo"], residual=x.view(nb, Sp, C), want_stats=(g == 1))
+        res = out.view(B, H, W, C)
+        if hasattr(out, "gn_stats"):
+            res.gn_stats = out.gn_stats
+        return res
 
     def __call__(self, t, x, y=None, *, sched=None, step_counter=None, out=None):
         """t: (B,1,1,1)/(B,)/scalar tensor or float; x: (B,H,W,C) fp32 NHWC on the device."""
@@ -264,19 +276,19 @@ class _Bound:
         h, dh = ops.groupnorm_swish_jvp(x, dx, a["g"], a["be"], swish=False)
         nb, Sp = B // g, g * S
         scale = C ** -0.5
-        qk = ops.conv_gemm([(h, 1)], a["w_qk"], bias=a["b_qk"]).view(nb, Sp, 2 * C)
-        dqk = ops.conv_gemm([(dh, 1)], a["w_qk"]).view(nb, Sp, 2 * C)
-        vt = ops.batched_gemm(a["w_vT"], h.view(nb, Sp, C))
-        dvt = ops.batched_gemm(a["w_vT"], dh.view(nb, Sp, C))
-        p = ops.attention_probs(qk[:, :, :C], qk[:, :, C:], scale, block=S, C=C)
-        ds1 = ops.batched_gemm(dqk[:, :, :C], qk[:, :, C:], out_f32=True, K=C)       # dq k^T
-        ds2 = ops.batched_gemm(qk[:, :, :C], dqk[:, :, C:], out_f32=True, K=C)       # q dk^T
+        hb, dhb = h.view(nb, Sp, C), dh.view(nb, Sp, C)
+        q2 = ops.conv_gemm([(h, 1)], a["w_q2"], bias=a["b_q2"]).view(nb, Sp, C)      # folded projections, see add_attn
+        dq2 = ops.conv_gemm([(dh, 1)], a["w_q2"]).view(nb, Sp, C)
+        vt = ops.batched_gemm(a["w_voT"], hb)
+        dvt = ops.batched_gemm(a["w_voT"], dhb)
+        p = ops.attention_probs(q2, hb, scale, block=S, C=C)
+        ds1 = ops.batched_gemm(dq2, hb, out_f32=True, K=C)                           # dq' h^T
+        ds2 = ops.batched_gemm(q2, dhb, out_f32=True, K=C)                           # q' dh^T
         dp = ops.softmax_jvp(p, ds1, ds2, scale)       # off-block entries of a packed tile: p = 0 -> dp = 0
-        o = ops.batched_gemm(p, vt, bias=a["b_v"])
-        do = ops.batched_gemm(p, dvt, residual=ops.batched_gemm(dp, vt))             # dP V + P dV
-        out = ops.conv_gemm([(o.view(B, H, W, C), 1), (x, 1)], a["w_o"], bias=a["b_o"])
-        dout = ops.conv_gemm([(do.view(B, H, W, C), 1), (dx, 1)], a["w_o"])
-        return out, dout
+        out = ops.batched_gemm(p, vt, bias=a["b_vo"], residual=x.view(nb, Sp, C))
+        do = ops.batched_gemm(dp, vt, residual=dx.view(nb, Sp, C))                   # dP V' + dx ...
+        dout = ops.batched_gemm(p, dvt, residual=do)                                 # ... + P dV'
+        return out.view(B, H, W, C), dout.view(B, H, W, C)
 
     def jvp(self, t, x, y, v, *, sched=None, step_counter=None, out=None, jvp_out=None):
         """(score(x), d/dh score(x + h v)|_0): what jax.jvp(sdlogdx_fn, (x,), (eps,)) returns at cifar/dynamics.py:84.

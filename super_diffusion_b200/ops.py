@@ -295,7 +295,7 @@ def upconv_gemm(x, w4, bias=None, out=None, want_stats=False):
     return out
 
 
-def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None):
+def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None, want_stats=False):
     """out[b] = A[b] @ Bt[b]^T (sd_batched_gemm).  A: bf16 [batch, M, >=K] or [M, K]
     (shared), Bt: bf16 [batch, N, >=K] or [N, K] (shared); row strides may exceed K."""
     lib = _lib.load()
@@ -313,12 +313,22 @@ def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, ou
     if out is None:
         out = torch.empty(batch, M, N, device=A.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
     flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0)
-    rc = lib.sd_batched_gemm(_ptr(a3), a3.stride(1), sA, _ptr(b3), b3.stride(1), sB, batch, M, N, K,
-                             _ptr(bias), _ptr(residual), flags, _ptr(out), out.stride(-2),
-                             out.stride(0) if out.dim() == 3 else 0, _stream())
+    stats = None
+    if want_stats and M % 128 == 0 and N % 16 == 0 and not out_f32 and batch > 0:
+        stats = torch.empty(batch, M // 128, 2, N, device=A.device, dtype=torch.float32)
+    if stats is not None:
+        rc = lib.sd_batched_gemm_stats(_ptr(a3), a3.stride(1), sA, _ptr(b3), b3.stride(1), sB, batch, M, N, K,
+                                       _ptr(bias), _ptr(residual), flags, _ptr(out), out.stride(-2),
+                                       out.stride(0) if out.dim() == 3 else 0, _ptr(stats), _stream())
+    else:
+        rc = lib.sd_batched_gemm(_ptr(a3), a3.stride(1), sA, _ptr(b3), b3.stride(1), sB, batch, M, N, K,
+                                 _ptr(bias), _ptr(residual), flags, _ptr(out), out.stride(-2),
+                                 out.stride(0) if out.dim() == 3 else 0, _stream())
     _lib.check(rc, "sd_batched_gemm")
     if batch > 0:
         _count()
+    if stats is not None:
+        out.gn_stats = (stats, M // 128)
     return out
 
 
