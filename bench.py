@@ -274,12 +274,12 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
-                     "traffic": None, "kernel": "gemm_tcgen05_kernel", "peak_kind": f"{peak_kind} sustained bf16",
+                     "traffic": None, "kernel": "gemm_tcgen05_kernel (+ attn_core_kernel, 7 of the launches)", "peak_kind": f"{peak_kind} sustained bf16",
                      "share_of_step": share, "gemm_ms_per_step": gemm_only_ms, "gemm_launches_per_step": gemm_launches,
                      "achieved_eager": gemm_tf_eager, "executed_tflop_per_step": gemm_flop_exec / 1e12,
                      "algorithmic_tflop_per_step": gemm_flop / 1e12,
                      "note": "algorithmic flops of one timestep (2 models x batch x 12.154 GFLOP, SURVEY 8d) / summed duration of "
-                             "the step's gemm_tcgen05_kernel launches, measured by replaying exactly those launches alone in a CUDA "
+                             "the step's tensor-core launches (every conv / NIN / Dense / attention product), measured by replaying exactly those launches alone in a CUDA "
                              "graph (events on the launching stream, 8 replays); share_of_step = that time / ms_per_step; "
                              "achieved_eager (events around every python call of an eager pass) includes host launch gaps"},
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
@@ -312,7 +312,7 @@ def _instrumented_step(sampler, ops, torch):
     """One eager timestep with CUDA events around every kernel launch made through ops.*; returns
     (gemm kernel ms, gemm algorithmic flop, all other kernels ms)."""
     recs = []
-    gemm_ops = ("conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs")   # all launch gemm_tcgen05_kernel
+    gemm_ops = ("conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs", "attention_core")   # tensor-core kernels
     names = list(gemm_ops) + ["groupnorm_swish", "attention_small", "softmax_rows", "upsample2x", "im2col_s2", "im2col_in",
                               "conv_in", "time_embedding", "step_vpsde", "counter_add"]
     orig = {n: getattr(ops, n) for n in names}
@@ -339,6 +339,8 @@ def _instrumented_step(sampler, ops, torch):
                 flop = 2.0 * r.numel() * (k.get("K") or a[0].shape[-1])
             elif n == "attention_probs":
                 flop = 2.0 * r.numel() * (k.get("C") or a[0].shape[-1])
+            elif n == "attention_core":
+                flop = 4.0 * a[0].shape[0] * a[0].shape[1] * a[0].shape[1] * (k.get("C") or a[0].shape[-1])
             recs.append((n, s, e, flop))
             return r
         return g
@@ -359,10 +361,10 @@ def _instrumented_step(sampler, ops, torch):
 
 
 def _gemm_only_time(sampler, ops, torch, reps=8):
-    """Time of all gemm_tcgen05_kernel launches of one timestep, measured directly: the GEMM calls of one step are recorded
+    """Time of all tensor-core kernel launches (gemm_tcgen05_kernel, attn_core_kernel) of one timestep, measured directly: the calls of one step are recorded
     (function + arguments) and replayed alone, back to back on one stream, inside a CUDA graph; CUDA events around `reps`
     replays.  No host launch latency, no other kernels; sustained clocks because the replays run for >= 50 ms."""
-    gemm_ops = ("conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs")
+    gemm_ops = ("conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs", "attention_core")
     calls = []
     orig = {n: getattr(ops, n) for n in gemm_ops}
 

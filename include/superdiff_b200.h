@@ -194,6 +194,17 @@ int sd_batched_gemm_stats(const void* A, int lda, long long strideA, const void*
                           int batch, int M, int N, int K, const float* bias, const void* residual, unsigned flags,
                           void* out, int ldc, long long strideC, float* stats_out, void* stream);
 
+/* Fused attention core (cifar/models/layers.py:505-511 after the projections):
+ *     out[b][i][:] = sum_j softmax_j(scale * <Q[b][i], K[b][j]>) V[b][j][:] + bias + residual[b][i][:]
+ * with the softmax restricted to the diagonal block of `block` key columns row i belongs to (block < S packs S/block small
+ * images into one batch entry).  Q, K: bf16 [batch][S][ld] (channel-contiguous), Vt: bf16 [batch][C][ldv] = V transposed
+ * (key-contiguous), residual / out: bf16 [batch][S][C]; S in {128, 256}, C in {64, 128, 192, 256}.  The probability matrix
+ * stays in shared memory (softmax epilogue writes the UMMA A operand of the second product).  stats_out (optional, block == S):
+ * fp32 [batch][S/128][2][C] channel sums of out for sd_groupnorm_swish. */
+int sd_attention_core(const void* Q, int ldq, long long strideQ, const void* K, int ldk, long long strideK,
+                      const void* Vt, int ldv, long long strideV, int batch, int S, int C, float scale, int block,
+                      const float* bias, const void* residual, void* out, float* stats_out, void* stream);
+
 /* Attention probabilities in one launch (cifar/models/layers.py:505-507):
  *     P[b][i][:] = softmax_j(scale * <Q[b][i], K[b][j]>)   restricted to the diagonal block of `block` columns
  * that row i belongs to (block = S for ordinary attention; block < S packs S/block small images into one

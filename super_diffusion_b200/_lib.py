@@ -46,6 +46,7 @@ SIGNATURES = {
     "sd_time_embedding": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sd_batched_gemm": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _I, _V, _V, _U, _V, _I, _LL, _V]),
     "sd_batched_gemm_stats": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _I, _V, _V, _U, _V, _I, _LL, _V, _V]),
+    "sd_attention_core": (_I, [_V, _I, _LL, _V, _I, _LL, _V, _I, _LL, _I, _I, _I, _F, _I, _V, _V, _V, _V, _V]),
     "sd_attention_probs": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _F, _I, _V, _V]),
     "sd_softmax_rows": (_I, [_V, _V, ctypes.c_long, _I, _F, _V]),
     "sd_cast_f32_to_bf16": (_I, [_V, _V, _SZ, _V]),

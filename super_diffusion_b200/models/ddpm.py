@@ -19,11 +19,15 @@ Activations are NHWC bf16 between kernels; the output score is fp32.
 There is no PyTorch / CPU fallback for the forward.
 """
 import math
+import os
 
 import torch
 
 from .. import _lib, ops
 from . import utils
+
+
+_FUSED_ATTENTION = os.environ.get("SDB_FUSED_ATTENTION", "1") != "0"      # tuning knob: 0 = probabilities + P V as two launches
 
 
 def _conv_w(p):
@@ -182,8 +186,13 @@ class _Bound:
         hb = h.view(nb, Sp, C)
         q2 = ops.conv_gemm([(h, 1)], a["w_q2"], bias=a["b_q2"]).view(nb, Sp, C)      # q' = h Wq Wk^T + Wk bq
         vt = ops.batched_gemm(a["w_voT"], hb)                                        # [nb, C, Sp] = (h Wv Wo)^T
-        p = ops.attention_probs(q2, hb, C ** -0.5, block=S, C=C)                     # [nb, Sp, Sp], block diagonal; keys = h
-        out = ops.batched_gemm(p, vt, bias=a["b_vo"], residual=x.view(nb, Sp, C), want_stats=(g == 1))
+        if Sp in (128, 256) and C % 64 == 0 and C <= 256 and _FUSED_ATTENTION:
+            # softmax(q' h^T) V' + bias + x in one kernel: the probabilities stay in shared memory (csrc/attn_core.cu)
+            out = ops.attention_core(q2, hb, vt, C ** -0.5, block=S, bias=a["b_vo"], residual=x.view(nb, Sp, C),
+                                     want_stats=(g == 1), C=C)
+        else:
+            p = ops.attention_probs(q2, hb, C ** -0.5, block=S, C=C)                 # [nb, Sp, Sp], block diagonal; keys = h
+            out = ops.batched_gemm(p, vt, bias=a["b_vo"], residual=x.view(nb, Sp, C), want_stats=(g == 1))
         res = out.view(B, H, W, C)
         if hasattr(out, "gn_stats"):
             res.gn_stats = out.gn_stats

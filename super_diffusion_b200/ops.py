@@ -349,6 +349,33 @@ def attention_probs(q, k, scale, block=None, out=None, C=None):
     return out
 
 
+def attention_core(q, k, vt, scale, block=None, bias=None, residual=None, want_stats=False, C=None):
+    """out = blockdiag-softmax(scale * q k^T) v + bias + residual in ONE launch (sd_attention_core).  q, k: bf16 [batch, S, >=C]
+    views with unit inner stride, vt: bf16 [batch, C, S] (V transposed), residual: bf16 [batch, S, C]; returns bf16 [batch, S, C]."""
+    lib = _lib.load()
+    batch, S = q.shape[0], q.shape[1]
+    C = q.shape[2] if C is None else C
+    block = S if block is None else block
+    for t in (q, k, vt):
+        if t.dtype != torch.bfloat16 or not t.is_cuda or t.stride(2) != 1:
+            raise ValueError("operands must be bf16 CUDA tensors with unit inner stride")
+    if residual is not None:
+        _bf16c(residual, "residual")
+    out = torch.empty(batch, S, C, device=q.device, dtype=torch.bfloat16)
+    stats = None
+    if want_stats and block == S and batch > 0:
+        stats = torch.empty(batch, S // 128, 2, C, device=q.device, dtype=torch.float32)
+    rc = lib.sd_attention_core(_ptr(q), q.stride(1), q.stride(0), _ptr(k), k.stride(1), k.stride(0), _ptr(vt), vt.stride(1),
+                               vt.stride(0), batch, S, C, float(scale), int(block), _ptr(bias), _ptr(residual), _ptr(out),
+                               _ptr(stats), _stream())
+    _lib.check(rc, "sd_attention_core")
+    if batch > 0:
+        _count()
+    if stats is not None:
+        out.gn_stats = (stats, S // 128)
+    return out
+
+
 def softmax_rows(x, scale, out=None):
     lib = _lib.load()
     _f32c(x, "x")

@@ -418,3 +418,41 @@ def test_conv_in_tensor_core_form(cuda, B, H, Cin, Cout):
     _close(out, ref)
     old = ops.conv_in(x.to(cuda), w.to(cuda), bias.to(cuda))
     _close(old, ref, rtol=2e-2)
+
+
+@pytest.mark.parametrize("nb,Sp,block,C,stats", [(5, 256, 256, 256, True), (150, 256, 256, 256, True), (6, 128, 64, 256, False),
+                                                  (7, 128, 16, 256, False), (3, 128, 128, 128, True)])
+def test_attention_core_fused(cuda, nb, Sp, block, C, stats):
+    """softmax_blocks(scale q k^T) v + bias + residual in one launch (probabilities stay in shared memory) vs torch math on the
+    same bf16 inputs; persistent over more tiles than SMs (nb = 150 -> 300 tiles); GroupNorm channel sums of the output."""
+    g = torch.Generator().manual_seed(nb * 7 + Sp + block)
+    q = _bf(torch.randn(nb, Sp, C, generator=g))
+    k = _bf(torch.randn(nb, Sp, C, generator=g))
+    v = _bf(torch.randn(nb, Sp, C, generator=g))
+    res = _bf(torch.randn(nb, Sp, C, generator=g))
+    bias = torch.randn(C, generator=g)
+    scale = C ** -0.5
+    vt = v.transpose(1, 2).contiguous()
+    out = ops.attention_core(q.to(cuda), k.to(cuda), vt.to(cuda), scale, block=block, bias=bias.to(cuda), residual=res.to(cuda),
+                             want_stats=stats)
+    torch.cuda.synchronize()
+    s = torch.einsum("bic,bjc->bij", q.double(), k.double()) * scale
+    blk = torch.arange(Sp) // block
+    s = s.masked_fill(blk[:, None] != blk[None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    ref = torch.einsum("bij,bjc->bic", _bf(p.float()).double(), v.double()) + bias.double() + res.double()
+    _close(out, ref)
+    if stats:
+        st, nt = out.gn_stats
+        tiles = out.float().reshape(nb, nt, 128, C)
+        assert torch.allclose(st[:, :, 0], tiles.sum(2), rtol=2e-2, atol=0.5)
+        assert torch.allclose(st[:, :, 1], (tiles ** 2).sum(2), rtol=2e-2, atol=1.0)
+    else:
+        assert not hasattr(out, "gn_stats")
+    # strided q / k views (row stride 2C), no bias / residual
+    qk = _bf(torch.randn(nb, Sp, 2 * C, generator=g)).to(cuda)
+    out2 = ops.attention_core(qk[:, :, :C], qk[:, :, C:], vt.to(cuda), scale, block=block, C=C)
+    s2 = torch.einsum("bic,bjc->bij", qk[:, :, :C].double().cpu(), qk[:, :, C:].double().cpu()) * scale
+    s2 = s2.masked_fill(blk[:, None] != blk[None, :], float("-inf"))
+    ref2 = torch.einsum("bij,bjc->bic", _bf(torch.softmax(s2, -1).float()).double(), v.double())
+    _close(out2, ref2)

@@ -26,7 +26,7 @@ out = torch.empty(B, 32, 32, 3, device=dev)
 net(0.5, x, out=out)
 torch.cuda.synchronize()
 
-NAMES = ["conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs", "groupnorm_swish", "attention_small",
+NAMES = ["conv_gemm", "conv_gemm_s2", "upconv_gemm", "batched_gemm", "attention_probs", "attention_core", "groupnorm_swish", "attention_small",
          "softmax_rows", "upsample2x", "im2col_s2", "im2col_in", "conv_in", "time_embedding", "cast_bf16"]
 calls = []
 orig = {}
@@ -88,6 +88,11 @@ def describe(name, a, k, r):
         C = k.get("C") or q.shape[2]
         return (f"attn_probs b{q.shape[0]} S{q.shape[1]} C{C}", 2.0 * q.shape[0] * q.shape[1] * q.shape[1] * C,
                 2 * q.shape[0] * q.shape[1] * C * 2 + nbytes(r))
+    if name == "attention_core":
+        q, vt = a[0], a[2]
+        C = k.get("C") or q.shape[2]
+        return (f"attn_core b{q.shape[0]} S{q.shape[1]} C{C} block{k.get('block')}", 4.0 * q.shape[0] * q.shape[1] * q.shape[1] * C,
+                4 * q.shape[0] * q.shape[1] * C * 2 + nbytes(r))
     if name == "groupnorm_swish":
         x0 = a[0]
         x1 = k.get("x1")
