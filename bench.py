@@ -274,7 +274,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
-                     "traffic": None, "kernel": "gemm_tcgen05_kernel (+ attn_core_kernel, 7 of the launches)", "peak_kind": f"{peak_kind} sustained bf16",
+                     "traffic": None, "kernel": "gemm_tcgen05_kernel (+ attn_core_kernel for the attention products)", "peak_kind": f"{peak_kind} sustained bf16",
                      "share_of_step": share, "gemm_ms_per_step": gemm_only_ms, "gemm_launches_per_step": gemm_launches,
                      "achieved_eager": gemm_tf_eager, "executed_tflop_per_step": gemm_flop_exec / 1e12,
                      "algorithmic_tflop_per_step": gemm_flop / 1e12,

@@ -684,8 +684,11 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     // cta_group::2 pairs for wide tiles: halves the weight bytes each SM has to receive per K-block
     static const int want_pair = [] { const char* e = getenv("SDB_GEMM_PAIR"); return e ? atoi(e) : 1; }();   // tuning knob
     p.pair = 0;
+    // pairs also for the 8x8 level (256 m-tiles at batch 512): same 1.73 waves as single 128 x 256 tiles, but each SM receives
+    // 32 KB instead of 48 KB per K-block of a layer that is bound by the L2 -> SM feed
+    static const int pair_min_tiles = [] { const char* e = getenv("SDB_GEMM_PAIR_MIN_TILES"); return e ? atoi(e) : 148; }();   // tuning knob
     if (want_pair && !p.dual && p.block_n == MAX_BN && !p.b_batched && !(flags & SD_EPI_SOFTMAX) &&
-        p.m_tiles * p.n_tiles >= 2 * num_sms()) {
+        p.m_tiles * p.n_tiles >= pair_min_tiles) {
       p.pair = 1;
       p.cluster = 2;
     }

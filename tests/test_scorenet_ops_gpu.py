@@ -456,3 +456,20 @@ def test_attention_core_fused(cuda, nb, Sp, block, C, stats):
     s2 = s2.masked_fill(blk[:, None] != blk[None, :], float("-inf"))
     ref2 = torch.einsum("bij,bjc->bic", _bf(torch.softmax(s2, -1).float()).double(), v.double())
     _close(out2, ref2)
+
+
+def test_conv_gemm_pair_two_images_per_tile(cuda):
+    """8x8 level at a batch that gives 148..295 m-tiles: cta_group::2 pairs with TWO images per 128-row tile (row-bias table
+    with two rows per CTA), 1-tap segments, odd pair count."""
+    B, H, C = 322, 8, 64                 # 161 m-tiles -> 81 pairs, the last one half empty
+    g = torch.Generator().manual_seed(61)
+    a2 = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    xa = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    w = _bf(torch.cat([torch.randn(256, 9 * C, generator=g) / math.sqrt(9 * C), torch.randn(256, C, generator=g) / 8], dim=1)).to(cuda)
+    bias = torch.randn(256, generator=g).to(cuda)
+    rowbias = torch.randn(B, 256, generator=g).to(cuda)
+    out = ops.conv_gemm([(a2, 9), (xa, 1)], w, bias=bias, rowbias=rowbias)
+    wf = w.float()
+    ref = F.conv2d(a2.float().permute(0, 3, 1, 2), wf[:, :9 * C].reshape(256, 3, 3, C).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) \
+        + torch.einsum("bhwc,nc->bhwn", xa.float(), wf[:, 9 * C:]) + bias + rowbias[:, None, None, :]
+    _close(out, ref.cpu())
