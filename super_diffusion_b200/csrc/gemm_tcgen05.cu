@@ -371,8 +371,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 // weights are the M = 128 operand, the two adjacent pixel tiles (contiguous in the slot: 256 rows) the N = 256 one
                 const uint64_t x_desc = umma_desc_sw128(slab ? sa + (uint32_t)g * row_pitch : sa);
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k)
-                  umma_bf16(d_tmem, b_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc_swap, accumulate | (uint32_t)k);
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  // pair: M = 256 channels (each CTA feeds the 128 weight rows it already loads as "its half of B"),
+                  // N = 256 pixels (each CTA feeds its own m-tile) -- the same bytes in shared memory, roles exchanged
+                  if constexpr (PAIR) umma_bf16_pair(d_tmem, b_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                  else umma_bf16(d_tmem, b_desc + (uint64_t)(k * 2), x_desc + (uint64_t)(k * 2), idesc_swap, accumulate | (uint32_t)k);
+                }
                 accumulate = 1;
                 continue;
               }
@@ -419,9 +423,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         // (no shuffles); a lane-pair exchange packs adjacent channels so every store instruction writes two 64-byte
         // runs of the NHWC row (even lanes pixel P, odd lanes pixel P + 1).
         const int et = threadIdx.x - 64;
-        const int ch = n_base + row;
+        const int ch_base = n_base + (PAIR ? crank * BM : 0);       // pair: this CTA's accumulator holds channels [crank*128, +128)
+        const int ch = ch_base + row;
         const bool ch_ok = ch < p.N_out;
-        const int m_tile0 = m_unit * 2;
+        const int m_tile0 = PAIR ? m_group * 2 : m_unit * 2;        // pair: columns 0..127 = CTA 0's m-tile, 128..255 = CTA 1's
         const size_t pix0 = (size_t)m_tile0 * BM;
         float bv = 0.f;
         if (ch_ok) {
@@ -478,17 +483,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           for (int i = et; i < 4 * BM; i += EPI_THREADS) {
             const int sub = i / (2 * BM), which = (i / BM) & 1, n = i & (BM - 1);
             const int m_tile = m_tile0 + sub;
-            if (m_tile < p.m_tiles && n_base + n < p.N_out) {
+            if (m_tile < p.m_tiles && ch_base + n < p.N_out) {
               const float t = wstat[((0 * 2 + sub) * 2 + which) * BM + n] + wstat[((1 * 2 + sub) * 2 + which) * BM + n];
               const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + p.stats_slot0 + (m_tile % p.tiles_per_img);
-              p.stats_out[(slot * 2 + which) * p.N_out + n_base + n] = t;
+              p.stats_out[(slot * 2 + which) * p.N_out + ch_base + n] = t;
             }
           }
           epi_bar();
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);
+          else mbar_arrive(&tmem_empty[acc]);
+        }
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
         continue;
@@ -699,6 +707,10 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // pixels the N = 256 operand: one 128-clk instruction per K step, 12 KB of operand reads (96 B/clk) -- the shape the
   // N = 256 layers already run at 85-95 % of peak with.  The accumulator is then [channel][pixel]; see the epilogue.
   p.swap = (swap_epi_ok && p.dual && !p.pair && p.cluster == 1 && p.block_n == 128) ? 1 : 0;
+  // pairs (N = 256 tiles): the same exchange of roles -- M = 256 channels over the two CTAs, N = 256 pixels -- gives the pair kernel
+  // the [channel][pixel] epilogue too (no shuffle butterfly for the GroupNorm sums, 64-byte store runs)
+  static const int want_pair_swap = [] { const char* e = getenv("SDB_GEMM_PAIR_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
+  if (want_pair_swap && swap_epi_ok && p.pair && p.block_n == MAX_BN && (N % MAX_BN) == 0) p.swap = 1;
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
     const int nsub_h = p.dual ? 2 : 1;
