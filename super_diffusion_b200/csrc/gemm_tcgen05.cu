@@ -25,12 +25,16 @@
 #include "../../include/superdiff_b200.h"
 #include <cstdlib>
 
+#ifndef SDB_RING_KB
+#define SDB_RING_KB 204    // 3 x 68 KB pair-slab stages; leaves ~12 KB of the SM for a co-resident GroupNorm CTA of the other stream
+#endif
+
 namespace sdb {
 
 constexpr int BM = 128;            // rows (pixels) per tile == TMEM lanes
 constexpr int BK = 64;             // bf16 elements per K-block == one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int RING_BYTES = 216 * 1024;     // operand ring, cut into 2..8 slots of the size a launch needs (48 KB K-blocks: 4)
+constexpr int RING_BYTES = SDB_RING_KB * 1024;     // operand ring, cut into 2..8 slots of the size a launch needs (48 KB K-blocks: 4)
 constexpr int MAX_STAGES = 8;
 constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
