@@ -217,7 +217,7 @@ def run_b200(args):
     ms_dev = timed("device", args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     launches = (sampler.launches_per_step + 0) * args.steps
-    ms_e2e = timed("host", args.steps, args.warmup)
+    ms_e2e = timed("host", args.steps, args.warmup) if not args.no_probes else ms_dev
 
     # final gather of samples + log-densities (the only communication of the job)
     gather_ms = None
@@ -238,16 +238,16 @@ def run_b200(args):
     # (the executed count is lower: upsample+conv folded into 2x2-tap phases, attention projections folded; identity
     # residual segments are extra work and are not counted)
     gemm_flop = M_MODELS * B * GFLOP_PER_SAMPLE_FWD * 1e9
-    gemm_only_ms, gemm_launches = _gemm_only_time(sampler, ops, torch)
+    gemm_only_ms, gemm_launches = _gemm_only_time(sampler, ops, torch) if not args.no_probes else (gemm_ms, 0)
     share = gemm_only_ms / ms_dev
     gemm_tf_eager = gemm_flop / (gemm_ms * 1e-3) / 1e12          # eager pass, events around every python call (host gaps included)
     gemm_tf = gemm_flop / (gemm_only_ms * 1e-3) / 1e12           # sum of the kernel's launch durations, measured directly
     # ---- fused step kernel alone, L2 flushed between launches ----
-    step_us, step_bytes = _step_kernel_time(sampler, ops, torch, noise_dev[0])
+    step_us, step_bytes = _step_kernel_time(sampler, ops, torch, noise_dev[0]) if not args.no_probes else (float("nan"), 4 * B * D * (M_MODELS + 3))
     step_gbs = step_bytes / (step_us * 1e-6) / 1e9
     # the same kernel at BASELINE config 3's single-GPU size (B = 8192, AND with the per-sample kappa solve, and OR)
     big = {}
-    if rank == 0:
+    if rank == 0 and not args.no_probes:
         for name, md in (("and", ops.MODE_AND), ("or", ops.MODE_OR)):
             us, by = _step_kernel_time(sampler, ops, torch, None, B=8192, mode=md)
             big[name] = {"us_per_launch": us, "achieved": by / (us * 1e-6) / 1e9, "frac": by / (us * 1e-6) / 1e9 / hbm_peak}
@@ -468,6 +468,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU (default: BASELINE config, 512)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
     ap.add_argument("--single-stream", action="store_true", help="run the M score-nets back to back on one stream")
+    ap.add_argument("--no-probes", action="store_true",
+                    help="skip the e2e leg and the roofline probes (GEMM-only graph, step-kernel timing): the short form used for the ncu launch list")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

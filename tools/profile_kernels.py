@@ -1,5 +1,5 @@
 """Small driver for `ncu --set full`: one launch each of the kernels that matter (after a warm-up pass).
-Matched kernels per pass (regex step_vpsde|gn_|gemm_tcgen05): 3 + 3 + 5 = 11 (ncu: -s 11 -c 11)."""
+Matched kernels per pass (regex step_vpsde|gn_|gemm_tcgen05|attn_core): 3 + 3 + 5 + 1 = 12 (ncu: -s 12 -c 12)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import math, torch
@@ -38,11 +38,15 @@ def run_all():
     w3 = (torch.randn(512, 256, device=dev) / 16).bfloat16()
     qk = ops.conv_gemm([(a2, 1)], w3).view(B, 256, 512)
     ops.attention_probs(qk[:, :, :256], qk[:, :, 256:], 256 ** -0.5, block=256, C=256)
+    # fused attention core on the same q / k with V^T and a residual (probabilities stay in shared memory)
+    vt = torch.randn(B, 256, 256, device=dev).bfloat16()
+    ops.attention_core(qk[:, :, :256], qk[:, :, 256:], vt, 256 ** -0.5, block=256, bias=torch.zeros(256, device=dev),
+                       residual=a2.view(B, 256, 256), want_stats=True, C=256)
     # low-resolution layer (4x4, few tiles)
     a4 = torch.randn(B, 4, 4, 256, device=dev).bfloat16()
     ops.conv_gemm([(a4, 9)], w2[:, :9 * 256].contiguous())
     torch.cuda.synchronize()
 
-run_all()   # warm-up (ncu skips these with -s 11)
+run_all()   # warm-up (ncu skips these with -s 12)
 run_all()
 print("profile driver done")
