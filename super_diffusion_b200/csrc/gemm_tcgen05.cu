@@ -16,10 +16,21 @@
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
 // MMA issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld -> bias /
-// time-embedding / swish / GroupNorm statistics -> global).  Persistent over
-// output tiles, a 192 KB smem ring cut into 4..8 stages, two TMEM accumulators
-// so the epilogue of tile i overlaps the MMAs of tile i+1.  Wide (N = 256)
-// layers run as cta_group::2 pairs (kernel<PAIR = true>).
+// time-embedding / GroupNorm statistics -> global).  Persistent over output
+// tiles, a 204 KB smem ring cut into 2..8 stages, two TMEM accumulators so the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Tile shapes (chosen per launch in launch_gemm):
+//   * N = 256 layers with >= 148 tiles: cta_group::2 pairs (kernel<PAIR = true>), each SM feeds its own pixel tile
+//     and half of the weight tile;
+//   * N = 128 layers and all 1x1 layers: two adjacent pixel tiles per CTA, OPERANDS SWAPPED -- the weights are the
+//     M = 128 operand, the 256 pixels the N = 256 operand, so one 128-clk instruction does the work of two 64-clk
+//     ones that would saturate the shared-memory port; pairs are swapped the same way (M = 256 channels);
+//   * swapped accumulators are [channel][pixel]: bias is one register, GroupNorm sums are thread-local, a lane-pair
+//     exchange packs channel pairs for 64-byte store runs;
+//   * 3x3 stride-1 segments are fed as activation slabs shared by the three vertical taps;
+//   * everything else (N < 128, flat / batched matrices, softmax epilogue of the attention probabilities used by the
+//     JVP path) runs unswapped with thread = pixel row.
 #include "common.cuh"
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"

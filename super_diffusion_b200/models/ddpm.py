@@ -8,12 +8,18 @@ sequence of hand-written sm_100a kernels reached through the C ABI:
 * every 3x3 conv / NIN / Dense is the tcgen05 implicit GEMM (``ops.conv_gemm``,
   ``ops.batched_gemm``) with bf16 operands and fp32 accumulation in TMEM;
   conv bias, the time-embedding projection (layers.py:556), the NIN shortcut
-  (:560-564, fused as extra K-blocks) and the residual add (:565, :511) live in
-  the GEMM epilogue / K loop;
-* GroupNorm+swish (normalization.py:38-39 + layers.py:552,557) is one
-  cluster-per-sample kernel that also performs the skip concat of ddpm.py:90;
-* attention (layers.py:505-509) is batched tcgen05 GEMMs + a row softmax at
-  S = 256 and a small CUDA-core kernel at S <= 64.
+  (:560-564) and the residual add (:565) are extra K segments / epilogue terms
+  of the same GEMM, which also emits the next GroupNorm's channel sums; the
+  3-channel input conv is a hi/lo-split im2col K-block on the same kernel;
+* GroupNorm+swish (normalization.py:38-39 + layers.py:552,557) is a streaming
+  apply pass over producer-emitted statistics (one register-resident kernel at
+  the 8x8 / 4x4 levels) that also performs the skip concat of ddpm.py:90;
+* attention (layers.py:493-511): projections folded at bind time
+  (q' = NIN(h; Wq Wk^T, Wk bq) against keys h, V' = h Wv Wo), then ONE fused
+  kernel softmax(q' h^T) V' + bias + x with the probabilities kept in shared
+  memory (``ops.attention_core``); low resolutions pack several images per tile;
+* ``jvp()`` is the forward-mode derivative (cifar/dynamics.py:84) built from the
+  same GEMMs plus tangent kernels for GroupNorm+swish and the softmax.
 
 Activations are NHWC bf16 between kernels; the output score is fp32.
 There is no PyTorch / CPU fallback for the forward.
