@@ -255,6 +255,11 @@ int sd_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* st
  * out[b,ho,wo, tap*C + c] = x[b, 2ho+kh, 2wo+kw, c] (0 outside). bf16. */
 int sd_im2col_s2(const void* x, int B, int H, int W, int C, void* out, void* stream);
 
+/* out[0..row_floats) = table[row][:] with row = *counter (device int, clamped to [0, rows)): the per-timestep row of a
+ * precomputed table inside a captured CUDA graph.  Used for the time-embedding biases: Dense_i(act(temb(t))) of
+ * cifar/models/ddpm.py:64-66 + layers.py:556 depends only on t, so the sampler tabulates it once for its n_steps times. */
+int sd_gather_row(const float* table, int rows, int row_floats, const int* counter, float* out, void* stream);
+
 /* Operand gather for the first conv (cifar/models/ddpm.py:71) on the tensor cores: out[pixel] = 64 bf16 =
  * [hi(9*Cin) | lo(9*Cin) | zeros], hi = bf16(v), lo = bf16(v - hi) of the zero-padded 3x3xCin fp32 neighbourhood (Cin <= 3).
  * The conv is then sd_conv_gemm with one 1-tap source of 64 channels against weights [w | w | 0] (bf16 [Cout, 64]). */

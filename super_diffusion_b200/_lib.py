@@ -41,6 +41,7 @@ SIGNATURES = {
     "sd_attention": (_I, [_V, _I, _I, _I, _V, _V]),
     "sd_upsample2x": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_im2col_s2": (_I, [_V, _I, _I, _I, _I, _V, _V]),
+    "sd_gather_row": (_I, [_V, _I, _I, _V, _V, _V]),
     "sd_im2col_in": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_conv_in": (_I, [_V, _I, _I, _I, _I, _V, _V, _I, _V, _V]),
     "sd_time_embedding": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),

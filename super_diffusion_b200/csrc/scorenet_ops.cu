@@ -508,6 +508,15 @@ __global__ void __launch_bounds__(256) temb_act_kernel(const float* __restrict__
   }
 }
 
+// out[0..n) = table[row * n .. ), row read from a device counter: lets a captured CUDA graph pick the current timestep's
+// precomputed row (time-embedding biases) without any host value baked in
+__global__ void __launch_bounds__(256) gather_row_kernel(const float4* __restrict__ table, int n4, const int* __restrict__ counter,
+                                                         int max_row, float4* __restrict__ out) {
+  int row = counter ? *counter : 0;
+  row = row < 0 ? 0 : (row > max_row ? max_row : row);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) out[i] = table[(size_t)row * n4 + i];
+}
+
 static unsigned grid_for(size_t total, int threads) {
   const size_t want = (total + threads - 1) / threads;
   const size_t cap = 148 * 16;
@@ -689,6 +698,15 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
     default: conv_in_kernel<4><<<grid, 256, smem, st>>>(x, B, H, W, w_hwio, bias, Cout, o); break;
   }
   return check_cuda(cudaGetLastError(), "sd_conv_in launch");
+}
+
+int sd_gather_row(const float* table, int rows, int row_floats, const int* counter, float* out, void* stream) {
+  using namespace sdb;
+  if (!table || !out || rows < 1 || row_floats < 4 || (row_floats % 4) || ((uintptr_t)table % 16) || ((uintptr_t)out % 16))
+    return fail(kErrInvalidArg, "sd_gather_row: row length must be a positive multiple of 4 floats, pointers 16-byte aligned");
+  const int n4 = row_floats / 4;
+  gather_row_kernel<<<(n4 + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float4*)table, n4, counter, rows - 1, (float4*)out);
+  return check_cuda(cudaGetLastError(), "sd_gather_row launch");
 }
 
 int sd_im2col_in(const float* x, int B, int H, int W, int Cin, void* out, void* stream) {

@@ -503,6 +503,18 @@ def im2col_s2(x, out=None):
     return out
 
 
+def gather_row(table, counter, out=None):
+    """out = table[counter] (sd_gather_row); table: fp32 [rows, n] on the device, counter: int32 device scalar."""
+    lib = _lib.load()
+    _f32c(table, "table")
+    rows, n = table.shape
+    if out is None:
+        out = torch.empty(1, n, device=table.device, dtype=torch.float32)
+    _lib.check(lib.sd_gather_row(_ptr(table), rows, n, _ptr(counter), _ptr(out), _stream()), "sd_gather_row")
+    _count()
+    return out
+
+
 def im2col_in(x, out=None):
     """fp32 NHWC [B,H,W,Cin<=3] -> bf16 [B,H,W,64] hi/lo-split 3x3 neighbourhoods (sd_im2col_in)."""
     lib = _lib.load()
