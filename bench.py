@@ -274,7 +274,7 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,
-                     "traffic": None, "kernel": "gemm_tcgen05_kernel (+ attn_core_kernel for the attention products)", "peak_kind": f"{peak_kind} sustained bf16",
+                     "traffic": _recorded_traffic(B), "kernel": "gemm_tcgen05_kernel (+ attn_core_kernel for the attention products)", "peak_kind": f"{peak_kind} sustained bf16",
                      "share_of_step": share, "gemm_ms_per_step": gemm_only_ms, "gemm_launches_per_step": gemm_launches,
                      "achieved_eager": gemm_tf_eager, "executed_tflop_per_step": gemm_flop_exec / 1e12,
                      "algorithmic_tflop_per_step": gemm_flop / 1e12,
@@ -306,6 +306,20 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _recorded_traffic(B):
+    """DRAM bytes (read + written) of one timestep's tensor-core launches at batch 512, from the committed ncu launch list
+    (profiles/r01d_step_traffic.json = tools/summarize_traffic.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+    of this bench; a profiler artefact, not measured in this run).  None at any other batch or when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r01d_step_traffic.json")
+    if B != BATCH_PER_GPU or not os.path.exists(p):
+        return None
+    try:
+        with open(p) as fh:
+            return float(json.load(fh)["tensor_core_kernels"]["dram_bytes"])
+    except (KeyError, ValueError, OSError):
+        return None
 
 
 def _instrumented_step(sampler, ops, torch):

@@ -73,7 +73,13 @@ int sd_step_vpsde(const float* x, const float* noise, const float* const* scores
 
 /* Same as sd_step_vpsde with explicit launch shape (tuning / benchmarks):
  * threads per CTA (64..256, multiple of 32), float4 chunks per thread (1..4),
- * CTAs per sample (thread-block cluster size 1,2,4,8).  0 = heuristic. */
+ * CTAs per sample (thread-block cluster size 1,2,4,8).  0 = heuristic.
+ * SD_MODE_AND only: cluster = -1 selects the two-pass streaming kernel (one CTA per
+ * sample, 1..2 chunks per thread per round, no limit on D) that the heuristic uses
+ * when a sample fits neither registers nor shared memory; cluster = -2 selects the
+ * shared-memory-resident kernel (bulk copies of noise + M scores into (M+1)*D*4 bytes
+ * of shared memory; needs 16-byte aligned rows and D <= 16*threads), the heuristic's
+ * choice for M >= 3 at D = 3072. */
 int sd_step_vpsde_ex(const float* x, const float* noise, const float* const* scores_host,
                      int M, int B, int D,
                      float a_t, float b_t, float sigma_t, float dt,

@@ -4,11 +4,39 @@
 #include "../../include/superdiff_b200.h"
 
 #include "step_vpsde_params.cuh"
+#include <cstdlib>
 
 namespace sdb {
 
 template <int M> cudaError_t launch_m(const StepParams& p, int threads, int nv, int cluster, int vec, cudaStream_t st);
 template <int M> cudaError_t launch_small(const StepParams& p, cudaStream_t st);
+template <int M> cudaError_t launch_and_stream(const StepParams& p, int threads, int nv, int vec, cudaStream_t st);
+template <int M> cudaError_t launch_and_smem(const StepParams& p, int threads, cudaStream_t st);
+
+// mirrors and_smem_bytes() in step_vpsde_kernel.cuh
+static size_t and_smem_need(int M, int D, int threads) {
+  const int K = (M - 1) * M / 2 + 2 * (M - 1) + 2;
+  return (size_t)(M + 1) * D * 4 + sizeof(double) * ((size_t)(threads / 32 + 2) * K + M) + 16;
+}
+
+// AND keeps the sample in shared memory (bulk-copy kernel) from this model count on (SDB_AND_SMEM_MIN_M overrides)
+static int and_smem_min_m() {
+  static const int v = [] {
+    const char* e = getenv("SDB_AND_SMEM_MIN_M");
+    return e && *e ? atoi(e) : 3;
+  }();
+  return v;
+}
+
+// AND switches from the register-resident kernel to the two-pass streaming kernel at this model count
+// (SDB_AND_STREAM_MIN_M overrides; measured crossover in profiles/r01d_step_sweep.txt).
+static int and_stream_min_m() {
+  static const int v = [] {
+    const char* e = getenv("SDB_AND_STREAM_MIN_M");
+    return e && *e ? atoi(e) : 5;
+  }();
+  return v;
+}
 
 }  // namespace sdb
 
@@ -60,6 +88,44 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
   const int vec = aligned ? 4 : 1;
   const int nunits = D / vec;
   const bool is_and = mode == SD_MODE_AND;
+  bool and_stream = is_and && cluster == -1;                       // explicit requests through sd_step_vpsde_ex
+  bool and_smem = is_and && cluster == -2;
+  if (is_and && !and_stream && !and_smem && (threads == 0 || nv == 0 || cluster == 0)) {
+    const int nv_cap = max(1, min(4, 24 / (M + 2)));
+    const bool smem_ok = vec == 4 && nunits <= 4 * 256 && and_smem_need(M, D, 256) <= 227 * 1024;
+    if (M >= and_smem_min_m() && smem_ok) {                        // sample resident in shared memory
+      and_smem = true;
+      threads = 256;
+    } else if (M >= and_stream_min_m() || 256L * nv_cap < nunits) { // does not stay resident in one CTA
+      and_stream = true;
+      threads = 256;
+      nv = M <= 4 ? 2 : 1;
+    }
+  }
+  if (and_smem) {
+    if (threads < 32 || threads > 256 || threads % 32)
+      return fail(kErrInvalidArg, "sd_step_vpsde_ex: bad launch shape (shared-memory AND: threads 32..256)");
+    if (vec != 4 || nunits > 4 * threads || and_smem_need(M, D, threads) > 227 * 1024)
+      return fail(kErrUnsupported, "sd_step_vpsde_ex: shared-memory AND needs 16-byte aligned rows, D <= 16*threads and (M+1)*D*4 bytes of shared memory");
+#define SDB_AM(Mv) case Mv: err = launch_and_smem<Mv>(p, threads, st); break;
+    switch (M) {
+      SDB_AM(1) SDB_AM(2) SDB_AM(3) SDB_AM(4) SDB_AM(5) SDB_AM(6) SDB_AM(7) SDB_AM(8)
+      default: err = cudaErrorInvalidValue;
+    }
+#undef SDB_AM
+    return check_cuda(err, "sd_step_vpsde launch (shared-memory AND)");
+  }
+  if (and_stream) {
+    if (threads < 32 || threads > 256 || threads % 32 || nv < 1 || nv > 2)
+      return fail(kErrInvalidArg, "sd_step_vpsde_ex: bad launch shape (streaming AND: threads 32..256, 1 or 2 vectors per thread)");
+#define SDB_AS(Mv) case Mv: err = launch_and_stream<Mv>(p, threads, nv, vec, st); break;
+    switch (M) {
+      SDB_AS(1) SDB_AS(2) SDB_AS(3) SDB_AS(4) SDB_AS(5) SDB_AS(6) SDB_AS(7) SDB_AS(8)
+      default: err = cudaErrorInvalidValue;
+    }
+#undef SDB_AS
+    return check_cuda(err, "sd_step_vpsde launch (streaming AND)");
+  }
   if (threads == 0 || nv == 0 || cluster == 0) {
     // Heuristic: keep (M+2)*NV float4 registers per thread <= 24, prefer 128..256 threads and
     // enough CTAs (>= ~8 per SM) that the 148 SMs stay balanced.

@@ -6,4 +6,8 @@ template cudaError_t launch_m<7>(const StepParams&, int, int, int, int, cudaStre
 template cudaError_t launch_m<8>(const StepParams&, int, int, int, int, cudaStream_t);
 template cudaError_t launch_small<7>(const StepParams&, cudaStream_t);
 template cudaError_t launch_small<8>(const StepParams&, cudaStream_t);
+template cudaError_t launch_and_stream<7>(const StepParams&, int, int, int, cudaStream_t);
+template cudaError_t launch_and_stream<8>(const StepParams&, int, int, int, cudaStream_t);
+template cudaError_t launch_and_smem<7>(const StepParams&, int, cudaStream_t);
+template cudaError_t launch_and_smem<8>(const StepParams&, int, cudaStream_t);
 }  // namespace sdb

@@ -91,6 +91,38 @@ def test_explicit_launch_shapes(cuda, shape, mode):
     _check(got, ref, w_tol=2e-4)
 
 
+@pytest.mark.parametrize("M,D,shape", [(2, 3072, (256, 2, -1)), (3, 3072, (256, 1, -1)), (4, 3072, (128, 2, -1)),
+                                       (6, 3072, (256, 1, -1)), (8, 3072, (192, 2, -1)), (3, 3070, (256, 1, -1)),
+                                       (2, 16384, (256, 2, -1)),
+                                       (2, 3072, (256, 1, -2)), (3, 3072, (256, 1, -2)), (4, 3072, (192, 1, -2)),
+                                       (5, 1024, (64, 1, -2)), (8, 3072, (256, 1, -2)), (8, 4096, (256, 1, -2)),
+                                       (1, 3072, (256, 1, -2))])
+def test_streaming_and_kernel(cuda, M, D, shape):
+    """cluster = -1: the two-pass streaming AND kernel; cluster = -2: the shared-memory-resident AND kernel fed by bulk
+    copies (the heuristic's choice for M >= 3) - against the oracle, and against the register-resident kernel where that
+    one can hold the sample (same reductions in the same order -> same kappa)."""
+    B, t, dt = 5, 0.55, 1e-3
+    x, eps, s, logq = _mk(B, D, M, seed=41 + M, dev=cuda)
+    kw = dict(temperature=1.0, ito_scale=float(D) * D)
+    got = _run(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, cuda, launch_shape=shape, **kw)
+    ref = _ref(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, **kw)
+    _check(got, ref, w_tol=2e-4)
+    if M <= 4 and D == 3072:
+        res = _run(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, cuda, launch_shape=(256, 3 if M <= 2 else 4, 1), **kw)
+        assert torch.allclose(res[2], got[2], rtol=0, atol=2e-6)
+        assert torch.allclose(res[0], got[0], rtol=1e-6, atol=1e-6)
+
+
+def test_and_sample_larger_than_one_cluster(cuda):
+    """D = 40000 with M = 3 exceeds what 8 CTAs x 256 threads x 4 float4 keep in registers: the heuristic streams it."""
+    B, D, M, t, dt = 3, 40000, 3, 0.4, 1e-3
+    x, eps, s, logq = _mk(B, D, M, seed=77, dev=cuda)
+    kw = dict(temperature=1.0, ito_scale=1.0)
+    got = _run(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, cuda, **kw)
+    ref = _ref(x, eps, s, logq, t, dt, O.MODE_AND, O.DLOGQ_ITO, **kw)
+    _check(got, ref, w_tol=2e-4)
+
+
 def test_cifar_reference_form_fp32_and_temperature(cuda):
     """The literal fp32 transcription of cifar/dynamics.py:123-136 and the kernel
     agree (both are compared with the fp64 truth; the kernel must sit at the same fp32 noise floor)."""
