@@ -288,8 +288,9 @@ __device__ __forceinline__ void write_logq(const StepParams& p, const StepScalar
 }
 
 // VEC = 4: float4 accesses (D % 4 == 0, 16B-aligned bases); VEC = 1: scalar.
+// (M+2)*NV <= 12 float4 per thread (M = 2 at D = 3072): hold the kernel to 3 CTAs of 256 threads per SM (<= 85 registers)
 template <int M, int NV, int VEC, bool AND, bool CLUSTER>
-__global__ void __launch_bounds__(256) step_vpsde_kernel(const __grid_constant__ StepParams p) {
+__global__ void __launch_bounds__(256, ((M + 2) * NV * (VEC / 4) <= 12 && VEC == 4) ? 3 : 1) step_vpsde_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ double scratch[];
   unsigned csize = 1, crank = 0;
   if (CLUSTER) {
