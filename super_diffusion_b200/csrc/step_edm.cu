@@ -8,6 +8,7 @@
 // slice stays in registers between the reduction and the write pass.
 // HBM bytes per sample: 4*D*6.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/superdiff_b200.h"
 
 namespace sdb {
@@ -136,6 +137,176 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
   }
 }
 
+// Large batches (B >= 256: enough samples to fill the chip with one CTA each): ONE CTA per sample, streaming.  None of the
+// eight reductions depends on kappa (the log-likelihood updates are written in Gram terms), so the modes whose kappa is
+// known up front (OR: softmax of the old ll; AVG: fixed) are a single pass - read the five tensors once, accumulate and
+// write in the same round.  AND / AND-ODE need <d,d>, <base,d>, ... before the first write: pass 1 reads z, v_obj, v_bg,
+// v_unc, the CTA forms kappa, pass 2 re-reads the sample (<= 320 KB that this CTA touched microseconds earlier: L2, not
+// HBM) and writes.  No clusters: the cluster-per-sample kernel above ran at 0.55-0.59 of the copy peak at batch 512-2048.
+// Old log-likelihoods / divergences are loaded at the start and consumed after the streaming loads (see step_vpsde_kernel).
+template <int NV>
+__global__ void __launch_bounds__(256) step_edm_stream_kernel(const __grid_constant__ EdmParams p) {
+  extern __shared__ double scratch[];
+  const int sample = blockIdx.x;
+  const int nunits = p.D / 4;
+  const size_t base_off = (size_t)sample * p.D;
+  const bool ode = p.mode == SD_EDM_MODE_AND_ODE;
+  const bool two_pass = ode || p.mode == SD_MODE_AND;
+  const float cn = ode ? 0.f : sqrtf(2.f * fabsf(p.dsigma) * p.sigma);
+  const float two_ds = ode ? p.dsigma : 2.f * p.dsigma;
+  float ll0 = p.ll[2 * sample], ll1 = p.ll[2 * sample + 1];
+  float dl0 = 0.f, dl1 = 0.f;
+  if (ode) { dl0 = p.dlog[2 * sample]; dl1 = p.dlog[2 * sample + 1]; }
+  float part[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[k] = 0.f;
+
+  auto accumulate = [&](const float4& z4, const float4& vo4, const float4& vb4, const float4& vu4, float4& d4, float4& bs4) {
+    const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, oo[4] = {vo4.x, vo4.y, vo4.z, vo4.w};
+    const float vb[4] = {vb4.x, vb4.y, vb4.z, vb4.w}, vu[4] = {vu4.x, vu4.y, vu4.z, vu4.w};
+    float dd[4], bb[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      dd[e] = oo[e] - vb[e];
+      bb[e] = vu[e] + p.g * (vb[e] - vu[e]);
+      const float vbe = oo[e] - dd[e];          // as in the resident kernel
+      part[0] = fmaf(dd[e], dd[e], part[0]);
+      part[1] = fmaf(bb[e], dd[e], part[1]);
+      part[2] = fmaf(zz[e], dd[e], part[2]);
+      part[3] = fmaf(oo[e], oo[e], part[3]);
+      part[4] = fmaf(vbe, vbe, part[4]);
+      part[5] = fmaf(oo[e], bb[e], part[5]);
+      part[6] = fmaf(oo[e], dd[e], part[6]);
+      part[7] = fmaf(oo[e], zz[e], part[7]);
+    }
+    d4 = make_float4(dd[0], dd[1], dd[2], dd[3]);
+    bs4 = make_float4(bb[0], bb[1], bb[2], bb[3]);
+  };
+  auto update = [&](const float4& x4, const float4& z4, const float4& d4, const float4& bs4, float kf, size_t off) {
+    float4 o;
+    // vf = base + g kappa d ; dx = 2 dsigma vf + cn z   (clip_eval.py:404-405; ODE: dsigma vf, :388)
+    o.x = x4.x + (two_ds * (bs4.x + p.g * kf * d4.x) + cn * z4.x);
+    o.y = x4.y + (two_ds * (bs4.y + p.g * kf * d4.y) + cn * z4.y);
+    o.z = x4.z + (two_ds * (bs4.z + p.g * kf * d4.z) + cn * z4.z);
+    o.w = x4.w + (two_ds * (bs4.w + p.g * kf * d4.w) + cn * z4.w);
+    st4(p.x_out + off, o);
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  double kappa = (double)p.kappa_fixed;
+  float kf = p.kappa_fixed;
+
+  if (!two_pass) {
+    bool have_k = false;
+    for (int r0 = 0; r0 < nunits; r0 += NV * blockDim.x) {
+      float4 x[NV], z[NV], vo[NV], vb[NV], vu[NV];
+      bool ok[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int u = r0 + j * blockDim.x + threadIdx.x;
+        ok[j] = u < nunits;
+        if (ok[j]) {
+          const size_t off = base_off + (size_t)u * 4;
+          x[j] = ld_stream4(p.x + off); z[j] = ld_stream4(p.z + off);
+          vo[j] = ld_stream4(p.vo + off); vb[j] = ld_stream4(p.vb + off); vu[j] = ld_stream4(p.vu + off);
+        }
+      }
+      if (!have_k) {
+        asm volatile("" : "+f"(ll0), "+f"(ll1));        // the softmax stays below the loads just issued
+        if (p.mode == SD_MODE_OR) {
+          // clip_eval.py:402: softmax([T (ll_obj + logp), T ll_bg])[0], fp32 like the reference
+          const float z0 = p.temperature * (ll0 + p.logp), z1 = p.temperature * ll1;
+          const float m = fmaxf(z0, z1);
+          const float e0 = expf(z0 - m), e1 = expf(z1 - m);
+          kappa = (double)(e0 / (e0 + e1));
+          kf = (float)kappa;
+        }
+        have_k = true;
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (!ok[j]) continue;
+        float4 d4, bs4;
+        accumulate(z[j], vo[j], vb[j], vu[j], d4, bs4);
+        update(x[j], z[j], d4, bs4, kf, base_off + (size_t)(r0 + j * blockDim.x + threadIdx.x) * 4);
+      }
+    }
+  } else {
+    for (int r0 = 0; r0 < nunits; r0 += NV * blockDim.x) {
+      float4 z[NV], vo[NV], vb[NV], vu[NV];
+      bool ok[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int u = r0 + j * blockDim.x + threadIdx.x;
+        ok[j] = u < nunits;
+        if (ok[j]) {
+          const size_t off = base_off + (size_t)u * 4;
+          z[j] = p.z ? ld_stream4(p.z + off) : zero4;
+          vo[j] = ld_stream4(p.vo + off); vb[j] = ld_stream4(p.vb + off); vu[j] = ld_stream4(p.vu + off);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (!ok[j]) continue;
+        float4 d4, bs4;
+        accumulate(z[j], vo[j], vb[j], vu[j], d4, bs4);
+      }
+    }
+  }
+  const double* t = block_cluster_sum<8, false>(part, scratch);
+  const double DD = t[0], BD = t[1], ZD = t[2], OO = t[3], BB = t[4], OB = t[5], OD = t[6], OZ = t[7];
+  const double ds = p.dsigma, sg = p.sigma, g = p.g;
+  if (two_pass) {
+    if (ode) {
+      // clip_eval.py:383-385
+      kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) / (g * DD);
+    } else {
+      // clip_eval.py:398-400 with dx_ind = 2 dsigma base + cn z
+      const double num = fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term;
+      kappa = num / (2.0 * ds * g * DD);
+    }
+    kf = (float)kappa;
+    for (int r0 = 0; r0 < nunits; r0 += NV * blockDim.x) {
+      float4 x[NV], z[NV], vo[NV], vb[NV], vu[NV];
+      bool ok[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int u = r0 + j * blockDim.x + threadIdx.x;
+        ok[j] = u < nunits;
+        if (ok[j]) {
+          const size_t off = base_off + (size_t)u * 4;
+          x[j] = ld_stream4(p.x + off);
+          z[j] = p.z ? ld_stream4(p.z + off) : zero4;
+          vo[j] = ld_stream4(p.vo + off); vb[j] = ld_stream4(p.vb + off); vu[j] = ld_stream4(p.vu + off);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (!ok[j]) continue;
+        const float4 d4 = make_float4(vo[j].x - vb[j].x, vo[j].y - vb[j].y, vo[j].z - vb[j].z, vo[j].w - vb[j].w);
+        const float4 bs4 = make_float4(vu[j].x + p.g * (vb[j].x - vu[j].x), vu[j].y + p.g * (vb[j].y - vu[j].y),
+                                       vu[j].z + p.g * (vb[j].z - vu[j].z), vu[j].w + p.g * (vb[j].w - vu[j].w));
+        update(x[j], z[j], d4, bs4, kf, base_off + (size_t)(r0 + j * blockDim.x + threadIdx.x) * 4);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    if (ode) {
+      // clip_eval.py:389-390
+      const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);
+      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) / sg));
+      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) / sg));
+    } else {
+      const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
+      const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
+      const double b_dx = o_dx - d_dx;
+      const double q = (p.mode == SD_MODE_OR) ? (-ds / sg) : (-fabs(ds) / sg);   // :412-413 vs :409-410
+      p.ll[2 * sample] = ll0 + (float)(-o_dx / sg + q * OO);
+      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx / sg + q * BB);
+    }
+    p.kappa_out[sample] = kf;
+  }
+}
+
 template <int NV>
 static cudaError_t launch_edm(const EdmParams& p, int threads, int cluster, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
@@ -177,6 +348,15 @@ static int step_edm_impl(const float* latents, const float* z, const float* v_ob
   EdmParams p{latents, z, v_obj, v_bg, v_unc, ll, latents_out, kappa_out, B, D,
               sigma, dsigma, guidance, lift_term, temperature, logp, kappa_fixed, mode, dlog};
   const int nunits = D / 4;
+  // enough samples to fill the chip with one CTA each: the streaming kernel (SDB_EDM_STREAM_MIN_B overrides the threshold)
+  static const int stream_min_b = [] { const char* e = getenv("SDB_EDM_STREAM_MIN_B"); return e && *e ? atoi(e) : 256; }();
+  if (B >= stream_min_b) {
+    const size_t smem = sizeof(double) * (size_t)(256 / 32 + 2) * 8;
+    static const int stream_nv = [] { const char* e = getenv("SDB_EDM_STREAM_NV"); return e && *e ? atoi(e) : 2; }();   // tuning knob: 2 measured 3-5 % ahead of 1 at batch 512
+    if (stream_nv == 2 && nunits >= 512) step_edm_stream_kernel<2><<<B, 256, smem, (cudaStream_t)stream>>>(p);
+    else step_edm_stream_kernel<1><<<B, 256, smem, (cudaStream_t)stream>>>(p);
+    return check_cuda(cudaGetLastError(), "sd_step_edm_cfg launch (streaming)");
+  }
   // smallest (cluster, threads, NV <= 2) that keeps the sample resident; prefer more CTAs when B is small
   int best_c = 0, best_t = 0, best_nv = 0;
   long best_cost = -1;

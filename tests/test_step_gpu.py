@@ -250,7 +250,8 @@ def test_full_size_properties(cuda):
 
 
 @pytest.mark.parametrize("mode", [O.MODE_AND, O.MODE_OR, O.MODE_AVG])
-@pytest.mark.parametrize("B,D", [(64, 16384), (3, 16384), (5, 4096), (2, 1024)])
+@pytest.mark.parametrize("B,D", [(64, 16384), (3, 16384), (5, 4096), (2, 1024),
+                                 (260, 16384), (300, 1024), (257, 1028)])   # B >= 256: the one-CTA-per-sample streaming kernel
 def test_edm_step_matches_oracle(cuda, mode, B, D):
     g = torch.Generator().manual_seed(B + D)
     lat = 14.6 * torch.randn(B, D, generator=g)
@@ -266,3 +267,29 @@ def test_edm_step_matches_oracle(cuda, mode, B, D):
     assert torch.allclose(lo.cpu().double(), lr, rtol=1e-5, atol=1e-4)
     scale = 1.0 + llr.abs().max().item()
     assert (l2.cpu().double() - llr).abs().max().item() <= 1e-5 * scale
+
+
+@pytest.mark.parametrize("kind", ["and", "or", "avg", "and_ode"])
+def test_edm_streaming_kernel_matches_resident_kernel(cuda, kind):
+    """B >= 256 takes the one-CTA-per-sample streaming kernel (two passes for AND / AND-ODE), smaller batches the
+    cluster-per-sample register-resident one: the same samples through both must agree to fp32 rounding."""
+    Bs, rep, D = 4, 65, 16384
+    g = torch.Generator().manual_seed(5)
+    lat = 14.6 * torch.randn(Bs, D, generator=g)
+    z, vo, vb, vu = (torch.randn(Bs, D, generator=g) for _ in range(4))
+    ll = 1.0 + 0.1 * torch.randn(Bs, 2, generator=g)
+    dlog = torch.randn(Bs, 2, generator=g)
+    sigma, dsigma = 3.2, -0.41
+
+    def run(n):
+        f = lambda t: t.repeat(n, 1).to(cuda).contiguous()
+        if kind == "and_ode":
+            return ops.step_edm_ode(f(lat), f(vo), f(vb), f(vu), f(dlog), f(ll), sigma, dsigma, guidance=7.5, lift_term=0.02)
+        return ops.step_edm_cfg(f(lat), f(z), f(vo), f(vb), f(vu), f(ll), sigma, dsigma, kind, guidance=7.5, lift_term=0.02,
+                                temperature=2.0, logp=0.1, kappa_fixed=0.5)
+    small, big = run(1), run(rep)
+    torch.cuda.synchronize()
+    for a, b in zip(small, big):
+        a, b = a.cpu(), b.cpu()
+        assert torch.allclose(b[:Bs], a, rtol=2e-6, atol=2e-5), (b[:Bs] - a).abs().max()
+        assert torch.equal(b[:Bs], b[-Bs:])          # every replica identical: deterministic reductions
