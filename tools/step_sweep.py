@@ -19,7 +19,7 @@ from super_diffusion_b200 import _lib, ops          # noqa: E402
 D = 3072
 
 
-def time_step(B, M, mode, dmode, dev, sched=False):
+def time_step(B, M, mode, dmode, dev, sched=False, shape=None):
     set_bytes = 4 * B * D * (M + 3)
     R = max(2, -(-2 * 126 * 1024 * 1024 // set_bytes) + 1)
     sets = []
@@ -34,7 +34,7 @@ def time_step(B, M, mode, dmode, dev, sched=False):
 
     def one(st):
         ops.step_vpsde(st["x"], st["nz"], st["sc"], st["lq"], -5.0, 5.0, 0.5, 1e-3, mode, dmode, temperature=1e6,
-                       x_out=st["xo"], weights=st["w"], sched=table, step_counter=counter)
+                       x_out=st["xo"], weights=st["w"], sched=table, step_counter=counter, launch_shape=shape)
     for st in sets:
         one(st)
     torch.cuda.synchronize()
@@ -69,6 +69,8 @@ def main():
     ap.add_argument("--models", type=int, nargs="+", default=[2, 3, 4, 8])
     ap.add_argument("--modes", nargs="+", default=["or", "and", "avg"])
     ap.add_argument("--sched", action="store_true", help="scalars from the device schedule table (the sampler's form)")
+    ap.add_argument("--shape", type=int, nargs=3, default=None, metavar=("THREADS", "NV", "CLUSTER"),
+                    help="explicit launch shape through sd_step_vpsde_ex instead of the heuristic")
     args = ap.parse_args()
     _lib.require_device()
     dev = torch.device("cuda", 0)
@@ -81,14 +83,15 @@ def main():
              # diagnostic combinations: log-density update without the softmax, softmax without the update
              ("avg_ito", ops.MODE_AVG, ops.DLOGQ_ITO), ("or_none", ops.MODE_OR, ops.DLOGQ_NONE))
     print(f"fused step kernel, D = {D}, fp32, HBM peak {peak:.1f} GB/s (measured copy)"
-          + (", scalars from the device schedule table" if args.sched else ", scalars as arguments"))
+          + (", scalars from the device schedule table" if args.sched else ", scalars as arguments")
+          + (f", launch shape {tuple(args.shape)}" if args.shape else ""))
     print(f"{'B':>6} {'M':>2} {'mode':>8} {'MB/launch':>10} {'us':>8} {'GB/s':>8} {'frac':>6}")
     for B in args.batches:
         for M in args.models:
             for name, md, dm in modes:
                 if name not in args.modes:
                     continue
-                us, by = time_step(B, M, md, dm, dev, sched=args.sched)
+                us, by = time_step(B, M, md, dm, dev, sched=args.sched, shape=tuple(args.shape) if args.shape else None)
                 gbs = by / (us * 1e-6) / 1e9
                 print(f"{B:>6} {M:>2} {name:>8} {by / 1e6:>10.1f} {us:>8.2f} {gbs:>8.1f} {gbs / peak:>6.3f}", flush=True)
 
