@@ -292,6 +292,41 @@ int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, cons
 int sd_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
 int sd_cast_bf16_to_f32(const void* in, float* out, size_t n, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Whole score network as one call (the reference's model seam: model_fn(t, x, y) from get_model_fn,
+ * cifar/models/utils.py:86-96, over ScoreNet.__call__, cifar/models/ddpm.py:47-101).
+ * The network structure follows the reference's config fields (configs/sm/cifar/vpsde.py: model.nf, ch_mult,
+ * num_res_blocks, attn_resolutions, conditioned; data.image_size, num_channels, num_classes); the weights are ONE device
+ * blob in GEMM layout, packed from a reference parameter tree by super_diffusion_b200/native.py (order and shapes:
+ * csrc/scorenet_forward.cu header).  Runs the same kernels in the same order as the Python-driven forward.
+ * ------------------------------------------------------------------------ */
+typedef struct sd_scorenet_desc {
+  int image_size;              /* config.data.image_size (multiple of 16) */
+  int channels;                /* config.data.num_channels (<= 3) */
+  int nf;                      /* config.model.nf (multiple of 64) */
+  int num_res_blocks;          /* config.model.num_res_blocks */
+  int n_levels;                /* len(config.model.ch_mult), <= 8 */
+  int ch_mult[8];
+  int n_attn_res;              /* len(config.model.attn_resolutions), <= 8 */
+  int attn_resolutions[8];
+  int conditioned;             /* config.model.conditioned */
+  int num_classes;             /* config.data.num_classes (conditioned models) */
+  const void* weights;         /* device blob, 256-byte aligned */
+  size_t weights_bytes;        /* must equal sd_scorenet_weights_bytes() */
+} sd_scorenet_desc;
+
+#define SD_PRECISION_BF16 1    /* bf16 operands / activations, fp32 accumulation (the only implemented precision) */
+
+/* size of the weight blob for a configuration (desc->weights is ignored) */
+int sd_scorenet_weights_bytes(const sd_scorenet_desc* desc, size_t* bytes_out);
+/* workspace a forward at batch B needs (activations are bump-allocated; t_stride as in sd_scorenet_forward) */
+int sd_scorenet_workspace_bytes(const sd_scorenet_desc* desc, int B, int t_stride, size_t* bytes_out);
+/* out_nhwc[B,H,W,C] (fp32) = model_fn(t, x, y) = sigma_t * grad log q_t(x).
+ * t_dev: device fp32, one value (t_stride = 0) or one per sample (t_stride = 1); x_nhwc: fp32 [B,H,W,C];
+ * y: int32 labels [B] (conditioned models) or NULL.  Asynchronous on `stream`, no host synchronisation. */
+int sd_scorenet_forward(const sd_scorenet_desc* desc, const float* t_dev, int t_stride, const float* x_nhwc, const int* y,
+                        int B, float* out_nhwc, void* workspace, size_t workspace_bytes, int precision, void* stream);
+
 const char* sd_last_error(void);
 int sd_version(void);
 /* 1 when the current device is compute capability 10.x (sm_100 family). */

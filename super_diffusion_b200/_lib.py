@@ -19,6 +19,14 @@ class GemmSrc(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("C", ctypes.c_int), ("taps", ctypes.c_int)]
 
 
+class ScoreNetDesc(ctypes.Structure):
+    """struct sd_scorenet_desc (include/superdiff_b200.h)."""
+    _fields_ = [("image_size", ctypes.c_int), ("channels", ctypes.c_int), ("nf", ctypes.c_int),
+                ("num_res_blocks", ctypes.c_int), ("n_levels", ctypes.c_int), ("ch_mult", ctypes.c_int * 8),
+                ("n_attn_res", ctypes.c_int), ("attn_resolutions", ctypes.c_int * 8), ("conditioned", ctypes.c_int),
+                ("num_classes", ctypes.c_int), ("weights", ctypes.c_void_p), ("weights_bytes", ctypes.c_size_t)]
+
+
 # name -> (restype, argtypes); must list every symbol include/superdiff_b200.h declares
 _F, _I, _V, _U, _SZ = ctypes.c_float, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint, ctypes.c_size_t
 _LL = ctypes.c_longlong
@@ -52,6 +60,9 @@ SIGNATURES = {
     "sd_softmax_rows": (_I, [_V, _V, ctypes.c_long, _I, _F, _V]),
     "sd_cast_f32_to_bf16": (_I, [_V, _V, _SZ, _V]),
     "sd_cast_bf16_to_f32": (_I, [_V, _V, _SZ, _V]),
+    "sd_scorenet_weights_bytes": (_I, [ctypes.POINTER(ScoreNetDesc), ctypes.POINTER(_SZ)]),
+    "sd_scorenet_workspace_bytes": (_I, [ctypes.POINTER(ScoreNetDesc), _I, _I, ctypes.POINTER(_SZ)]),
+    "sd_scorenet_forward": (_I, [ctypes.POINTER(ScoreNetDesc), _V, _I, _V, _V, _I, _V, _V, _SZ, _I, _V]),
     "sd_last_error": (ctypes.c_char_p, []),
     "sd_version": (_I, []),
     "sd_device_ok": (_I, []),
