@@ -319,7 +319,8 @@ typedef struct sd_scorenet_desc {
 
 /* size of the weight blob for a configuration (desc->weights is ignored) */
 int sd_scorenet_weights_bytes(const sd_scorenet_desc* desc, size_t* bytes_out);
-/* workspace a forward at batch B needs (activations are bump-allocated; t_stride as in sd_scorenet_forward) */
+/* workspace a forward at batch B needs (activation arena, 1.5 GiB at batch 512 for the CIFAR configuration; t_stride as in
+ * sd_scorenet_forward) */
 int sd_scorenet_workspace_bytes(const sd_scorenet_desc* desc, int B, int t_stride, size_t* bytes_out);
 /* out_nhwc[B,H,W,C] (fp32) = model_fn(t, x, y) = sigma_t * grad log q_t(x).
  * t_dev: device fp32, one value (t_stride = 0) or one per sample (t_stride = 1); x_nhwc: fp32 [B,H,W,C];

@@ -11,11 +11,12 @@
 //     [cout, 9 cout + cin] | bias   |  per AttnBlock (projections folded, see models/ddpm.py::add_attn): GN scale, bias |
 //     Wq Wk^T bf16 [c, c] + Wk bq | (Wv Wo)^T bf16 [c, c] + bv Wo + bo  |  per Downsample: bf16 [c, 9c] + bias  |
 //   per Upsample: four 2x2-tap phase matrices bf16 [4, c, 4c] + bias  |  output GN scale, bias | output conv bf16 [16, 9 nf] + bias.
-// Every array starts on a 256-byte boundary.  Workspace: activations are bump-allocated (no reuse inside one forward).
+// Every array starts on a 256-byte boundary.  Workspace: a best-fit arena; a block is reused as soon as its last reader is enqueued.
 #include "common.cuh"
 #include "../../include/superdiff_b200.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace sdb {
@@ -163,12 +164,54 @@ struct Runner {
   size_t gn_scratch_floats = 0;
   int rc = SD_OK;
 
-  void* alloc(size_t bytes) {
-    void* p = ws ? ws + used : nullptr;
-    used = align_up(used + bytes);
-    if (ws && used > ws_bytes && rc == SD_OK) rc = fail(kErrInvalidArg, "sd_scorenet_forward: workspace too small (see sd_scorenet_workspace_bytes)");
-    return p;
+  // Workspace allocator: best-fit from the blocks released so far, else bump.  Everything is enqueued on ONE stream, so a block
+  // may be handed out again as soon as the launches that read it have been enqueued.  Reuse matters for speed, not only for
+  // size: with pure bump allocation (6.6 GiB of distinct addresses at batch 512) the same kernels ran 3-6 % slower than the
+  // Python-driven plan, whose caching allocator keeps re-using a few hot buffers.
+  struct Block { size_t off, size; };
+  std::vector<Block> free_list;
+  static size_t ws_align() {     // SDB_NATIVE_WS_ALIGN: granularity of workspace blocks (tuning knob)
+    static const size_t v = [] { const char* e = getenv("SDB_NATIVE_WS_ALIGN"); const long a = e && *e ? atol(e) : 0; return a >= 256 ? (size_t)a : kAlign; }();
+    return v;
   }
+  void* alloc(size_t bytes) {
+    bytes = (bytes ? bytes : 1);
+    bytes = (bytes + ws_align() - 1) / ws_align() * ws_align();
+    int best = -1;
+    for (int i = 0; i < (int)free_list.size(); ++i)
+      if (free_list[i].size >= bytes && (best < 0 || free_list[i].size < free_list[best].size)) best = i;
+    size_t off;
+    if (best >= 0) {
+      off = free_list[best].off;
+      if (free_list[best].size == bytes) free_list.erase(free_list.begin() + best);
+      else { free_list[best].off += bytes; free_list[best].size -= bytes; }
+    } else {
+      off = used;
+      used += bytes;
+      if (ws && used > ws_bytes && rc == SD_OK) rc = fail(kErrInvalidArg, "sd_scorenet_forward: workspace too small (see sd_scorenet_workspace_bytes)");
+    }
+    sizes.push_back({off, bytes});
+    return ws ? ws + off : reinterpret_cast<char*>(kAlign) + off;      // dry run: fake addresses keep the bookkeeping identical
+  }
+  std::vector<Block> sizes;                     // live allocations (offset -> size)
+  void release(const void* p) {
+    if (!p) return;
+    const size_t off = (size_t)(static_cast<const char*>(p) - (ws ? ws : reinterpret_cast<char*>(kAlign)));
+    for (int i = (int)sizes.size() - 1; i >= 0; --i)
+      if (sizes[i].off == off) {
+        Block b = sizes[i];
+        sizes.erase(sizes.begin() + i);
+        // coalesce with neighbours
+        for (int j = 0; j < (int)free_list.size();) {
+          if (free_list[j].off + free_list[j].size == b.off) { b.off = free_list[j].off; b.size += free_list[j].size; free_list.erase(free_list.begin() + j); }
+          else if (b.off + b.size == free_list[j].off) { b.size += free_list[j].size; free_list.erase(free_list.begin() + j); }
+          else ++j;
+        }
+        free_list.push_back(b);
+        return;
+      }
+  }
+  void release(Act& a) { release(a.p); release(a.stats); a.p = nullptr; a.stats = nullptr; }
   bool live() const { return ws != nullptr && rc == SD_OK; }
   void check(int r) { if (rc == SD_OK && r != SD_OK) rc = r; }
 
@@ -204,9 +247,13 @@ struct Runner {
     Act a1 = gn(x0, x1, r.g1, r.be1, true);
     sd_gemm_src s1[1] = {{a1.p, a1.C, 9}};
     Act h1 = conv(s1, 1, x0.H, x0.W, r.w1, r.cout, nullptr, rowbias ? rowbias + r.off : nullptr, net.dense_n, true);
+    release(a1);
     Act a2 = gn(h1, nullptr, r.g2, r.be2, true);
+    release(h1);
     sd_gemm_src s2[3] = {{a2.p, a2.C, 9}, {x0.p, x0.C, 1}, {x1 ? x1->p : nullptr, x1 ? x1->C : 0, 1}};
-    return conv(s2, x1 ? 3 : 2, x0.H, x0.W, r.w2, r.cout, r.b2, nullptr, 0, true);
+    Act o = conv(s2, x1 ? 3 : 2, x0.H, x0.W, r.w2, r.cout, r.b2, nullptr, 0, true);
+    release(a2);
+    return o;
   }
 
   // AttnBlock (layers.py:493-511) with the projections folded at export time: GN -> q' = NIN(h) -> V'^T = (Wv Wo)^T h^T ->
@@ -232,6 +279,7 @@ struct Runner {
       check(sd_attention_core(q2.p, C, (long long)Sp * C, h.p, C, (long long)Sp * C, vt, Sp, (long long)C * Sp, nb, Sp, C,
                               (float)std::pow((double)C, -0.5), S, a.b_vo, x.p, o.p, o.stats, st));
     }
+    release(h); release(q2); release(vt);
     return o;
   }
 
@@ -257,13 +305,14 @@ struct Runner {
     if (live()) check(sd_im2col_in(x, B, H0, H0, d.channels, cols, st));
     sd_gemm_src s0[1] = {{cols, 64, 1}};
     Act h = conv(s0, 1, H0, H0, net.conv_in_w64, nf, net.conv_in_b, nullptr, 0, true);
+    release(cols);
     std::vector<Act> hs{h};
     for (const Op& op : net.plan) {
       if (rc != SD_OK) return;
       switch (op.kind) {
         case OP_DOWN_BLOCK:
           h = res_block(hs.back(), nullptr, op.a, rowbias);
-          if (op.b >= 0) h = attn_block(h, op.b);
+          if (op.b >= 0) { Act r = h; h = attn_block(r, op.b); if (h.p != r.p) release(r); }
           hs.push_back(h);
           break;
         case OP_DOWNSAMPLE: {
@@ -276,20 +325,29 @@ struct Runner {
           hs.push_back(h);
           break;
         }
-        case OP_MID:
-          h = res_block(hs.back(), nullptr, op.a, rowbias);
-          h = attn_block(h, op.b);
-          h = res_block(h, nullptr, op.c, rowbias);
-          break;
-        case OP_UP_BLOCK: {
-          const Act skip = hs.back();
-          hs.pop_back();
-          h = res_block(h, &skip, op.a, rowbias);
+        case OP_MID: {
+          Act r0 = res_block(hs.back(), nullptr, op.a, rowbias);        // its input stays alive as a skip connection
+          Act a0 = attn_block(r0, op.b);
+          if (a0.p != r0.p) release(r0);
+          h = res_block(a0, nullptr, op.c, rowbias);
+          release(a0);
           break;
         }
-        case OP_ATTN:
-          h = attn_block(h, op.a);
+        case OP_UP_BLOCK: {
+          Act skip = hs.back();
+          hs.pop_back();
+          Act prev = h;
+          h = res_block(prev, &skip, op.a, rowbias);
+          if (prev.p != skip.p) release(prev);
+          release(skip);
           break;
+        }
+        case OP_ATTN: {
+          Act prev = h;
+          h = attn_block(prev, op.a);
+          if (h.p != prev.p) release(prev);
+          break;
+        }
         case OP_UPSAMPLE: {
           const UpW& w = net.up[op.a];
           Act o = new_act(2 * h.H, 2 * h.W, w.c);
@@ -298,6 +356,7 @@ struct Runner {
             o.stats = static_cast<float*>(alloc((size_t)B * o.nchunk * 2 * w.c * 4));
           }
           if (live()) check(sd_upconv_gemm(h.p, B, h.H, h.W, h.C, w.w4, w.c, w.b, 0u, o.p, o.stats, st));
+          release(h);
           h = o;
           break;
         }
@@ -305,6 +364,7 @@ struct Runner {
     }
     if (rc != SD_OK) return;
     Act a = gn(h, nullptr, net.out_g, net.out_be, true);
+    release(h);
     sd_gemm_src so[1] = {{a.p, a.C, 9}};
     if (live())
       check(sd_conv_gemm(so, 1, B, h.H, h.W, net.out_w, d.channels, net.out_b, nullptr, 0, nullptr, SD_EPI_OUT_F32, out, d.channels,
