@@ -293,3 +293,20 @@ def test_edm_streaming_kernel_matches_resident_kernel(cuda, kind):
         a, b = a.cpu(), b.cpu()
         assert torch.allclose(b[:Bs], a, rtol=2e-6, atol=2e-5), (b[:Bs] - a).abs().max()
         assert torch.equal(b[:Bs], b[-Bs:])          # every replica identical: deterministic reductions
+
+
+@pytest.mark.parametrize("M,mode", [(2, O.MODE_AND), (3, O.MODE_AND), (8, O.MODE_AND), (4, O.MODE_OR), (8, O.MODE_OR)])
+def test_step_replicas_are_bit_identical(cuda, M, mode):
+    """The same three samples repeated 400 times through one launch (every SM, several waves): every replica must carry the
+    same bits - fixed-order reductions, the warp-parallel kappa solve and the bulk-copy kernel have no race to lose."""
+    Bs, rep, D, t, dt = 3, 400, 3072, 0.7, 1e-3
+    x, eps, s, logq = _mk(Bs, D, M, seed=900 + M, dev=cuda)
+    xr, er, lr = x.repeat(rep, 1), eps.repeat(rep, 1), logq.repeat(rep, 1)
+    sr = s.repeat(1, rep, 1)
+    dm = O.DLOGQ_ITO if mode == O.MODE_AND else O.DLOGQ_CIFAR_MAXSUB
+    xo, lq, w = _run(xr, er, sr, lr, t, dt, mode, dm, cuda, temperature=1.0, ito_scale=1.0)
+    for out in (xo, lq, w):
+        blocks = out.view(rep, Bs, -1)
+        assert torch.equal(blocks, blocks[:1].expand_as(blocks))
+    ref = _ref(x, eps, s, logq, t, dt, mode, dm, temperature=1.0, ito_scale=1.0)
+    _check((xo[:Bs], lq[:Bs], w[:Bs]), ref, w_tol=2e-4)
