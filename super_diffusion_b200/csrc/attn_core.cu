@@ -10,7 +10,8 @@
 //   phase 2   O[128 x C]   = P . (V^T)^T             A operand = P from shared memory, B = V^T tiles by TMA, TMEM cols [256, 256+C)
 //   epilogue  + bias + residual -> bf16 out, optional per-tile channel sums for the following GroupNorm
 //
-// One CTA per SM, persistent over (batch entry, 128-row query tile); warp 0 = TMA producer (runs ahead through a 3-stage ring,
+// One CTA per SM, persistent over (batch entry, 128-row query tile); the MMA issuer starts the next tile's phase 1 as soon as
+// this tile's phase 2 is issued (S is free by then), so it overlaps the epilogue; warp 0 = TMA producer (runs ahead through a 3-stage ring,
 // so the V^T tiles of phase 2 and the next tile's Q / K arrive during the softmax), warp 1 = MMA issuer, warps 2..9 = softmax +
 // epilogue.  Before: two launches (probabilities 70 us + P V 91 us at batch 512, S = 256) with P written to and re-read from HBM.
 #include "common.cuh"
@@ -130,7 +131,9 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_kernel(const __grid_c
       int stage = 0;
       uint32_t phase = 0, it = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        mbar_wait(tile_done, (it & 1) ^ 1);          // the previous tile's epilogue has drained TMEM and released P
+        // No wait for the previous tile's epilogue here: S was released when its softmax arrived on p_ready (which this thread
+        // waited for before issuing that tile's phase 2), and O / P are only touched again after the NEXT p_ready, which the
+        // epilogue warps reach after they have drained O.  So the next tile's S = Q K^T runs under the current epilogue.
         tcgen05_fence_after();
         for (int kb = 0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
