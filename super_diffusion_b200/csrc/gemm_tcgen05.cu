@@ -395,6 +395,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 accumulate = 1;
                 continue;
               }
+              if (!PAIR && nsub == 2 && p.block_n <= 64) {
+                // narrow N (the 3-channel output conv): a 128 x 16 x 16 MMA is all latency, and the four K steps of one
+                // sub-tile are a dependent chain on the same TMEM columns (ncu: one UTCHMMA per ~120 clocks).  Alternate the
+                // two sub-tiles' independent chains instead of running them back to back; per-accumulator order is unchanged.
+                const uint64_t a0 = umma_desc_sw128(slab ? sa + (uint32_t)g * row_pitch : sa);
+                const uint64_t a1 = umma_desc_sw128(slab ? sa + (uint32_t)(g + p.h_box) * row_pitch : sa + (uint32_t)A_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                  umma_bf16(d_tmem, a0 + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                  umma_bf16(d_tmem + 128u, a1 + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, accumulate | (uint32_t)k);
+                }
+                accumulate = 1;
+                continue;
+              }
               for (int sub = 0; sub < nsub; ++sub) {
                 // slab: vertical tap g of sub-tile `sub` = the slab rows starting (g + sub * h_box) image rows in
                 const uint32_t a_addr = slab ? sa + (uint32_t)(g + sub * p.h_box) * row_pitch : sa + (uint32_t)sub * A_BYTES;
