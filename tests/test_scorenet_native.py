@@ -139,3 +139,54 @@ def test_plain_c_host_gets_the_same_scores(cuda, tmp_path):
     got = torch.from_numpy(np.fromfile(str(tmp_path / "out.bin"), dtype=np.float32).reshape(B, 32, 32, 3))
     want = bound(t, x.to(cuda)).cpu()
     assert torch.equal(got, want), (got - want).abs().max()
+
+
+@pytest.mark.gpu
+def test_plain_c_sampler_matches_the_python_loop(cuda, tmp_path):
+    """examples/native_sampler.c: the SuperDiff-OR loop (cifar/eval_utils.py:72-86 over cifar/dynamics.py:115-136) from C - per
+    timestep two sd_scorenet_forward calls and one sd_step_vpsde.  Same noise in, same bits out as the Python-driven loop."""
+    import os
+    import shutil
+    import subprocess
+    import numpy as np
+    from super_diffusion_b200 import ops, sde
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc on this box")
+    exe = str(tmp_path / "native_sampler")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(root, "include"), "-I", "/usr/local/cuda/include",
+                    os.path.join(root, "examples", "native_sampler.c"), "-o", exe,
+                    "-L", os.path.join(root, "super_diffusion_b200"), "-lsuperdiff_b200", "-L", "/usr/local/cuda/lib64", "-lcudart",
+                    "-Wl,-rpath," + os.path.join(root, "super_diffusion_b200")], check=True)
+    cfg = vpsde.get_config()
+    B, n_steps, dt, M = 8, 4, 1e-3, 2
+    bounds = []
+    for m in range(M):
+        model, params = mutils.init_model(20 + m, cfg, zero_init_scale=1.0)
+        b = model.bind(params, cuda)
+        bounds.append(b)
+        native.NativeScoreNet(b).save(str(tmp_path / f"model{m}"))
+    g = torch.Generator().manual_seed(8)
+    x0 = torch.randn(B, 32, 32, 3, generator=g)
+    noise = torch.randn(n_steps, B, 32, 32, 3, generator=g)
+    x0.numpy().tofile(str(tmp_path / "x0.bin"))
+    noise.numpy().tofile(str(tmp_path / "noise.bin"))
+    r = subprocess.run([exe, str(tmp_path / "x0.bin"), str(tmp_path / "noise.bin"), str(tmp_path / "x.bin"), str(tmp_path / "logq.bin"),
+                        str(B), str(n_steps), repr(dt)] + [str(tmp_path / f"model{m}.bin") for m in range(M)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    got_x = torch.from_numpy(np.fromfile(str(tmp_path / "x.bin"), dtype=np.float32).reshape(B, 32, 32, 3))
+    got_l = torch.from_numpy(np.fromfile(str(tmp_path / "logq.bin"), dtype=np.float32).reshape(B, M))
+    # the same calls from Python
+    x = x0.to(cuda).clone()
+    logq = torch.zeros(B, M, device=cuda)
+    t = 1.0
+    for i in range(n_steps):
+        tt = torch.full((1,), t, device=cuda, dtype=torch.float32)
+        scores = [b(tt, x) for b in bounds]
+        ops.step_vpsde(x, noise[i].to(cuda), scores, logq, sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t), dt, ops.MODE_OR,
+                       ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, x_out=x)
+        t += -dt
+    torch.cuda.synchronize()
+    assert torch.equal(got_x, x.cpu()), (got_x - x.cpu()).abs().max()
+    assert torch.equal(got_l, logq.cpu())
