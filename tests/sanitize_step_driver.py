@@ -1,4 +1,5 @@
-"""Small driver for compute-sanitizer (memcheck / racecheck) over the fused step kernels added in r01d: shared-memory AND,
+"""Test infrastructure (lives under tests/ because it checks against oracle/): small driver for compute-sanitizer (memcheck /
+racecheck) over the fused step kernels added in r01d: shared-memory AND,
 streaming AND, OR with preloaded log-densities, warp kappa solve, streaming EDM step.  Tiny shapes; checks results too."""
 import os
 import sys
