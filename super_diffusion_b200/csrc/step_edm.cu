@@ -307,6 +307,99 @@ __global__ void __launch_bounds__(256) step_edm_stream_kernel(const __grid_const
   }
 }
 
+// AND / AND-ODE at large batches: kappa needs <d,d>, <base,d>, ... before the first write, and the two-pass streaming form
+// above re-reads the sample through L2 (0.54-0.60 of the copy peak).  Here ONE 1024-thread CTA per sample keeps what the
+// write pass needs - d = v_obj - v_bg, base = v_unc + g (v_bg - v_unc) and z, 3 x D x 4 bytes = 192 KB at D = 16384 - in
+// SHARED memory and x in registers, so HBM is read exactly once (4*D*6 bytes per sample, like the resident kernel) with no
+// cluster.  One CTA per SM (the sample fills the shared memory): the reduction and the solve are not overlapped by a
+// second CTA, which is what separates it from the single-pass `or` / `avg` form.
+constexpr int kEdmSmemThreads = 1024, kEdmSmemNX = 4;      // x units held per thread: D <= 4 * 4 * 1024
+__global__ void __launch_bounds__(kEdmSmemThreads, 1) step_edm_smem_kernel(const __grid_constant__ EdmParams p) {
+  extern __shared__ __align__(16) unsigned char edm_smem[];
+  const int sample = blockIdx.x;
+  const int nunits = p.D / 4;
+  const size_t base_off = (size_t)sample * p.D;
+  const bool ode = p.mode == SD_EDM_MODE_AND_ODE;
+  const float cn = ode ? 0.f : sqrtf(2.f * fabsf(p.dsigma) * p.sigma);
+  const float two_ds = ode ? p.dsigma : 2.f * p.dsigma;
+  float4* d_sh = reinterpret_cast<float4*>(edm_smem);
+  float4* bs_sh = d_sh + nunits;
+  float4* z_sh = bs_sh + nunits;
+  double* scratch = reinterpret_cast<double*>(z_sh + nunits);
+  float ll0 = p.ll[2 * sample], ll1 = p.ll[2 * sample + 1];
+  float dl0 = 0.f, dl1 = 0.f;
+  if (ode) { dl0 = p.dlog[2 * sample]; dl1 = p.dlog[2 * sample + 1]; }
+  float part[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) part[k] = 0.f;
+  float4 x[kEdmSmemNX];
+#pragma unroll
+  for (int j = 0; j < kEdmSmemNX; ++j) {
+    const int u = j * kEdmSmemThreads + threadIdx.x;
+    x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < nunits) {
+      const size_t off = base_off + (size_t)u * 4;
+      x[j] = ld_stream4(p.x + off);
+      const float4 z4 = p.z ? ld_stream4(p.z + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 vo4 = ld_stream4(p.vo + off), vb4 = ld_stream4(p.vb + off), vu4 = ld_stream4(p.vu + off);
+      const float zz[4] = {z4.x, z4.y, z4.z, z4.w}, oo[4] = {vo4.x, vo4.y, vo4.z, vo4.w};
+      const float vb[4] = {vb4.x, vb4.y, vb4.z, vb4.w}, vu[4] = {vu4.x, vu4.y, vu4.z, vu4.w};
+      float dd[4], bb[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dd[e] = oo[e] - vb[e];
+        bb[e] = vu[e] + p.g * (vb[e] - vu[e]);
+        const float vbe = oo[e] - dd[e];
+        part[0] = fmaf(dd[e], dd[e], part[0]);
+        part[1] = fmaf(bb[e], dd[e], part[1]);
+        part[2] = fmaf(zz[e], dd[e], part[2]);
+        part[3] = fmaf(oo[e], oo[e], part[3]);
+        part[4] = fmaf(vbe, vbe, part[4]);
+        part[5] = fmaf(oo[e], bb[e], part[5]);
+        part[6] = fmaf(oo[e], dd[e], part[6]);
+        part[7] = fmaf(oo[e], zz[e], part[7]);
+      }
+      d_sh[u] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+      bs_sh[u] = make_float4(bb[0], bb[1], bb[2], bb[3]);
+      z_sh[u] = z4;
+    }
+  }
+  const double* t = block_cluster_sum<8, false>(part, scratch);
+  const double DD = t[0], BD = t[1], ZD = t[2], OO = t[3], BB = t[4], OB = t[5], OD = t[6], OZ = t[7];
+  const double ds = p.dsigma, sg = p.sigma, g = p.g;
+  double kappa;
+  if (ode) kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) / (g * DD);        // clip_eval.py:383-385
+  else kappa = (fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term) / (2.0 * ds * g * DD);   // :398-400
+  const float kf = (float)kappa;
+#pragma unroll
+  for (int j = 0; j < kEdmSmemNX; ++j) {
+    const int u = j * kEdmSmemThreads + threadIdx.x;
+    if (u >= nunits) continue;
+    const float4 d4 = d_sh[u], b4 = bs_sh[u], z4 = z_sh[u];      // this thread's own writes: no barrier needed
+    float4 o;
+    o.x = x[j].x + (two_ds * (b4.x + p.g * kf * d4.x) + cn * z4.x);
+    o.y = x[j].y + (two_ds * (b4.y + p.g * kf * d4.y) + cn * z4.y);
+    o.z = x[j].z + (two_ds * (b4.z + p.g * kf * d4.z) + cn * z4.z);
+    o.w = x[j].w + (two_ds * (b4.w + p.g * kf * d4.w) + cn * z4.w);
+    st4(p.x_out + base_off + (size_t)u * 4, o);
+  }
+  if (threadIdx.x == 0) {
+    if (ode) {
+      const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);     // clip_eval.py:389-390
+      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) / sg));
+      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) / sg));
+    } else {
+      const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
+      const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
+      const double b_dx = o_dx - d_dx;
+      const double q = -fabs(ds) / sg;                                                     // :409-410
+      p.ll[2 * sample] = ll0 + (float)(-o_dx / sg + q * OO);
+      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx / sg + q * BB);
+    }
+    p.kappa_out[sample] = kf;
+  }
+}
+
 template <int NV>
 static cudaError_t launch_edm(const EdmParams& p, int threads, int cluster, cudaStream_t st) {
   cudaLaunchConfig_t cfg{};
@@ -350,6 +443,15 @@ static int step_edm_impl(const float* latents, const float* z, const float* v_ob
   const int nunits = D / 4;
   // enough samples to fill the chip with one CTA each: the streaming kernel (SDB_EDM_STREAM_MIN_B overrides the threshold)
   static const int stream_min_b = [] { const char* e = getenv("SDB_EDM_STREAM_MIN_B"); return e && *e ? atoi(e) : 256; }();
+  // AND / AND-ODE with one sample per SM resident in shared memory (batch >= 148: a CTA for every SM)
+  static const int smem_and = [] { const char* e = getenv("SDB_EDM_SMEM_AND"); return e && *e ? atoi(e) : 1; }();   // tuning knob
+  const size_t smem_need = (size_t)D * 12 + sizeof(double) * (size_t)(kEdmSmemThreads / 32 + 2) * 8;
+  if (smem_and && (ode || mode == SD_MODE_AND) && B >= 148 && nunits <= kEdmSmemNX * kEdmSmemThreads && smem_need <= 227 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(step_edm_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_need);
+    if (e != cudaSuccess) return check_cuda(e, "sd_step_edm_cfg (shared-memory AND)");
+    step_edm_smem_kernel<<<B, kEdmSmemThreads, smem_need, (cudaStream_t)stream>>>(p);
+    return check_cuda(cudaGetLastError(), "sd_step_edm_cfg launch (shared-memory AND)");
+  }
   if (B >= stream_min_b) {
     const size_t smem = sizeof(double) * (size_t)(256 / 32 + 2) * 8;
     static const int stream_nv = [] { const char* e = getenv("SDB_EDM_STREAM_NV"); return e && *e ? atoi(e) : 2; }();   // tuning knob: 2 measured 3-5 % ahead of 1 at batch 512
