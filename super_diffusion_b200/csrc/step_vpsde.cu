@@ -126,6 +126,16 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
 #undef SDB_AS
     return check_cuda(err, "sd_step_vpsde launch (streaming AND)");
   }
+  if ((threads == 0 || nv == 0 || cluster == 0) && !is_and && nunits >= 384 && B >= (M == 2 ? 768 : 384)) {
+    // Weights known up front (OR / AVG / FIXED, stochastic or ODE) at batches that fill the chip: SMALL CTAs that walk the
+    // sample in rounds - 128 threads x 3 float4 (x 1 for M >= 5).  ~1000 CTA slots instead of 444 make the last wave cheap and
+    // keep more independent loads in flight per SM; measured (tools/step_sweep.py --shape, profiles/r01d_step_shapes*.txt)
+    // 4-17 % ahead of one 256 x 3 round at batch 1024-4096 and, at batch 8192, OR at 1.01-1.02 of the copy peak for
+    // M = 2, 3, 4, 8 (was 0.98 / 0.89 / 0.92 / 0.92) - what had looked like the cost of the softmax was the launch shape.
+    threads = 128;
+    nv = M <= 4 ? 3 : 1;
+    cluster = 1;
+  }
   if (threads == 0 || nv == 0 || cluster == 0) {
     // Heuristic: keep (M+2)*NV float4 registers per thread <= 24, prefer 128..256 threads and
     // enough CTAs (>= ~8 per SM) that the 148 SMs stay balanced.
