@@ -52,12 +52,11 @@ __device__ __forceinline__ StepScalars finish_scalars(const StepParams& p, int r
 }
 __device__ __forceinline__ StepScalars load_scalars(const StepParams& p) { return finish_scalars(p, begin_scalars(p)); }
 
-// Mixing weights that do not need this step's reductions, in two halves so the caller can put the sample's streaming
-// loads between them: raw_weights only ISSUES the (uncached, ~1 us) logq / weights loads, finish_weights consumes them.
-// With the softmax ahead of the streaming loads every CTA started with a dependent DRAM round trip during which it had
-// nothing in flight: OR ran at 0.81-0.87 of the copy peak for M >= 3 (2 CTAs / SM) while AVG, same code, reached 0.99.
-// finish_weights consumes values whose loads were ISSUED before the sample's streaming loads (LogqState::old, and the
-// caller's predicated load of the FIXED weights) and must itself come after them - see the call site.
+// Mixing weights that do not need this step's reductions.  finish_weights consumes values whose loads were ISSUED before the
+// sample's streaming loads (LogqState::old, and the caller's predicated load of the FIXED weights) and must itself come
+// after them - see the call site: with the softmax ahead of the streaming loads every CTA starts with a dependent DRAM
+// round trip during which it has nothing in flight (worth 3-5 % at 2 CTAs / SM; the larger part of the old OR-vs-AVG gap
+// turned out to be the launch shape, see step_vpsde.cu).
 template <int M>
 __device__ __forceinline__ void finish_weights(const StepParams& p, const float (&logq_old)[M], const float (&wfix)[M],
                                                float (&w)[M]) {
@@ -248,7 +247,7 @@ __device__ __forceinline__ void and_increments(const double* tot, const double* 
 
 // The old log-densities (and the optional additive term) are loaded at the START of the kernel (load_logq_state), next to
 // the streaming loads: read here, at the tail, they were a dependent ~0.7 us DRAM round trip by one thread while the CTA
-// still held its slot on the SM (OR ran 10 % behind AVG, which writes no log-densities).
+// still held its slot on the SM.
 template <int M>
 struct LogqState {
   float old[M];
@@ -353,8 +352,8 @@ __global__ void __launch_bounds__(256, ((M + 2) * NV * (VEC / 4) <= 12 && VEC ==
       }
       if (!have_w) {
         // Nothing may touch the loaded log-densities before this point: any use (even a register move merging the
-        // per-mode sources) waits for the ~1 us uncached load while the CTA has no data load in flight - OR then ran
-        // 13-16 % behind AVG at 2 CTAs / SM.  The empty volatile asm pins the softmax below the streaming loads (volatile
+        // per-mode sources) waits for the ~1 us uncached load while the CTA has no data load in flight.
+        // The empty volatile asm pins the softmax below the streaming loads (volatile
         // asm statements keep their order; otherwise the loop-invariant softmax is hoisted to the loop pre-header).
 #pragma unroll
         for (int i = 0; i < M; ++i) asm volatile("" : "+f"(lqs.old[i]), "+f"(wfix[i]));
