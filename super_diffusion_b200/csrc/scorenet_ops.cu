@@ -568,6 +568,10 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   };
   auto chunks_for = [&](int k, int& px_per_chunk) {
     int nchunk = (cta_target + B - 1) / B;
+    // 16x16 (and smaller) images at batches that fill the chip on their own: one CTA per sample.  Measured at batch 512
+    // (tools/layer_bench.py with SDB_GN_CTAS, profiles/r01d_notes.md): 24.8 vs 28.2 us for 16^2 x 256, while the 32^2 layers
+    // prefer two chunks per sample (48.1 vs 50.8 us); more, smaller CTAs are slower everywhere (1184 .. 9472: +6 .. +40 %).
+    if (HW <= 256 && B >= 296) nchunk = 1;
     const int max_chunks = (HW + 4 * k - 1) / (4 * k);
     if (nchunk > max_chunks) nchunk = max_chunks;
     if (nchunk < 1) nchunk = 1;
