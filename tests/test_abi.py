@@ -48,3 +48,19 @@ def test_no_oracle_import_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_examples_compile_as_plain_c(tmp_path):
+    """include/superdiff_b200.h is a C header (extern "C" guards, no C++ types): the two example hosts build with gcc and
+    link against the shared library.  Compile + link only; running them needs a GPU (tests/test_scorenet_native.py)."""
+    import shutil
+    import subprocess
+    import pytest
+    if shutil.which("gcc") is None or not os.path.exists("/usr/local/cuda/include/cuda_runtime_api.h"):
+        pytest.skip("needs gcc and the CUDA runtime headers")
+    for name in ("native_forward", "native_sampler"):
+        r = subprocess.run(["gcc", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", "/usr/local/cuda/include",
+                            os.path.join(ROOT, "examples", name + ".c"), "-o", str(tmp_path / name),
+                            "-L", os.path.join(ROOT, "super_diffusion_b200"), "-lsuperdiff_b200", "-L", "/usr/local/cuda/lib64",
+                            "-lcudart"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
