@@ -328,6 +328,13 @@ int sd_scorenet_workspace_bytes(const sd_scorenet_desc* desc, int B, int t_strid
 int sd_scorenet_forward(const sd_scorenet_desc* desc, const float* t_dev, int t_stride, const float* x_nhwc, const int* y,
                         int B, float* out_nhwc, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
+/* Same network with the time read on the device: t = sched[*step_counter].sigma (rows (a_t, b_t, sigma_t, dt) as in
+ * sd_step_vpsde; sigma_t = t for this SDE).  Every argument is then fixed across timesteps, so one captured CUDA graph of
+ * M x sd_scorenet_forward_sched + sd_step_vpsde(sched, step_counter) + sd_counter_add replays for the whole sampling loop. */
+int sd_scorenet_forward_sched(const sd_scorenet_desc* desc, const float* sched, const int* step_counter, const float* x_nhwc,
+                              const int* y, int B, float* out_nhwc, void* workspace, size_t workspace_bytes, int precision,
+                              void* stream);
+
 const char* sd_last_error(void);
 int sd_version(void);
 /* 1 when the current device is compute capability 10.x (sm_100 family). */

@@ -63,6 +63,7 @@ SIGNATURES = {
     "sd_scorenet_weights_bytes": (_I, [ctypes.POINTER(ScoreNetDesc), ctypes.POINTER(_SZ)]),
     "sd_scorenet_workspace_bytes": (_I, [ctypes.POINTER(ScoreNetDesc), _I, _I, ctypes.POINTER(_SZ)]),
     "sd_scorenet_forward": (_I, [ctypes.POINTER(ScoreNetDesc), _V, _I, _V, _V, _I, _V, _V, _SZ, _I, _V]),
+    "sd_scorenet_forward_sched": (_I, [ctypes.POINTER(ScoreNetDesc), _V, _V, _V, _V, _I, _V, _V, _SZ, _I, _V]),
     "sd_last_error": (ctypes.c_char_p, []),
     "sd_version": (_I, []),
     "sd_device_ok": (_I, []),

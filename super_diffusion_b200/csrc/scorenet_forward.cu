@@ -283,6 +283,8 @@ struct Runner {
     return o;
   }
 
+  const float* sched = nullptr;         // optional device schedule table + step counter instead of t_dev (sd_scorenet_forward_sched)
+  const int* step_counter = nullptr;
   void run(const float* t_dev, int t_stride, const float* x, const int* y, float* out) {
     const int nf = d.nf, H0 = d.image_size;
     int max_c = nf;                       // widest GroupNorm input (a skip concatenation)
@@ -295,7 +297,7 @@ struct Runner {
     void* act_temb = alloc((size_t)B * 4 * nf * 2);
     float* rowbias = static_cast<float*>(alloc((size_t)B * net.dense_n * 4));
     if (live()) {
-      check(sd_time_embedding(t_dev, t_stride, nullptr, nullptr, B, nf, net.temb_w0, net.temb_b0, net.temb_w1, net.temb_b1,
+      check(sd_time_embedding(t_dev, t_stride, sched, step_counter, B, nf, net.temb_w0, net.temb_b0, net.temb_w1, net.temb_b1,
                               net.class_emb, net.class_emb ? y : nullptr, temb_scratch, act_temb, st));
       check(sd_batched_gemm(act_temb, 4 * nf, 0, net.dense_w, 4 * nf, 0, 1, B, net.dense_n, 4 * nf, net.dense_b, nullptr,
                             SD_EPI_OUT_F32, rowbias, net.dense_n, (long long)B * net.dense_n, st));
@@ -431,6 +433,27 @@ int sd_scorenet_forward(const sd_scorenet_desc* desc, const float* t_dev, int t_
   if (desc->conditioned && !y) return fail(kErrInvalidArg, "sd_scorenet_forward: conditioned score-net needs labels");
   Runner r{*desc, net, B, static_cast<char*>(workspace), workspace_bytes, 0, (cudaStream_t)stream};
   r.run(t_dev, t_stride, x_nhwc, y, out_nhwc);
+  return r.rc;
+}
+
+int sd_scorenet_forward_sched(const sd_scorenet_desc* desc, const float* sched, const int* step_counter, const float* x_nhwc,
+                              const int* y, int B, float* out_nhwc, void* workspace, size_t workspace_bytes, int precision,
+                              void* stream) {
+  using namespace sdb;
+  if (precision != SD_PRECISION_BF16)
+    return fail(kErrUnsupported, "sd_scorenet_forward_sched: only SD_PRECISION_BF16 (bf16 operands, fp32 accumulation) is implemented");
+  if (B < 0) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: B >= 0 required");
+  if (B == 0) return SD_OK;
+  if (!sched || !step_counter || !x_nhwc || !out_nhwc || !workspace) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: null pointer argument");
+  if ((uintptr_t)workspace % 256) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: workspace must be 256-byte aligned");
+  Net net;
+  int rc = prepare(desc, net, true);
+  if (rc != SD_OK) return rc;
+  if (desc->conditioned && !y) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: conditioned score-net needs labels");
+  Runner r{*desc, net, B, static_cast<char*>(workspace), workspace_bytes, 0, (cudaStream_t)stream};
+  r.sched = sched;
+  r.step_counter = step_counter;
+  r.run(nullptr, 0, x_nhwc, y, out_nhwc);
   return r.rc;
 }
 

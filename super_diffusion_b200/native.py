@@ -121,6 +121,28 @@ class NativeScoreNet:
         _lib.check(rc, "sd_scorenet_forward")
         return out
 
+    def forward_sched(self, sched, step_counter, x, y=None, out=None):
+        """model_fn at t = sched[*step_counter].sigma, read on the device (sd_scorenet_forward_sched): every argument is
+        fixed across timesteps, so the call can sit in a CUDA graph that replays for the whole loop."""
+        _lib.require_device()
+        B = x.shape[0]
+        labels = None
+        if self.desc.conditioned:
+            if y is None:
+                raise ValueError("conditioned score-net needs labels")
+            labels = y.to(device=x.device, dtype=torch.int32).contiguous()
+        need = self.workspace_bytes(B, 0)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=x.device)
+        if out is None:
+            out = torch.empty_like(x)
+        rc = _lib.load().sd_scorenet_forward_sched(ctypes.byref(self.desc), sched.data_ptr(), step_counter.data_ptr(), x.data_ptr(),
+                                                   labels.data_ptr() if labels is not None else None, B, out.data_ptr(),
+                                                   self._ws.data_ptr(), self._ws.numel(), PRECISION_BF16,
+                                                   torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "sd_scorenet_forward_sched")
+        return out
+
     def save(self, path):
         """<path>.bin: the weight blob; <path>.json: the sd_scorenet_desc fields."""
         self.blob.cpu().numpy().tofile(path + ".bin")

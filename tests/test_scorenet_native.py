@@ -190,3 +190,60 @@ def test_plain_c_sampler_matches_the_python_loop(cuda, tmp_path):
     torch.cuda.synchronize()
     assert torch.equal(got_x, x.cpu()), (got_x - x.cpu()).abs().max()
     assert torch.equal(got_l, logq.cpu())
+
+
+@pytest.mark.gpu
+def test_native_sampling_loop_as_one_cuda_graph(cuda):
+    """sd_scorenet_forward_sched + sd_step_vpsde(sched, counter) + sd_counter_add captured ONCE and replayed for every timestep:
+    the same samples and log-densities as the eager loop with host-side scalars."""
+    from super_diffusion_b200 import ops, sde
+    cfg = vpsde.get_config()
+    B, n_steps, dt, M = 8, 5, 1e-3, 2
+    nets, bounds = [], []
+    for m in range(M):
+        model, params = mutils.init_model(30 + m, cfg, zero_init_scale=1.0)
+        b = model.bind(params, cuda)
+        bounds.append(b)
+        nets.append(native.NativeScoreNet(b))
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(B, 32, 32, 3, generator=g).to(cuda)
+    noise = torch.randn(n_steps, B, 32, 32, 3, generator=g).to(cuda)
+    ts = sde.time_grid(n_steps, dt)
+    sched = sde.schedule_table(ts, dt, cuda)
+    counter = torch.zeros(1, dtype=torch.int32, device=cuda)
+    x, nz = x0.clone(), torch.empty_like(x0)
+    logq, w = torch.zeros(B, M, device=cuda), torch.zeros(B, M, device=cuda)
+    scores = [torch.empty_like(x0) for _ in range(M)]
+
+    def step():
+        for m in range(M):
+            nets[m].forward_sched(sched, counter, x, out=scores[m])
+        ops.step_vpsde(x, nz, scores, logq, 0.0, 0.0, 1.0, 0.0, ops.MODE_OR, ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, x_out=x,
+                       weights=w, sched=sched, step_counter=counter)
+        ops.counter_add(counter, 1)
+    nz.copy_(noise[0])
+    side = torch.cuda.Stream(device=cuda)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()                                  # warm-up outside the capture (workspaces, function attributes)
+    torch.cuda.current_stream().wait_stream(side)
+    x.copy_(x0); logq.zero_(); counter.zero_()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step()
+    x.copy_(x0); logq.zero_(); counter.zero_()
+    for i in range(n_steps):
+        nz.copy_(noise[i])
+        graph.replay()
+    torch.cuda.synchronize()
+    # eager loop, scalars by value, Python-driven forward
+    xr, lr = x0.clone(), torch.zeros(B, M, device=cuda)
+    for i in range(n_steps):
+        t = float(ts[i])
+        sc = [b(torch.full((1,), t, device=cuda, dtype=torch.float32), xr) for b in bounds]
+        ops.step_vpsde(xr, noise[i], sc, lr, sde.dlog_alphadt(t), sde.beta(t), sde.sigma(t), dt, ops.MODE_OR,
+                       ops.DLOGQ_CIFAR_MAXSUB, temperature=1e6, x_out=xr)
+    torch.cuda.synchronize()
+    assert int(counter.item()) == n_steps
+    assert torch.allclose(x, xr, rtol=1e-5, atol=1e-5), (x - xr).abs().max()
+    assert torch.allclose(logq, lr, rtol=1e-4, atol=1e-3), (logq - lr).abs().max()
