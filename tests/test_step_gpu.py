@@ -310,3 +310,16 @@ def test_step_replicas_are_bit_identical(cuda, M, mode):
         assert torch.equal(blocks, blocks[:1].expand_as(blocks))
     ref = _ref(x, eps, s, logq, t, dt, mode, dm, temperature=1.0, ito_scale=1.0)
     _check((xo[:Bs], lq[:Bs], w[:Bs]), ref, w_tol=2e-4)
+
+
+@pytest.mark.parametrize("B,D,M", [(400, 3070, 3), (384, 1540, 5), (800, 3072, 2), (390, 16384, 2)])
+@pytest.mark.parametrize("mode,dmode", [(O.MODE_OR, O.DLOGQ_CIFAR_MAXSUB), (O.MODE_AVG, O.DLOGQ_ITO)])
+def test_small_cta_launch_rule_on_ragged_sizes(cuda, B, D, M, mode, dmode):
+    """Batches >= 384 take the 128-thread multi-round launch shape (step_vpsde.cu): unaligned D (scalar loads), a partial last
+    round, many rounds (D = 16384) - against the oracle."""
+    t, dt = 0.52, 1e-3
+    x, eps, s, logq = _mk(B, D, M, seed=B + D + M, dev=cuda)
+    kw = dict(temperature=1.0, ito_scale=2.0 if dmode == O.DLOGQ_ITO else 0.0)
+    got = _run(x, eps, s, logq, t, dt, mode, dmode, cuda, **kw)
+    ref = _ref(x, eps, s, logq, t, dt, mode, dmode, **kw)
+    _check(got, ref)
