@@ -159,10 +159,12 @@ def run_b200(args):
     hbm_peak, tf_peak, peak_kind = _peaks()
     B = args.batch
     cfg = vpsde.get_config()
-    nets = []
+    nets, models, states = [], [], []
     for m in range(M_MODELS):
         model, params = mutils.init_model(10 + m, cfg, zero_init_scale=1.0)   # random init, non-degenerate
-        nets.append(model.bind(params, dev))
+        models.append(model)
+        states.append(mutils.State(params_ema=params, model_params=params))
+        nets.append(model.bound_for(params, dev))
     sampler = SuperDiffSampler(nets, B, mode="or", n_steps=N_STEPS, temperature=1e6, device=dev,
                                multi_stream=not args.single_stream)
     sampler.capture()
@@ -182,6 +184,7 @@ def run_b200(args):
         sampler.reset(x0)
         for i in range(W):
             sampler.step(noise_dev[i % n_noise] if kind == "device" else noise_host[i % n_noise])
+        sampler.reset(x0)         # the timed region starts at schedule row 0: K <= n_steps timesteps of one trajectory
         barrier()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
@@ -192,6 +195,8 @@ def run_b200(args):
         if pipelined:           # the first step's noise crosses PCIe inside the timed region too
             sampler.prefetch(noise_host[0])
         for i in range(K):
+            if i and i % sampler.n_steps == 0:      # more timed steps than one trajectory has: start the next one
+                sampler.reset()
             if kind == "device":
                 sampler.step(noise_dev[i % n_noise])
             elif pipelined:     # e2e: pinned host noise in (every step, copy stream, overlapped with the previous step), log-densities out
@@ -218,7 +223,38 @@ def run_b200(args):
     ms_dev = timed("device", args.steps, args.warmup)
     clk = clocks.stop() if rank == 0 else None
     launches = (sampler.launches_per_step + 0) * args.steps
-    ms_e2e = timed("host", args.steps, args.warmup) if not args.no_probes else ms_dev
+    ms_sampler_host = timed("host", args.steps, args.warmup) if not args.no_probes else ms_dev
+    # ---- e2e: the reference-named entry points, end to end.  dynamics.get_joint_stoch_vf (cifar/dynamics.py:100) ->
+    # eval_utils.get_generator (cifar/eval_utils.py:47) -> artifact_generator(key, labels): x0 draw, K Euler-Maruyama steps
+    # with each step's noise copied from pinned host memory and the log-densities read back to pinned host memory, final
+    # samples to the host.  One warm-up call (graph capture), one timed call.
+    ms_e2e = ms_sampler_host
+    if not args.no_probes:
+        from super_diffusion_b200 import dynamics, eval_utils
+        K = args.steps
+        gdt = 1.0 / K
+        while int(1.0 / gdt) != K:
+            gdt = 1.0 / (K + 1e-9 if int(1.0 / gdt) < K else K - 1e-9)
+        cfg.eval.batch_size = B * world
+        vf = dynamics.get_joint_stoch_vf(0, models, states)
+        gen = eval_utils.get_generator(models, cfg, vf, dt=gdt, device=dev, return_logq=True)
+        noise_k = lambda i: noise_host[i % n_noise]            # pinned host tensors, one H2D copy per step
+        trace = torch.empty(K, B, M_MODELS).pin_memory()
+        x_host = torch.empty(sampler.shape).pin_memory()
+        gen(1 + rank, None, noise=noise_k, logq_trace=trace)
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        xg, ng, lqg = gen(2 + rank, None, noise=noise_k, logq_trace=trace)
+        x_host.copy_(xg, non_blocking=True)
+        e.record()
+        barrier()
+        assert ng == K
+        ms_e2e = s.elapsed_time(e) / K
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
 
     # final gather of samples + log-densities (the only communication of the job)
     gather_ms = None
@@ -271,7 +307,10 @@ def run_b200(args):
                    "step": "one Euler-Maruyama timestep = 2 score-net forwards + fused SuperDiff step, CUDA graph",
                    "l2": "per-step working set (>2 GB of activations at batch 512) exceeds the 126 MB L2; no explicit flush"},
         "e2e": {"value": e2e, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * M_MODELS * 4,
-                "ms_per_step": ms_e2e},
+                "ms_per_step": ms_e2e, "d2h_bytes_final": B * D * 4,
+                "path": "dynamics.get_joint_stoch_vf -> eval_utils.get_generator(...)(key, labels, noise=pinned host, logq_trace=pinned host): "
+                        "x0 draw + K steps + final samples to the host, one call (the reference's cifar/eval_utils.py:47-88 entry)",
+                "sampler_host_noise_ms_per_step": ms_sampler_host},
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": {"bound": "tensor", "achieved": gemm_tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": gemm_tf / tf_peak,

@@ -132,6 +132,11 @@ int sd_step_edm_ode(const float* latents, const float* v_obj, const float* v_bg,
 /* In-graph helper: *counter += delta (single thread).  Lets a captured graph
  * advance the row of `sched` it reads. */
 int sd_counter_add(int* counter, int delta, void* stream);
+/* Same, saturating: *counter = clamp(*counter + delta, 0, rows - 1).  The kernels that read `sched[*step_counter]`
+ * (sd_step_vpsde*, sd_time_embedding, sd_scorenet_forward_sched) do not know the table length, so the row index must stay
+ * inside the table: a sampler that advances its counter ONLY through this entry can be replayed past the last timestep
+ * without reading out of bounds (it then repeats the last row). */
+int sd_counter_add_sat(int* counter, int delta, int rows, void* stream);
 
 /* ------------------------------------------------------------------------
  * Score-network ops (cifar/models/ddpm.py:47-101 and the layers it uses).

@@ -42,6 +42,7 @@ SIGNATURES = {
     "sd_step_edm_cfg": (_I, [_V, _V, _V, _V, _V, _I, _I, _F, _F, _F, _F, _I, _F, _F, _F, _V, _V, _V, _V]),
     "sd_step_edm_ode": (_I, [_V, _V, _V, _V, _V, _I, _I, _F, _F, _F, _F, _V, _V, _V, _V]),
     "sd_counter_add": (_I, [_V, _I, _V]),
+    "sd_counter_add_sat": (_I, [_V, _I, _I, _V]),
     "sd_conv_gemm": (_I, [ctypes.POINTER(GemmSrc), _I, _I, _I, _I, _V, _I, _V, _V, _I, _V, _U, _V, _I, _V, _V]),
     "sd_conv_gemm_s2": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),
     "sd_upconv_gemm": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),

@@ -215,7 +215,10 @@ struct Runner {
   bool live() const { return ws != nullptr && rc == SD_OK; }
   void check(int r) { if (rc == SD_OK && r != SD_OK) rc = r; }
 
-  Act new_act(int H, int W, int C) { Act a; a.H = H; a.W = W; a.C = C; a.p = alloc((size_t)B * H * W * C * 2); return a; }
+  // every activation has room for the batch rounded up to a multiple of 8 images: low-resolution attention packs up to 8 images
+  // per 128-row tile and pads the last tile with zero images (attn_block)
+  int Bp() const { return (B + 7) / 8 * 8; }
+  Act new_act(int H, int W, int C) { Act a; a.H = H; a.W = W; a.C = C; a.p = alloc((size_t)Bp() * H * W * C * 2); return a; }
   void want_stats(Act& a, int tiles_per_img) {
     if ((a.H * a.W) % 128 == 0 && a.C % 16 == 0 && B > 0) {
       a.nchunk = tiles_per_img;
@@ -262,13 +265,19 @@ struct Runner {
     const AttnW& a = net.attn[i];
     const int S = x.H * x.W, C = x.C;
     const int g = S >= 128 ? 1 : 128 / S;
-    const int Sp = g * S, nb = g ? B / g : 0;
-    if (S < 16 || B % g || !(Sp == 128 || Sp == 256) || C % 64 || C > 256) {
+    // a batch that does not fill its last tile (B % g != 0, e.g. the reference's eval batch of 100 at the 4x4 level) is padded
+    // with zero images: the block-diagonal softmax keeps images independent, and zero keys / values keep the 0 * v products of
+    // the masked blocks finite.  The padded output rows land in the spare room every activation has (new_act) and are ignored.
+    const int Sp = g * S, nb = (B + g - 1) / g;
+    if (S < 16 || !(Sp == 128 || Sp == 256) || C % 64 || C > 256) {
       if (rc == SD_OK)
-        rc = fail(kErrUnsupported, "sd_scorenet_forward: attention needs 16..256 pixels per image, C <= 256 and a batch that packs into 128-row tiles");
+        rc = fail(kErrUnsupported, "sd_scorenet_forward: attention needs 16..256 pixels per image and C <= 256 (multiple of 64)");
       return x;
     }
     Act h = gn(x, nullptr, a.g, a.be, false);
+    if (live() && nb * g > B)
+      check(check_cuda(cudaMemsetAsync(static_cast<char*>(h.p) + (size_t)B * S * C * 2, 0, (size_t)(nb * g - B) * S * C * 2, st),
+                       "sd_scorenet_forward: zeroing the attention padding"));
     sd_gemm_src sq[1] = {{h.p, C, 1}};
     Act q2 = conv(sq, 1, x.H, x.W, a.w_q2, C, a.b_q2, nullptr, 0, false);
     void* vt = alloc((size_t)nb * C * Sp * 2);

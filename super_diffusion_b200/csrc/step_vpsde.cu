@@ -185,6 +185,7 @@ static int step_vpsde_impl(const float* x, const float* noise, const float* cons
 }
 
 __global__ void counter_add_kernel(int* c, int d) { *c += d; }
+__global__ void counter_add_sat_kernel(int* c, int d, int last) { const int v = *c + d; *c = v > last ? last : (v < 0 ? 0 : v); }
 
 }  // namespace sdb
 
@@ -221,6 +222,12 @@ int sd_counter_add(int* counter, int delta, void* stream) {
   if (!counter) return sdb::fail(sdb::kErrInvalidArg, "sd_counter_add: null counter");
   sdb::counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta);
   return sdb::check_cuda(cudaGetLastError(), "sd_counter_add launch");
+}
+
+int sd_counter_add_sat(int* counter, int delta, int rows, void* stream) {
+  if (!counter || rows < 1) return sdb::fail(sdb::kErrInvalidArg, "sd_counter_add_sat: null counter or rows < 1");
+  sdb::counter_add_sat_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter, delta, rows - 1);
+  return sdb::check_cuda(cudaGetLastError(), "sd_counter_add_sat launch");
 }
 
 }  // extern "C"

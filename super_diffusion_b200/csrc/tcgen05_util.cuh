@@ -146,16 +146,44 @@ inline EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// Encoded maps are cached per thread, direct-mapped on a hash of every encode argument (base pointer included): the eager
+// (non-graph) path of the score-net issues ~1000 encodes per timestep for a few dozen distinct (buffer, geometry) pairs,
+// because the caching allocator hands the same activation buffers back every step.  A hit is a 128-byte copy.
+struct MapKey {
+  const void* base; int rank; cuuint64_t dims[5]; cuuint64_t strides[4]; cuuint32_t box[5]; cuuint32_t estr[5];
+  bool operator==(const MapKey& o) const {
+    if (base != o.base || rank != o.rank) return false;
+    for (int i = 0; i < 5; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i] || estr[i] != o.estr[i]) return false;
+    for (int i = 0; i < 4; ++i) if (strides[i] != o.strides[i]) return false;
+    return true;
+  }
+};
+struct MapCacheEntry { MapKey key; CUtensorMap map; bool valid; };
+constexpr int kMapCacheSlots = 2048;
+
 inline int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                       const cuuint32_t* box, const cuuint32_t* elem_strides = nullptr) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return fail(kErrCuda, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
+  MapKey key{};
+  key.base = base; key.rank = rank;
+  for (int i = 0; i < 5; ++i) { key.dims[i] = i < rank ? dims[i] : 0; key.box[i] = i < rank ? box[i] : 0; key.estr[i] = 1; }
+  for (int i = 0; i < 4; ++i) key.strides[i] = i < rank - 1 ? strides_bytes[i] : 0;
+  if (elem_strides) for (int i = 0; i < rank; ++i) key.estr[i] = elem_strides[i];
+  uint64_t h = 1469598103934665603ull;
+  auto mix = [&h](uint64_t v) { h = (h ^ v) * 1099511628211ull; h ^= h >> 29; };
+  mix((uint64_t)(uintptr_t)base); mix((uint64_t)rank);
+  for (int i = 0; i < 5; ++i) { mix(key.dims[i]); mix(((uint64_t)key.box[i] << 32) | key.estr[i]); }
+  for (int i = 0; i < 4; ++i) mix(key.strides[i]);
+  static thread_local MapCacheEntry* cache = nullptr;
+  if (!cache) cache = new MapCacheEntry[kMapCacheSlots]();
+  MapCacheEntry& e = cache[h % kMapCacheSlots];
+  if (e.valid && e.key == key) { *map = e.map; return SD_OK; }
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  box, key.estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(kErrCuda, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+  e.key = key; e.map = *map; e.valid = true;
   return SD_OK;
 }
 

@@ -70,6 +70,13 @@ def _make(nets, mode, dlogq_mode, temperature, n_models, ode=False):
 
     joint_vf.step = step
     joint_vf.num_models = n_models
+    # what eval_utils.get_generator needs to run this vector field as a replayed CUDA graph (SuperDiffSampler) instead of
+    # ~280 eager launches per timestep: the bound repo-native score-nets and the step configuration.  Only the stochastic
+    # fields qualify (the ODE fields draw Hutchinson probes / run JVPs per step), and only over repo-native nets.
+    bound = [getattr(n, "bound", None) for n in nets]
+    if not ode and all(b is not None and hasattr(b, "plan") for b in bound):
+        joint_vf.sampler_spec = {"nets": bound, "mode": {ops.MODE_OR: "or", ops.MODE_AND: "and", ops.MODE_AVG: "avg"}[mode],
+                                 "temperature": temperature, "noise_for": _noise_for}
     return joint_vf
 
 
@@ -154,10 +161,16 @@ def get_vpsde(config, model, train):
     def loss(*a, **k):
         raise NotImplementedError("training (DSM loss) is outside the sampling path")
 
+    vf_cache = {}
+
     def vector_field(t, data, args):
         # cifar/dynamics.py:48-54: dx = -dt*(a x - b s) with the raw (non-EMA) parameters, dlogq = zeros (B, 1)
-        net = mutils.get_model_fn(model, args["state"].model_params, train=False)
-        vf = _make([net], ops.MODE_AVG, ops.DLOGQ_NONE, 1.0, 1, ode=True)
-        return vf(t, (data[0], None), args)
+        # the bound net is cached per parameter-tree object (ScoreNet.bound_for): an Euler loop over this field uploads the
+        # weights once, not once per step
+        params = args["state"].model_params
+        if vf_cache.get("params") is not params:
+            net = mutils.get_model_fn(model, params, train=False)
+            vf_cache["params"], vf_cache["vf"] = params, _make([net], ops.MODE_AVG, ops.DLOGQ_NONE, 1.0, 1, ode=True)
+        return vf_cache["vf"](t, (data[0], None), args)
 
     return q_t, loss, vector_field

@@ -253,14 +253,20 @@ class _Bound:
             # sampler mode, unconditioned model: the biases depend only on t, so they are tabulated once for the schedule's
             # n_steps times (one time-embedding launch + one GEMM at set-up) and each timestep gathers its row -- instead of a
             # single-CTA MLP (58 us), an activation pass and a [B, 4 nf] x [sum cout] GEMM on the critical path of every forward
-            key = (sched.data_ptr(), sched.shape[0])
-            if getattr(self, "_rb_key", None) != key:
+            # keyed on the schedule tensor itself (kept alive by the cache entry, so its address cannot be recycled) and
+            # its version counter (in-place edits of the table re-tabulate); old tables stay alive because a captured
+            # CUDA graph of another sampler may still read them
+            cache = self.__dict__.setdefault("_rb_cache", {})
+            key = (id(sched), sched._version)
+            ent = cache.get(key)
+            if ent is None or ent[0] is not sched:
                 ts = sched[:, 2].contiguous()                     # sigma_t = t (cifar/dynamics.py:105)
                 act = ops.time_embedding(ts.shape[0], self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
                                          t=ts, t_stride=1)
-                self._rb_table = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0].contiguous()
-                self._rb_row = torch.empty(1, self._rb_table.shape[1], device=x.device, dtype=torch.float32)
-                self._rb_key = key
+                table = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0].contiguous()
+                row = torch.empty(1, table.shape[1], device=x.device, dtype=torch.float32)
+                ent = cache[key] = (sched, table, row)
+            self._rb_table, self._rb_row = ent[1], ent[2]
             ops.gather_row(self._rb_table, step_counter, out=self._rb_row)
             return self._rb_row.expand(B, -1)                     # row stride 0: every sample reads the same biases
         labels = None
@@ -300,8 +306,16 @@ class _Bound:
         B, H, W, C = x.shape
         S = H * W
         g = max(1, 128 // S)
-        if S < 16 or B % g or (g * S) % 16:
-            raise NotImplementedError(f"score-net JVP needs the batch to pack into 128-row attention tiles (B % {g} == 0)")
+        if S < 16 or (g * S) % 16:
+            raise NotImplementedError("score-net JVP needs at least 16 pixels per image at the attention resolutions")
+        if B % g:
+            # low-resolution blocks pack g images per 128-row tile: pad the batch with zero images (the block-diagonal
+            # softmax keeps images independent, zeros keep the padded keys / values finite) and drop them again.
+            # The reference's eval batch (100; 12 per GPU on 8 GPUs) is not a multiple of 8.
+            pad = g - B % g
+            z = x.new_zeros((pad,) + tuple(x.shape[1:]))
+            o, do = self._attn_jvp(torch.cat([x, z]), torch.cat([dx, z]), i)
+            return o[:B], do[:B]
         h, dh = ops.groupnorm_swish_jvp(x, dx, a["g"], a["be"], swish=False)
         nb, Sp = B // g, g * S
         scale = C ** -0.5
@@ -383,8 +397,17 @@ class ScoreNet:
         """Flax-style entry used by the reference's get_model_fn (models/utils.py:91-95)."""
         if train:
             raise NotImplementedError("train=True (dropout) is outside the sampling path")
-        key = id(variables["params"])
+        return self.bound_for(variables["params"], x.device)(t, x, y)
+
+    def bound_for(self, params, device=None):
+        """The bound net of a parameter tree, uploaded once per (tree object, device).  The entry holds the tree, so an
+        id() can never be recycled for another tree while it is cached; a handful of trees at most (the M models)."""
+        device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         cache = self.__dict__.setdefault("_bound_cache", {})
-        if key not in cache:
-            cache[key] = self.bind(variables["params"], x.device)
-        return cache[key](t, x, y)
+        key = (id(params), str(device))
+        ent = cache.get(key)
+        if ent is None or ent[0] is not params:
+            if len(cache) >= 16:
+                cache.clear()
+            ent = cache[key] = (params, self.bind(params, device))
+        return ent[1]

@@ -192,11 +192,12 @@ def get_model_fn(model, params, train=False):
         raise NotImplementedError(
             "train=True (dropout) is outside the sampling path; the reference only "
             "uses it in the DSM loss (cifar/dynamics.py:36)")
-    bound = model.bind(params)
+    bound = model.bound_for(params) if hasattr(model, "bound_for") else model.bind(params)
 
     def model_fn(t, x, y, rng=None):
         return bound(t, x, y)
 
+    model_fn.bound = bound      # lets get_generator drive repo-native nets through the CUDA-graph sampler
     return model_fn
 
 
@@ -204,7 +205,7 @@ def get_model_jvp_fn(model, params):
     """``jvp_fn(t, x, y, v) -> (model_fn(t, x, y), d/dh model_fn(t, x + h v, y)|_0)`` -- the pair jax.jvp returns at
     cifar/dynamics.py:84.  The B200 score-net has tangent kernels (``_Bound.jvp``); any other bound model that is a
     differentiable PyTorch callable goes through ``torch.func.jvp``."""
-    bound = model.bind(params)
+    bound = model.bound_for(params) if hasattr(model, "bound_for") else model.bind(params)
     if hasattr(bound, "jvp"):
         return lambda t, x, y, v: bound.jvp(t, x, y, v)
 

@@ -177,8 +177,13 @@ def step_edm_ode(latents, v_obj, v_bg, v_unc, dlog, ll, sigma, dsigma, guidance=
     return latents_out, ll, kappa_out
 
 
-def counter_add(counter, delta=1):
-    _lib.check(_lib.load().sd_counter_add(_ptr(counter), int(delta), _stream()), "sd_counter_add")
+def counter_add(counter, delta=1, rows=None):
+    """*counter += delta on the device; with ``rows`` the result saturates at rows - 1 (sd_counter_add_sat) so a schedule
+    table of that many rows is never indexed out of bounds."""
+    if rows is None:
+        _lib.check(_lib.load().sd_counter_add(_ptr(counter), int(delta), _stream()), "sd_counter_add")
+    else:
+        _lib.check(_lib.load().sd_counter_add_sat(_ptr(counter), int(delta), int(rows), _stream()), "sd_counter_add_sat")
     _count()
 
 

@@ -243,6 +243,7 @@ class SuperDiffSampler:
         self._stage_free = None       # per staging buffer: the D2D that consumed it finished
         self._stage_next = 0
         self._staged = None
+        self._steps_done = 0          # host mirror of the device step counter (guards the schedule table)
 
     def _step_body(self):
         # The M score-net forwards are independent: run them on M streams (forked from / joined into the current
@@ -262,11 +263,16 @@ class SuperDiffSampler:
         ops.step_vpsde(self.x, self.noise, self.scores, self.logq, 0.0, 0.0, 1.0, 0.0, self.mode, self.dlogq_mode,
                        temperature=self.temperature, x_out=self.x, weights=self.weights, sched=self.sched,
                        step_counter=self.counter)
-        ops.counter_add(self.counter, 1)
+        # saturating: replaying the graph past the last timestep repeats the last schedule row instead of reading beyond the table
+        ops.counter_add(self.counter, 1, rows=self.n_steps)
 
     def capture(self):
-        """Warm up once on a side stream (lazy init, allocator), then capture one timestep."""
+        """Warm up once on a side stream (lazy init, allocator), then capture one timestep.  The warm-up really executes a
+        timestep, so the sampler state (x, logq, weights, noise, step counter) is saved before and restored after: a caller
+        that did ``reset(x0)`` first and lets ``step()`` capture lazily still starts from x0 at schedule row 0."""
         before = ops.launch_count()
+        saved = [t.clone() for t in (self.x, self.logq, self.weights, self.counter)]
+        done = self._steps_done
         s = torch.cuda.Stream(device=self.device)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -278,13 +284,20 @@ class SuperDiffSampler:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self._step_body()
-        self.reset()
+        for t, v in zip((self.x, self.logq, self.weights, self.counter), saved):
+            t.copy_(v)
+        self._steps_done = done
 
-    def reset(self, x0=None):
+    def reset(self, x0=None, logq0=None):
+        """Back to schedule row 0 with logq = 0 (cifar/eval_utils.py:74) or ``logq0``; ``x0`` replaces the state."""
         self.counter.zero_()
-        self.logq.zero_()
+        self._steps_done = 0
+        if logq0 is None:
+            self.logq.zero_()
+        else:
+            self.logq.copy_(logq0)
         if x0 is not None:
-            self.x.copy_(x0)
+            self.x.copy_(x0.reshape(self.shape))
 
     def prefetch(self, noise_host):
         """Start the host -> device copy of a later step's noise (pinned host tensor) on the copy stream; the next
@@ -316,12 +329,16 @@ class SuperDiffSampler:
             ev = torch.cuda.Event()
             ev.record(cur)
             self._stage_free[k] = ev
+        if self._steps_done >= self.n_steps:
+            raise RuntimeError(f"SuperDiffSampler.step(): all {self.n_steps} timesteps of the schedule have been taken; "
+                               "call reset() before sampling again")
         if self.launches_per_step is None:
             self.capture()
         if self.graph is not None:
             self.graph.replay()
         else:
             self._step_body()
+        self._steps_done += 1
 
     def sample(self, x0=None, noise=None, seed=0):
         """Run all n_steps from x0 (default N(0, I) from `seed`).  Returns (x, logq, weights)."""

@@ -152,6 +152,42 @@ def test_cifar_sampler_graph_equals_eager_and_generator(cuda):
     xb, nb, lqb = gen(7, None)
     assert na == 4 and xa.shape == (4, 32, 32, 3) and torch.equal(xa, xb) and torch.equal(lqa, lqb)
     assert (lqa.max(dim=1).values == 0).all()
+    # the generator ran as a replayed CUDA graph (vector_field.sampler_spec); the per-launch path gives the same bits
+    assert getattr(vf, "sampler_spec", None) is not None
+    xe, ne, lqe = gen(7, None, eager=True)
+    assert torch.equal(xa, xe) and torch.equal(lqa, lqe)
+    # ... also with caller-supplied noise and a log-density trace (pinned host memory, one D2H per step)
+    nz = torch.randn(4, 4, 32, 32, 3, generator=torch.Generator().manual_seed(3)).pin_memory()
+    tr_g, tr_e = torch.empty(4, 4, 2).pin_memory(), torch.empty(4, 4, 2).pin_memory()
+    xg2, _, lqg2 = gen(7, None, noise=nz, logq_trace=tr_g)
+    xe2, _, lqe2 = gen(7, None, noise=nz, logq_trace=tr_e, eager=True)
+    torch.cuda.synchronize()
+    assert torch.equal(xg2, xe2) and torch.equal(lqg2, lqe2) and torch.equal(tr_g, tr_e) and torch.equal(tr_g[-1], lqg2.cpu())
+
+
+def test_sampler_lazy_capture_keeps_state_and_guards_the_schedule(cuda):
+    """step() without an explicit capture(): the warm-up inside capture() must not advance the state (the first timestep was
+    applied twice before), and stepping past the last schedule row raises instead of reading beyond the table."""
+    cfg, models, states, _ = _two_models(cuda)
+    B, n = 8, 3
+    nets = [m.bind(s.params_ema, cuda) for m, s in zip(models, states)]
+    g = torch.Generator(device=cuda).manual_seed(11)
+    x0 = torch.randn(B, 32, 32, 3, generator=g, device=cuda)
+    noise = torch.randn(n, B, 32, 32, 3, generator=g, device=cuda)
+    ref = SuperDiffSampler(nets, B, mode="or", n_steps=n, dt=5e-3, device=cuda)
+    ref.capture()
+    ref.reset(x0)
+    lazy = SuperDiffSampler(nets, B, mode="or", n_steps=n, dt=5e-3, device=cuda)
+    lazy.reset(x0)                       # state set BEFORE the lazy capture
+    for i in range(n):
+        ref.step(noise[i]); lazy.step(noise[i])
+    torch.cuda.synchronize()
+    assert torch.equal(ref.x, lazy.x) and torch.equal(ref.logq, lazy.logq)
+    assert int(lazy.counter.item()) == n - 1          # saturating device counter: never past the last row
+    with pytest.raises(RuntimeError, match="reset"):
+        lazy.step(noise[0])
+    lazy.reset(x0)
+    lazy.step(noise[0])
 
 
 def test_cifar_or_steps_against_cpu_oracle(cuda):

@@ -105,3 +105,17 @@ def test_scorenet_jvp_matches_autodiff_of_oracle(cuda):
     # the (partly cancelling) sum itself
     scale = ref_j.reshape(B, -1).norm(dim=1)
     assert ((d - d_ref).abs() / scale).max().item() <= 1e-1, (d.tolist(), d_ref.tolist(), scale.tolist())   # ~3 sigma of |J v| * 3e-2
+
+
+def test_scorenet_jvp_pads_batches_that_do_not_fill_attention_tiles(cuda):
+    """The reference's eval batch is 100 (12 per GPU on 8 GPUs): not a multiple of the 8 images a 4x4 attention tile packs.
+    The JVP pads with zero images; the first 12 samples of a batch of 16 and the batch of 12 give the same pair."""
+    cfg, model, params = _setup(False, 1.0, seed=7)
+    net = model.bind(params, cuda)
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(16, 32, 32, 3, generator=gen).to(cuda)
+    v = (torch.randint(0, 2, (16, 32, 32, 3), generator=gen) * 2 - 1).float().to(cuda)
+    s16, j16 = net.jvp(0.37, x, None, v)
+    s12, j12 = net.jvp(0.37, x[:12].contiguous(), None, v[:12].contiguous())
+    tol = lambda r: 1e-6 + 1e-3 * r.abs().max().item()
+    assert torch.allclose(s16[:12], s12, rtol=0, atol=tol(s16)) and torch.allclose(j16[:12], j12, rtol=0, atol=tol(j16))

@@ -40,9 +40,10 @@ def test_workspace_dry_run_and_validation(lib):
     assert sizes[0] < sizes[1] < sizes[2] < 16 * 2 ** 30
     assert 6.5 < sizes[2] / sizes[1] < 8.5                      # activations scale with the batch
     w = ctypes.c_size_t()
-    # the 4x4 mid-block attention packs 8 images per 128-row tile
-    assert lib.sd_scorenet_workspace_bytes(ctypes.byref(desc), 2, 0, ctypes.byref(w)) == -2
-    assert b"attention" in lib.sd_last_error()
+    # the 4x4 mid-block attention packs 8 images per 128-row tile: smaller / ragged batches are padded internally, so every
+    # activation has room for the batch rounded up to 8 images
+    assert lib.sd_scorenet_workspace_bytes(ctypes.byref(desc), 2, 0, ctypes.byref(w)) == 0
+    assert 0 < w.value <= sizes[0]
     bad = native.make_desc(cfg)
     bad.nf = 100
     assert lib.sd_scorenet_weights_bytes(ctypes.byref(bad), ctypes.byref(w)) == -2
@@ -92,8 +93,11 @@ def test_native_forward_errors(cuda):
     model, params = mutils.init_model(5, cfg, zero_init_scale=1.0)
     net = native.NativeScoreNet(model.bind(params, cuda))
     x = torch.randn(8, 32, 32, 3, device=cuda)
-    with pytest.raises(RuntimeError, match="attention"):
-        net(0.5, x[:2].contiguous())
+    # a batch that does not fill the packed low-resolution attention tiles (4x4: 8 images per tile) is padded internally
+    # (the reference's eval batch is 100): same scores as inside the full batch
+    full = net(0.5, x)
+    part = net(0.5, x[:2].contiguous())
+    assert torch.allclose(full[:2], part, rtol=0, atol=1e-6 + 1e-3 * full.abs().max().item())
     lib = _lib.load()
     out = torch.empty_like(x)
     t = torch.full((1,), 0.5, device=cuda)
