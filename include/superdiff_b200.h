@@ -146,14 +146,23 @@ int sd_counter_add_sat(int* counter, int delta, int rows, void* stream);
 /* One A-operand segment of an implicit GEMM: an NHWC bf16 tensor [B,H,W,C]
  * read through `taps` filter taps (9 = 3x3 SAME stride 1, 1 = 1x1 / NIN). */
 typedef struct sd_gemm_src {
-  const void* ptr; /* bf16 [B, H, W, C] */
+  const void* ptr; /* bf16 [B, H, W, C] ([B, H, W, 2C] hi|lo under SD_GEMM_SPLIT3) */
   int C;           /* channels (multiple of 64) */
   int taps;        /* 1 or 9 */
+  int ld;          /* elements between consecutive pixels; 0 = dense (C, or 2C under SD_GEMM_SPLIT3) */
 } sd_gemm_src;
 
 #define SD_EPI_SWISH 1u     /* out = swish(out) after everything else */
 #define SD_EPI_OUT_F32 2u   /* `out` is fp32 instead of bf16 */
 #define SD_EPI_SOFTMAX 4u   /* internal: row softmax epilogue (sd_attention_probs) */
+/* 3 x bf16 split precision (the FP32-faithful arm, SD_PRECISION_FP32_FAITHFUL): every ACTIVATION operand of the call --
+ * the sources / A / Bt-as-activation, `residual`, and `out` unless SD_EPI_OUT_F32 -- is a hi|lo pair of bf16 tensors stored
+ * side by side along the channel (K / N) axis: [.., 2C] = [hi(C) | lo(C)], value = hi + lo, hi = bf16(v), lo = bf16(v - hi)
+ * (~16 mantissa bits).  Weights are [N, 2K] = [hi(K) | lo(K)] of the fp32 weights.  The product is evaluated as
+ * hi*hi + lo*hi + hi*lo on the tensor cores with fp32 accumulation (the dropped lo*lo term is ~2^-18 relative), i.e. three
+ * K segments per source that share the weight columns.  C / K / N arguments keep their LOGICAL meaning (channels per half);
+ * leading dimensions are the physical ones (>= 2C). */
+#define SD_GEMM_SPLIT3 8u
 
 /* out[b,h,w,n] = sum_seg sum_tap sum_c src[b,h+dh,w+dw,c] * Wt[n, k(seg,tap,c)]
  *               + bias[n] + rowbias[b, n] + residual[b,h,w,n]
@@ -229,6 +238,11 @@ int sd_attention_probs(const void* Q, int ldq, long long strideQ, const void* Kt
  * (jax.nn.softmax at cifar/models/layers.py:507 with the C^-1/2 scale of :505). */
 int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale, void* stream);
 
+/* FP32-faithful form: X fp32 [rows, cols] -> P as a hi|lo bf16 pair [rows, 2*cols] (SD_GEMM_SPLIT3 layout); the softmax runs
+ * over the diagonal block of `block` columns that row (row % rows_per_entry) belongs to, other entries are 0 (packed
+ * low-resolution images, as sd_attention_probs). */
+int sd_softmax_rows_split(const float* x, void* out, long rows, int cols, float scale, int block, int rows_per_entry, void* stream);
+
 /* GroupNorm(32 groups, eps) + optional swish over the channel-concatenation of
  * up to two NHWC bf16 tensors; writes bf16 [B,H,W,C0+C1].
  * Replaces act(normalize()(x)) at cifar/models/layers.py:552,557,498 and
@@ -239,6 +253,13 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
                        const float* stats1 /* same for x1, [B][nchunk1][2][C1] */, int nchunk1,
                        float* scratch /* >= 2*(4736+B)*(C0+C1) + 64*B floats: channel sums of sources without stats, group stats */,
                        size_t scratch_floats, void* out, void* stream);
+
+/* Same with flags: SD_GEMM_SPLIT3 = sources and `out` are hi|lo bf16 pairs ([B,HW,2C], see the flag) and the swish is evaluated
+ * exactly (v / (1 + exp(-v)) instead of the one-MUFU tanh form, whose 2^-11 error is below bf16 rounding but not below fp32). */
+int sd_groupnorm_swish_ex(const void* x0, int C0, const void* x1, int C1, int B, int HW,
+                          const float* gamma, const float* beta, float eps, int apply_swish,
+                          const float* stats0, int nchunk0, const float* stats1, int nchunk1,
+                          float* scratch, size_t scratch_floats, void* out, unsigned flags, void* stream);
 
 /* Forward-mode derivative of sd_groupnorm_swish: given the primal sources and their tangents (same layouts) writes
  * out = act(GN(x)) and dout = d/dh act(GN(x + h*dx)) at h = 0, both bf16 [B,HW,C0+C1]:
@@ -276,6 +297,10 @@ int sd_gather_row(const float* table, int rows, int row_floats, const int* count
  * The conv is then sd_conv_gemm with one 1-tap source of 64 channels against weights [w | w | 0] (bf16 [Cout, 64]). */
 int sd_im2col_in(const float* x, int B, int H, int W, int Cin, void* out /* bf16 [B,H,W,64] */, void* stream);
 
+/* Same with flags: SD_GEMM_SPLIT3 writes 128-wide rows [block(64) | zeros(64)], i.e. the block as the hi half of a hi|lo pair,
+ * for sd_conv_gemm(SD_GEMM_SPLIT3) against weights [Cout, 128] = [w_hi | w_hi | 0 || w_lo | 0 | 0]. */
+int sd_im2col_in_ex(const float* x, int B, int H, int W, int Cin, void* out, unsigned flags, void* stream);
+
 /* First conv (cifar/models/ddpm.py:71): fp32 NHWC [B,H,W,Cin<=4] -> bf16
  * [B,H,W,Cout], 3x3 SAME, fp32 weights [3,3,Cin,Cout] (Flax HWIO) + bias. */
 int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio, const float* bias,
@@ -292,6 +317,12 @@ int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, cons
                       const float* class_emb /*[ncls,4nf] or NULL*/, const int* labels,
                       float* temb_scratch /* fp32 [B,4nf] ([1,4nf] when t is shared) */,
                       void* act_temb_out /* bf16 [B,4nf] */, void* stream);
+
+/* Same with flags: SD_GEMM_SPLIT3 = exact swish everywhere and act_temb_out as a hi|lo bf16 pair [B, 2*4nf]. */
+int sd_time_embedding_ex(const float* t_dev, int t_stride, const float* sched, const int* step_counter,
+                         int B, int nf, const float* w0, const float* b0, const float* w1, const float* b1,
+                         const float* class_emb, const int* labels, float* temb_scratch, void* act_temb_out,
+                         unsigned flags, void* stream);
 
 /* fp32 -> bf16 and bf16 -> fp32 converts (weights upload, debugging). */
 int sd_cast_f32_to_bf16(const float* in, void* out, size_t n, void* stream);
@@ -318,9 +349,14 @@ typedef struct sd_scorenet_desc {
   int num_classes;             /* config.data.num_classes (conditioned models) */
   const void* weights;         /* device blob, 256-byte aligned */
   size_t weights_bytes;        /* must equal sd_scorenet_weights_bytes() */
+  int precision;               /* SD_PRECISION_*; 0 = SD_PRECISION_BF16.  Decides the blob layout (GEMM weights are [N, K] bf16
+                                  or [N, 2K] hi|lo pairs) and the workspace size. */
 } sd_scorenet_desc;
 
-#define SD_PRECISION_BF16 1    /* bf16 operands / activations, fp32 accumulation (the only implemented precision) */
+#define SD_PRECISION_BF16 1           /* bf16 operands / activations, fp32 accumulation */
+#define SD_PRECISION_FP32_FAITHFUL 2  /* the reference's fp32 arithmetic (cifar/models/ddpm.py runs in fp32) to ~1e-5: every
+                                         operand a hi|lo bf16 pair, products hi*hi + lo*hi + hi*lo on the tensor cores with fp32
+                                         accumulation (SD_GEMM_SPLIT3), GroupNorm / swish / softmax in fp32; ~3x the tensor work */
 
 /* size of the weight blob for a configuration (desc->weights is ignored) */
 int sd_scorenet_weights_bytes(const sd_scorenet_desc* desc, size_t* bytes_out);

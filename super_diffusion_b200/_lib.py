@@ -16,7 +16,7 @@ c_void_p = ctypes.c_void_p
 
 class GemmSrc(ctypes.Structure):
     """struct sd_gemm_src (include/superdiff_b200.h)."""
-    _fields_ = [("ptr", ctypes.c_void_p), ("C", ctypes.c_int), ("taps", ctypes.c_int)]
+    _fields_ = [("ptr", ctypes.c_void_p), ("C", ctypes.c_int), ("taps", ctypes.c_int), ("ld", ctypes.c_int)]
 
 
 class ScoreNetDesc(ctypes.Structure):
@@ -24,7 +24,8 @@ class ScoreNetDesc(ctypes.Structure):
     _fields_ = [("image_size", ctypes.c_int), ("channels", ctypes.c_int), ("nf", ctypes.c_int),
                 ("num_res_blocks", ctypes.c_int), ("n_levels", ctypes.c_int), ("ch_mult", ctypes.c_int * 8),
                 ("n_attn_res", ctypes.c_int), ("attn_resolutions", ctypes.c_int * 8), ("conditioned", ctypes.c_int),
-                ("num_classes", ctypes.c_int), ("weights", ctypes.c_void_p), ("weights_bytes", ctypes.c_size_t)]
+                ("num_classes", ctypes.c_int), ("weights", ctypes.c_void_p), ("weights_bytes", ctypes.c_size_t),
+                ("precision", ctypes.c_int)]
 
 
 # name -> (restype, argtypes); must list every symbol include/superdiff_b200.h declares
@@ -47,11 +48,15 @@ SIGNATURES = {
     "sd_conv_gemm_s2": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),
     "sd_upconv_gemm": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),
     "sd_groupnorm_swish": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _I, _V, _I, _V, _SZ, _V, _V]),
+    "sd_groupnorm_swish_ex": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _I, _V, _I, _V, _SZ, _V, _U, _V]),
     "sd_attention": (_I, [_V, _I, _I, _I, _V, _V]),
     "sd_upsample2x": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_im2col_s2": (_I, [_V, _I, _I, _I, _I, _V, _V]),
     "sd_gather_row": (_I, [_V, _I, _I, _V, _V, _V]),
     "sd_im2col_in": (_I, [_V, _I, _I, _I, _I, _V, _V]),
+    "sd_im2col_in_ex": (_I, [_V, _I, _I, _I, _I, _V, _U, _V]),
+    "sd_softmax_rows_split": (_I, [_V, _V, ctypes.c_long, _I, _F, _I, _I, _V]),
+    "sd_time_embedding_ex": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _U, _V]),
     "sd_conv_in": (_I, [_V, _I, _I, _I, _I, _V, _V, _I, _V, _V]),
     "sd_time_embedding": (_I, [_V, _I, _V, _V, _I, _I, _V, _V, _V, _V, _V, _V, _V, _V, _V]),
     "sd_batched_gemm": (_I, [_V, _I, _LL, _V, _I, _LL, _I, _I, _I, _I, _V, _V, _U, _V, _I, _LL, _V]),

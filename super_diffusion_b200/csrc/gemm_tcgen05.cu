@@ -51,7 +51,8 @@ constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;          // 16 KB
 constexpr int B_BYTES_MAX = MAX_BN * BK * 2;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
-constexpr int MAX_SEGS = 3;
+constexpr int MAX_SEGS = 9;            // 3 sources x the three terms of the 3xbf16 split product (SD_GEMM_SPLIT3)
+constexpr int MAX_SLABS = 3;           // 9-tap stride-1 segments that may be fed as activation slabs
 constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, each takes alternate 32-column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
@@ -62,17 +63,19 @@ struct GemmParams {
   CUtensorMap a_map[MAX_SEGS];
   CUtensorMap b_map;
   int nseg;
-  int seg_kb_end[MAX_SEGS];   // cumulative K-block count at the end of each segment
   int seg_taps[MAX_SEGS];
   int seg_cblocks[MAX_SEGS];  // C / 64
+  int seg_bk0[MAX_SEGS];      // K-block (column / 64 of the B operand) where the segment's weights start: several segments may
+                              // share B columns (split precision: hi and lo activations against the same hi weights)
+  int seg_slab[MAX_SEGS];     // -1, or the index of the segment's slab tensor map (3x3 stride-1 segment fed as slabs)
   int flat;                   // 1: matrix mode, A is [batch][M][K] (batch stride may be 0 = shared)
   int a_batched, b_batched;   // matrix mode: does the batch index select an A / B slice
   int m_tiles_per_batch, M_per_batch;
-  const void* slab_src;       // host-only: segment-0 source for the slab tensor map (nullptr = not a slab candidate)
-  int slab_C, slab_B;
-  int slab;                   // 1: segment 0 (3x3, stride 1) is fed as activation slabs shared by the three vertical taps
+  const void* seg_src[MAX_SEGS];    // host-only: segment sources (slab tensor maps are built from the 9-tap stride-1 ones)
+  int seg_C[MAX_SEGS], seg_ld[MAX_SEGS], slab_B;
+  int slab;                   // 1: the 3x3 stride-1 segments (seg_slab >= 0) are fed as activation slabs shared by the three vertical taps
   int slab_bytes, a_region_bytes;   // bytes of one slab; bytes reserved for A at the start of a ring slot
-  CUtensorMap a_slab_map;     // segment-0 map with a (64, W, hb+2, 1) box
+  CUtensorMap a_slab_map[MAX_SLABS];     // per slab segment: map with a (64, W, hb+2, 1) box
   int num_stages, stage_bytes; // operand ring geometry: stage_bytes = A bytes + B bytes of one K-block (1 KB multiple)
   int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
                               //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
@@ -119,17 +122,22 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
     }
   }
   const bool full = (n0 + 16 <= p.N_out);
+  const bool split = (p.flags & SD_GEMM_SPLIT3) != 0;     // residual / out rows are [hi(N) | lo(N)] bf16 pairs, value = hi + lo
   if (full) {
     if (p.residual) {
-      const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const uint4 u = rp[h];
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+      for (int part = 0; part < 2; ++part) {
+        if (part == 1 && !split) break;
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + row_off + n0 + (part ? p.N_out : 0));
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          v[h * 8 + 2 * j] += __uint_as_float(w[j] << 16);
-          v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+        for (int h = 0; h < 2; ++h) {
+          const uint4 u = rp[h];
+          const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[h * 8 + 2 * j] += __uint_as_float(w[j] << 16);
+            v[h * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u);
+          }
         }
       }
     }
@@ -137,7 +145,22 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = swishf(v[j]);
     }
-    if (p.flags & SD_EPI_OUT_F32) {
+    if (split && !(p.flags & SD_EPI_OUT_F32)) {
+      uint32_t wh[8], wl[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const __nv_bfloat162 l2 = __floats2bfloat162_rn(v[2 * j] - __low2float(h2), v[2 * j + 1] - __high2float(h2));
+        wh[j] = *reinterpret_cast<const uint32_t*>(&h2);
+        wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+      }
+      uint4* oh = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0);
+      uint4* ol = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n0 + p.N_out);
+      oh[0] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+      oh[1] = make_uint4(wh[4], wh[5], wh[6], wh[7]);
+      ol[0] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+      ol[1] = make_uint4(wl[4], wl[5], wl[6], wl[7]);
+    } else if (p.flags & SD_EPI_OUT_F32) {
       float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + row_off + n0);
 #pragma unroll
       for (int j = 0; j < 4; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -158,10 +181,14 @@ __device__ __forceinline__ void epilogue_store16(const GemmParams& p, const uint
       const int n = n0 + j;
       if (n >= p.N_out) break;
       float x = v[j];
-      if (p.residual) x += __bfloat162float(p.residual[row_off + n]);
+      if (p.residual) x += __bfloat162float(p.residual[row_off + n]) + (split ? __bfloat162float(p.residual[row_off + p.N_out + n]) : 0.f);
       if (p.flags & SD_EPI_SWISH) x = swishf(x);
       if (p.flags & SD_EPI_OUT_F32) reinterpret_cast<float*>(p.out)[row_off + n] = x;
-      else reinterpret_cast<__nv_bfloat16*>(p.out)[row_off + n] = __float2bfloat16_rn(x);
+      else {
+        const __nv_bfloat16 hb = __float2bfloat16_rn(x);
+        reinterpret_cast<__nv_bfloat16*>(p.out)[row_off + n] = hb;
+        if (split) reinterpret_cast<__nv_bfloat16*>(p.out)[row_off + p.N_out + n] = __float2bfloat16_rn(x - __bfloat162float(hb));
+      }
     }
   }
 }
@@ -311,17 +338,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             c3[sub] = (m_tile / p.tiles_per_img) * p.imgs_per_tile;
           }
         }
-        int kb_base = 0;                                // K-block index (weight column / 64) where the segment starts
         for (int seg = 0; seg < p.nseg; ++seg) {
           const int cblocks = p.seg_cblocks[seg], taps = p.seg_taps[seg];
-          if (p.slab && seg == 0) {
+          const int kb_base = p.seg_bk0[seg];           // K-block index (weight column / 64) where the segment starts
+          if (p.slab && p.seg_slab[seg] >= 0) {
+            const CUtensorMap* smap = &p.a_slab_map[p.seg_slab[seg]];
             const uint32_t tx = (PAIR ? 2u : 1u) * ((uint32_t)p.slab_bytes + 3u * b_cta_bytes);
             for (int cb = 0; cb < cblocks; ++cb)
               for (int kw = 0; kw < 3; ++kw) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
                 if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], tx);
-                load_a(&p.a_slab_map, sa, &full_bar[stage], cb * BK, kw - 1, c2[0] - 1, c3[0]);
+                load_a(smap, sa, &full_bar[stage], cb * BK, kw - 1, c2[0] - 1, c3[0]);
                 for (int kh = 0; kh < 3; ++kh)
                   load_b(sa + b_off + kh * b_tile_bytes, &full_bar[stage], (kb_base + (kh * 3 + kw) * cblocks + cb) * BK, n_tile, bz);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -352,7 +380,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 }
               }
           }
-          kb_base += taps * cblocks;
         }
       }
     }
@@ -373,7 +400,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
         uint32_t accumulate = 0;
         for (int seg = 0; seg < p.nseg; ++seg) {
-          const bool slab = p.slab && seg == 0;
+          const bool slab = p.slab && p.seg_slab[seg] >= 0;
           const int nsteps = slab ? p.seg_cblocks[seg] * 3 : p.seg_taps[seg] * p.seg_cblocks[seg];
           const int groups = slab ? 3 : 1;
           for (int st = 0; st < nsteps; ++st) {
@@ -467,6 +494,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         __nv_bfloat16* obase = reinterpret_cast<__nv_bfloat16*>(p.out) + (ch & ~1);
         const bool pair_ok = (ch | 1) < p.N_out;
         const bool do_stats = p.stats_out != nullptr;
+        const bool split = (p.flags & SD_GEMM_SPLIT3) != 0;     // out rows are [hi(N) | lo(N)]: the lo half is stored N_out channels further
         float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
         float ssum = 0.f, ssq = 0.f;
         if (!(p.flags & 0x100u)) {      // 0x100: timing probe (tools/gemm_probe.py) -- release the accumulator without draining it
@@ -495,8 +523,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
               for (int j = 0; j < 16; j += 2) {
                 const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
-                const __nv_bfloat162 h2 = odd ? __floats2bfloat162_rn(recv, v[j + 1]) : __floats2bfloat162_rn(v[j], recv);
+                const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;       // channels (ch & ~1, ch | 1) of one pixel
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
                 if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = h2;
+                if (split && ok)
+                  *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld + p.N_out) =
+                      __floats2bfloat162_rn(e0 - __low2float(h2), e1 - __high2float(h2));
               }
             }
             if (do_stats && (it & 1)) {
@@ -689,6 +721,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, long long strideB, int nbatchB,
                        const float* bias, const float* rowbias, int rowbias_ld, const void* residual, unsigned flags,
                        void* out, int out_ld, cudaStream_t st, const char* who, float* stats_out = nullptr) {
+  if (flags & SD_GEMM_SPLIT3) {
+    if (flags & SD_EPI_SOFTMAX) return fail(kErrInvalidArg, std::string(who) + ": no softmax epilogue in split precision (use sd_softmax_rows_split)");
+    if (!(flags & SD_EPI_OUT_F32) && ((N % 16) != 0 || out_ld < 2 * N))
+      return fail(kErrInvalidArg, std::string(who) + ": split output needs N % 16 == 0 and out_ld >= 2N");
+  }
   const int n_pad = (N + 15) / 16 * 16;
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
   // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
@@ -748,24 +785,34 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     p.slab = 0;
     p.a_region_bytes = nsub_h * A_BYTES;
     int groups = 1;
-    if (want_slab && p.slab_src && (p.dual || p.pair) && (p.cluster == 1 || p.pair) && p.imgs_per_tile == 1 &&
+    bool any_cand = false;
+    for (int sgi = 0; sgi < p.nseg; ++sgi) any_cand = any_cand || p.seg_slab[sgi] >= 0;
+    bool slab_on = false;
+    if (want_slab && any_cand && (p.dual || p.pair) && (p.cluster == 1 || p.pair) && p.imgs_per_tile == 1 &&
         (nsub_h == 1 || (p.tiles_per_img % 2) == 0)) {
       const int hb = nsub_h * p.h_box;
       const int slab_bytes = (hb + 2) * p.img_W * BK * 2;
       int a_region = slab_bytes > nsub_h * A_BYTES ? slab_bytes : nsub_h * A_BYTES;
       a_region = (a_region + 1023) / 1024 * 1024;
       if (2 * (a_region + 3 * b_cta) <= RING_BYTES && hb + 2 <= 256) {
-        cuuint64_t dims[4] = {(cuuint64_t)p.slab_C, (cuuint64_t)p.img_W, (cuuint64_t)p.img_H, (cuuint64_t)p.slab_B};
-        cuuint64_t strides[3] = {(cuuint64_t)p.slab_C * 2, (cuuint64_t)p.slab_C * 2 * p.img_W, (cuuint64_t)p.slab_C * 2 * p.img_W * p.img_H};
-        cuuint32_t box[4] = {BK, (cuuint32_t)p.img_W, (cuuint32_t)(hb + 2), 1};
-        int rc = encode_map(&p.a_slab_map, p.slab_src, 4, dims, strides, box);
-        if (rc != SD_OK) return rc;
+        for (int sgi = 0; sgi < p.nseg; ++sgi) {
+          if (p.seg_slab[sgi] < 0) continue;
+          const cuuint64_t ld = (cuuint64_t)p.seg_ld[sgi];
+          cuuint64_t dims[4] = {(cuuint64_t)p.seg_C[sgi], (cuuint64_t)p.img_W, (cuuint64_t)p.img_H, (cuuint64_t)p.slab_B};
+          cuuint64_t strides[3] = {ld * 2, ld * 2 * p.img_W, ld * 2 * p.img_W * p.img_H};
+          cuuint32_t box[4] = {BK, (cuuint32_t)p.img_W, (cuuint32_t)(hb + 2), 1};
+          int rc = encode_map(&p.a_slab_map[p.seg_slab[sgi]], p.seg_src[sgi], 4, dims, strides, box);
+          if (rc != SD_OK) return rc;
+        }
+        slab_on = true;
         p.slab = 1;
         p.slab_bytes = slab_bytes;
         p.a_region_bytes = a_region;
         groups = 3;
       }
     }
+    if (!slab_on)
+      for (int sgi = 0; sgi < MAX_SEGS; ++sgi) p.seg_slab[sgi] = -1;
     int sb = p.a_region_bytes + groups * b_cta;
     sb = (sb + 1023) / 1024 * 1024;
     int ns = RING_BYTES / sb;
@@ -847,7 +894,7 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
                           unsigned flags, void* out, int out_ld, float* stats_out, void* stream, int up_phase,
                           int stats_tpi_total, int stats_slot0, const char* who, int stride2 = 0) {
   using namespace sdb;
-  if (!srcs || num_srcs < 1 || num_srcs > MAX_SEGS) return fail(kErrInvalidArg, std::string(who) + ": 1..3 sources required");
+  if (!srcs || num_srcs < 1 || num_srcs > 3) return fail(kErrInvalidArg, std::string(who) + ": 1..3 sources required");
   if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, std::string(who) + ": bad argument");
   if (B == 0) return SD_OK;
   GemmParams p{};
@@ -866,38 +913,54 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.img_W = W;
   p.stats_tpi_total = stats_tpi_total > 0 ? stats_tpi_total : p.tiles_per_img;
   p.stats_slot0 = stats_slot0;
-  int kb = 0;
-  long K = 0;
+  // Segments.  Plain: one per source, weight columns in source order.  SD_GEMM_SPLIT3: every source is a hi|lo pair
+  // [.., 2C] and contributes three segments -- (hi, W_hi), (lo, W_hi), (hi, W_lo) -- against weights [N, 2*K_half] = [hi | lo].
+  const bool split = (flags & SD_GEMM_SPLIT3) != 0;
+  long K_half = 0;
+  for (int s = 0; s < num_srcs; ++s) K_half += (long)srcs[s].taps * srcs[s].C;
+  const long K = split ? 2 * K_half : K_half;
+  for (int s = 0; s < MAX_SEGS; ++s) p.seg_slab[s] = -1;
+  int nseg = 0, nslab = 0;
+  long k_off = 0;
   for (int s = 0; s < num_srcs; ++s) {
     const sd_gemm_src& src = srcs[s];
     if (!src.ptr || src.C < BK || (src.C % BK) != 0) return fail(kErrInvalidArg, std::string(who) + ": source channels must be a multiple of 64");
     if (!(src.taps == 1 || src.taps == 9 || (src.taps == 4 && up_phase >= 0))) return fail(kErrInvalidArg, std::string(who) + ": taps must be 1 or 9");
     if (((uintptr_t)src.ptr % 16) != 0) return fail(kErrInvalidArg, std::string(who) + ": source must be 16-byte aligned");
-    p.seg_taps[s] = src.taps;
-    p.seg_cblocks[s] = src.C / BK;
-    kb += src.taps * (src.C / BK);
-    p.seg_kb_end[s] = kb;
-    K += (long)src.taps * src.C;
-    int rc;
-    if (stride2) {
-      // the source is the (2H x 2W) input; to load N elements at element stride 2 the box extent is 2N
-      cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)(2 * W), (cuuint64_t)(2 * H), (cuuint64_t)B};
-      cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * (2 * W), (cuuint64_t)src.C * 2 * (2 * W) * (2 * H)};
-      cuuint32_t box[4] = {BK, (cuuint32_t)(2 * W), (cuuint32_t)(2 * p.h_box), (cuuint32_t)p.imgs_per_tile};
-      cuuint32_t estr[4] = {1, 2, 2, 1};
-      rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box, estr);
-    } else {
-      cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-      cuuint64_t strides[3] = {(cuuint64_t)src.C * 2, (cuuint64_t)src.C * 2 * W, (cuuint64_t)src.C * 2 * W * H};
-      cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)p.h_box, (cuuint32_t)p.imgs_per_tile};
-      rc = encode_map(&p.a_map[s], src.ptr, 4, dims, strides, box);
+    const int ld = src.ld > 0 ? src.ld : (split ? 2 * src.C : src.C);
+    if (ld < (split ? 2 : 1) * src.C || (ld % 8) != 0) return fail(kErrInvalidArg, std::string(who) + ": source ld must cover the channels and be a multiple of 8");
+    const int nterm = split ? 3 : 1;
+    for (int term = 0; term < nterm; ++term) {
+      if (nseg >= MAX_SEGS) return fail(kErrInvalidArg, std::string(who) + ": too many K segments");
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(src.ptr) + (term == 1 ? src.C : 0);     // lo half
+      p.seg_taps[nseg] = src.taps;
+      p.seg_cblocks[nseg] = src.C / BK;
+      p.seg_bk0[nseg] = (int)(((term == 2 ? K_half : 0) + k_off) / BK);
+      p.seg_src[nseg] = base; p.seg_C[nseg] = src.C; p.seg_ld[nseg] = ld;
+      if (src.taps == 9 && !stride2 && up_phase < 0 && nslab < MAX_SLABS) p.seg_slab[nseg] = nslab++;
+      int rc;
+      const cuuint64_t l2 = (cuuint64_t)ld * 2;
+      if (stride2) {
+        // the source is the (2H x 2W) input; to load N elements at element stride 2 the box extent is 2N
+        cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)(2 * W), (cuuint64_t)(2 * H), (cuuint64_t)B};
+        cuuint64_t strides[3] = {l2, l2 * (2 * W), l2 * (2 * W) * (2 * H)};
+        cuuint32_t box[4] = {BK, (cuuint32_t)(2 * W), (cuuint32_t)(2 * p.h_box), (cuuint32_t)p.imgs_per_tile};
+        cuuint32_t estr[4] = {1, 2, 2, 1};
+        rc = encode_map(&p.a_map[nseg], base, 4, dims, strides, box, estr);
+      } else {
+        cuuint64_t dims[4] = {(cuuint64_t)src.C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t strides[3] = {l2, l2 * W, l2 * W * H};
+        cuuint32_t box[4] = {BK, (cuuint32_t)W, (cuuint32_t)p.h_box, (cuuint32_t)p.imgs_per_tile};
+        rc = encode_map(&p.a_map[nseg], base, 4, dims, strides, box);
+      }
+      if (rc != SD_OK) return rc;
+      ++nseg;
     }
-    if (rc != SD_OK) return rc;
+    k_off += (long)src.taps * src.C;
   }
-  for (int s = num_srcs; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
-  p.nseg = num_srcs;
-  p.num_kb = kb;
-  if (srcs[0].taps == 9 && !stride2 && up_phase < 0) { p.slab_src = srcs[0].ptr; p.slab_C = srcs[0].C; p.slab_B = B; }
+  p.nseg = nseg;
+  p.num_kb = (int)(K / BK);
+  p.slab_B = B;
   p.M_total = B * H * W;
   p.HW = H * W;
   p.m_tiles = (p.M_total + BM - 1) / BM;
@@ -918,7 +981,8 @@ extern "C" int sd_conv_gemm_s2(const void* x, int B, int H_in, int W_in, int C, 
   using namespace sdb;
   if (!x || (H_in % 2) || (W_in % 2)) return fail(kErrInvalidArg, "sd_conv_gemm_s2: even input size required");
   sd_gemm_src src{x, C, 9};
-  return conv_gemm_impl(&src, 1, B, H_in / 2, W_in / 2, Wt, N, bias, nullptr, 0, nullptr, flags, out, N, stats_out, stream,
+  const int out_ld = (flags & SD_GEMM_SPLIT3) && !(flags & SD_EPI_OUT_F32) ? 2 * N : N;
+  return conv_gemm_impl(&src, 1, B, H_in / 2, W_in / 2, Wt, N, bias, nullptr, 0, nullptr, flags, out, out_ld, stats_out, stream,
                         -1, 0, 0, "sd_conv_gemm_s2", 1);
 }
 
@@ -931,8 +995,9 @@ extern "C" int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const v
   const int tpi = (H * W >= BM) ? (H * W) / BM : 1;
   sd_gemm_src src{x, C, 4};
   for (int ph = 0; ph < 4; ++ph) {
-    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(Wt4) + (size_t)ph * N * 4 * C;
-    int rc = conv_gemm_impl(&src, 1, B, H, W, w, N, bias, nullptr, 0, nullptr, flags, out, N, stats_out, stream, ph,
+    const int kmul = (flags & SD_GEMM_SPLIT3) ? 2 : 1;        // split: per phase [N, 2 * 4C] = [hi | lo]; out rows [hi(N) | lo(N)]
+    const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(Wt4) + (size_t)ph * N * 4 * C * kmul;
+    int rc = conv_gemm_impl(&src, 1, B, H, W, w, N, bias, nullptr, 0, nullptr, flags, out, kmul * N, stats_out, stream, ph,
                             4 * tpi, ph * tpi, "sd_upconv_gemm");
     if (rc != SD_OK) return rc;
   }
@@ -969,22 +1034,27 @@ static int batched_gemm_impl(const void* A, int lda, long long strideA, const vo
   p.imgs_per_tile = 1;
   p.up_phase = -1;
   p.out_batch_stride = strideC;
-  p.nseg = 1;
-  p.seg_taps[0] = 1;
-  p.seg_cblocks[0] = K / BK;
-  p.seg_kb_end[0] = K / BK;
-  for (int s = 1; s < MAX_SEGS; ++s) p.seg_kb_end[s] = 1 << 30;
-  p.num_kb = K / BK;
+  const bool split = (flags & SD_GEMM_SPLIT3) != 0;      // A [.., 2K] and Bt [.., 2K] are hi|lo pairs: hi*hi + lo*hi + hi*lo
+  if (split && (lda < 2 * K || ldb < 2 * K)) return fail(kErrInvalidArg, "sd_batched_gemm: split operands need lda, ldb >= 2K");
+  p.nseg = split ? 3 : 1;
+  for (int s = 0; s < MAX_SEGS; ++s) p.seg_slab[s] = -1;
+  p.num_kb = (split ? 3 : 1) * (K / BK);
   p.M_total = M * batch;
   p.HW = 1;
   const int nbA = p.a_batched ? batch : 1;
-  cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)M, 1, (cuuint64_t)nbA};
-  const cuuint64_t bstride = (cuuint64_t)(p.a_batched ? strideA : (long long)M * lda) * 2;
-  cuuint64_t strides[3] = {(cuuint64_t)lda * 2, bstride, bstride};
-  cuuint32_t box[4] = {BK, BM, 1, 1};
-  int rc = encode_map(&p.a_map[0], A, 4, dims, strides, box);
-  if (rc != SD_OK) return rc;
-  return launch_gemm(p, N, K, Bt, ldb, strideB, p.b_batched ? batch : 1, bias, nullptr, 0, residual, flags, out, ldc,
+  for (int s = 0; s < p.nseg; ++s) {
+    p.seg_taps[s] = 1;
+    p.seg_cblocks[s] = K / BK;
+    p.seg_bk0[s] = s == 2 ? K / BK : 0;
+    cuuint64_t dims[4] = {(cuuint64_t)K, (cuuint64_t)M, 1, (cuuint64_t)nbA};
+    const cuuint64_t bstride = (cuuint64_t)(p.a_batched ? strideA : (long long)M * lda) * 2;
+    cuuint64_t strides[3] = {(cuuint64_t)lda * 2, bstride, bstride};
+    cuuint32_t box[4] = {BK, BM, 1, 1};
+    int rc = encode_map(&p.a_map[s], reinterpret_cast<const __nv_bfloat16*>(A) + (s == 1 ? K : 0), 4, dims, strides, box);
+    if (rc != SD_OK) return rc;
+  }
+  const int KB = split ? 2 * K : K;
+  return launch_gemm(p, N, KB, Bt, ldb, strideB, p.b_batched ? batch : 1, bias, nullptr, 0, residual, flags, out, ldc,
                      (cudaStream_t)stream, "sd_batched_gemm", stats_out);
 }
 

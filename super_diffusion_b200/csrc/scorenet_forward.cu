@@ -55,7 +55,11 @@ struct Cursor {
   }
   const float* f32(size_t n) { return static_cast<const float*>(take(n * 4)); }
   const void* bf16(size_t n) { return take(n * 2); }
+  int kmul = 1;          // 2 in the FP32-faithful arm: every GEMM weight is [N, 2K] = [hi | lo] (SD_GEMM_SPLIT3)
+  const void* gemm_w(size_t n) { return take(n * 2 * kmul); }
 };
+
+inline bool desc_split(const sd_scorenet_desc& d) { return d.precision == SD_PRECISION_FP32_FAITHFUL; }
 
 bool in_list(const int* v, int n, int x) {
   for (int i = 0; i < n; ++i)
@@ -69,12 +73,15 @@ int layout(const sd_scorenet_desc& d, Net& net) {
       d.image_size < 16 || d.image_size % 16 || d.n_attn_res < 0 || d.n_attn_res > 8)
     return fail(kErrUnsupported, "sd_scorenet: unsupported configuration (nf multiple of 64, <= 3 image channels, image size multiple of 16)");
   if (d.conditioned && d.num_classes < 1) return fail(kErrInvalidArg, "sd_scorenet: conditioned model needs num_classes");
+  if (d.precision != 0 && d.precision != SD_PRECISION_BF16 && d.precision != SD_PRECISION_FP32_FAITHFUL)
+    return fail(kErrUnsupported, "sd_scorenet: desc.precision must be 0 (= bf16), SD_PRECISION_BF16 or SD_PRECISION_FP32_FAITHFUL");
   const int nf = d.nf;
   Cursor cur{static_cast<const char*>(d.weights)};
+  cur.kmul = desc_split(d) ? 2 : 1;
   net.temb_w0 = cur.f32((size_t)nf * 4 * nf); net.temb_b0 = cur.f32(4 * nf);
   net.temb_w1 = cur.f32((size_t)4 * nf * 4 * nf); net.temb_b1 = cur.f32(4 * nf);
   net.class_emb = d.conditioned ? cur.f32((size_t)d.num_classes * 4 * nf) : nullptr;
-  net.conv_in_w64 = cur.bf16((size_t)nf * 64); net.conv_in_b = cur.f32(nf);
+  net.conv_in_w64 = cur.gemm_w((size_t)nf * 64); net.conv_in_b = cur.f32(nf);
 
   // pass 1: block shapes in creation order (add_res / add_attn of models/ddpm.py)
   int off = 0;
@@ -127,25 +134,25 @@ int layout(const sd_scorenet_desc& d, Net& net) {
   net.out_c = c;
 
   // pass 2: blob offsets
-  net.dense_w = cur.bf16((size_t)off * 4 * nf); net.dense_b = cur.f32(off);
+  net.dense_w = cur.gemm_w((size_t)off * 4 * nf); net.dense_b = cur.f32(off);
   for (ResW& r : net.res) {
     r.g1 = cur.f32(r.cin); r.be1 = cur.f32(r.cin);
-    r.w1 = cur.bf16((size_t)r.cout * 9 * r.cin);
+    r.w1 = cur.gemm_w((size_t)r.cout * 9 * r.cin);
     r.g2 = cur.f32(r.cout); r.be2 = cur.f32(r.cout);
     // conv1 + shortcut: NIN over the block input when C_in != C_out (layers.py:560-564), identity segment otherwise (:565)
-    r.w2 = cur.bf16((size_t)r.cout * (9 * r.cout + r.cin));
+    r.w2 = cur.gemm_w((size_t)r.cout * (9 * r.cout + r.cin));
     r.b2 = cur.f32(r.cout);
     if (r.cin == r.cout && r.nparts != 1) return fail(kErrUnsupported, "sd_scorenet: identity shortcut over a concatenation");
   }
   for (AttnW& a : net.attn) {
     a.g = cur.f32(a.c); a.be = cur.f32(a.c);
-    a.w_q2 = cur.bf16((size_t)a.c * a.c); a.b_q2 = cur.f32(a.c);
-    a.w_voT = cur.bf16((size_t)a.c * a.c); a.b_vo = cur.f32(a.c);
+    a.w_q2 = cur.gemm_w((size_t)a.c * a.c); a.b_q2 = cur.f32(a.c);
+    a.w_voT = cur.gemm_w((size_t)a.c * a.c); a.b_vo = cur.f32(a.c);
   }
-  for (DownW& w : net.down) { w.w = cur.bf16((size_t)w.c * 9 * w.c); w.b = cur.f32(w.c); }
-  for (UpW& w : net.up) { w.w4 = cur.bf16((size_t)4 * w.c * 4 * w.c); w.b = cur.f32(w.c); }
+  for (DownW& w : net.down) { w.w = cur.gemm_w((size_t)w.c * 9 * w.c); w.b = cur.f32(w.c); }
+  for (UpW& w : net.up) { w.w4 = cur.gemm_w((size_t)4 * w.c * 4 * w.c); w.b = cur.f32(w.c); }
   net.out_g = cur.f32(c); net.out_be = cur.f32(c);
-  net.out_w = cur.bf16((size_t)16 * 9 * c); net.out_b = cur.f32(d.channels);
+  net.out_w = cur.gemm_w((size_t)16 * 9 * c); net.out_b = cur.f32(d.channels);
   net.bytes = cur.off;
   return SD_OK;
 }
@@ -163,6 +170,11 @@ struct Runner {
   float* gn_scratch = nullptr;
   size_t gn_scratch_floats = 0;
   int rc = SD_OK;
+  // FP32-faithful arm: activations are hi|lo bf16 pairs [.., 2C] and every kernel gets SD_GEMM_SPLIT3 (see the header); the
+  // attention runs unfused (fp32 scores, fp32 softmax).  Same plan otherwise.
+  bool split() const { return desc_split(d); }
+  int sm() const { return split() ? 2 : 1; }
+  unsigned fl() const { return split() ? SD_GEMM_SPLIT3 : 0u; }
 
   // Workspace allocator: best-fit from the blocks released so far, else bump.  Everything is enqueued on ONE stream, so a block
   // may be handed out again as soon as the launches that read it have been enqueued.  Reuse matters for speed, not only for
@@ -218,7 +230,7 @@ struct Runner {
   // every activation has room for the batch rounded up to a multiple of 8 images: low-resolution attention packs up to 8 images
   // per 128-row tile and pads the last tile with zero images (attn_block)
   int Bp() const { return (B + 7) / 8 * 8; }
-  Act new_act(int H, int W, int C) { Act a; a.H = H; a.W = W; a.C = C; a.p = alloc((size_t)Bp() * H * W * C * 2); return a; }
+  Act new_act(int H, int W, int C) { Act a; a.H = H; a.W = W; a.C = C; a.p = alloc((size_t)Bp() * H * W * C * 2 * sm()); return a; }
   void want_stats(Act& a, int tiles_per_img) {
     if ((a.H * a.W) % 128 == 0 && a.C % 16 == 0 && B > 0) {
       a.nchunk = tiles_per_img;
@@ -230,9 +242,9 @@ struct Runner {
   Act gn(const Act& x0, const Act* x1, const float* gamma, const float* beta, bool swish) {
     Act o = new_act(x0.H, x0.W, x0.C + (x1 ? x1->C : 0));
     if (live())
-      check(sd_groupnorm_swish(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, B, x0.H * x0.W, gamma, beta, 1e-6f, swish ? 1 : 0,
-                               x0.stats, x0.nchunk, x1 ? x1->stats : nullptr, x1 ? x1->nchunk : 0, gn_scratch, gn_scratch_floats,
-                               o.p, st));
+      check(sd_groupnorm_swish_ex(x0.p, x0.C, x1 ? x1->p : nullptr, x1 ? x1->C : 0, B, x0.H * x0.W, gamma, beta, 1e-6f, swish ? 1 : 0,
+                                  x0.stats, x0.nchunk, x1 ? x1->stats : nullptr, x1 ? x1->nchunk : 0, gn_scratch, gn_scratch_floats,
+                                  o.p, fl(), st));
     return o;
   }
 
@@ -240,7 +252,7 @@ struct Runner {
            int rb_ld, bool stats) {
     Act o = new_act(H, W, N);
     if (stats) want_stats(o, H * W / 128);
-    if (live()) check(sd_conv_gemm(srcs, nsrc, B, H, W, Wt, N, bias, rowbias, rb_ld, nullptr, 0u, o.p, N, o.stats, st));
+    if (live()) check(sd_conv_gemm(srcs, nsrc, B, H, W, Wt, N, bias, rowbias, rb_ld, nullptr, fl(), o.p, N * sm(), o.stats, st));
     return o;
   }
 
@@ -276,10 +288,30 @@ struct Runner {
     }
     Act h = gn(x, nullptr, a.g, a.be, false);
     if (live() && nb * g > B)
-      check(check_cuda(cudaMemsetAsync(static_cast<char*>(h.p) + (size_t)B * S * C * 2, 0, (size_t)(nb * g - B) * S * C * 2, st),
+      check(check_cuda(cudaMemsetAsync(static_cast<char*>(h.p) + (size_t)B * S * C * 2 * sm(), 0, (size_t)(nb * g - B) * S * C * 2 * sm(), st),
                        "sd_scorenet_forward: zeroing the attention padding"));
     sd_gemm_src sq[1] = {{h.p, C, 1}};
     Act q2 = conv(sq, 1, x.H, x.W, a.w_q2, C, a.b_q2, nullptr, 0, false);
+    if (split()) {
+      // five launches: V'^T, fp32 scores, fp32 block softmax -> hi|lo probabilities, P V' + bias + x (all products 3 x bf16)
+      void* vt = alloc((size_t)nb * C * Sp * 2 * 2);
+      float* sc = static_cast<float*>(alloc((size_t)nb * Sp * Sp * 4));
+      void* pr = alloc((size_t)nb * Sp * Sp * 2 * 2);
+      Act o = new_act(x.H, x.W, C);
+      if (g == 1) { o.nchunk = Sp / 128; o.stats = static_cast<float*>(alloc((size_t)nb * o.nchunk * 2 * C * 4)); }
+      if (live()) {
+        const long long sA = (long long)Sp * 2 * C;
+        check(sd_batched_gemm(a.w_voT, 2 * C, 0, h.p, 2 * C, sA, nb, C, Sp, C, nullptr, nullptr, SD_GEMM_SPLIT3, vt, 2 * Sp,
+                              (long long)C * 2 * Sp, st));
+        check(sd_batched_gemm(q2.p, 2 * C, sA, h.p, 2 * C, sA, nb, Sp, Sp, C, nullptr, nullptr, SD_GEMM_SPLIT3 | SD_EPI_OUT_F32, sc, Sp,
+                              (long long)Sp * Sp, st));
+        check(sd_softmax_rows_split(sc, pr, (long)nb * Sp, Sp, (float)std::pow((double)C, -0.5), S, Sp, st));
+        check(sd_batched_gemm_stats(pr, 2 * Sp, (long long)Sp * 2 * Sp, vt, 2 * Sp, (long long)C * 2 * Sp, nb, Sp, C, Sp, a.b_vo, x.p,
+                                    SD_GEMM_SPLIT3, o.p, 2 * C, sA, o.stats, st));
+      }
+      release(h); release(q2); release(vt); release(sc); release(pr);
+      return o;
+    }
     void* vt = alloc((size_t)nb * C * Sp * 2);
     Act o = new_act(x.H, x.W, C);
     if (g == 1) { o.nchunk = Sp / 128; o.stats = static_cast<float*>(alloc((size_t)nb * o.nchunk * 2 * C * 4)); }
@@ -303,17 +335,17 @@ struct Runner {
     // time embedding (ddpm.py:64-68) -> per-sample bias of every block's Dense(temb) (layers.py:556): one [B, 4nf] x [4nf, sum cout] GEMM
     const bool shared_t = t_stride == 0;
     float* temb_scratch = static_cast<float*>(alloc((size_t)(shared_t ? 1 : B) * 4 * nf * 4));
-    void* act_temb = alloc((size_t)B * 4 * nf * 2);
+    void* act_temb = alloc((size_t)B * 4 * nf * 2 * sm());
     float* rowbias = static_cast<float*>(alloc((size_t)B * net.dense_n * 4));
     if (live()) {
-      check(sd_time_embedding(t_dev, t_stride, sched, step_counter, B, nf, net.temb_w0, net.temb_b0, net.temb_w1, net.temb_b1,
-                              net.class_emb, net.class_emb ? y : nullptr, temb_scratch, act_temb, st));
-      check(sd_batched_gemm(act_temb, 4 * nf, 0, net.dense_w, 4 * nf, 0, 1, B, net.dense_n, 4 * nf, net.dense_b, nullptr,
-                            SD_EPI_OUT_F32, rowbias, net.dense_n, (long long)B * net.dense_n, st));
+      check(sd_time_embedding_ex(t_dev, t_stride, sched, step_counter, B, nf, net.temb_w0, net.temb_b0, net.temb_w1, net.temb_b1,
+                                 net.class_emb, net.class_emb ? y : nullptr, temb_scratch, act_temb, fl(), st));
+      check(sd_batched_gemm(act_temb, 4 * nf * sm(), 0, net.dense_w, 4 * nf * sm(), 0, 1, B, net.dense_n, 4 * nf, net.dense_b, nullptr,
+                            SD_EPI_OUT_F32 | fl(), rowbias, net.dense_n, (long long)B * net.dense_n, st));
     }
     // first conv (ddpm.py:71) on the tensor cores: hi/lo-split im2col K-block
-    void* cols = alloc((size_t)B * H0 * H0 * 64 * 2);
-    if (live()) check(sd_im2col_in(x, B, H0, H0, d.channels, cols, st));
+    void* cols = alloc((size_t)B * H0 * H0 * 64 * 2 * sm());
+    if (live()) check(sd_im2col_in_ex(x, B, H0, H0, d.channels, cols, fl(), st));
     sd_gemm_src s0[1] = {{cols, 64, 1}};
     Act h = conv(s0, 1, H0, H0, net.conv_in_w64, nf, net.conv_in_b, nullptr, 0, true);
     release(cols);
@@ -331,7 +363,7 @@ struct Runner {
           const Act& src = hs.back();
           Act o = new_act(src.H / 2, src.W / 2, w.c);
           want_stats(o, o.H * o.W / 128);
-          if (live()) check(sd_conv_gemm_s2(src.p, B, src.H, src.W, src.C, w.w, w.c, w.b, 0u, o.p, o.stats, st));
+          if (live()) check(sd_conv_gemm_s2(src.p, B, src.H, src.W, src.C, w.w, w.c, w.b, fl(), o.p, o.stats, st));
           h = o;
           hs.push_back(h);
           break;
@@ -366,7 +398,7 @@ struct Runner {
             o.nchunk = 4 * h.H * h.W / 128;
             o.stats = static_cast<float*>(alloc((size_t)B * o.nchunk * 2 * w.c * 4));
           }
-          if (live()) check(sd_upconv_gemm(h.p, B, h.H, h.W, h.C, w.w4, w.c, w.b, 0u, o.p, o.stats, st));
+          if (live()) check(sd_upconv_gemm(h.p, B, h.H, h.W, h.C, w.w4, w.c, w.b, fl(), o.p, o.stats, st));
           release(h);
           h = o;
           break;
@@ -378,7 +410,7 @@ struct Runner {
     release(h);
     sd_gemm_src so[1] = {{a.p, a.C, 9}};
     if (live())
-      check(sd_conv_gemm(so, 1, B, h.H, h.W, net.out_w, d.channels, net.out_b, nullptr, 0, nullptr, SD_EPI_OUT_F32, out, d.channels,
+      check(sd_conv_gemm(so, 1, B, h.H, h.W, net.out_w, d.channels, net.out_b, nullptr, 0, nullptr, SD_EPI_OUT_F32 | fl(), out, d.channels,
                          nullptr, st));
   }
 };
@@ -430,8 +462,10 @@ int sd_scorenet_workspace_bytes(const sd_scorenet_desc* desc, int B, int t_strid
 int sd_scorenet_forward(const sd_scorenet_desc* desc, const float* t_dev, int t_stride, const float* x_nhwc, const int* y, int B,
                         float* out_nhwc, void* workspace, size_t workspace_bytes, int precision, void* stream) {
   using namespace sdb;
-  if (precision != SD_PRECISION_BF16)
-    return fail(kErrUnsupported, "sd_scorenet_forward: only SD_PRECISION_BF16 (bf16 operands, fp32 accumulation) is implemented");
+  if (precision != SD_PRECISION_BF16 && precision != SD_PRECISION_FP32_FAITHFUL)
+    return fail(kErrUnsupported, "sd_scorenet_forward: precision must be SD_PRECISION_BF16 or SD_PRECISION_FP32_FAITHFUL");
+  if (desc && (desc->precision ? desc->precision : SD_PRECISION_BF16) != precision)
+    return fail(kErrInvalidArg, "sd_scorenet_forward: `precision` does not match desc->precision (the weight blob layout depends on it)");
   if (B < 0 || (t_stride != 0 && t_stride != 1)) return fail(kErrInvalidArg, "sd_scorenet_forward: B >= 0 and t_stride in {0, 1} required");
   if (B == 0) return SD_OK;
   if (!t_dev || !x_nhwc || !out_nhwc || !workspace) return fail(kErrInvalidArg, "sd_scorenet_forward: null pointer argument");
@@ -449,8 +483,10 @@ int sd_scorenet_forward_sched(const sd_scorenet_desc* desc, const float* sched, 
                               const int* y, int B, float* out_nhwc, void* workspace, size_t workspace_bytes, int precision,
                               void* stream) {
   using namespace sdb;
-  if (precision != SD_PRECISION_BF16)
-    return fail(kErrUnsupported, "sd_scorenet_forward_sched: only SD_PRECISION_BF16 (bf16 operands, fp32 accumulation) is implemented");
+  if (precision != SD_PRECISION_BF16 && precision != SD_PRECISION_FP32_FAITHFUL)
+    return fail(kErrUnsupported, "sd_scorenet_forward_sched: precision must be SD_PRECISION_BF16 or SD_PRECISION_FP32_FAITHFUL");
+  if (desc && (desc->precision ? desc->precision : SD_PRECISION_BF16) != precision)
+    return fail(kErrInvalidArg, "sd_scorenet_forward_sched: `precision` does not match desc->precision (the weight blob layout depends on it)");
   if (B < 0) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: B >= 0 required");
   if (B == 0) return SD_OK;
   if (!sched || !step_counter || !x_nhwc || !out_nhwc || !workspace) return fail(kErrInvalidArg, "sd_scorenet_forward_sched: null pointer argument");

@@ -36,6 +36,38 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// exact form for the FP32-faithful arm (SD_GEMM_SPLIT3 activations): ex2.approx + division, ~1e-6 relative
+__device__ __forceinline__ float swish_exact_f(float v) { return v / (1.f + __expf(-v)); }
+template <bool SPLIT>
+__device__ __forceinline__ float act_swish(float v) { return SPLIT ? swish_exact_f(v) : swish_f(v); }
+
+// Split activations (SD_GEMM_SPLIT3): a pixel row is [hi(C) | lo(C)] bf16, value = hi + lo.  load8 / store8 move 8 channels.
+template <bool SPLIT>
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, int lo_off, float (&f)[8]) {
+  const uint4 h = *reinterpret_cast<const uint4*>(p);
+  if (SPLIT) {
+    const uint4 l = *reinterpret_cast<const uint4*>(p + lo_off);
+    float g[8];
+    unpack8(h, f); unpack8(l, g);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] += g[e];
+  } else {
+    unpack8(h, f);
+  }
+}
+template <bool SPLIT>
+__device__ __forceinline__ void store8(__nv_bfloat16* p, int lo_off, const float (&f)[8]) {
+  const uint4 h = pack8(f);
+  *reinterpret_cast<uint4*>(p) = h;
+  if (SPLIT) {
+    float hf[8], l[8];
+    unpack8(h, hf);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) l[e] = f[e] - hf[e];
+    *reinterpret_cast<uint4*>(p + lo_off) = pack8(l);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // GroupNorm(32) + swish over concat(x0, x1) along channels, as two streaming passes:
 //   gn_stats_kernel : per (sample, pixel chunk) per-channel sum / sum-of-squares -> partial[B][nchunk][2][C]
@@ -65,13 +97,15 @@ struct GnParams {
   int reverse;                    // walk the CTAs from the last sample to the first (see sd_groupnorm_swish)
 };
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ GnStatsParams p) {
   extern __shared__ float gn_smem[];   // [rows_per_pass][2*C]
   const int C = p.C, VC = C / 8;
   const int sample = blockIdx.x / p.nchunk, chunk = blockIdx.x - sample * p.nchunk;
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
   const int c0 = cv * 8;
-  const __nv_bfloat16* src = p.x + (size_t)sample * p.HW * C + c0;
+  const int ld = SPLIT ? 2 * C : C;              // split rows are [hi(C) | lo(C)]
+  const __nv_bfloat16* src = p.x + (size_t)sample * p.HW * ld + c0;
   const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
   pdl_wait();
   pdl_launch_dependents();
@@ -80,20 +114,18 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
   int px = px0 + r;
   for (; px + 3 * rows_per_pass < px1; px += 4 * rows_per_pass) {      // 4 independent 16-byte loads in flight
-    uint4 v[4];
+    float fv[4][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * C);
+    for (int j = 0; j < 4; ++j) load8<SPLIT>(src + (size_t)(px + j * rows_per_pass) * ld, C, fv[j]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float f[8];
-      unpack8(v[j], f);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+      for (int e = 0; e < 8; ++e) { s[e] += fv[j][e]; q[e] = fmaf(fv[j][e], fv[j][e], q[e]); }
     }
   }
   for (; px < px1; px += rows_per_pass) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * C), f);
+    load8<SPLIT>(src + (size_t)px * ld, C, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
   }
@@ -111,6 +143,7 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const __grid_constant__ G
   }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ GnParams p) {
   extern __shared__ float ch_tot[];     // [2][C] (dynamic: a small footprint lets these CTAs share an SM with a resident GEMM CTA)
   __shared__ float g_stat[64];
@@ -148,9 +181,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
   const int c0 = cv * 8;
   const bool from0 = c0 < p.C0;
-  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0
-                                   : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
-  const int src_ld = from0 ? p.C0 : p.C1;
+  const int smul = SPLIT ? 2 : 1;
+  const int src_ld = smul * (from0 ? p.C0 : p.C1), src_lo = from0 ? p.C0 : p.C1;
+  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * src_ld + c0
+                                   : p.x1 + (size_t)sample * p.HW * src_ld + (c0 - p.C0);
+  const int dst_ld = smul * C;
   float sc[8], sh[8];                       // y = x * sc + sh
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -159,34 +194,32 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
     sc[e] = rs;
     sh[e] = p.beta[c] - g_stat[(c / cpg) * 2] * rs;
   }
-  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
+  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * dst_ld + c0;
   const int px0 = chunk * p.px_per_chunk, px1 = min(p.HW, px0 + p.px_per_chunk);
   int px = px0 + r;
   for (; px + 3 * rows_per_pass < px1; px += 4 * rows_per_pass) {
-    uint4 v[4];
+    float fv[4][8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(px + j * rows_per_pass) * src_ld);
+    for (int j = 0; j < 4; ++j) load8<SPLIT>(src + (size_t)(px + j * rows_per_pass) * src_ld, src_lo, fv[j]);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float f[8];
-      unpack8(v[j], f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        const float y = fmaf(f[e], sc[e], sh[e]);
-        f[e] = p.apply_swish ? swish_f(y) : y;
+        const float y = fmaf(fv[j][e], sc[e], sh[e]);
+        fv[j][e] = p.apply_swish ? act_swish<SPLIT>(y) : y;
       }
-      *reinterpret_cast<uint4*>(dst + (size_t)(px + j * rows_per_pass) * C) = pack8(f);
+      store8<SPLIT>(dst + (size_t)(px + j * rows_per_pass) * dst_ld, C, fv[j]);
     }
   }
   for (; px < px1; px += rows_per_pass) {
     float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(src + (size_t)px * src_ld), f);
+    load8<SPLIT>(src + (size_t)px * src_ld, src_lo, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float y = fmaf(f[e], sc[e], sh[e]);
-      f[e] = p.apply_swish ? swish_f(y) : y;
+      f[e] = p.apply_swish ? act_swish<SPLIT>(y) : y;
     }
-    *reinterpret_cast<uint4*>(dst + (size_t)px * C) = pack8(f);
+    store8<SPLIT>(dst + (size_t)px * dst_ld, C, f);
   }
 }
 
@@ -194,7 +227,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
 // register-resident -> ONE kernel, one read and one write (the streaming form needs a statistics launch + an apply
 // launch and re-reads the tensor; at 4-33 MB per tensor that was 22-41 us per GroupNorm, launch-latency bound).
 // Requires C/8 to divide 256 and C/32 to be a multiple of 8 (C = 256, 512), so a thread's 8 channels sit in one group.
-template <int NV>
+template <int NV, bool SPLIT>
 __global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ GnParams p) {
   __shared__ float part[256 * 2];
   __shared__ float g_stat[64];
@@ -203,18 +236,28 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ G
   const int cv = tid % VC, r = tid / VC, rows_per_pass = 256 / VC;
   const int c0 = cv * 8;
   const bool from0 = c0 < p.C0;
-  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * p.C0 + c0 : p.x1 + (size_t)sample * p.HW * p.C1 + (c0 - p.C0);
-  const int src_ld = from0 ? p.C0 : p.C1;
+  const int smul = SPLIT ? 2 : 1;
+  const int src_ld = smul * (from0 ? p.C0 : p.C1), src_lo = from0 ? p.C0 : p.C1;
+  const __nv_bfloat16* src = from0 ? p.x0 + (size_t)sample * p.HW * src_ld + c0 : p.x1 + (size_t)sample * p.HW * src_ld + (c0 - p.C0);
   pdl_wait();
   pdl_launch_dependents();
-  uint4 v[NV];
+  uint4 v[NV], vl[SPLIT ? NV : 1];
 #pragma unroll
-  for (int j = 0; j < NV; ++j) v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(r + j * rows_per_pass) * src_ld);
+  for (int j = 0; j < NV; ++j) {
+    v[j] = *reinterpret_cast<const uint4*>(src + (size_t)(r + j * rows_per_pass) * src_ld);
+    if (SPLIT) vl[j] = *reinterpret_cast<const uint4*>(src + (size_t)(r + j * rows_per_pass) * src_ld + src_lo);
+  }
   float s = 0.f, q = 0.f;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     float f[8];
     unpack8(v[j], f);
+    if (SPLIT) {
+      float g[8];
+      unpack8(vl[j], g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += g[e];
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) { s += f[e]; q = fmaf(f[e], f[e], q); }
   }
@@ -246,17 +289,23 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ G
     sc[e] = rs;
     sh[e] = p.beta[c0 + e] - mean * rs;
   }
-  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * C + c0;
+  __nv_bfloat16* dst = p.out + (size_t)sample * p.HW * smul * C + c0;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     float f[8];
     unpack8(v[j], f);
+    if (SPLIT) {
+      float g[8];
+      unpack8(vl[j], g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] += g[e];
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const float y = fmaf(f[e], sc[e], sh[e]);
-      f[e] = p.apply_swish ? swish_f(y) : y;
+      f[e] = p.apply_swish ? act_swish<SPLIT>(y) : y;
     }
-    *reinterpret_cast<uint4*>(dst + (size_t)(r + j * rows_per_pass) * C) = pack8(f);
+    store8<SPLIT>(dst + (size_t)(r + j * rows_per_pass) * smul * C, C, f);
   }
 }
 
@@ -331,6 +380,34 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   const float inv = 1.f / sum;
   for (int j = lane; j < cols; j += 32) out[row * cols + j] = __float2bfloat16_rn(expf(xr[j] * scale - mx) * inv);
+}
+
+// FP32-faithful attention probabilities: P[r, :] = softmax over the row's diagonal block of `block` columns of scale * X[r, :]
+// (rows of a batch entry of `rows_per_entry` rows; off-block entries 0), fp32 in, hi|lo bf16 pair out [rows][2*cols]; one warp per row.
+__global__ void __launch_bounds__(256) softmax_rows_split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                                 long rows, int cols, float scale, int block, int rows_per_entry) {
+  const long row = (long)blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * cols;
+  const int rl = (int)(row % rows_per_entry);
+  const int lo = (rl / block) * block, hi = lo + block;
+  float mx = -INFINITY;
+  for (int j = lo + lane; j < hi; j += 32) mx = fmaxf(mx, xr[j] * scale);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.f;
+  for (int j = lo + lane; j < hi; j += 32) sum += expf(xr[j] * scale - mx);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float inv = 1.f / sum;
+  __nv_bfloat16* orow = out + row * 2 * cols;
+  for (int j = lane; j < cols; j += 32) {
+    const float pj = (j >= lo && j < hi) ? expf(xr[j] * scale - mx) * inv : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(pj);
+    orow[j] = h;
+    orow[cols + j] = __float2bfloat16_rn(pj - __bfloat162float(h));
+  }
 }
 
 // Nearest x2 upsample, 16-byte vectors.
@@ -433,7 +510,7 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
 // split as hi = bf16(v), lo = bf16(v - hi) so the fp32 input keeps ~16 mantissa bits:  row = [hi(9*Cin) | lo(9*Cin) | 0...].
 // The conv is then a 1-tap implicit GEMM with K = 64 against [w | w | 0] (sd_conv_gemm: bias, GroupNorm statistics for free).
 __global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict__ x, int B, int H, int W, int Cin,
-                                                        __nv_bfloat16* __restrict__ out) {
+                                                        __nv_bfloat16* __restrict__ out, int row_elems) {
   const size_t npix = (size_t)B * H * W;
   const int K = 9 * Cin;
   for (size_t pix = blockIdx.x * (size_t)blockDim.x + threadIdx.x; pix < npix; pix += (size_t)gridDim.x * blockDim.x) {
@@ -456,10 +533,13 @@ __global__ void __launch_bounds__(256) im2col_in_kernel(const float* __restrict_
           row[K + (kh * 3 + kw) * Cin + c] = __float2bfloat16_rn(v - __bfloat162float(h16));
         }
       }
-    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64);
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * row_elems);
     const uint4* r4 = reinterpret_cast<const uint4*>(row);
 #pragma unroll
     for (int i = 0; i < 8; ++i) dst[i] = r4[i];
+    // SD_GEMM_SPLIT3 layout: the 64-wide block above is the "hi" half of a [hi(64) | lo(64)] pair whose lo half is zero
+    // (the fp32 input is already carried as hi/lo inside the block)
+    for (int i = 8; i < row_elems / 8; ++i) dst[i] = make_uint4(0, 0, 0, 0);
   }
 }
 
@@ -468,7 +548,7 @@ __global__ void __launch_bounds__(512) temb_dense_kernel(const float* __restrict
                                                          const float* __restrict__ sched, const int* __restrict__ step_counter,
                                                          int nf, const float* __restrict__ w0, const float* __restrict__ b0,
                                                          const float* __restrict__ w1, const float* __restrict__ b1,
-                                                         float* __restrict__ temb) {
+                                                         float* __restrict__ temb, int exact) {
   extern __shared__ float te_smem[];    // emb[nf], h1[4nf]
   float* emb = te_smem;
   float* h1 = te_smem + nf;
@@ -487,7 +567,7 @@ __global__ void __launch_bounds__(512) temb_dense_kernel(const float* __restrict
   for (int j = threadIdx.x; j < nh; j += blockDim.x) {
     float acc = b0[j];
     for (int k = 0; k < nf; ++k) acc = fmaf(emb[k], w0[(size_t)k * nh + j], acc);
-    h1[j] = swish_f(acc);
+    h1[j] = exact ? swish_exact_f(acc) : swish_f(acc);
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nh; j += blockDim.x) {
@@ -500,13 +580,20 @@ __global__ void __launch_bounds__(512) temb_dense_kernel(const float* __restrict
 // act_temb[b, :] = swish(temb[b or 0, :] + class_emb[label_b, :])  -> bf16
 __global__ void __launch_bounds__(256) temb_act_kernel(const float* __restrict__ temb, int temb_stride,
                                                        const float* __restrict__ class_emb, const int* __restrict__ labels,
-                                                       int B, int nh, __nv_bfloat16* __restrict__ out) {
+                                                       int B, int nh, __nv_bfloat16* __restrict__ out, int split) {
   const size_t total = (size_t)B * nh;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const int b = i / nh, j = i % nh;
     float v = temb[(size_t)b * temb_stride + j];
     if (class_emb) v += class_emb[(size_t)labels[b] * nh + j];
-    out[i] = __float2bfloat16_rn(swish_f(v));
+    if (split) {        // exact swish, rows [hi(nh) | lo(nh)]
+      const float a = swish_exact_f(v);
+      const __nv_bfloat16 h = __float2bfloat16_rn(a);
+      out[(size_t)b * 2 * nh + j] = h;
+      out[(size_t)b * 2 * nh + nh + j] = __float2bfloat16_rn(a - __bfloat162float(h));
+    } else {
+      out[i] = __float2bfloat16_rn(swish_f(v));
+    }
   }
 }
 
@@ -533,7 +620,16 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
                        const float* beta, float eps, int apply_swish, const float* stats0, int nchunk0,
                        const float* stats1, int nchunk1, float* scratch, size_t scratch_floats, void* out,
                        void* stream) {
+  return sd_groupnorm_swish_ex(x0, C0, x1, C1, B, HW, gamma, beta, eps, apply_swish, stats0, nchunk0, stats1, nchunk1, scratch,
+                               scratch_floats, out, 0u, stream);
+}
+
+int sd_groupnorm_swish_ex(const void* x0, int C0, const void* x1, int C1, int B, int HW, const float* gamma,
+                          const float* beta, float eps, int apply_swish, const float* stats0, int nchunk0,
+                          const float* stats1, int nchunk1, float* scratch, size_t scratch_floats, void* out,
+                          unsigned flags, void* stream) {
   using namespace sdb;
+  const bool split = (flags & SD_GEMM_SPLIT3) != 0;
   if (!x0 || !gamma || !beta || !out || !scratch || (C1 > 0 && !x1)) return fail(kErrInvalidArg, "sd_groupnorm_swish: null pointer");
   if (C1 < 0) C1 = 0;
   const int C = C0 + C1;
@@ -548,13 +644,13 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   static const bool carve_once = [] {
     const char* e = getenv("SDB_GN_CARVEOUT");
     if (!e || atoi(e) == 0) return false;
-    cudaFuncSetAttribute(gn_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_small_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_small_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_small_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_small_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(gn_small_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_apply_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_small_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_small_kernel<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_small_kernel<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_small_kernel<8, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(gn_small_kernel<16, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     return true;
   }();
   (void)carve_once;
@@ -591,11 +687,11 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
   if (!stats0 && !stats1 && (C == 256 || C == 512) && ((size_t)HW * C / 8) % 256 == 0) {
     const size_t nv = (size_t)HW * C / 8 / 256;
     void (*kern)(const GnParams) = nullptr;
-    if (nv == 1) kern = gn_small_kernel<1>;
-    else if (nv == 2) kern = gn_small_kernel<2>;
-    else if (nv == 4) kern = gn_small_kernel<4>;
-    else if (nv == 8) kern = gn_small_kernel<8>;
-    else if (nv == 16) kern = gn_small_kernel<16>;
+    if (nv == 1) kern = split ? gn_small_kernel<1, true> : gn_small_kernel<1, false>;
+    else if (nv == 2) kern = split ? gn_small_kernel<2, true> : gn_small_kernel<2, false>;
+    else if (nv == 4) kern = split ? gn_small_kernel<4, true> : gn_small_kernel<4, false>;
+    else if (nv == 8) kern = split ? gn_small_kernel<8, true> : gn_small_kernel<8, false>;
+    else if (nv == 16) kern = split ? gn_small_kernel<16, true> : gn_small_kernel<16, false>;
     if (kern) {
       return check_cuda(launch_pdl(kern, dim3((unsigned)B), dim3(256), 0, st, p), "sd_groupnorm_swish (small) launch");
     }
@@ -619,14 +715,16 @@ int sd_groupnorm_swish(const void* x0, int C0, const void* x1, int C1, int B, in
     if (used + need > scratch_floats) return fail(kErrInvalidArg, "sd_groupnorm_swish: scratch too small");
     used += need;
     if (srcI == 0) { p.part0 = sp.partial; p.nch0 = sp.nchunk; } else { p.part1 = sp.partial; p.nch1 = sp.nchunk; }
-    cudaError_t err = launch_pdl(gn_stats_kernel, dim3((unsigned)(B * sp.nchunk)), dim3(T), sizeof(float) * (size_t)k * 2 * Cs, st, sp);
+    cudaError_t err = launch_pdl(split ? gn_stats_kernel<true> : gn_stats_kernel<false>, dim3((unsigned)(B * sp.nchunk)), dim3(T),
+                                 sizeof(float) * (size_t)k * 2 * Cs, st, sp);
     if (err != cudaSuccess) return check_cuda(err, "sd_groupnorm_swish (stats) launch");
   }
   int k;
   const int T = threads_for(C, k);
   if (T % 32 || T > 256) return fail(kErrUnsupported, "sd_groupnorm_swish: unsupported channel count");
   p.nchunk = chunks_for(k, p.px_per_chunk);
-  return check_cuda(launch_pdl(gn_apply_kernel, dim3((unsigned)(B * p.nchunk)), dim3(T), sizeof(float) * 2 * (size_t)C, st, p),
+  return check_cuda(launch_pdl(split ? gn_apply_kernel<true> : gn_apply_kernel<false>, dim3((unsigned)(B * p.nchunk)), dim3(T),
+                               sizeof(float) * 2 * (size_t)C, st, p),
                     "sd_groupnorm_swish (apply) launch");
 }
 
@@ -662,6 +760,17 @@ int sd_softmax_rows(const float* x, void* out, long rows, int cols, float scale,
   const unsigned blocks = (unsigned)((rows + 7) / 8);
   softmax_rows_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, rows, cols, scale);
   return check_cuda(cudaGetLastError(), "sd_softmax_rows launch");
+}
+
+int sd_softmax_rows_split(const float* x, void* out, long rows, int cols, float scale, int block, int rows_per_entry, void* stream) {
+  using namespace sdb;
+  if (!x || !out || rows < 0 || cols < 1 || block < 1 || rows_per_entry < 1 || (cols % block) != 0 || (rows_per_entry % block) != 0 ||
+      rows_per_entry > cols)
+    return fail(kErrInvalidArg, "sd_softmax_rows_split: block must divide cols and rows_per_entry (<= cols)");
+  if (rows == 0) return SD_OK;
+  const unsigned blocks = (unsigned)((rows + 7) / 8);
+  softmax_rows_split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, (__nv_bfloat16*)out, rows, cols, scale, block, rows_per_entry);
+  return check_cuda(cudaGetLastError(), "sd_softmax_rows_split launch");
 }
 
 int sd_upsample2x(const void* x, int B, int H, int W, int C, void* out, void* stream) {
@@ -720,19 +829,32 @@ int sd_gather_row(const float* table, int rows, int row_floats, const int* count
 }
 
 int sd_im2col_in(const float* x, int B, int H, int W, int Cin, void* out, void* stream) {
+  return sd_im2col_in_ex(x, B, H, W, Cin, out, 0u, stream);
+}
+
+int sd_im2col_in_ex(const float* x, int B, int H, int W, int Cin, void* out, unsigned flags, void* stream) {
   using namespace sdb;
   if (!x || !out || B < 0 || H < 1 || W < 1 || Cin < 1 || 18 * Cin > 64)
     return fail(kErrInvalidArg, "sd_im2col_in: 1 <= Cin <= 3 required (hi/lo split of 9*Cin values must fit one 64-wide K-block)");
   if (B == 0) return SD_OK;
   const size_t npix = (size_t)B * H * W;
-  im2col_in_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cin, (__nv_bfloat16*)out);
+  im2col_in_kernel<<<grid_for(npix, 256), 256, 0, (cudaStream_t)stream>>>(x, B, H, W, Cin, (__nv_bfloat16*)out,
+                                                                          (flags & SD_GEMM_SPLIT3) ? 128 : 64);
   return check_cuda(cudaGetLastError(), "sd_im2col_in launch");
 }
 
 int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, const int* step_counter, int B, int nf,
                       const float* w0, const float* b0, const float* w1, const float* b1, const float* class_emb,
                       const int* labels, float* temb_scratch, void* act_temb_out, void* stream) {
+  return sd_time_embedding_ex(t_dev, t_stride, sched, step_counter, B, nf, w0, b0, w1, b1, class_emb, labels, temb_scratch,
+                              act_temb_out, 0u, stream);
+}
+
+int sd_time_embedding_ex(const float* t_dev, int t_stride, const float* sched, const int* step_counter, int B, int nf,
+                         const float* w0, const float* b0, const float* w1, const float* b1, const float* class_emb,
+                         const int* labels, float* temb_scratch, void* act_temb_out, unsigned flags, void* stream) {
   using namespace sdb;
+  const int split = (flags & SD_GEMM_SPLIT3) ? 1 : 0;
   if ((!t_dev && !sched) || !w0 || !b0 || !w1 || !b1 || !temb_scratch || !act_temb_out)
     return fail(kErrInvalidArg, "sd_time_embedding: null pointer");
   if (class_emb && !labels) return fail(kErrInvalidArg, "sd_time_embedding: class embedding needs labels");
@@ -741,12 +863,12 @@ int sd_time_embedding(const float* t_dev, int t_stride, const float* sched, cons
   const bool shared_t = sched != nullptr || t_stride == 0;
   const int n_t = shared_t ? 1 : B;
   cudaStream_t st = (cudaStream_t)stream;
-  temb_dense_kernel<<<n_t, 512, sizeof(float) * 5 * nf, st>>>(t_dev, t_stride, sched, step_counter, nf, w0, b0, w1, b1, temb_scratch);
+  temb_dense_kernel<<<n_t, 512, sizeof(float) * 5 * nf, st>>>(t_dev, t_stride, sched, step_counter, nf, w0, b0, w1, b1, temb_scratch, split);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return check_cuda(err, "sd_time_embedding (dense) launch");
   const size_t total = (size_t)B * 4 * nf;
   temb_act_kernel<<<grid_for(total, 256), 256, 0, st>>>(temb_scratch, shared_t ? 0 : 4 * nf, class_emb, labels, B, 4 * nf,
-                                                        (__nv_bfloat16*)act_temb_out);
+                                                        (__nv_bfloat16*)act_temb_out, split);
   return check_cuda(cudaGetLastError(), "sd_time_embedding (act) launch");
 }
 

@@ -45,15 +45,29 @@ def _conv_w(p):
 class _Bound:
     """ScoreNet bound to one parameter tree, weights resident on the device in GEMM layout."""
 
-    def __init__(self, model, params, device):
+    def __init__(self, model, params, device, precision="bf16"):
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
         self.model = model
         self.config = model.config
         self.device = device
+        self.precision = precision
+        # 'fp32' = the FP32-faithful arm (SD_PRECISION_FP32_FAITHFUL): every activation and weight is a hi|lo pair of bf16
+        # tensors, products are hi*hi + lo*hi + hi*lo on the tensor cores with fp32 accumulation (SD_GEMM_SPLIT3 in
+        # include/superdiff_b200.h), GroupNorm / swish / softmax run in fp32 with exact transcendental forms.  ~3x the
+        # tensor work of the bf16 arm for ~2^-17 relative operand error instead of 2^-9.
+        self.split = precision == "fp32"
         self._prepare(params)
 
     # -- weight upload -------------------------------------------------------
     def _dev(self, t, dtype=torch.float32):
         return t.detach().to(device=self.device, dtype=dtype).contiguous()
+
+    def _w(self, t):
+        """GEMM weight [N, K] fp32 -> device bf16 [N, K] (bf16 arm) or [N, 2K] = [hi | lo] (FP32-faithful arm)."""
+        if self.split:
+            return self._dev(ops.split_pair(t.detach().to(torch.float32)), torch.bfloat16)
+        return self._dev(t, torch.bfloat16)
 
     def _prepare(self, P):
         cfg = self.config
@@ -68,7 +82,12 @@ class _Bound:
         self.conv_in_w = self._dev(P["Conv_0"]["kernel"]); self.conv_in_b = self._dev(P["Conv_0"]["bias"])
         # tensor-core form of the first conv: one 64-wide K-block of hi/lo-split 3x3 neighbourhoods (ops.im2col_in)
         self.conv_in_tc = cfg.data.num_channels <= 3 and cfg.data.image_size % 16 == 0
-        self.conv_in_w64 = self._dev(ops.conv_in_weights(P["Conv_0"]["kernel"]), bf) if self.conv_in_tc else None
+        if self.split and not self.conv_in_tc:
+            raise NotImplementedError("the FP32-faithful arm needs the tensor-core first conv (<= 3 channels, image size % 16 == 0)")
+        if self.split:
+            self.conv_in_w64 = self._dev(ops.conv_in_weights_split(P["Conv_0"]["kernel"]), bf)
+        else:
+            self.conv_in_w64 = self._dev(ops.conv_in_weights(P["Conv_0"]["kernel"]), bf) if self.conv_in_tc else None
 
         dense_w, dense_b = [], []
         self.res = []
@@ -94,9 +113,9 @@ class _Bound:
             dense_w.append(blk["Dense_0"]["kernel"].T)                       # [cout, 4nf]
             dense_b.append(blk["Dense_0"]["bias"] + blk["Conv_0"]["bias"])   # conv1 bias folded into the row bias
             r = dict(g1=self._dev(blk["GroupNorm_0"]["scale"]), be1=self._dev(blk["GroupNorm_0"]["bias"]),
-                     w1=self._dev(_conv_w(blk["Conv_0"]), bf),
+                     w1=self._w(_conv_w(blk["Conv_0"])),
                      g2=self._dev(blk["GroupNorm_1"]["scale"]), be2=self._dev(blk["GroupNorm_1"]["bias"]),
-                     w2=self._dev(w2, bf), b2=self._dev(b2), nin=nin, cout=cout, off=off, cin=cin)
+                     w2=self._w(w2), b2=self._dev(b2), nin=nin, cout=cout, off=off, cin=cin)
             off += cout
             self.res.append(r)
             counters["res"] += 1
@@ -117,7 +136,7 @@ class _Bound:
             b_vo = (bv.double() @ wo64 + bo.double()).float()
             a = dict(g=self._dev(blk["GroupNorm_0"]["scale"]), be=self._dev(blk["GroupNorm_0"]["bias"]),
                      w_qkv=self._dev(torch.cat([wq.T, wk.T, wv.T], 0), bf), b_qkv=self._dev(torch.cat([bq, bk, bv])),
-                     w_q2=self._dev(w_q2, bf), b_q2=self._dev(b_q2), w_voT=self._dev(w_vo.T, bf), b_vo=self._dev(b_vo),
+                     w_q2=self._w(w_q2), b_q2=self._dev(b_q2), w_voT=self._w(w_vo.T.contiguous()), b_vo=self._dev(b_vo),
                      w_o=self._dev(torch.cat([wo.T, torch.eye(c)], dim=1), bf), b_o=self._dev(bo), c=c)   # + x (layers.py:511)
             self.attn.append(a)
             counters["attn"] += 1
@@ -136,7 +155,7 @@ class _Bound:
                 chans.append(c)
             if lvl != nres - 1:
                 blk = P[f"Downsample_{counters['down']}"]["Conv_0"]
-                self.down.append(dict(w=self._dev(_conv_w(blk), bf), b=self._dev(blk["bias"])))
+                self.down.append(dict(w=self._w(_conv_w(blk)), b=self._dev(blk["bias"])))
                 self.plan.append(("downsample", len(self.down) - 1))
                 counters["down"] += 1
                 size //= 2
@@ -152,7 +171,7 @@ class _Bound:
                 self.plan.append(("attn", add_attn(c)))
             if lvl != 0:
                 blk = P[f"Upsample_{counters['up']}"]["Conv_0"]
-                self.up.append(dict(w4=self._dev(ops.upconv_weights(blk["kernel"]), bf), b=self._dev(blk["bias"])))
+                self.up.append(dict(w4=self._w(ops.upconv_weights(blk["kernel"])), b=self._dev(blk["bias"])))
                 self.plan.append(("upsample", len(self.up) - 1))
                 counters["up"] += 1
                 size *= 2
@@ -161,9 +180,9 @@ class _Bound:
         wout = _conv_w(P["Conv_1"])                       # [C_img, 9*nf]
         self.n_img = wout.shape[0]
         pad = (-wout.shape[0]) % 16
-        self.out_w = self._dev(torch.cat([wout, torch.zeros(pad, wout.shape[1])], 0), bf)
+        self.out_w = self._w(torch.cat([wout, torch.zeros(pad, wout.shape[1])], 0))
         self.out_b = self._dev(P["Conv_1"]["bias"])
-        self.dense_w = self._dev(torch.cat(dense_w, 0), bf)   # [sum cout, 4nf]
+        self.dense_w = self._w(torch.cat(dense_w, 0))         # [sum cout, 4nf]
         self.dense_b = self._dev(torch.cat(dense_b, 0))
         self.dense_n = off
 
@@ -172,13 +191,41 @@ class _Bound:
         r = self.res[i]
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
-        a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1)
-        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True)
-        a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"])
+        sp = self.split
+        a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1, split=sp)
+        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True, split=sp)
+        a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"], split=sp)
         # NIN shortcut (C_in != C_out) or identity residual: both are extra 1-tap K segments of the same GEMM
-        return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True)
+        return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True, split=sp)
+
+    def _attn_split(self, x, i):
+        """AttnBlock in the FP32-faithful arm: same folded algebra, every product as a 3 x bf16 split GEMM, the softmax in fp32
+        on the fp32 scores (five launches; the fused bf16 core keeps its probabilities in bf16 and is not used here)."""
+        a = self.attn[i]
+        B, H, W, C2 = x.shape
+        C, S = C2 // 2, H * W
+        g = max(1, 128 // S)
+        if S < 16 or (g * S) % 16:
+            raise NotImplementedError("the FP32-faithful attention needs at least 16 pixels per image")
+        if B % g:      # pad the last packed tile with zero images (block-diagonal softmax keeps images independent)
+            z = x.new_zeros((g - B % g,) + tuple(x.shape[1:]))
+            return self._attn_split(torch.cat([x, z]), i)[:B]
+        h = ops.groupnorm_swish(x, a["g"], a["be"], swish=False, split=True)
+        nb, Sp = B // g, g * S
+        hb = h.view(nb, Sp, C2)
+        q2 = ops.conv_gemm([(h, 1)], a["w_q2"], bias=a["b_q2"], split=True).view(nb, Sp, C2)
+        vt = ops.batched_gemm(a["w_voT"], hb, split=True)                                # [nb, C, 2 Sp]
+        sc = ops.batched_gemm(q2, hb, out_f32=True, split=True)                          # fp32 scores [nb, Sp, Sp]
+        p = ops.softmax_rows_split(sc, C ** -0.5, block=S)                               # [nb, Sp, 2 Sp], block diagonal
+        out = ops.batched_gemm(p, vt, bias=a["b_vo"], residual=x.view(nb, Sp, C2), want_stats=(g == 1), split=True)
+        res = out.view(B, H, W, C2)
+        if hasattr(out, "gn_stats"):
+            res.gn_stats = out.gn_stats
+        return res
 
     def _attn(self, x, i):
+        if self.split:
+            return self._attn_split(x, i)
         a = self.attn[i]
         B, H, W, C = x.shape
         S = H * W
@@ -222,7 +269,7 @@ class _Bound:
                 hs.append(h)
             elif kind == "downsample":
                 d = self.down[op[1]]
-                h = ops.conv_gemm_s2(hs[-1], d["w"], bias=d["b"], want_stats=True)
+                h = ops.conv_gemm_s2(hs[-1], d["w"], bias=d["b"], want_stats=True, split=self.split)
                 hs.append(h)
             elif kind == "mid":
                 h = self._res([hs[-1]], op[1], rowbias)
@@ -234,16 +281,17 @@ class _Bound:
                 h = self._attn(h, op[1])
             elif kind == "upsample":
                 u = self.up[op[1]]
-                h = ops.upconv_gemm(h, u["w4"], bias=u["b"], want_stats=True)
+                h = ops.upconv_gemm(h, u["w4"], bias=u["b"], want_stats=True, split=self.split)
         assert not hs
-        a = ops.groupnorm_swish(h, self.out_g, self.out_be)
-        return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out)
+        a = ops.groupnorm_swish(h, self.out_g, self.out_be, split=self.split)
+        return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out, split=self.split)
 
     def _conv_in(self, x, bias, want_stats):
         """conv3x3(x, nf) (ddpm.py:71).  Tensor-core form: 166 -> ~55 us at batch 512 and the GEMM epilogue emits the channel
         sums the first GroupNorm needs; the CUDA-core kernel remains for inputs the gather does not cover."""
         if self.conv_in_tc:
-            return ops.conv_gemm([(ops.im2col_in(x), 1)], self.conv_in_w64, bias=bias, want_stats=want_stats)
+            return ops.conv_gemm([(ops.im2col_in(x, split=self.split), 1)], self.conv_in_w64, bias=bias, want_stats=want_stats,
+                                 split=self.split)
         return ops.conv_in(x, self.conv_in_w, bias)
 
     def _rowbias(self, t, x, y, sched, step_counter):
@@ -262,8 +310,8 @@ class _Bound:
             if ent is None or ent[0] is not sched:
                 ts = sched[:, 2].contiguous()                     # sigma_t = t (cifar/dynamics.py:105)
                 act = ops.time_embedding(ts.shape[0], self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
-                                         t=ts, t_stride=1)
-                table = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0].contiguous()
+                                         t=ts, t_stride=1, split=self.split)
+                table = ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True, split=self.split)[0].contiguous()
                 row = torch.empty(1, table.shape[1], device=x.device, dtype=torch.float32)
                 ent = cache[key] = (sched, table, row)
             self._rb_table, self._rb_row = ent[1], ent[2]
@@ -276,7 +324,8 @@ class _Bound:
             labels = y.to(device=x.device, dtype=torch.int32).contiguous()
         if sched is not None:
             act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
-                                     sched=sched, step_counter=step_counter, class_emb=self.class_emb, labels=labels)
+                                     sched=sched, step_counter=step_counter, class_emb=self.class_emb, labels=labels,
+                                     split=self.split)
         else:
             if not torch.is_tensor(t):
                 t = torch.full((1,), float(t), device=x.device, dtype=torch.float32)
@@ -285,8 +334,8 @@ class _Bound:
             if stride and t.numel() != B:
                 raise ValueError("t must have one entry per sample")
             act = ops.time_embedding(B, self.nf, self.temb_w0, self.temb_b0, self.temb_w1, self.temb_b1,
-                                     t=t, t_stride=stride, class_emb=self.class_emb, labels=labels)
-        return ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True)[0]    # [B, sum cout]
+                                     t=t, t_stride=stride, class_emb=self.class_emb, labels=labels, split=self.split)
+        return ops.batched_gemm(act, self.dense_w, bias=self.dense_b, out_f32=True, split=self.split)[0]    # [B, sum cout]
 
     # -- forward-mode derivative (Hutchinson probes of the deterministic sampler, cifar/dynamics.py:84) -------------
     def _res_jvp(self, srcs, dsrcs, i, rowbias):
@@ -338,6 +387,8 @@ class _Bound:
         Linear layers reuse the tcgen05 GEMMs on the tangent stream (no bias); GroupNorm+swish and the attention softmax
         have tangent kernels (csrc/scorenet_jvp.cu).  Tangents travel in bf16 like the activations."""
         _lib.require_device()
+        if self.split:
+            raise NotImplementedError("the tangent kernels exist for the bf16 arm only (bind with precision='bf16')")
         for name, ten in (("x", x), ("v", v)):
             if not (ten.is_cuda and ten.dtype == torch.float32 and ten.is_contiguous()):
                 raise ValueError(f"{name} must be a contiguous float32 CUDA tensor (NHWC)")
@@ -389,9 +440,13 @@ class ScoreNet:
         if m.nf % 64 or config.data.num_channels > 4:
             raise NotImplementedError("nf must be a multiple of 64 and the image must have <= 4 channels")
 
-    def bind(self, params, device=None):
+    def bind(self, params, device=None, precision=None):
+        """precision: 'bf16' (default; bf16 operands / activations, fp32 accumulation) or 'fp32' (the FP32-faithful arm);
+        None reads config.model.precision when the config carries it."""
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        return _Bound(self, params, device)
+        if precision is None:
+            precision = getattr(self.config.model, "precision", "bf16") if hasattr(self.config, "model") else "bf16"
+        return _Bound(self, params, device, precision)
 
     def apply(self, variables, t, x, y, train=False, mutable=False, rngs=None):
         """Flax-style entry used by the reference's get_model_fn (models/utils.py:91-95)."""
@@ -399,15 +454,17 @@ class ScoreNet:
             raise NotImplementedError("train=True (dropout) is outside the sampling path")
         return self.bound_for(variables["params"], x.device)(t, x, y)
 
-    def bound_for(self, params, device=None):
+    def bound_for(self, params, device=None, precision=None):
         """The bound net of a parameter tree, uploaded once per (tree object, device).  The entry holds the tree, so an
         id() can never be recycled for another tree while it is cached; a handful of trees at most (the M models)."""
         device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         cache = self.__dict__.setdefault("_bound_cache", {})
-        key = (id(params), str(device))
+        if precision is None:
+            precision = getattr(self.config.model, "precision", "bf16")
+        key = (id(params), str(device), precision)
         ent = cache.get(key)
         if ent is None or ent[0] is not params:
             if len(cache) >= 16:
                 cache.clear()
-            ent = cache[key] = (params, self.bind(params, device))
+            ent = cache[key] = (params, self.bind(params, device, precision))
         return ent[1]

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 
 ALIGN = 256
-PRECISION_BF16 = 1
+PRECISION_BF16, PRECISION_FP32_FAITHFUL = 1, 2
 
 
 def _arrays(bound):
@@ -52,9 +52,10 @@ def pack_weights(bound):
     return blob
 
 
-def make_desc(config, blob=None):
+def make_desc(config, blob=None, precision=PRECISION_BF16):
     m, d = config.model, config.data
     desc = _lib.ScoreNetDesc()
+    desc.precision = int(precision)
     desc.image_size, desc.channels, desc.nf = int(d.image_size), int(d.num_channels), int(m.nf)
     desc.num_res_blocks = int(m.num_res_blocks)
     ch_mult, attn = tuple(m.ch_mult), tuple(m.attn_resolutions)
@@ -79,7 +80,8 @@ class NativeScoreNet:
         self.config = bound.config
         self.device = bound.device
         self.blob = pack_weights(bound)
-        self.desc = make_desc(self.config, self.blob)
+        self.precision = PRECISION_FP32_FAITHFUL if getattr(bound, "split", False) else PRECISION_BF16
+        self.desc = make_desc(self.config, self.blob, self.precision)
         lib = _lib.load()
         need = ctypes.c_size_t()
         _lib.check(lib.sd_scorenet_weights_bytes(ctypes.byref(self.desc), ctypes.byref(need)), "sd_scorenet_weights_bytes")
@@ -116,7 +118,7 @@ class NativeScoreNet:
             out = torch.empty_like(x)
         rc = _lib.load().sd_scorenet_forward(ctypes.byref(self.desc), t.data_ptr(), stride, x.data_ptr(),
                                              labels.data_ptr() if labels is not None else None, B, out.data_ptr(),
-                                             self._ws.data_ptr(), self._ws.numel(), PRECISION_BF16,
+                                             self._ws.data_ptr(), self._ws.numel(), self.precision,
                                              torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "sd_scorenet_forward")
         return out
@@ -138,7 +140,7 @@ class NativeScoreNet:
             out = torch.empty_like(x)
         rc = _lib.load().sd_scorenet_forward_sched(ctypes.byref(self.desc), sched.data_ptr(), step_counter.data_ptr(), x.data_ptr(),
                                                    labels.data_ptr() if labels is not None else None, B, out.data_ptr(),
-                                                   self._ws.data_ptr(), self._ws.numel(), PRECISION_BF16,
+                                                   self._ws.data_ptr(), self._ws.numel(), self.precision,
                                                    torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "sd_scorenet_forward_sched")
         return out
@@ -150,4 +152,5 @@ class NativeScoreNet:
         with open(path + ".json", "w") as fh:
             json.dump({"image_size": d.image_size, "channels": d.channels, "nf": d.nf, "num_res_blocks": d.num_res_blocks,
                        "ch_mult": list(d.ch_mult)[:d.n_levels], "attn_resolutions": list(d.attn_resolutions)[:d.n_attn_res],
-                       "conditioned": d.conditioned, "num_classes": d.num_classes, "weights_bytes": int(d.weights_bytes)}, fh)
+                       "conditioned": d.conditioned, "num_classes": d.num_classes, "weights_bytes": int(d.weights_bytes),
+                       "precision": int(d.precision)}, fh)

@@ -190,7 +190,21 @@ def counter_add(counter, delta=1, rows=None):
 # ---------------------------------------------------------------------------
 # score-net ops (NHWC bf16 activations)
 # ---------------------------------------------------------------------------
-EPI_SWISH, EPI_OUT_F32 = 1, 2
+EPI_SWISH, EPI_OUT_F32, GEMM_SPLIT3 = 1, 2, 8
+
+
+def split_pair(x):
+    """fp32 [..., C] -> bf16 [..., 2C] = [hi | lo], hi = bf16(x), lo = bf16(x - hi): the operand format of the FP32-faithful
+    arm (SD_GEMM_SPLIT3 in include/superdiff_b200.h).  Host / torch helper for weights and test inputs."""
+    hi = x.to(torch.bfloat16)
+    lo = (x.to(torch.float32) - hi.to(torch.float32)).to(torch.bfloat16)
+    return torch.cat([hi, lo], dim=-1).contiguous()
+
+
+def merge_pair(x):
+    """Inverse of split_pair up to ~2^-17 relative: bf16 [..., 2C] -> fp32 [..., C] = hi + lo."""
+    C = x.shape[-1] // 2
+    return x[..., :C].to(torch.float32) + x[..., C:].to(torch.float32)
 
 
 def _bf16c(t, name):
@@ -200,31 +214,34 @@ def _bf16c(t, name):
 
 
 def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False, out_f32=False, out=None,
-              n_out=None, want_stats=False):
+              n_out=None, want_stats=False, split=False):
     """Implicit GEMM over NHWC bf16 sources (sd_conv_gemm).  srcs: list of
     (tensor [B,H,W,C], taps) with taps in {1, 9}; weight: bf16 [N, K].  want_stats: also emit per-128-pixel-tile
     channel sums of the output (attached as ``out.gn_stats = (tensor [B, HW/128, 2, N], HW/128)``) so a following
-    groupnorm_swish skips its statistics pass; silently ignored where the layout does not allow it."""
+    groupnorm_swish skips its statistics pass; silently ignored where the layout does not allow it.
+    split: 3 x bf16 split precision (SD_GEMM_SPLIT3) -- sources / residual / out are hi|lo pairs [B,H,W,2C], weight [N, 2K]."""
     lib = _lib.load()
     x0 = srcs[0][0]
     B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
     arr = (_lib.GemmSrc * len(srcs))()
     K = 0
+    sm = 2 if split else 1
     for i, (t, taps) in enumerate(srcs):
         _bf16c(t, f"srcs[{i}]")
         if t.shape[:3] != x0.shape[:3]:
             raise ValueError("all sources must share (B, H, W)")
         arr[i].ptr = t.data_ptr()
-        arr[i].C = t.shape[3]
+        arr[i].C = t.shape[3] // sm
         arr[i].taps = taps
+        arr[i].ld = t.shape[3]
         K += taps * t.shape[3]
     _bf16c(weight, "weight")
     N = weight.shape[0] if n_out is None else n_out
     if weight.shape[1] != K:
         raise ValueError(f"weight K {weight.shape[1]} != {K}")
     if out is None:
-        out = torch.empty(B, H, W, N, device=x0.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0)
+        out = torch.empty(B, H, W, N if out_f32 else sm * N, device=x0.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0) | (GEMM_SPLIT3 if split else 0)
     rb_ld = rowbias.stride(0) if rowbias is not None else 0
     if residual is not None:
         _bf16c(residual, "residual")
@@ -241,20 +258,23 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     return out
 
 
-def conv_gemm_s2(x, weight, bias=None, out=None, want_stats=False):
+def conv_gemm_s2(x, weight, bias=None, out=None, want_stats=False, split=False):
     """3x3 stride-2 SAME conv (flax pad (0,1)) with the stride in the TMA descriptor (sd_conv_gemm_s2).
     x: bf16 [B,H,W,C]; weight: bf16 [N, 9C]."""
     lib = _lib.load()
     _bf16c(x, "x"); _bf16c(weight, "weight")
     B, H, W, C = x.shape
+    sm = 2 if split else 1
+    C //= sm
     N = weight.shape[0]
     Ho, Wo = H // 2, W // 2
     if out is None:
-        out = torch.empty(B, Ho, Wo, N, device=x.device, dtype=torch.bfloat16)
+        out = torch.empty(B, Ho, Wo, sm * N, device=x.device, dtype=torch.bfloat16)
     stats = None
     if want_stats and (Ho * Wo) % 128 == 0 and N % 16 == 0 and B > 0:
         stats = torch.empty(B, (Ho * Wo) // 128, 2, N, device=x.device, dtype=torch.float32)
-    rc = lib.sd_conv_gemm_s2(_ptr(x), B, H, W, C, _ptr(weight), N, _ptr(bias), 0, _ptr(out), _ptr(stats), _stream())
+    rc = lib.sd_conv_gemm_s2(_ptr(x), B, H, W, C, _ptr(weight), N, _ptr(bias), GEMM_SPLIT3 if split else 0, _ptr(out), _ptr(stats),
+                             _stream())
     _lib.check(rc, "sd_conv_gemm_s2")
     if B > 0:
         _count()
@@ -279,19 +299,22 @@ def upconv_weights(kernel_hwio):
     return torch.stack(out)
 
 
-def upconv_gemm(x, w4, bias=None, out=None, want_stats=False):
+def upconv_gemm(x, w4, bias=None, out=None, want_stats=False, split=False):
     """Fused nearest-x2 upsample + 3x3 conv as four 2x2-tap implicit GEMMs (sd_upconv_gemm).
     x: bf16 [B,H,W,C]; w4: bf16 [4, N, 4C] from upconv_weights()."""
     lib = _lib.load()
     _bf16c(x, "x"); _bf16c(w4, "w4")
     B, H, W, C = x.shape
+    sm = 2 if split else 1
+    C //= sm
     N = w4.shape[1]
     if out is None:
-        out = torch.empty(B, 2 * H, 2 * W, N, device=x.device, dtype=torch.bfloat16)
+        out = torch.empty(B, 2 * H, 2 * W, sm * N, device=x.device, dtype=torch.bfloat16)
     stats = None
     if want_stats and (H * W) % 128 == 0 and N % 16 == 0 and B > 0:
         stats = torch.empty(B, 4 * (H * W) // 128, 2, N, device=x.device, dtype=torch.float32)
-    rc = lib.sd_upconv_gemm(_ptr(x), B, H, W, C, _ptr(w4), N, _ptr(bias), 0, _ptr(out), _ptr(stats), _stream())
+    rc = lib.sd_upconv_gemm(_ptr(x), B, H, W, C, _ptr(w4), N, _ptr(bias), GEMM_SPLIT3 if split else 0, _ptr(out), _ptr(stats),
+                            _stream())
     _lib.check(rc, "sd_upconv_gemm")
     if B > 0:
         _count(4)
@@ -300,24 +323,26 @@ def upconv_gemm(x, w4, bias=None, out=None, want_stats=False):
     return out
 
 
-def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None, want_stats=False):
+def batched_gemm(A, Bt, bias=None, residual=None, swish=False, out_f32=False, out=None, K=None, want_stats=False, split=False):
     """out[b] = A[b] @ Bt[b]^T (sd_batched_gemm).  A: bf16 [batch, M, >=K] or [M, K]
-    (shared), Bt: bf16 [batch, N, >=K] or [N, K] (shared); row strides may exceed K."""
+    (shared), Bt: bf16 [batch, N, >=K] or [N, K] (shared); row strides may exceed K.
+    split: A, Bt, residual and (unless out_f32) out are hi|lo pairs along their last axis (SD_GEMM_SPLIT3); K, N logical."""
     lib = _lib.load()
     a3 = A if A.dim() == 3 else A.unsqueeze(0)
     b3 = Bt if Bt.dim() == 3 else Bt.unsqueeze(0)
     batch = max(a3.shape[0], b3.shape[0])
     M, N = a3.shape[1], b3.shape[1]
     if K is None:
-        K = a3.shape[2]
+        K = a3.shape[2] // (2 if split else 1)
     for t in (a3, b3):
         if t.dtype != torch.bfloat16 or not t.is_cuda or t.stride(2) != 1:
             raise ValueError("operands must be bf16 CUDA tensors with unit inner stride")
     sA = a3.stride(0) if (A.dim() == 3 and a3.shape[0] > 1) else 0
     sB = b3.stride(0) if (Bt.dim() == 3 and b3.shape[0] > 1) else 0
     if out is None:
-        out = torch.empty(batch, M, N, device=A.device, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0)
+        out = torch.empty(batch, M, N if (out_f32 or not split) else 2 * N, device=A.device,
+                          dtype=torch.float32 if out_f32 else torch.bfloat16)
+    flags = (EPI_SWISH if swish else 0) | (EPI_OUT_F32 if out_f32 else 0) | (GEMM_SPLIT3 if split else 0)
     stats = None
     if want_stats and M % 128 == 0 and N % 16 == 0 and not out_f32 and batch > 0:
         stats = torch.empty(batch, M // 128, 2, N, device=A.device, dtype=torch.float32)
@@ -393,6 +418,22 @@ def softmax_rows(x, scale, out=None):
     return out
 
 
+def softmax_rows_split(x, scale, block=None, out=None):
+    """FP32-faithful attention probabilities (sd_softmax_rows_split): x fp32 [batch, S, S] -> hi|lo bf16 pair [batch, S, 2S];
+    softmax over the diagonal block of ``block`` columns each row belongs to, zeros elsewhere."""
+    lib = _lib.load()
+    _f32c(x, "x")
+    batch, S, cols = x.shape
+    block = cols if block is None else block
+    if out is None:
+        out = torch.empty(batch, S, 2 * cols, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_softmax_rows_split(_ptr(x), _ptr(out), batch * S, cols, float(scale), int(block), S, _stream()),
+               "sd_softmax_rows_split")
+    if batch > 0:
+        _count()
+    return out
+
+
 _gn_scratch = {}
 
 
@@ -407,27 +448,29 @@ def _gn_scratch_for(device, floats):
     return buf
 
 
-def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None):
+def groupnorm_swish(x0, gamma, beta, x1=None, eps=1e-6, swish=True, out=None, split=False):
     """GroupNorm(32) + swish over concat(x0, x1) (sd_groupnorm_swish).  Sources carrying ``gn_stats`` (set by
-    conv_gemm(want_stats=True)) skip the statistics pass."""
+    conv_gemm(want_stats=True)) skip the statistics pass.  split: sources and out are hi|lo pairs [B,H,W,2C], exact swish."""
     lib = _lib.load()
     _bf16c(x0, "x0")
     B = x0.shape[0]
     HW = x0.shape[1] * x0.shape[2]
-    C0 = x0.shape[3]
+    sm = 2 if split else 1
+    C0 = x0.shape[3] // sm
     C1 = 0
     if x1 is not None:
         _bf16c(x1, "x1")
-        C1 = x1.shape[3]
+        C1 = x1.shape[3] // sm
     if out is None:
-        out = torch.empty(B, x0.shape[1], x0.shape[2], C0 + C1, device=x0.device, dtype=torch.bfloat16)
+        out = torch.empty(B, x0.shape[1], x0.shape[2], sm * (C0 + C1), device=x0.device, dtype=torch.bfloat16)
     st0, n0 = getattr(x0, "gn_stats", (None, 0))
     st1, n1 = getattr(x1, "gn_stats", (None, 0)) if x1 is not None else (None, 0)
     # channel sums of sources without stats + group stats; stream-ordered reuse of one buffer per (device, stream)
     scratch = _gn_scratch_for(x0.device, (4736 + B) * 2 * (C0 + C1) + 64 * B)
-    rc = lib.sd_groupnorm_swish(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
-                                _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(st0), int(n0),
-                                _ptr(st1), int(n1), _ptr(scratch), scratch.numel(), _ptr(out), _stream())
+    rc = lib.sd_groupnorm_swish_ex(_ptr(x0), C0, _ptr(x1), C1, B, HW, _ptr(_f32c(gamma, "gamma")),
+                                   _ptr(_f32c(beta, "beta")), float(eps), int(bool(swish)), _ptr(st0), int(n0),
+                                   _ptr(st1), int(n1), _ptr(scratch), scratch.numel(), _ptr(out),
+                                   GEMM_SPLIT3 if split else 0, _stream())
     _lib.check(rc, "sd_groupnorm_swish")
     if B > 0:
         C, nv = C0 + C1, HW * (C0 + C1) // 8
@@ -520,14 +563,15 @@ def gather_row(table, counter, out=None):
     return out
 
 
-def im2col_in(x, out=None):
-    """fp32 NHWC [B,H,W,Cin<=3] -> bf16 [B,H,W,64] hi/lo-split 3x3 neighbourhoods (sd_im2col_in)."""
+def im2col_in(x, out=None, split=False):
+    """fp32 NHWC [B,H,W,Cin<=3] -> bf16 [B,H,W,64] hi/lo-split 3x3 neighbourhoods (sd_im2col_in); split: [B,H,W,128] with a
+    zero upper half (the block as the hi half of a hi|lo pair)."""
     lib = _lib.load()
     _f32c(x, "x")
     B, H, W, Cin = x.shape
     if out is None:
-        out = torch.empty(B, H, W, 64, device=x.device, dtype=torch.bfloat16)
-    _lib.check(lib.sd_im2col_in(_ptr(x), B, H, W, Cin, _ptr(out), _stream()), "sd_im2col_in")
+        out = torch.empty(B, H, W, 128 if split else 64, device=x.device, dtype=torch.bfloat16)
+    _lib.check(lib.sd_im2col_in_ex(_ptr(x), B, H, W, Cin, _ptr(out), GEMM_SPLIT3 if split else 0, _stream()), "sd_im2col_in")
     if B > 0:
         _count()
     return out
@@ -539,6 +583,18 @@ def conv_in_weights(w_hwio):
     w = w_hwio.reshape(-1, cout).T                       # [Cout, 9*Cin], (kh, kw, c) order
     pad = torch.zeros(cout, 64 - 2 * w.shape[1], dtype=w.dtype, device=w.device)
     return torch.cat([w, w, pad], dim=1)
+
+
+def conv_in_weights_split(w_hwio):
+    """Flax HWIO [3,3,Cin,Cout] fp32 -> bf16 [Cout, 128] = [w_hi | w_hi | 0 || w_lo | 0 | 0] for im2col_in(split=True) rows
+    [x_hi | x_lo | 0 || 0]: x_hi w_hi + x_lo w_hi + x_hi w_lo."""
+    cout = w_hwio.shape[-1]
+    w = w_hwio.reshape(-1, cout).T.to(torch.float32)     # [Cout, 9*Cin]
+    k = w.shape[1]
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.to(torch.float32)).to(torch.bfloat16)
+    z = lambda n: torch.zeros(cout, n, dtype=torch.bfloat16, device=w.device)
+    return torch.cat([hi, hi, z(64 - 2 * k), lo, z(64 - k)], dim=1).contiguous()
 
 
 def conv_in(x, w_hwio, bias, out=None):
@@ -556,16 +612,17 @@ def conv_in(x, w_hwio, bias, out=None):
 
 
 def time_embedding(B, nf, w0, b0, w1, b1, t=None, t_stride=0, sched=None, step_counter=None, class_emb=None,
-                   labels=None, scratch=None, out=None):
+                   labels=None, scratch=None, out=None, split=False):
     lib = _lib.load()
     dev = w0.device
     shared = sched is not None or t_stride == 0
     if scratch is None:
         scratch = torch.empty(1 if shared else B, 4 * nf, device=dev, dtype=torch.float32)
     if out is None:
-        out = torch.empty(B, 4 * nf, device=dev, dtype=torch.bfloat16)
-    rc = lib.sd_time_embedding(_ptr(t), int(t_stride), _ptr(sched), _ptr(step_counter), B, nf, _ptr(w0), _ptr(b0),
-                               _ptr(w1), _ptr(b1), _ptr(class_emb), _ptr(labels), _ptr(scratch), _ptr(out), _stream())
+        out = torch.empty(B, (8 if split else 4) * nf, device=dev, dtype=torch.bfloat16)
+    rc = lib.sd_time_embedding_ex(_ptr(t), int(t_stride), _ptr(sched), _ptr(step_counter), B, nf, _ptr(w0), _ptr(b0),
+                                  _ptr(w1), _ptr(b1), _ptr(class_emb), _ptr(labels), _ptr(scratch), _ptr(out),
+                                  GEMM_SPLIT3 if split else 0, _stream())
     _lib.check(rc, "sd_time_embedding")
     if B > 0:
         _count(2)

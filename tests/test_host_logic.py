@@ -104,3 +104,21 @@ def test_uint8_conversion_matches_reference_formula():
     ref = np.clip((x.numpy() * 0.5 + 0.5) * 255.0, 0.0, 255.0).astype(np.uint8)
     assert np.array_equal(out.numpy(), ref)
     assert run_lib.get_image_scaler(cfg)(torch.tensor(0.75)).item() == 0.5
+
+
+def test_toy_mlp_module_is_the_notebook_mlp():
+    """models/toy_mlp.py (superposition_edu.ipynb:157-173) against the oracle restatement on the same Flax-shaped tree."""
+    import torch
+    from oracle import scorenet as OS
+    from super_diffusion_b200.models import utils as mutils
+    from super_diffusion_b200.models.toy_mlp import MLP, get_sscore
+    m = MLP.init(5)
+    tree = m.to_flax()
+    assert [tuple(tree[f"Dense_{i}"]["kernel"].shape) for i in range(5)] == [(3, 512), (512, 512), (512, 512), (512, 512), (512, 2)]
+    assert sum(p.numel() for p in m.parameters()) == 791_042          # SURVEY 8a6: 0.79 M parameters
+    g = torch.Generator().manual_seed(0)
+    t, x = torch.rand(33, 1, generator=g), torch.randn(33, 2, generator=g)
+    ref = OS.toy_mlp_apply(OS.params_to(tree, dtype=torch.float64), t.double(), x.double())
+    assert (get_sscore(m)(t, x).double() - ref).abs().max() < 1e-5
+    assert torch.equal(MLP.from_flax({"params": tree})(t, x), m(t, x))
+    assert mutils.get_model("toy-mlp") is MLP

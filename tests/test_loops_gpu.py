@@ -72,6 +72,30 @@ def test_toy_config1_trajectories(cuda, mode):
         assert torch.allclose(lo.cpu().double()[wellc], llr1[wellc], rtol=1e-5, atol=1e-4 * (1 + llr1[wellc].abs().max().item()))
 
 
+@pytest.mark.parametrize("mode", ["or", "and"])
+def test_toy_config1_with_the_notebook_mlp(cuda, mode):
+    """BASELINE config 1 as the reference runs it: two MLP score models (superposition_edu.ipynb:157-173, 3 -> 512 x 4 -> 2,
+    swish) feeding the SuperDiff OR / AND loops.  The product ships the MLP as a PyTorch module (models/toy_mlp.py); here two
+    lecun-normal-initialised instances run on the GPU in fp32 against the fp64 oracle MLP on the same parameters, free-running
+    for 1000 steps (float32 time accumulation like the notebook)."""
+    from super_diffusion_b200.models.toy_mlp import MLP, get_sscore
+    B, n, dt = 1024, 1000, 1e-3
+    x0 = torch.randn(B, 2, generator=torch.Generator().manual_seed(0))
+    noise = torch.randn(n, B, 2, generator=torch.Generator().manual_seed(3))
+    mlps = [MLP.init(1), MLP.init(2)]
+    p64 = [OS.params_to(m.to_flax(), dtype=torch.float64) for m in mlps]
+    with torch.no_grad():
+        xr, llr, tr = toy.loop_toy([lambda t, x, p=p: OS.toy_mlp_apply(p, t, x) for p in p64], x0.double(), noise, mode, n, dt,
+                                   record=True)
+    fns = [get_sscore(m.to(cuda)) for m in mlps]
+    run = superdiff_or if mode == "or" else superdiff_and
+    x, ll, w, traj = run(fns, x0.to(cuda), n_steps=n, dt=dt, noise=noise.to(cuda), record=True)
+    torch.cuda.synchronize()
+    tx, tl = traj["x"].cpu().double(), traj["ll"].cpu().double()
+    assert torch.isfinite(tx).all() and torch.isfinite(tl).all()
+    assert _rel(tx, tr["x"]) <= 1e-3 and _rel(tl, tr["ll"]) <= 1e-3, (_rel(tx, tr["x"]), _rel(tl, tr["ll"]))
+
+
 def _gauss_sscore(mu, var):
     """Exact sigma_t * grad log q_t of N(mu, var I) data under the forward process (any dimension)."""
     def fn(t, x):

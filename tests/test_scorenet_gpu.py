@@ -109,7 +109,8 @@ def test_scorenet_jvp_matches_autodiff_of_oracle(cuda):
 
 def test_scorenet_jvp_pads_batches_that_do_not_fill_attention_tiles(cuda):
     """The reference's eval batch is 100 (12 per GPU on 8 GPUs): not a multiple of the 8 images a 4x4 attention tile packs.
-    The JVP pads with zero images; the first 12 samples of a batch of 16 and the batch of 12 give the same pair."""
+    The JVP pads with zero images.  Batch 12 must agree with the first 12 samples of a batch of 16 as well as an unpadded
+    sub-batch (8 of 16) does -- tile shapes change with the batch, so agreement is at bf16 rounding level, not bit-exact."""
     cfg, model, params = _setup(False, 1.0, seed=7)
     net = model.bind(params, cuda)
     gen = torch.Generator().manual_seed(3)
@@ -117,5 +118,9 @@ def test_scorenet_jvp_pads_batches_that_do_not_fill_attention_tiles(cuda):
     v = (torch.randint(0, 2, (16, 32, 32, 3), generator=gen) * 2 - 1).float().to(cuda)
     s16, j16 = net.jvp(0.37, x, None, v)
     s12, j12 = net.jvp(0.37, x[:12].contiguous(), None, v[:12].contiguous())
-    tol = lambda r: 1e-6 + 1e-3 * r.abs().max().item()
-    assert torch.allclose(s16[:12], s12, rtol=0, atol=tol(s16)) and torch.allclose(j16[:12], j12, rtol=0, atol=tol(j16))
+    s8, j8 = net.jvp(0.37, x[:8].contiguous(), None, v[:8].contiguous())
+    rel = lambda a, b: ((a - b).norm() / b.norm()).item()
+    es, ej = rel(s12, s16[:12]), rel(j12, j16[:12])
+    es8, ej8 = rel(s8, s16[:8]), rel(j8, j16[:8])
+    assert torch.isfinite(s12).all() and torch.isfinite(j12).all()
+    assert es <= max(2 * es8, 2e-3) and ej <= max(2 * ej8, 4e-3), (es, ej, es8, ej8)

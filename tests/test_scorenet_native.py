@@ -16,17 +16,20 @@ def _cfgs():
     return [("vpsde", vpsde.get_config()), ("vpsdeA", vpsde.get_config(conditioned=True))]
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
 @pytest.mark.parametrize("name,cfg", _cfgs())
-def test_blob_layout_matches_the_native_walk(lib, name, cfg):
+def test_blob_layout_matches_the_native_walk(lib, name, cfg, precision):
     model, params = mutils.init_model(3, cfg, zero_init_scale=1.0)
-    bound = model.bind(params, torch.device("cpu"))          # weight preparation is plain tensor code
+    bound = model.bind(params, torch.device("cpu"), precision=precision)          # weight preparation is plain tensor code
     blob = native.pack_weights(bound)
-    desc = native.make_desc(cfg)
+    desc = native.make_desc(cfg, precision=native.PRECISION_FP32_FAITHFUL if precision == "fp32" else native.PRECISION_BF16)
     n = ctypes.c_size_t()
     assert lib.sd_scorenet_weights_bytes(ctypes.byref(desc), ctypes.byref(n)) == 0
     assert n.value == blob.numel() and n.value % native.ALIGN == 0
-    # 36.0 M parameters: bf16 GEMM weights + fp32 vectors + the identity / padding segments
-    assert 70e6 < n.value < 80e6
+    # 36.0 M parameters: bf16 GEMM weights (hi|lo pairs in the FP32-faithful arm) + fp32 vectors + the
+    # identity / padding segments
+    k = 2 if precision == "fp32" else 1
+    assert k * 70e6 < n.value < k * 80e6
 
 
 def test_workspace_dry_run_and_validation(lib):
@@ -50,14 +53,17 @@ def test_workspace_dry_run_and_validation(lib):
     null = ctypes.c_void_p(0)
     assert lib.sd_scorenet_forward(ctypes.byref(desc), null, 0, null, null, 8, null, null, 0, 1, null) == -1
     assert lib.sd_scorenet_forward(ctypes.byref(desc), null, 0, null, null, 8, null, null, 0, 0, null) == -2      # precision
+    assert lib.sd_scorenet_forward(ctypes.byref(desc), null, 0, null, null, 8, null, null, 0, 2, null) == -1      # blob is bf16
+    assert b"precision" in lib.sd_last_error()
     assert lib.sd_scorenet_forward(ctypes.byref(desc), null, 0, null, null, 0, null, null, 0, 1, null) == 0       # empty batch
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
 @pytest.mark.parametrize("name,cfg", _cfgs())
-def test_native_forward_is_the_python_forward(cuda, name, cfg):
+def test_native_forward_is_the_python_forward(cuda, name, cfg, precision):
     model, params = mutils.init_model(7, cfg, zero_init_scale=1.0)
-    bound = model.bind(params, cuda)
+    bound = model.bind(params, cuda, precision=precision)
     net = native.NativeScoreNet(bound)
     B = 16
     g = torch.Generator().manual_seed(11)
