@@ -164,7 +164,7 @@ def run_b200(args):
         model, params = mutils.init_model(10 + m, cfg, zero_init_scale=1.0)   # random init, non-degenerate
         models.append(model)
         states.append(mutils.State(params_ema=params, model_params=params))
-        nets.append(model.bound_for(params, dev))
+        nets.append(model.bound_for(params, dev, precision=args.precision))
     sampler = SuperDiffSampler(nets, B, mode="or", n_steps=N_STEPS, temperature=1e6, device=dev,
                                multi_stream=not args.single_stream)
     sampler.capture()
@@ -236,6 +236,7 @@ def run_b200(args):
         while int(1.0 / gdt) != K:
             gdt = 1.0 / (K + 1e-9 if int(1.0 / gdt) < K else K - 1e-9)
         cfg.eval.batch_size = B * world
+        cfg.model.precision = args.precision
         vf = dynamics.get_joint_stoch_vf(0, models, states)
         gen = eval_utils.get_generator(models, cfg, vf, dt=gdt, device=dev, return_logq=True)
         noise_k = lambda i: noise_host[i % n_noise]            # pinned host tensors, one H2D copy per step
@@ -289,6 +290,11 @@ def run_b200(args):
             us, by = _step_kernel_time(sampler, ops, torch, None, B=8192, mode=md)
             big[name] = {"us_per_launch": us, "achieved": by / (us * 1e-6) / 1e9, "frac": by / (us * 1e-6) / 1e9 / hbm_peak}
 
+    extras = None
+    if not args.no_extras and not args.no_probes:
+        del sampler
+        torch.cuda.empty_cache()
+        extras = _extras(args, torch, dist, dev, rank, world, hbm_peak, tf_peak, models, states)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -300,8 +306,10 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": "cifar_superdiff_or_b512_m2_1000steps", "batch_per_gpu": B, "models": M_MODELS,
+                   "precision": ("bf16 operands / activations, fp32 accumulation" if args.precision == "bf16" else
+                                 "FP32-faithful: hi|lo bf16 operand pairs, hi*hi + lo*hi + hi*lo with fp32 accumulation (3x the tensor work)"),
                    "n_steps": N_STEPS, "image": "32x32x3", "mode": "OR T=1e6 (cifar/dynamics.py:124)",
                    "weights": "random init, zero-init layers drawn at scale 1",
                    "step": "one Euler-Maruyama timestep = 2 score-net forwards + fused SuperDiff step, CUDA graph",
@@ -331,6 +339,7 @@ def run_b200(args):
                                 "note": "same fused step kernel at BASELINE config 3's single-GPU batch (8192): 503 MB per launch, input sets rotate so nothing is L2-resident"},
         "scorenet_tflops_whole_step": fwd_tf,
         "gather_ms": gather_ms,
+        "extras": extras,
     }
     if world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -347,6 +356,239 @@ def run_b200(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# extras: the other precision arm and BASELINE.json configs 1, 3, 4, 5 (configs[1] is the headline above)
+# ---------------------------------------------------------------------------------------------------------------------
+def _max_over_ranks(v, torch, dist, dev, world):
+    if world > 1:
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return v
+
+
+def _time_sampler(nets, B, mode, torch, dist, dev, world, steps=6, warmup=3, temperature=1e6):
+    """ms per timestep of the CUDA-graph sampler at batch B (device-resident noise), max over ranks; None on CUDA OOM."""
+    from super_diffusion_b200.superposition import SuperDiffSampler
+    try:
+        smp = SuperDiffSampler(nets, B, mode=mode, n_steps=max(steps, warmup) + 1, dt=1e-3, temperature=temperature, device=dev)
+        smp.capture()
+        g = torch.Generator(device=dev).manual_seed(77)
+        x0 = torch.randn(smp.shape, generator=g, device=dev)
+        nz = [torch.randn(smp.shape, generator=g, device=dev) for _ in range(2)]
+        smp.reset(x0)
+        for i in range(warmup):
+            smp.step(nz[i % 2])
+        smp.reset(x0)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for i in range(steps):
+            smp.step(nz[i % 2])
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / steps
+        launches = smp.launches_per_step
+        del smp
+    except torch.cuda.OutOfMemoryError:
+        torch.cuda.empty_cache()
+        return None, 0
+    torch.cuda.empty_cache()
+    return _max_over_ranks(ms, torch, dist, dev, world), launches
+
+
+class _StepProbe:
+    """minimal stand-in for the sampler fields _step_kernel_time reads"""
+    def __init__(self, B, M, dev):
+        self.B, self.M, self.device = B, M, dev
+
+
+def _extras(args, torch, dist, dev, rank, world, hbm_peak, tf_peak, models, states):
+    from super_diffusion_b200 import ops
+    from super_diffusion_b200.configs import vpsde
+    from super_diffusion_b200.models import utils as mutils
+    out = {}
+    cfg = vpsde.get_config()
+
+    def nets_for(n_models, precision):
+        ms, ps = list(models), [s_.params_ema for s_ in states]
+        for m in range(len(ms), n_models):
+            model, params = mutils.init_model(10 + m, cfg, zero_init_scale=1.0)
+            ms.append(model); ps.append(params)
+        return [ms[i].bound_for(ps[i], dev, precision=precision) for i in range(n_models)]
+
+    def gemm_frac(M, B, ms):
+        return M * B * GFLOP_PER_SAMPLE_FWD * 1e9 / (ms * 1e-3) / 1e12 / tf_peak
+
+    # ---- the other precision arm on the headline config (config 2: OR, batch 512 per GPU, M = 2) ----
+    other = "fp32" if args.precision == "bf16" else "bf16"
+    ms, launches = _time_sampler(nets_for(2, other), args.batch, "or", torch, dist, dev, world, steps=8)
+    if ms is not None:
+        out["config2_other_precision"] = {
+            "precision": other, "dtype": "f32" if other == "fp32" else "bf16", "ms_per_step": ms,
+            "samples_per_s": world * args.batch / (N_STEPS * ms * 1e-3), "gpu_launches_per_step": launches,
+            "tensor_frac_algorithmic_whole_step": gemm_frac(2, args.batch, ms),
+            "note": "same sampler, same config, the other score-net arm; fraction = 2 x batch x 12.154 GFLOP (algorithmic, SURVEY 8d) / "
+                    "whole-step time / sustained bf16 peak (the FP32-faithful arm executes 3x those flops)"}
+    # ---- config 3: CIFAR SuperDiff AND (per-sample kappa solve), batch 8192 sharded over the GPUs: STRONG scaling ----
+    total3 = 8192
+    shard = total3 // world
+    chunk = min(shard, 2048)
+    nets2 = nets_for(2, args.precision)
+    ms, launches = _time_sampler(nets2, chunk, "and", torch, dist, dev, world, steps=5, temperature=1.0)
+    if ms is not None:
+        ms_shard = ms * shard / chunk
+        us, by = _step_kernel_time(_StepProbe(chunk, 2, dev), ops, torch, None, B=chunk, mode=ops.MODE_AND)
+        out["config3_and_b8192_strong"] = {
+            "workload": "cifar_superdiff_and_b8192_m2_1000steps", "scaling": "strong", "n_gpus": world, "shard_per_gpu": shard,
+            "chunk": chunk, "ms_per_chunk_step": ms, "ms_per_step": ms_shard, "samples_per_s": total3 / (N_STEPS * ms_shard * 1e-3),
+            "tensor_frac_algorithmic_whole_step": gemm_frac(2, chunk, ms),
+            "step_kernel": {"mode": "AND", "us_per_launch": us, "GBps": by / (us * 1e-6) / 1e9, "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / hbm_peak},
+            "precision": args.precision,
+            "note": "every GPU owns 8192 / n_gpus samples and walks them as sequential chunks of <= 2048 through ONE captured graph "
+                    "(samples are independent; ms_per_step = chunks x measured chunk step); no per-step communication. "
+                    "What limits the curve: GEMM tile quantisation once the chunk drops below 2048 (1024 per GPU at 8 GPUs)"}
+    # ---- config 5: SuperDiff OR, M = 2, 4, 8 models, batch 16384 on 8 GPUs = 2048 per GPU (weak scaling in n_gpus) ----
+    c5 = {}
+    for M in (2, 4, 8):
+        netsM = nets_for(M, args.precision)
+        ms, launches = _time_sampler(netsM, 2048, "or", torch, dist, dev, world, steps=4)
+        if ms is None:
+            c5[f"M{M}"] = {"skipped": "CUDA out of memory"}
+            continue
+        us, by = _step_kernel_time(_StepProbe(2048, M, dev), ops, torch, None, B=2048, mode=ops.MODE_OR)
+        c5[f"M{M}"] = {"ms_per_step": ms, "samples_per_s": world * 2048 / (N_STEPS * ms * 1e-3), "gpu_launches_per_step": launches,
+                       "tensor_frac_algorithmic_whole_step": gemm_frac(M, 2048, ms),
+                       "step_kernel": {"mode": "OR", "us_per_launch": us, "bytes_per_launch": by, "GBps": by / (us * 1e-6) / 1e9,
+                                       "frac_of_hbm_peak": by / (us * 1e-6) / 1e9 / hbm_peak}}
+        del netsM
+    out["config5_or_b2048_per_gpu_m248"] = {"workload": "cifar_superdiff_or_b16384_over_8gpus_1000steps", "scaling": "weak",
+                                            "n_gpus": world, "batch_per_gpu": 2048, "precision": args.precision, **c5}
+    if rank == 0 and world == 1:
+        try:
+            out["config1_toy_mlp"] = _config1_toy(torch, dev)
+            out["config4_sd_latent_and"] = _config4_sd(torch, dev, ops, hbm_peak)
+        except Exception as exc:      # an extra must never cost the headline line
+            out["config1_or_4_error"] = repr(exc)
+    return out
+
+
+def _config1_toy(torch, dev):
+    """BASELINE configs[0]: 2-D mixture toy, two MLP score models (superposition_edu.ipynb:157-173), SuperDiff OR and AND,
+    VP-SDE 1000 steps, batch 4096.  GPU: superposition.superdiff_or / superdiff_and (fused step kernel, torch MLPs);
+    CPU: the oracle loop (oracle/toy.py) over the same MLPs, a bounded 100-step sample scaled to 1000."""
+    from oracle import scorenet as OS
+    from oracle import toy
+    from super_diffusion_b200.models.toy_mlp import MLP, get_sscore
+    from super_diffusion_b200.superposition import superdiff_and, superdiff_or
+    B, n = 4096, 1000
+    mlps = [MLP.init(1), MLP.init(2)]
+    x0 = torch.randn(B, 2, generator=torch.Generator().manual_seed(0))
+    res = {"workload": "toy_2d_mixture_two_mlps_b4096_1000steps", "batch": B, "n_steps": n}
+    trees = [OS.params_to(m.to_flax(), dtype=torch.float32) for m in mlps]
+    cpu_fns = [lambda t, x, p=p: OS.toy_mlp_apply(p, t, x) for p in trees]
+    k_cpu = 100
+    nz_cpu = torch.randn(k_cpu, B, 2, generator=torch.Generator().manual_seed(3))
+    fns = [get_sscore(m.to(dev)) for m in mlps]
+    nz = torch.randn(n, B, 2, generator=torch.Generator(device=dev).manual_seed(3), device=dev)
+    for mode, run in (("or", superdiff_or), ("and", superdiff_and)):
+        run(fns, x0.to(dev), n_steps=20, dt=1e-3, noise=nz)          # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        x, ll, w, _ = run(fns, x0.to(dev), n_steps=n, dt=1e-3, noise=nz)
+        x_host = x.cpu()                                              # end to end: final samples on the host
+        sec = time.perf_counter() - t0
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            toy.loop_toy(cpu_fns, x0, nz_cpu, mode, k_cpu, 1e-3)
+            cpu_sec = (time.perf_counter() - t0) * n / k_cpu
+        res[mode] = {"gpu_seconds_per_1000_steps": sec, "gpu_samples_per_s": B / sec, "gpu_us_per_step": sec / n * 1e6,
+                     "cpu_seconds_per_1000_steps_scaled": cpu_sec, "cpu_samples_per_s": B / cpu_sec,
+                     "cpu_sample": f"{k_cpu} oracle steps (fp32, {os.cpu_count()} threads) scaled to {n}",
+                     "finite": bool(torch.isfinite(x_host).all())}
+    res["note"] = ("launch-bound on the GPU (164 KB per step): two eager torch MLP forwards + one fused step launch per timestep; "
+                   "the score model stays a caller-supplied PyTorch module (SURVEY 8 a6)")
+    return res
+
+
+def _config4_sd(torch, dev, ops, hbm_peak):
+    """BASELINE configs[3]: Stable-Diffusion latent SuperDiff AND, 64x64x4 latents, batch 64, 50 steps.  diffusers is absent:
+    a random-init PyTorch UNet stand-in with the reference's call shape (latents / sqrt(sigma^2 + 1), t, prompt) supplies the
+    three velocities (clip_eval.py:89-105); the judged piece is the fused step (sd_step_edm_cfg), timed alone as well."""
+    from super_diffusion_b200.superposition import sd_superdiff
+    B, N = 64, 50
+    torch.manual_seed(0)
+
+    class TinyUNet(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.inp = torch.nn.Conv2d(4, 64, 3, padding=1)
+            self.mid = torch.nn.Conv2d(64, 64, 3, padding=1)
+            self.out = torch.nn.Conv2d(64, 4, 3, padding=1)
+            self.emb = torch.nn.Embedding(3, 64)
+
+        def forward(self, h, t, which):
+            e = self.emb.weight[which][None, :, None, None] * (1.0 + 1e-3 * t)
+            h = torch.nn.functional.silu(self.inp(h) + e)
+            return self.out(torch.nn.functional.silu(self.mid(h)))
+    net = TinyUNet().to(dev)
+    idx = {"obj": 0, "bg": 1, "uncond": 2}
+
+    def get_vel(t, sigma, latents, which):
+        with torch.no_grad():
+            return net(latents / ((sigma ** 2 + 1) ** 0.5), t, idx[which])
+    lat0 = torch.randn(B, 4, 64, 64, generator=torch.Generator().manual_seed(1)).to(dev)
+    z = torch.randn(N, B, 4, 64, 64, generator=torch.Generator(device=dev).manual_seed(2), device=dev)
+    sd_superdiff(get_vel, lat0, method="and", num_inference_steps=N, noise=z)       # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    x, ll, kappa, _ = sd_superdiff(get_vel, lat0, method="and", num_inference_steps=N, noise=z)
+    x.cpu()
+    sec = time.perf_counter() - t0
+    # the fused step alone: rotating input sets (> 2x L2), one CUDA graph
+    D_ = 4 * 64 * 64
+    set_bytes = 4 * B * D_ * 6
+    R = -(-2 * 126 * 1024 * 1024 // set_bytes) + 1
+    sets = [dict(x=torch.randn(B, D_, device=dev), z=torch.randn(B, D_, device=dev), vo=torch.randn(B, D_, device=dev),
+                 vb=torch.randn(B, D_, device=dev), vu=torch.randn(B, D_, device=dev), ll=torch.ones(B, 2, device=dev),
+                 xo=torch.empty(B, D_, device=dev), k=torch.empty(B, device=dev)) for _ in range(R)]
+
+    def one(st):
+        ops.step_edm_cfg(st["x"], st["z"], st["vo"], st["vb"], st["vu"], st["ll"], 5.0, -0.3, ops.MODE_AND, latents_out=st["xo"],
+                         kappa_out=st["k"])
+    for st in sets:
+        one(st)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        one(sets[0])
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    reps = 4
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            for st in sets:
+                one(st)
+    ts = []
+    for i in range(6):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); g.replay(); e.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(s.elapsed_time(e) * 1e3 / (reps * R))
+    us = statistics.median(ts)
+    return {"workload": "sd_latent_superdiff_and_b64_64x64x4_50steps", "batch": B, "n_steps": N,
+            "loop_seconds": sec, "samples_per_s": B / sec, "ms_per_step": sec / N * 1e3,
+            "unet": "random-init PyTorch stand-in (3 convs), 3 evaluations per step; diffusers / SD weights are absent",
+            "step_kernel": {"kernel": "step_edm_kernel (sd_step_edm_cfg, AND)", "us_per_launch": us, "bytes_per_launch": set_bytes,
+                            "GBps": set_bytes / (us * 1e-6) / 1e9, "frac_of_hbm_peak": set_bytes / (us * 1e-6) / 1e9 / hbm_peak,
+                            "floor_note": "25 MB per launch = 3.9 us at the copy peak; launch + one DRAM round trip is ~4-5 us"},
+            "finite": bool(torch.isfinite(x).all())}
 
 
 def _recorded_traffic(B):
@@ -523,6 +765,11 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU (default: BASELINE config, 512)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU-oracle baseline leg")
     ap.add_argument("--single-stream", action="store_true", help="run the M score-nets back to back on one stream")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"],
+                    help="score-net arm of the headline line: bf16 (bf16 operands / activations, fp32 accumulation) or fp32 "
+                         "(FP32-faithful: 3 x bf16 split products, the reference's arithmetic to ~1e-5); the other arm and the "
+                         "other BASELINE configs are summarised under 'extras'")
+    ap.add_argument("--no-extras", action="store_true", help="skip the other precision arm and BASELINE configs 1, 3, 4, 5")
     ap.add_argument("--no-probes", action="store_true",
                     help="skip the e2e leg and the roofline probes (GEMM-only graph, step-kernel timing): the short form used for the ncu launch list")
     args = ap.parse_args()
