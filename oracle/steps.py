@@ -231,6 +231,62 @@ MODE_OR, MODE_AND, MODE_AVG, MODE_FIXED = 0, 1, 2, 3
 DLOGQ_CIFAR_MAXSUB, DLOGQ_ITO, DLOGQ_NONE = 0, 1, 2
 
 
+# ---------------------------------------------------------------------------
+# applications/proteins/superdiff/composition.py -- two-component (translations / rotations) mixing
+# ---------------------------------------------------------------------------
+
+def protein_kappa_and_literal(s1, s2, eps, f_x, beta_t, dt, lift=0.0):
+    """composition.py:378-420 (CompositionDiffusion.kappa_AND) for one component: s1 = 'proteus' score, s2 = 'framediff'
+    score (true scores, no sigma factor), f_x = drift (r3_diffuser.drift_coef for translations, 0 for rotations), beta_t =
+    diffusion_coef(t)^2 / 2, ``lift`` = logp * normalised sigma_t / num_inference_steps (:417).  Sums run over the whole
+    tensor like the reference's ``.sum()`` (it samples one protein at a time).  Returns the scalar kappa."""
+    s1, s2 = s1.double(), s2.double()                                   # :379-380
+    noise = math.sqrt(2 * beta_t * dt) * eps                            # :405
+    dx_ind = -dt * (f_x - 2 * beta_t * s2) + noise                      # :406
+    d = s1 - s2                                                         # :408
+    kappa = -dt * beta_t * d * (s1 + s2)                                # :410
+    kappa = kappa + (dx_ind + dt * f_x) * d                             # :412
+    kappa_div = (dt * 2 * beta_t * d ** 2).sum()                        # :413
+    kappa = -(kappa / kappa_div).sum()                                  # :414-415
+    return kappa + lift / kappa_div                                     # :419
+
+
+def protein_stoch_dll_literal(score, dx, f_x, dlog_alphadt, beta_t, dt, component):
+    """composition.py:333-358 (compute_stoch_dll) for one model and component; ndim = score.shape[1] * score.shape[2]."""
+    ndim = score.shape[1] * score.shape[2]
+    if component == "trans":
+        out = ndim * dt * dlog_alphadt - dt * beta_t * score ** 2      # :346
+        out = out + (dx + dt * f_x) * score                            # :347
+    else:
+        out = -dt * beta_t * score ** 2                                # :352
+        out = out + dx * score                                         # :353
+    return out.sum()
+
+
+def protein_step_literal(x_trans, scores, eps, ll, a_trans, beta_trans, beta_rots, dt, operator, T=1.0, logp=0.0,
+                         lift_trans=0.0, lift_rots=0.0):
+    """One timestep of the 'composition' branch of CompositionDiffusion.latent_mixing (composition.py:483-531) up to the SE(3)
+    update: scores = dict(pt=proteus trans, ft=framediff trans, pr=proteus rots, fr=framediff rots), all [1, L, 3];
+    ll = (ll_proteus_trans, ll_framediff_trans, ll_proteus_rots, ll_framediff_rots) BEFORE the step; f_x = a_trans * x
+    (FrameDiff's VP drift -b_t x / 2).  Returns (dx_trans, dx_rots, kappa_trans, kappa_rots, ll_next[4])."""
+    f_x = a_trans * x_trans
+    if operator == "AND":                                                              # :440-442
+        kt = protein_kappa_and_literal(scores["pt"], scores["ft"], eps, f_x, beta_trans, dt, lift_trans)
+        kr = protein_kappa_and_literal(scores["pr"], scores["fr"], eps, 0.0, beta_rots, dt, lift_rots)
+    else:                                                                              # :422-434
+        kt = torch.softmax(torch.stack([torch.as_tensor(T * (ll[0] + logp)), torch.as_tensor(T * ll[1])]).double(), 0)[0]
+        kr = torch.softmax(torch.stack([torch.as_tensor(T * (ll[2] + logp)), torch.as_tensor(T * ll[3])]).double(), 0)[0]
+    dx_trans = -dt * (f_x - 2 * beta_trans * (scores["ft"] + kt * (scores["pt"] - scores["ft"])))   # :514-515
+    dx_trans = dx_trans + math.sqrt(2 * beta_trans * dt) * eps                                      # :516
+    dx_rots = dt * 2 * beta_rots * (scores["fr"] + kr * (scores["pr"] - scores["fr"]))              # :518
+    dx_rots = dx_rots + math.sqrt(2 * beta_rots * dt) * eps                                         # :519
+    ll_next = [ll[0] + protein_stoch_dll_literal(scores["pt"], dx_trans, f_x, a_trans, beta_trans, dt, "trans"),   # :526-529
+               ll[1] + protein_stoch_dll_literal(scores["ft"], dx_trans, f_x, a_trans, beta_trans, dt, "trans"),
+               ll[2] + protein_stoch_dll_literal(scores["pr"], dx_rots, 0.0, 0.0, beta_rots, dt, "rots"),
+               ll[3] + protein_stoch_dll_literal(scores["fr"], dx_rots, 0.0, 0.0, beta_rots, dt, "rots")]
+    return dx_trans, dx_rots, kt, kr, ll_next
+
+
 def and_kappa_general(G, N, dt, b, c):
     """General-M AND weights: equalise R_i.  NOT in the
     reference for M > 2 (it only has the M = 2 closed form); reduces to

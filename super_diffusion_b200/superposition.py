@@ -199,6 +199,56 @@ def _sd_and_ode(get_vel, latents0, num_inference_steps, guidance_scale, lift, pr
     return x, ll, kappa, traj
 
 
+def protein_superdiff_step(x_trans, scores, eps, ll, a_trans, beta_trans, beta_rots, dt, operator="AND", T=1.0, logp=0.0,
+                           lift_trans=0.0, lift_rots=0.0):
+    """Two-component (translations / rotations) SuperDiff mixing of two SE(3) diffusion models -- one timestep of the
+    'composition' branch of CompositionDiffusion.latent_mixing (applications/proteins/superdiff/composition.py:483-531 with
+    kappa_AND :378-420, kappa_OR :422-434 and compute_stoch_dll :333-358), up to the SE(3) update that consumes the result.
+
+    Each component is the fused VP-SDE step kernel with sigma = 1 (the protein code works with true scores, not sigma * score):
+      translations: drift f = a_trans * x (FrameDiff R3 diffuser: a = -b_t / 2), b = beta_trans, Ito constant ndim^2 * dt * a (:346)
+      rotations:    no drift (a = 0; the state does not enter, dx is applied on SO(3) by the caller), b = beta_rots (:352-353)
+    and the SAME noise ``eps`` in both (:483,516,519).  AND: kappa equalises the two models' density increments (the kernel's
+    M = 2 closed form, identical to :405-415); a non-zero ``lift`` (= logp * normalised sigma_t / num_inference_steps, :417)
+    is added as lift / (2 dt b |s_1 - s_2|^2) and the step re-run with that kappa.  OR: kappa = softmax([T (ll_1 + logp), T ll_2])[0].
+
+    x_trans, eps and the four score tensors (dict keys 'pt', 'ft', 'pr', 'fr' = proteus / framediff x trans / rots) are
+    [B, L, 3] float32 CUDA tensors; ll: [B, 4] float32 = (proteus trans, framediff trans, proteus rots, framediff rots), updated
+    in place.  Reductions are per sample (the reference samples one protein at a time, B = 1, and sums over the whole tensor).
+    Returns (dx_trans, dx_rots, kappa_trans [B], kappa_rots [B], ll)."""
+    _lib.require_device()
+    if operator not in ("AND", "OR"):
+        raise ValueError("operator must be 'AND' or 'OR' (composition.py:195)")
+    B = x_trans.shape[0]
+    D = x_trans[0].numel()
+    dev = x_trans.device
+    x = x_trans.contiguous()
+    zeros = torch.zeros_like(x)
+    out = []
+    for comp, (k1, k2), xin, a, b, lift, cols in (("trans", ("pt", "ft"), x, float(a_trans), float(beta_trans), float(lift_trans), (0, 1)),
+                                                   ("rots", ("pr", "fr"), zeros, 0.0, float(beta_rots), float(lift_rots), (2, 3))):
+        sc = [scores[k1].contiguous(), scores[k2].contiguous()]
+        llc = ll[:, cols[0]:cols[1] + 1].contiguous()
+        w = torch.empty(B, 2, device=dev, dtype=torch.float32)
+        if operator == "OR":
+            bias = torch.tensor([float(logp), 0.0], device=dev, dtype=torch.float32)
+            xo, llc, w = ops.step_vpsde(xin, eps, sc, llc, a, b, 1.0, dt, ops.MODE_OR, ops.DLOGQ_ITO, temperature=float(T),
+                                        logp_bias=bias, ito_scale=float(D * D), weights=w)
+        elif lift == 0.0:
+            xo, llc, w = ops.step_vpsde(xin, eps, sc, llc, a, b, 1.0, dt, ops.MODE_AND, ops.DLOGQ_ITO, ito_scale=float(D * D), weights=w)
+        else:
+            # kappa without the lift from a dry run on a copy of ll, then kappa += lift / (2 dt b |s_1 - s_2|^2) (:413,419)
+            _, _, w = ops.step_vpsde(xin, eps, sc, llc.clone(), a, b, 1.0, dt, ops.MODE_AND, ops.DLOGQ_ITO, ito_scale=float(D * D), weights=w)
+            d = (sc[0] - sc[1]).contiguous()
+            div = 2.0 * dt * b * ops.rowdot(d, d)
+            w[:, 0] += lift / div
+            w[:, 1] = 1.0 - w[:, 0]
+            xo, llc, w = ops.step_vpsde(xin, eps, sc, llc, a, b, 1.0, dt, ops.MODE_FIXED, ops.DLOGQ_ITO, ito_scale=float(D * D), weights=w)
+        ll[:, cols[0]:cols[1] + 1] = llc
+        out.append((xo - xin if comp == "trans" else xo, w[:, 0].clone()))
+    return out[0][0], out[1][0], out[0][1], out[1][1], ll
+
+
 class SuperDiffSampler:
     """CIFAR SuperDiff sampler with one CUDA graph per timestep.
 

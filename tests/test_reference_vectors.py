@@ -523,3 +523,58 @@ def test_cuda_matches_reference_sd_and_ode(cuda):
     assert _rel(x.cpu().numpy(), c["latents"]) <= 2e-3, _rel(x.cpu().numpy(), c["latents"])
     ref_ll = np.stack([c["ll_obj"][-1], c["ll_bg"][-1]], 1)
     assert np.abs(ll.cpu().numpy() - ref_ll).max() <= 2e-3 * np.abs(ref_ll).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# applications/proteins/superdiff/composition.py: two-component (translations / rotations) AND / OR mixing.
+# Fixture = the reference's own kappa_AND / kappa_OR / compute_kappas / compute_stoch_dll method bodies executed on a stub
+# object (tests/golden/make_protein_vectors.py).
+# ---------------------------------------------------------------------------------------------------------------------
+def _protein_cases():
+    z = np.load(os.path.join(HERE, "ref_protein.npz"))
+    for case, op in (("and", "AND"), ("or", "OR"), ("and_lift", "AND")):
+        yield case, op, (lambda k, case=case: z[f"{case}/{k}"])
+
+
+def test_oracle_matches_reference_protein_mixing():
+    for case, op, g in _protein_cases():
+        n, dt = int(g("n_steps")), float(g("dt"))
+        ll = [0.0, 0.0, 0.0, 0.0]
+        for i in range(n):
+            sc = {k: _t(g("s_" + k)[i], torch.float64) for k in ("pt", "ft", "pr", "fr")}
+            dxt, dxr, kt, kr, ll = O.protein_step_literal(
+                _t(g("x")[i], torch.float64), sc, _t(g("eps")[i], torch.float64), ll, float(g("a_trans")[i]), float(g("beta_trans")[i]),
+                float(g("beta_rots")[i]), dt, op, T=float(g("T")), logp=float(g("logp")), lift_trans=float(g("lift_trans")[i]),
+                lift_rots=float(g("lift_rots")[i]))
+            tol = 1e-10 if op == "AND" else 2e-7       # OR: the reference's kappa is a float32 softmax of float32 accumulators (:178-181,434)
+            assert _rel(dxt, g("dx_trans")[i]) < tol and _rel(dxr, g("dx_rots")[i]) < tol, (case, i)
+            assert abs(float(kt) - float(g("kappa_trans")[i].ravel()[0])) < 1e-7, (case, i)     # OR: softmax of float32 accumulators
+            assert abs(float(kr) - float(g("kappa_rots")[i].ravel()[0])) < 1e-7, (case, i)
+            ref_ll = g("ll")[i]
+            assert max(abs(float(a) - b) / (1 + abs(b)) for a, b in zip(ll, ref_ll)) < 1e-6, (case, i)   # reference accumulates ll in float32
+            ll = [float(v) for v in ref_ll]
+
+
+@pytest.mark.gpu
+def test_cuda_matches_reference_protein_mixing(cuda):
+    """superposition.protein_superdiff_step (two launches of the fused VP-SDE step kernel per timestep, sigma = 1) teacher-forced on
+    the reference's recorded states: dx and kappa within 1e-4, log-likelihood increments within 1e-5 of their magnitude."""
+    from super_diffusion_b200.superposition import protein_superdiff_step
+    for case, op, g in _protein_cases():
+        n, dt = int(g("n_steps")), float(g("dt"))
+        prev = np.zeros(4)
+        for i in range(n):
+            f = lambda a: _t(a.astype(np.float32)).to(cuda).contiguous()
+            sc = {k: f(g("s_" + k)[i]) for k in ("pt", "ft", "pr", "fr")}
+            ll = _t(prev.astype(np.float32)).to(cuda).reshape(1, 4).contiguous()
+            dxt, dxr, kt, kr, ll = protein_superdiff_step(
+                f(g("x")[i]), sc, f(g("eps")[i]), ll, float(g("a_trans")[i]), float(g("beta_trans")[i]), float(g("beta_rots")[i]), dt,
+                operator=op, T=float(g("T")), logp=float(g("logp")), lift_trans=float(g("lift_trans")[i]), lift_rots=float(g("lift_rots")[i]))
+            torch.cuda.synchronize()
+            assert _rel(dxt.cpu(), g("dx_trans")[i]) <= 1e-4 and _rel(dxr.cpu(), g("dx_rots")[i]) <= 1e-4, (case, i)
+            assert abs(float(kt) - float(g("kappa_trans")[i].ravel()[0])) <= 1e-4, (case, i)
+            assert abs(float(kr) - float(g("kappa_rots")[i].ravel()[0])) <= 1e-4, (case, i)
+            ref_ll = g("ll")[i]
+            inc, ref_inc = ll.cpu().numpy().ravel().astype(np.float64) - prev.astype(np.float32), ref_ll - prev
+            assert np.abs(inc - ref_inc).max() <= 1e-5 * (1 + np.abs(ref_inc).max()) + 1e-7 * np.abs(ref_ll).max(), (case, i)
+            prev = ref_ll
