@@ -2,8 +2,9 @@
 
 The reference keeps its models in orbax checkpoints of a ``State`` whose ``params_ema`` pytree uses Flax's
 auto-generated module names and layouts (cifar/run_lib.py:43-52, cifar/models/utils.py:30-39; names pinned against the
-reference's own init in tests/test_reference_vectors.py).  orbax / tensorstore are not available here, so the importer
-takes the two portable dumps a reference user can produce in three lines next to their checkpoint::
+reference's own init in tests/test_reference_vectors.py).  ``load_orbax`` reads the checkpoint directory itself -- through orbax
+when it is importable, or the per-leaf zarr layout directly -- and the importer also takes the two portable dumps a reference
+user can produce in three lines next to their checkpoint (the only route for OCDBT-packed checkpoints without orbax)::
 
     state = ckpt_mgr.restore(step, items=state)                                  # cifar/run_lib.py:50-52
     np.savez("modelA.npz", **flatten_dict(state.params_ema, sep="/"))            # (a) flat .npz, keys "Conv_0/kernel"
@@ -104,15 +105,121 @@ def load_msgpack(path):
         return from_msgpack_bytes(fh.read())
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# orbax checkpoint directories (cifar/run_lib.py:43-52: CheckpointManager(workdir/checkpoints, step_prefix='chkpt') over a
+# PyTreeCheckpointHandler; orbax-checkpoint==0.6.4, cifar/requirements.txt:78)
+# ---------------------------------------------------------------------------------------------------------------------
+def _latest_step_dir(path, step_prefix="chkpt"):
+    """``path`` may be the manager root (``.../checkpoints``, holds chkpt_<step> directories), one step directory, or the item
+    directory inside it (CheckpointManager stores a single unnamed item under ``default/``)."""
+    import os
+    import re
+    steps = []
+    for name in os.listdir(path):
+        m = re.fullmatch(rf"{re.escape(step_prefix)}_(\d+)", name)
+        if m and os.path.isdir(os.path.join(path, name)):
+            steps.append((int(m.group(1)), name))
+    if steps:                                              # ckpt_mgr.latest_step(), cifar/run_lib.py:50
+        path = os.path.join(path, max(steps)[1])
+    if os.path.isdir(os.path.join(path, "default")):
+        path = os.path.join(path, "default")
+    return path
+
+
+def _zarr_leaf(dirpath):
+    """One array stored by tensorstore's zarr (v2) driver: ``.zarray`` JSON + chunk files named by dot-joined chunk indices.
+    Compressors: none / gzip / zlib (stdlib) and zstd when the ``zstandard`` module is importable."""
+    import json
+    import os
+    import zlib
+    with open(os.path.join(dirpath, ".zarray")) as fh:
+        meta = json.load(fh)
+    shape, chunks = [int(v) for v in meta["shape"]], [int(v) for v in meta["chunks"]]
+    dtype = np.dtype(meta["dtype"])
+    if meta.get("order", "C") != "C":
+        raise ValueError(f"{dirpath}: only C-ordered zarr arrays are supported")
+    comp = (meta.get("compressor") or {}).get("id")
+
+    def decode(buf):
+        if comp in (None, "none"):
+            return buf
+        if comp in ("gzip", "zlib"):
+            return zlib.decompress(buf, 47)                 # auto-detect gzip / zlib headers
+        if comp == "zstd":
+            try:
+                import zstandard
+            except ImportError as exc:
+                raise RuntimeError(f"{dirpath}: zstd-compressed zarr chunks need the `zstandard` module (or orbax itself)") from exc
+            return zstandard.ZstdDecompressor().decompress(buf, max_output_size=int(np.prod(chunks)) * dtype.itemsize)
+        raise ValueError(f"{dirpath}: unsupported zarr compressor {comp!r}")
+    out = np.zeros(shape, dtype=dtype)
+    if not shape:
+        with open(os.path.join(dirpath, "0"), "rb") as fh:
+            return np.frombuffer(decode(fh.read()), dtype=dtype)[0]
+    grid = [-(-s // c) for s, c in zip(shape, chunks)]
+    sep = meta.get("dimension_separator", ".")
+    for idx in np.ndindex(*grid):
+        f = os.path.join(dirpath, sep.join(str(i) for i in idx))
+        if not os.path.exists(f):
+            continue                                        # missing chunk = fill value
+        with open(f, "rb") as fh:
+            block = np.frombuffer(decode(fh.read()), dtype=dtype).reshape(chunks)
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
+        out[sl] = block[tuple(slice(0, s.stop - s.start) for s in sl)]
+    return out
+
+
+def load_orbax(path, item="params_ema", step_prefix="chkpt"):
+    """Parameter tree ``item`` of the reference's orbax checkpoint (a ``State``, cifar/models/utils.py:30-39) -> nested dict of
+    torch tensors.  Three routes, in this order:
+      1. ``orbax.checkpoint`` itself when it is importable (a reference user's environment has it): PyTreeCheckpointer.restore;
+      2. the per-leaf zarr layout (one directory per leaf named by the dotted key path, orbax without OCDBT), read here
+         without tensorstore;
+      3. otherwise (OCDBT-packed checkpoints -- ``manifest.ocdbt`` -- and no orbax): an error naming the export recipe at the
+         top of this file.  No orbax / tensorstore exists in the build image, so route 1 is exercised against a stub module and
+         route 2 against directories written by the tests in the documented layout: parity unpinned against a real checkpoint."""
+    import os
+    d = _latest_step_dir(str(path), step_prefix)
+    try:
+        import orbax.checkpoint as ocp
+    except ImportError:
+        ocp = None
+    if ocp is not None:
+        tree = ocp.PyTreeCheckpointer().restore(d)
+        tree = tree[item] if isinstance(tree, dict) and item in tree else getattr(tree, item, tree)
+        return _tree_to_torch(tree)
+    if os.path.exists(os.path.join(d, "manifest.ocdbt")) or os.path.isdir(os.path.join(d, "ocdbt.process_0")):
+        raise RuntimeError(f"{d} is an OCDBT-packed orbax checkpoint; reading it needs orbax / tensorstore.  In the reference's "
+                           "environment export the tree once (recipe at the top of super_diffusion_b200/checkpoint.py).")
+    flat = {}
+    prefix = item + "."
+    for name in sorted(os.listdir(d)):
+        leaf = os.path.join(d, name)
+        if name.startswith(prefix) and os.path.isfile(os.path.join(leaf, ".zarray")):
+            flat[name[len(prefix):]] = _to_tensor(_zarr_leaf(leaf))
+    if not flat:
+        raise ValueError(f"{d}: no '{item}.*' zarr leaves found (not an orbax PyTree checkpoint directory?)")
+    return unflatten_params(flat, sep=".")
+
+
+def _tree_to_torch(tree):
+    if isinstance(tree, dict):
+        return {str(k): _tree_to_torch(v) for k, v in tree.items()}
+    return _to_tensor(np.asarray(tree))
+
+
 def load_params(path):
-    """Dispatch on the file extension: .npz (flat keys joined with '/') or .msgpack (Flax)."""
+    """Dispatch: .npz (flat keys joined with '/'), .msgpack / .flax (Flax serialization), or an orbax checkpoint directory
+    (the manager root ``<workdir>/checkpoints``, a ``chkpt_<step>`` directory or its ``default`` item; cifar/run_lib.py:43-52)."""
+    import os
     p = str(path)
+    if os.path.isdir(p):
+        return load_orbax(p)
     if p.endswith(".npz"):
         return load_npz(p)
     if p.endswith(".msgpack") or p.endswith(".flax"):
         return load_msgpack(p)
-    raise ValueError(f"unknown checkpoint format: {p} (expected .npz or .msgpack; orbax directories must be exported "
-                     "with the three-line recipe in super_diffusion_b200/checkpoint.py)")
+    raise ValueError(f"unknown checkpoint format: {p} (expected .npz, .msgpack or an orbax checkpoint directory)")
 
 
 def expected_shapes(config):

@@ -3,7 +3,7 @@ hi*hi + lo*hi + hi*lo on the tensor cores, fp32 accumulation, exact swish / soft
 
 north_star: "final samples and log-density trajectories within rel 1e-3 in fp32".  The gate here is rel 1e-3 on the
 score-net output against the reference's own ddpm.py output (tests/golden/ref_scorenet.npz) and the fp64 oracle; what the
-arm actually achieves (~1e-5) is asserted at 1e-4 so a regression of one order of magnitude fails."""
+arm actually achieves (2.3e-5 .. 2.7e-5) is asserted at 4e-5 (1.5x measured)."""
 import numpy as np
 import pytest
 import torch
@@ -17,7 +17,8 @@ from super_diffusion_b200.models import utils as mutils
 pytestmark = pytest.mark.gpu
 
 GATE = 1e-3        # the north_star's fp32 tolerance
-ACHIEVED = 1e-4    # regression bar for this arm (measured ~1e-5, see profiles/r02_notes.md)
+ACHIEVED = 4e-5    # regression bar for this arm: 1.5x the worst measured rel-L2 (2.3e-5 .. 2.7e-5; max error 2.5e-5 .. 3.6e-5 of the
+                   # output range; the fp32 CPU oracle itself sits at 3e-6 of fp64) -- profiles/r02_precision_report.json
 
 
 def _rel(a, b):
@@ -153,7 +154,7 @@ def test_forward_fp32_faithful_matches_fp64_oracle(cuda, conditioned, B, t):
     torch.cuda.synchronize()
     rel, mx = _rel(out, ref), _maxrel(out, ref)
     assert rel < GATE and mx < GATE, (rel, mx)
-    assert rel < ACHIEVED and mx < 3 * ACHIEVED, (rel, mx)
+    assert rel < ACHIEVED and mx < 1.5 * ACHIEVED, (rel, mx)
     # the bf16 arm on the same inputs, for the stated-separately deviation
     bf = model.bind(params, cuda)(torch.full((B,), t), x.to(cuda), y.to(cuda) if y is not None else None)
     assert 5e-4 < _rel(bf, ref) < 2e-2

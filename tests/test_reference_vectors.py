@@ -387,8 +387,8 @@ def test_cuda_matches_reference_cifar_loop(cuda):
 @pytest.mark.gpu
 def test_cuda_matches_reference_scorenet(cuda):
     """The reference ScoreNet's output (fp64, reference source over the shims) vs the tcgen05 forward.
-    bf16 operands / fp32 accumulation: stated separately from the fp32 gate (north_star) — rel-RMS <= 2e-2,
-    max error <= 8e-2 of the output range (the oracle-vs-CUDA tests in test_scorenet_gpu.py use the same gate)."""
+    bf16 operands / fp32 accumulation: stated separately from the fp32 gate (north_star) — rel-RMS <= 1.8e-2,
+    max error <= 2.4e-2 of the output range (1.5x measured) (the oracle-vs-CUDA tests in test_scorenet_gpu.py use the same gate)."""
     from super_diffusion_b200.models import utils as mutils
     for name, c in _load("ref_scorenet.npz").items():
         config, model, params = _our_params(c)
@@ -397,8 +397,8 @@ def test_cuda_matches_reference_scorenet(cuda):
         torch.cuda.synchronize()
         got, ref = out.double().cpu().numpy(), c["out"]
         rms = float(np.sqrt(((got - ref) ** 2).mean()) / np.sqrt((ref ** 2).mean()))
-        assert rms <= 2e-2, (name, rms)
-        assert np.abs(got - ref).max() <= 8e-2 * np.abs(ref).max(), (name, np.abs(got - ref).max())
+        assert rms <= 1.8e-2, (name, rms)          # measured 1.20e-2 / 1.06e-2 (profiles/r02_precision_report.json)
+        assert np.abs(got - ref).max() <= 2.4e-2 * np.abs(ref).max(), (name, np.abs(got - ref).max())   # measured 1.56e-2 / 1.50e-2
 
 
 @pytest.mark.gpu

@@ -3,8 +3,9 @@
 
 The GEMM operands and inter-kernel activations are bf16 (fp32 accumulate), so the
 tolerance is stated separately from the fp32 1e-3 gate of the sampler
-(north_star): relative L2 error of the score <= 2e-2, max abs error <= 6e-2 of
-the score's max magnitude.
+(north_star): relative L2 error of the score <= 1.9e-2, max abs error <= 2.4e-2 of
+the score's max magnitude (1.5x what the bf16 arm measures; the FP32-faithful arm is
+gated at 1e-3 in tests/test_fp32_faithful_gpu.py).
 """
 import pytest
 import torch
@@ -15,8 +16,10 @@ from super_diffusion_b200.models import utils as mutils
 
 pytestmark = pytest.mark.gpu
 
-REL_L2_BF16 = 2e-2
-MAX_REL_BF16 = 6e-2
+# measured on B200 (profiles/r02_precision_report.json): rel-L2 1.06e-2 .. 1.27e-2, max error 1.15e-2 .. 1.60e-2 of the output range;
+# the gates are 1.5x the worst measured value
+REL_L2_BF16 = 1.9e-2
+MAX_REL_BF16 = 2.4e-2
 
 
 def _setup(conditioned, zero_init_scale, seed):
@@ -124,3 +127,28 @@ def test_scorenet_jvp_pads_batches_that_do_not_fill_attention_tiles(cuda):
     es8, ej8 = rel(s8, s16[:8]), rel(j8, j16[:8])
     assert torch.isfinite(s12).all() and torch.isfinite(j12).all()
     assert es <= max(2 * es8, 2e-3) and ej <= max(2 * ej8, 4e-3), (es, ej, es8, ej8)
+
+
+def test_forward_at_the_benched_batch_512(cuda):
+    """Batch 512 is the batch bench.py runs and the only one where every tile mode of the implicit GEMM is live inside one
+    forward (cta_group::2 pairs need >= 148 tiles, dual / operand-swapped tiles >= 296).  Two checks:
+      * the first 64 samples against the fp32 CPU oracle (bf16 arm: same gates as the small-batch tests; FP32-faithful arm: 1e-3);
+      * every sample against the same network run on sub-batches of 8 (tile shapes differ, results agree to bf16 rounding)."""
+    cfg, model, params = _setup(False, 1.0, seed=9)
+    gen = torch.Generator().manual_seed(4)
+    x = torch.randn(512, 32, 32, 3, generator=gen)
+    t = 0.44
+    with torch.no_grad():
+        ref = OS.scorenet_apply(params, cfg, torch.full((64, 1, 1, 1), t), x[:64], None)
+    xd = x.to(cuda)
+    for precision, l2_gate, max_gate, sub_gate in (("bf16", REL_L2_BF16, MAX_REL_BF16, 1.5e-2), ("fp32", 1e-3, 1e-3, 1e-4)):
+        net = model.bind(params, cuda, precision=precision)
+        full = net(t, xd)
+        torch.cuda.synchronize()
+        got = full[:64].cpu()
+        rel = ((got - ref).norm() / ref.norm()).item()
+        mx = ((got - ref).abs().max() / ref.abs().max()).item()
+        assert rel <= l2_gate and mx <= max_gate, (precision, rel, mx)
+        sub = torch.cat([net(t, xd[i:i + 8].contiguous()) for i in range(0, 512, 8)])
+        rsub = ((full - sub).norm() / sub.norm()).item()
+        assert rsub <= sub_gate, (precision, rsub)

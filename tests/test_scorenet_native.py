@@ -90,7 +90,7 @@ def test_native_forward_against_the_oracle(cuda):
         ref = OS.scorenet_apply(params, cfg, torch.full((B, 1, 1, 1), t), x, None)
     got = net(t, x.to(cuda)).cpu()
     rel = ((got - ref).norm() / ref.norm()).item()
-    assert rel < 2e-2, rel          # bf16 operands / activations, fp32 accumulation (stated separately from the fp32 step bound)
+    assert rel < 1.9e-2, rel          # bf16 operands / activations, fp32 accumulation (stated separately from the fp32 step bound)
 
 
 @pytest.mark.gpu
