@@ -79,7 +79,13 @@ struct GemmParams {
   int num_stages, stage_bytes; // operand ring geometry: stage_bytes = A bytes + B bytes of one K-block (1 KB multiple)
   int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
                               //    each CTA feeds its own A tile and HALF of the weight tile, so an SM receives 32 KB instead of 48 KB per K-block
-  int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile, share the B tile via TMA multicast
+  int cluster;                // CTAs per thread-block cluster (1, 2, 4): consecutive m-units, same n-tile
+  int mcast;                  // CTAs that share one B tile through TMA multicast (== cluster), or 1: the cluster exists only so that
+                              //    the CTAs holding one image can exchange GroupNorm sums through distributed shared memory
+  const float* gn_gamma;      // fused GroupNorm + swish epilogue (swapped tiles only): out = swish(GN(acc + bias) * gamma + beta)
+  const float* gn_beta;       //    with the 32-group statistics of the whole image formed in the epilogue
+  float gn_eps;
+  int gn_swish;
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   int swap;                   // 1 (dual, conv mode, N = 128): operands swapped inside the MMA -- D^T[128 channels x 256 pixels] =
                               //    W[128 x K] * X^T: ONE M=128, N=256 instruction per K step instead of two N=128 ones (see launch_gemm)
@@ -106,6 +112,13 @@ struct GemmParams {
 };
 
 __device__ __forceinline__ float swishf(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+// one-MUFU form used by the GroupNorm kernels of the bf16 arm (scorenet_ops.cu::swish_f): v/2 * (1 + tanh(v/2))
+__device__ __forceinline__ float swish_tanh_f(float v) {
+  const float h = 0.5f * v;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 // Epilogue for 16 consecutive output columns of one row.  `eb`: 16 floats of (bias + row bias) in shared memory or
 // nullptr.  p.residual (generic API) is read straight from global memory; the score-net itself adds its residuals
@@ -244,7 +257,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   uint64_t* empty_bar = full_bar + MAX_STAGES;
   uint64_t* tmem_full = empty_bar + MAX_STAGES;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* gn_bar = tmem_empty + 2;          // [2]: cluster exchange of GroupNorm sums, one per tile parity
+  uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(gn_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_units = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
@@ -254,7 +268,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / csize, num_clusters = gridDim.x / csize;
   const int total_tiles = ((m_units + csize - 1) / csize) * p.n_tiles;       // tile groups
-  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
+  const int msize = p.mcast;                                                  // multicast group (1 = every CTA loads its own B tile)
+  const uint16_t cmask = (uint16_t)((1u << msize) - 1u);
   const int nsub = p.dual ? 2 : 1;
 
   if (warp == 0 && lane == 0) {
@@ -264,8 +279,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : csize); }
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], PAIR ? 1 : msize); }
       for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], PAIR ? 2 * EPI_WARPS : EPI_WARPS); }
+      for (int s = 0; s < 2; ++s) mbar_init(&gn_bar[s], (uint32_t)csize);      // one arrival per CTA of the cluster
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -311,10 +327,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       auto load_b = [&](uint8_t* dst, uint64_t* bar, int kcol, int n_tile, int bz) {
         if constexpr (PAIR) {
           tma_load_3d_pair(&p.b_map, dst, bar, kcol, n_tile * p.block_n + crank * (p.block_n / 2), bz);
-        } else if (csize == 1) {
+        } else if (msize == 1) {
           tma_load_3d(&p.b_map, dst, bar, kcol, n_tile * p.block_n, bz);
-        } else {      // this CTA fetches its 1/csize slice of the B tile for the whole cluster
-          const int rows_per = p.block_n / csize;
+        } else {      // this CTA fetches its 1/msize slice of the B tile for the whole cluster
+          const int rows_per = p.block_n / msize;
           tma_load_3d_mcast(&p.b_map, dst + (size_t)crank * rows_per * (BK * 2), bar, kcol, n_tile * p.block_n + crank * rows_per, bz, cmask);
         }
       };
@@ -450,7 +466,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             }
             // frees the smem slot once these MMAs retire (in every CTA whose TMA writes land here)
             if constexpr (PAIR) umma_commit_pair(&empty_bar[stage]);
-            else if (csize == 1) umma_commit(&empty_bar[stage]);
+            else if (msize == 1) umma_commit(&empty_bar[stage]);
             else umma_commit_mcast(&empty_bar[stage], cmask);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -467,6 +483,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     const int chalf = (warp - 2) >> 2;             // which alternate 32-column groups this warp handles
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t gn_it = 0;                            // tiles this CTA has normalised (parity selects the exchange buffer / barrier)
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
       const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -495,6 +512,103 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const bool pair_ok = (ch | 1) < p.N_out;
         const bool do_stats = p.stats_out != nullptr;
         const bool split = (p.flags & SD_GEMM_SPLIT3) != 0;     // out rows are [hi(N) | lo(N)]: the lo half is stored N_out channels further
+        if (p.gn_gamma != nullptr) {
+          // ---- fused GroupNorm(32 groups) + swish: the conv output feeds ONLY act(normalize(h)) (cifar/models/layers.py:552-558), so
+          // the raw tensor is never written.  Pass 1 reads the accumulator for the per-channel sums (thread = channel: no shuffles),
+          // the sums of the image's other tiles arrive from the cluster peers through distributed shared memory (32x32 images: four
+          // 256-pixel units = a cluster of 4; 16x16: the unit IS the image, in pair mode each CTA holds the whole image for its 128
+          // channels), pass 2 reads the accumulator again (TMEM reads are 64 B/clk: ~2k cycles per pass against >= 9k cycles of MMAs
+          // per tile), normalises and stores.  Saves one write + one read + one write of the activation per GroupNorm.
+          float* gsum = ebias + MAX_BN;            // [chalf][which][128]
+          float* ctot = gsum + 4 * BM;             // [which][128]: channel totals over the image
+          float* xsum = ctot + 2 * BM;             // [parity][which][128]: this CTA's channel sums, read by its cluster peers
+          const bool xchg = !PAIR && csize > 1;
+          float ssum = 0.f, ssq = 0.f;
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            const int c = chalf * 32 + it * 64;
+            uint32_t r[2][16];
+            tmem_ld16(taddr + c, r[0]);
+            tmem_ld16(taddr + c + 16, r[1]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float x = __uint_as_float(r[h][j]) + bv;
+                ssum += x;
+                ssq = fmaf(x, x, ssq);
+              }
+          }
+          gsum[(chalf * 2 + 0) * BM + row] = ssum;
+          gsum[(chalf * 2 + 1) * BM + row] = ssq;
+          epi_bar();
+          const int gbuf = (int)(gn_it & 1u);
+          const int gw = et / BM, gn_n = et - gw * BM;                   // threads 0..255: (which, channel)
+          if (xchg) {
+            xsum[(gbuf * 2 + gw) * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
+            epi_bar();                                                    // every channel sum of this CTA is written ...
+            if (et == 0)
+              for (int r = 0; r < csize; ++r) mbar_arrive_rank(&gn_bar[gbuf], (uint32_t)r);     // ... and released to the cluster
+            mbar_wait_cluster(&gn_bar[gbuf], (gn_it >> 1) & 1u);
+            float t = 0.f;
+            for (int r = 0; r < csize; ++r) t += ld_dsmem_f32(&xsum[(gbuf * 2 + gw) * BM + gn_n], (uint32_t)r);    // fixed order
+            ctot[gw * BM + gn_n] = t;
+          } else {
+            ctot[gw * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
+          }
+          ++gn_it;
+          epi_bar();
+          const int cpg = p.N_out >> 5;                                   // channels per group (32 groups); divides 128
+          const int g0 = (row / cpg) * cpg;
+          double gs = 0.0, gq = 0.0;
+          for (int cc = 0; cc < cpg; ++cc) { gs += (double)ctot[g0 + cc]; gq += (double)ctot[BM + g0 + cc]; }
+          const double gcnt = (double)p.HW * cpg;
+          const double gmean = gs / gcnt;
+          double gvar = gq / gcnt - gmean * gmean;                         // flax: E[x^2] - E[x]^2, clipped at 0
+          if (gvar < 0.0) gvar = 0.0;
+          const float rs = (float)(1.0 / sqrt(gvar + (double)p.gn_eps)) * (ch_ok ? p.gn_gamma[ch] : 0.f);
+          const float sh = (ch_ok ? p.gn_beta[ch] : 0.f) - (float)gmean * rs;
+          const float sh2 = fmaf(bv, rs, sh);                             // y = (acc + bv) * rs + sh
+#pragma unroll 1
+          for (int it = 0; it < 4; ++it) {
+            const int c = chalf * 32 + it * 64;
+            uint32_t r[2][16];
+            tmem_ld16(taddr + c, r[0]);
+            tmem_ld16(taddr + c + 16, r[1]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              float v[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float y = fmaf(__uint_as_float(r[h][j]), rs, sh2);
+                v[j] = !p.gn_swish ? y : (split ? swishf(y) : swish_tanh_f(y));
+              }
+              __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+              const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
+                const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
+                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = h2;
+                if (split && ok)
+                  *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld + p.N_out) =
+                      __floats2bfloat162_rn(e0 - __low2float(h2), e1 - __high2float(h2));
+              }
+            }
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
+          continue;
+        }
         float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
         float ssum = 0.f, ssq = 0.f;
         if (!(p.flags & 0x100u)) {      // 0x100: timing probe (tools/gemm_probe.py) -- release the accumulator without draining it
@@ -777,6 +891,30 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // the [channel][pixel] epilogue too (no shuffle butterfly for the GroupNorm sums, 64-byte store runs)
   static const int want_pair_swap = [] { const char* e = getenv("SDB_GEMM_PAIR_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
   if (want_pair_swap && swap_epi_ok && p.pair && p.block_n == MAX_BN && (N % MAX_BN) == 0) p.swap = 1;
+  p.mcast = p.pair ? 2 : p.cluster;          // B-tile slices per CTA (pair halves or multicast slices)
+  // Fused GroupNorm + swish epilogue (p.gn_gamma set by the caller): only in the [channel][pixel] epilogue of swapped tiles, and only
+  // when the CTAs that hold one image can exchange their channel sums -- the unit is the image (16x16: pair-swapped, or dual-swapped
+  // with N = 128), or the image's 2 / 4 units form a thread-block cluster (32x32 dual-swapped: 4 units) that exists for the
+  // distributed-shared-memory exchange only (no multicast: measured slower, see above).  Otherwise the launch runs unfused and
+  // emits stats_out for sd_groupnorm_swish as before; *p_fused tells the caller which happened.
+  {
+    static const int want_gn_fuse = [] { const char* e = getenv("SDB_GN_FUSE"); return e ? atoi(e) : 1; }();   // tuning knob
+    bool fuse = want_gn_fuse && p.gn_gamma != nullptr && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
+    if (fuse) {
+      if (p.pair) {
+        fuse = p.tiles_per_img == 2;
+      } else {
+        // images spanning several units (32x32: four) need a thread-block cluster for the exchange.  Measured on B200
+        // (profiles/r02_notes.md): clusters of 4 CTAs with 204 KB of shared memory each do not all fit at once (148 SMs in GPCs of
+        // 16-20 SMs: fewer than 37 clusters are co-resident, the persistent grid runs a second wave) -- 119 -> 275 us at K = 1152.
+        // Off unless SDB_GN_FUSE=2 asks for it.
+        const int units_per_img = p.tiles_per_img / 2;
+        fuse = (units_per_img == 1 || (want_gn_fuse >= 2 && (units_per_img == 2 || units_per_img == 4))) && (num_sms() % units_per_img) == 0;
+        if (fuse && units_per_img > 1) { p.cluster = units_per_img; p.mcast = 1; }
+      }
+    }
+    if (!fuse) p.gn_gamma = nullptr;
+  }
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
     const int nsub_h = p.dual ? 2 : 1;
@@ -788,7 +926,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     bool any_cand = false;
     for (int sgi = 0; sgi < p.nseg; ++sgi) any_cand = any_cand || p.seg_slab[sgi] >= 0;
     bool slab_on = false;
-    if (want_slab && any_cand && (p.dual || p.pair) && (p.cluster == 1 || p.pair) && p.imgs_per_tile == 1 &&
+    if (want_slab && any_cand && (p.dual || p.pair) && (p.mcast == 1 || p.pair) && p.imgs_per_tile == 1 &&
         (nsub_h == 1 || (p.tiles_per_img % 2) == 0)) {
       const int hb = nsub_h * p.h_box;
       const int slab_bytes = (hb + 2) * p.img_W * BK * 2;
@@ -828,7 +966,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     // rows beyond N inside the last box are zero-filled by TMA (OOB) and masked at the store
     cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)N, (cuuint64_t)nbatchB};
     cuuint64_t strides[2] = {(cuuint64_t)ldb * 2, (cuuint64_t)(nbatchB > 1 ? strideB : (long long)N * ldb) * 2};
-    cuuint32_t box[3] = {BK, (cuuint32_t)(p.block_n / p.cluster), 1};   // multicast slice or pair half
+    cuuint32_t box[3] = {BK, (cuuint32_t)(p.block_n / p.mcast), 1};   // multicast slice or pair half
     int rc = encode_map(&p.b_map, Wt, 3, dims, strides, box);
     if (rc != SD_OK) return rc;
   }
@@ -842,7 +980,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.out_ld = out_ld;
   p.flags = flags;
   p.imgs_in_tile = (!p.flat && p.HW < BM) ? BM / p.HW : 1;
-  p.stats_out = stats_out;
+  p.stats_out = p.gn_gamma ? nullptr : stats_out;        // a fused GroupNorm epilogue needs no channel sums downstream
   if (stats_out && ((p.flat ? (p.M_per_batch % BM) != 0 : (p.HW % BM) != 0) || (N % 16) != 0 || (flags & SD_EPI_SOFTMAX)))
     return fail(kErrInvalidArg, std::string(who) + ": stats_out needs whole 128-row tiles per image / batch entry and N a multiple of 16");
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
@@ -889,11 +1027,14 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
 
 }  // namespace sdb
 
+struct GnFuse { const float* gamma; const float* beta; float eps; int swish; int* fused; };
+
 static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
                           const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
                           unsigned flags, void* out, int out_ld, float* stats_out, void* stream, int up_phase,
-                          int stats_tpi_total, int stats_slot0, const char* who, int stride2 = 0) {
+                          int stats_tpi_total, int stats_slot0, const char* who, int stride2 = 0, const GnFuse* gn = nullptr) {
   using namespace sdb;
+  if (gn && gn->fused) *gn->fused = 0;
   if (!srcs || num_srcs < 1 || num_srcs > 3) return fail(kErrInvalidArg, std::string(who) + ": 1..3 sources required");
   if (!Wt || !out || B < 0 || H < 1 || W < 1 || N < 1) return fail(kErrInvalidArg, std::string(who) + ": bad argument");
   if (B == 0) return SD_OK;
@@ -961,12 +1102,15 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.nseg = nseg;
   p.num_kb = (int)(K / BK);
   p.slab_B = B;
+  if (gn && gn->gamma && gn->beta) { p.gn_gamma = gn->gamma; p.gn_beta = gn->beta; p.gn_eps = gn->eps; p.gn_swish = gn->swish; }
   p.M_total = B * H * W;
   p.HW = H * W;
   p.m_tiles = (p.M_total + BM - 1) / BM;
   p.m_tiles_per_batch = 1;
-  return launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
-                     (cudaStream_t)stream, who, stats_out);
+  const int rc = launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
+                             (cudaStream_t)stream, who, stats_out);
+  if (rc == SD_OK && gn && gn->fused) *gn->fused = p.gn_gamma != nullptr ? 1 : 0;
+  return rc;
 }
 
 extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
@@ -974,6 +1118,16 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
                             unsigned flags, void* out, int out_ld, float* stats_out, void* stream) {
   return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
                         stats_out, stream, -1, 0, 0, "sd_conv_gemm");
+}
+
+extern "C" int sd_conv_gemm_gn(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
+                               const float* bias, const float* rowbias, int rowbias_ld, unsigned flags, void* out, int out_ld,
+                               float* stats_out, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_swish,
+                               int* fused_host, void* stream) {
+  if (!gn_gamma || !gn_beta || !fused_host) return sdb::fail(sdb::kErrInvalidArg, "sd_conv_gemm_gn: null GroupNorm parameters / fused flag");
+  GnFuse gn{gn_gamma, gn_beta, gn_eps, gn_swish, fused_host};
+  return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, nullptr, flags, out, out_ld, stats_out, stream, -1,
+                        0, 0, "sd_conv_gemm_gn", 0, &gn);
 }
 
 extern "C" int sd_conv_gemm_s2(const void* x, int B, int H_in, int W_in, int C, const void* Wt, int N, const float* bias,

@@ -256,15 +256,32 @@ struct Runner {
     return o;
   }
 
-  // ResnetBlockDDPM (layers.py:540-565): GN+swish -> conv3x3 + temb bias -> GN+swish -> conv3x3 + shortcut, 4 launches
+  // ResnetBlockDDPM (layers.py:540-565): GN+swish -> conv3x3 + temb bias -> GN+swish -> conv3x3 + shortcut.  The second GroupNorm
+  // runs inside conv1's epilogue where the tile shape allows it (sd_conv_gemm_gn): 3 launches instead of 4.
   Act res_block(const Act& x0, const Act* x1, int i, const float* rowbias) {
     const ResW& r = net.res[i];
     Act a1 = gn(x0, x1, r.g1, r.be1, true);
     sd_gemm_src s1[1] = {{a1.p, a1.C, 9}};
-    Act h1 = conv(s1, 1, x0.H, x0.W, r.w1, r.cout, nullptr, rowbias ? rowbias + r.off : nullptr, net.dense_n, true);
+    Act h1 = new_act(x0.H, x0.W, r.cout);
+    want_stats(h1, x0.H * x0.W / 128);
+    int fused = 0;
+    if (live())
+      check(sd_conv_gemm_gn(s1, 1, B, x0.H, x0.W, r.w1, r.cout, nullptr, rowbias ? rowbias + r.off : nullptr, net.dense_n, fl(), h1.p,
+                            r.cout * sm(), h1.stats, r.g2, r.be2, 1e-6f, 1, &fused, st));
     release(a1);
-    Act a2 = gn(h1, nullptr, r.g2, r.be2, true);
-    release(h1);
+    Act a2;
+    if (fused) {
+      // h1 already holds act(normalize(conv1)).  The buffer the separate GroupNorm pass would have written is still taken and given
+      // back, so the arena sees the same allocation sequence as the workspace dry run (which cannot know the tile shape).
+      Act dummy = new_act(h1.H, h1.W, h1.C);
+      release(dummy);
+      a2 = h1;
+      release(a2.stats);
+      a2.stats = nullptr;
+    } else {
+      a2 = gn(h1, nullptr, r.g2, r.be2, true);
+      release(h1);
+    }
     sd_gemm_src s2[3] = {{a2.p, a2.C, 9}, {x0.p, x0.C, 1}, {x1 ? x1->p : nullptr, x1 ? x1->C : 0, 1}};
     Act o = conv(s2, x1 ? 3 : 2, x0.H, x0.W, r.w2, r.cout, r.b2, nullptr, 0, true);
     release(a2);

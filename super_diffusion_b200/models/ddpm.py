@@ -193,8 +193,11 @@ class _Bound:
         x1 = srcs[1] if len(srcs) > 1 else None
         sp = self.split
         a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1, split=sp)
-        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True, split=sp)
-        a2 = ops.groupnorm_swish(h1, r["g2"], r["be2"], split=sp)
+        # conv1 + temb bias, then act(normalize(.)) (layers.py:553-557): the GroupNorm runs inside the GEMM epilogue where the tile
+        # shape lets one CTA / cluster see the whole image (sd_conv_gemm_gn), as its own pass otherwise
+        h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True, split=sp,
+                           gn=(r["g2"], r["be2"]))
+        a2 = h1 if h1.gn_fused else ops.groupnorm_swish(h1, r["g2"], r["be2"], split=sp)
         # NIN shortcut (C_in != C_out) or identity residual: both are extra 1-tap K segments of the same GEMM
         return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True, split=sp)
 

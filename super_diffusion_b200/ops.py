@@ -214,12 +214,15 @@ def _bf16c(t, name):
 
 
 def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False, out_f32=False, out=None,
-              n_out=None, want_stats=False, split=False):
+              n_out=None, want_stats=False, split=False, gn=None):
     """Implicit GEMM over NHWC bf16 sources (sd_conv_gemm).  srcs: list of
     (tensor [B,H,W,C], taps) with taps in {1, 9}; weight: bf16 [N, K].  want_stats: also emit per-128-pixel-tile
     channel sums of the output (attached as ``out.gn_stats = (tensor [B, HW/128, 2, N], HW/128)``) so a following
     groupnorm_swish skips its statistics pass; silently ignored where the layout does not allow it.
-    split: 3 x bf16 split precision (SD_GEMM_SPLIT3) -- sources / residual / out are hi|lo pairs [B,H,W,2C], weight [N, 2K]."""
+    split: 3 x bf16 split precision (SD_GEMM_SPLIT3) -- sources / residual / out are hi|lo pairs [B,H,W,2C], weight [N, 2K].
+    gn: (gamma, beta) of a GroupNorm + swish that is the ONLY consumer of this output (sd_conv_gemm_gn): where the tile shape
+    allows it the normalised, activated tensor is written directly and ``out.gn_fused`` is True; otherwise the raw output (with
+    ``gn_stats``) comes back with ``out.gn_fused`` False and the caller applies groupnorm_swish."""
     lib = _lib.load()
     x0 = srcs[0][0]
     B, H, W = x0.shape[0], x0.shape[1], x0.shape[2]
@@ -248,12 +251,22 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     stats = None
     if want_stats and (H * W) % 128 == 0 and N % 16 == 0 and not out_f32 and B > 0:
         stats = torch.empty(B, (H * W) // 128, 2, N, device=x0.device, dtype=torch.float32)
-    rc = lib.sd_conv_gemm(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld,
-                          _ptr(residual), flags, _ptr(out), out.shape[-1], _ptr(stats), _stream())
-    _lib.check(rc, "sd_conv_gemm")
+    if gn is not None:
+        if residual is not None or out_f32 or swish:
+            raise ValueError("gn fusion: no residual / fp32 output / extra swish")
+        fused = ctypes.c_int(0)
+        rc = lib.sd_conv_gemm_gn(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld, flags, _ptr(out),
+                                 out.shape[-1], _ptr(stats), _ptr(_f32c(gn[0], "gamma")), _ptr(_f32c(gn[1], "beta")), 1e-6, 1,
+                                 ctypes.byref(fused), _stream())
+        _lib.check(rc, "sd_conv_gemm_gn")
+        out.gn_fused = bool(fused.value)
+    else:
+        rc = lib.sd_conv_gemm(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld,
+                              _ptr(residual), flags, _ptr(out), out.shape[-1], _ptr(stats), _stream())
+        _lib.check(rc, "sd_conv_gemm")
     if B > 0:
         _count()
-    if stats is not None:
+    if stats is not None and not getattr(out, "gn_fused", False):
         out.gn_stats = (stats, (H * W) // 128)
     return out
 

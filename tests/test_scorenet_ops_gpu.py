@@ -2,6 +2,7 @@
 same bf16-rounded inputs (fp32/fp64 reference; tolerance = bf16 output rounding,
 2^-8 relative, plus fp32 accumulation-order noise)."""
 import math
+import os
 
 import pytest
 import torch
@@ -473,3 +474,48 @@ def test_conv_gemm_pair_two_images_per_tile(cuda):
     ref = F.conv2d(a2.float().permute(0, 3, 1, 2), wf[:, :9 * C].reshape(256, 3, 3, C).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) \
         + torch.einsum("bhwc,nc->bhwn", xa.float(), wf[:, 9 * C:]) + bias + rowbias[:, None, None, :]
     _close(out, ref.cpu())
+
+
+@pytest.mark.parametrize("split", [False, True])
+@pytest.mark.parametrize("B,H,C,N,expect_fused", [
+    (300, 16, 256, 256, True),     # pair-swapped tiles: the pair unit is the image, each CTA holds it for 128 channels
+    (296, 32, 128, 128, None),     # dual-swapped tiles: four 256-pixel units per image = a cluster of 4 exchanging sums through DSMEM
+    (297, 32, 128, 128, None),     # ... with a ragged last cluster round   (None: fused only under SDB_GN_FUSE=2, see launch_gemm)
+    (600, 16, 128, 128, True),     # dual-swapped, unit == image (no exchange)
+    (512, 32, 256, 128, None),     # K = 2304 (the widest 32x32 conv1 of the up path takes 384 channels; 256 here)
+    (8, 32, 128, 128, False),      # too few tiles for the swapped shapes: unfused fallback, raw output + stats
+    (64, 8, 256, 256, False),      # low resolution: several images per tile
+])
+def test_conv_gemm_with_fused_groupnorm(cuda, B, H, C, N, expect_fused, split):
+    """sd_conv_gemm_gn: conv3x3 + per-sample (time-embedding) bias -> GroupNorm(32) -> swish in one launch, against the fp64
+    composition and against the unfused two-launch path on the same inputs."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(B + H + C + N)
+    x = torch.randn(B, H, H, C, generator=g)
+    w = torch.randn(N, 9, C, generator=g) / (9 * C) ** 0.5
+    rowbias = torch.randn(B, N, generator=g)
+    gamma, beta = 1 + 0.3 * torch.randn(N, generator=g), 0.2 * torch.randn(N, generator=g)
+    prep = ops.split_pair if split else (lambda t: t.to(torch.bfloat16))
+    xs, ws = prep(x).to(cuda), prep(w.view(N, -1)).to(cuda)
+    out = ops.conv_gemm([(xs, 9)], ws, rowbias=rowbias.to(cuda), want_stats=True, split=split, gn=(gamma.to(cuda), beta.to(cuda)))
+    torch.cuda.synchronize()
+    if expect_fused is None:
+        expect_fused = os.environ.get("SDB_GN_FUSE") == "2"
+    assert out.gn_fused == expect_fused
+    a2 = out if out.gn_fused else ops.groupnorm_swish(out, gamma.to(cuda), beta.to(cuda), split=split)
+    raw = ops.conv_gemm([(xs, 9)], ws, rowbias=rowbias.to(cuda), want_stats=True, split=split)
+    unfused = ops.groupnorm_swish(raw, gamma.to(cuda), beta.to(cuda), split=split)
+    merge = ops.merge_pair if split else (lambda t: t.float())
+    # fp64 composition on the operands the kernel saw (bf16-rounded in the bf16 arm)
+    xe, we = merge(xs).double().cpu(), merge(ws).double().cpu().view(N, 3, 3, C)
+    h = F.conv2d(xe.permute(0, 3, 1, 2), we.permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1) + rowbias.double()[:, None, None, :]
+    hg = h.reshape(B, H * H, 32, N // 32)
+    mean, var = hg.mean((1, 3), keepdim=True), hg.var((1, 3), unbiased=False, keepdim=True)
+    y = ((hg - mean) / (var + 1e-6).sqrt()).reshape(B, H, H, N) * gamma.double() + beta.double()
+    ref = y * torch.sigmoid(y)
+    tol = 3e-5 if split else 1.2e-2        # bf16 arm: output rounding (2^-9) + the unfused path's bf16 round trip of the raw tensor
+    err = ((merge(a2).double().cpu() - ref).abs().max() / ref.abs().max()).item()
+    err_unfused = ((merge(unfused).double().cpu() - ref).abs().max() / ref.abs().max()).item()
+    assert err <= tol, (err, err_unfused)
+    if out.gn_fused and not split:
+        assert err <= err_unfused * 1.05 + 1e-3      # normalising the fp32 accumulator is at least as accurate as the bf16 round trip

@@ -65,7 +65,8 @@ def describe(name, a, k, r):
         N = w.shape[0] if k.get("n_out") is None else k["n_out"]
         Mrows = t0.shape[0] * t0.shape[1] * t0.shape[2]
         segs = "+".join(f"{tp}x{s.shape[3]}" for s, tp in srcs)
-        return (f"conv_gemm H{t0.shape[1]} [{segs}] N{N}" + (" stats" if k.get("want_stats") else ""), 2.0 * Mrows * N * K,
+        tag = (" +GN fused" if getattr(r, "gn_fused", False) else " (GN unfused)") if k.get("gn") is not None else ""
+        return (f"conv_gemm H{t0.shape[1]} [{segs}] N{N}" + (" stats" if k.get("want_stats") else "") + tag, 2.0 * Mrows * N * K,
                 sum(nbytes(s) for s, _ in srcs) + nbytes(w) + nbytes(r))
     if name == "conv_gemm_s2":
         xx, w = a[0], a[1]
