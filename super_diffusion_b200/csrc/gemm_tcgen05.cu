@@ -34,6 +34,7 @@
 #include "common.cuh"
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"
+#include <cstdio>
 #include <cstdlib>
 
 #ifndef SDB_RING_KB
@@ -514,17 +515,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         const bool split = (p.flags & SD_GEMM_SPLIT3) != 0;     // out rows are [hi(N) | lo(N)]: the lo half is stored N_out channels further
         if (p.gn_gamma != nullptr) {
           // ---- fused GroupNorm(32 groups) + swish: the conv output feeds ONLY act(normalize(h)) (cifar/models/layers.py:552-558), so
-          // the raw tensor is never written.  Pass 1 reads the accumulator for the per-channel sums (thread = channel: no shuffles),
-          // the sums of the image's other tiles arrive from the cluster peers through distributed shared memory (32x32 images: four
-          // 256-pixel units = a cluster of 4; 16x16: the unit IS the image, in pair mode each CTA holds the whole image for its 128
-          // channels), pass 2 reads the accumulator again (TMEM reads are 64 B/clk: ~2k cycles per pass against >= 9k cycles of MMAs
-          // per tile), normalises and stores.  Saves one write + one read + one write of the activation per GroupNorm.
+          // the raw tensor is never written.  ONE pass over the accumulator: + bias, per-channel sums (thread = channel: no
+          // shuffles), and the 128 values of this thread are parked as 64 packed bf16 pairs in registers -- the same rounding the
+          // separate GroupNorm pass sees when it re-reads the raw bf16 tensor -- so the accumulator is released to the MMA warp
+          // BEFORE the statistics are complete.  (A first version re-read TMEM for the second pass: tcgen05.ld competes with the
+          // running MMAs for TMEM bandwidth and the launches became epilogue-bound, 185 -> 206 us at 16x16 / K = 4608.)
+          // The sums of an image's other tiles (32x32: four units) would come from the cluster peers through distributed shared
+          // memory (SDB_GN_FUSE=2, see launch_gemm); at 16x16 the unit IS the image.
           float* gsum = ebias + MAX_BN;            // [chalf][which][128]
           float* ctot = gsum + 4 * BM;             // [which][128]: channel totals over the image
           float* xsum = ctot + 2 * BM;             // [parity][which][128]: this CTA's channel sums, read by its cluster peers
           const bool xchg = !PAIR && csize > 1;
+          uint32_t pk[64];
           float ssum = 0.f, ssq = 0.f;
-#pragma unroll 1
+#pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = chalf * 32 + it * 64;
             uint32_t r[2][16];
@@ -534,12 +538,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float x = __uint_as_float(r[h][j]) + bv;
-                ssum += x;
-                ssq = fmaf(x, x, ssq);
+              for (int jj = 0; jj < 8; ++jj) {
+                const float x0 = __uint_as_float(r[h][2 * jj]) + bv, x1 = __uint_as_float(r[h][2 * jj + 1]) + bv;
+                ssum += x0 + x1;
+                ssq = fmaf(x0, x0, fmaf(x1, x1, ssq));
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+                pk[it * 16 + h * 8 + jj] = *reinterpret_cast<const uint32_t*>(&h2);
               }
           }
+          tcgen05_fence_before();                  // accumulator drained: hand it back to the MMA warp now
+          __syncwarp();
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+          }
+          acc ^= 1;
+          if (acc == 0) acc_phase ^= 1;
           gsum[(chalf * 2 + 0) * BM + row] = ssum;
           gsum[(chalf * 2 + 1) * BM + row] = ssq;
           epi_bar();
@@ -558,32 +572,38 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             ctot[gw * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
           }
           ++gn_it;
+          const float gam = ch_ok ? p.gn_gamma[ch] : 0.f, bet = ch_ok ? p.gn_beta[ch] : 0.f;    // issued ahead of the barrier
           epi_bar();
+          // group statistics: ONE thread per group in fp64 like the stand-alone GroupNorm kernel.  (Every thread doing its own
+          // fp64 division / rsqrt made the launch epilogue-bound: ncu showed half of all stall samples as stall_math in the fp64
+          // subroutines -- 185 -> 206 us at 16x16 / K = 4608, 119 -> 275 us at 32x32 / K = 1152.)
           const int cpg = p.N_out >> 5;                                   // channels per group (32 groups); divides 128
-          const int g0 = (row / cpg) * cpg;
-          double gs = 0.0, gq = 0.0;
-          for (int cc = 0; cc < cpg; ++cc) { gs += (double)ctot[g0 + cc]; gq += (double)ctot[BM + g0 + cc]; }
-          const double gcnt = (double)p.HW * cpg;
-          const double gmean = gs / gcnt;
-          double gvar = gq / gcnt - gmean * gmean;                         // flax: E[x^2] - E[x]^2, clipped at 0
-          if (gvar < 0.0) gvar = 0.0;
-          const float rs = (float)(1.0 / sqrt(gvar + (double)p.gn_eps)) * (ch_ok ? p.gn_gamma[ch] : 0.f);
-          const float sh = (ch_ok ? p.gn_beta[ch] : 0.f) - (float)gmean * rs;
-          const float sh2 = fmaf(bv, rs, sh);                             // y = (acc + bv) * rs + sh
-#pragma unroll 1
+          float* gstat = xsum + 4 * BM;                                   // [group][mean, rstd]
+          if (et < BM / cpg) {
+            double gs = 0.0, gq = 0.0;
+            for (int cc = 0; cc < cpg; ++cc) { gs += (double)ctot[et * cpg + cc]; gq += (double)ctot[BM + et * cpg + cc]; }
+            const double gcnt = (double)p.HW * cpg;
+            const double gmean = gs / gcnt;
+            double gvar = gq / gcnt - gmean * gmean;                       // flax: E[x^2] - E[x]^2, clipped at 0
+            if (gvar < 0.0) gvar = 0.0;
+            gstat[2 * et] = (float)gmean;
+            gstat[2 * et + 1] = (float)(1.0 / sqrt(gvar + (double)p.gn_eps));
+          }
+          epi_bar();
+          const float rs = gstat[2 * (row / cpg) + 1] * gam;
+          const float sh = bet - gstat[2 * (row / cpg)] * rs;
+#pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = chalf * 32 + it * 64;
-            uint32_t r[2][16];
-            tmem_ld16(taddr + c, r[0]);
-            tmem_ld16(taddr + c + 16, r[1]);
-            tmem_wait_ld();
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float y = fmaf(__uint_as_float(r[h][j]), rs, sh2);
-                v[j] = !p.gn_swish ? y : (split ? swishf(y) : swish_tanh_f(y));
+              for (int jj = 0; jj < 8; ++jj) {
+                const uint32_t w = pk[it * 16 + h * 8 + jj];
+                const float y0 = fmaf(__uint_as_float(w << 16), rs, sh), y1 = fmaf(__uint_as_float(w & 0xFFFF0000u), rs, sh);
+                v[2 * jj] = p.gn_swish ? swish_tanh_f(y0) : y0;
+                v[2 * jj + 1] = p.gn_swish ? swish_tanh_f(y1) : y1;
               }
               __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
               const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;
@@ -591,22 +611,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               for (int j = 0; j < 16; j += 2) {
                 const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
                 const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = h2;
-                if (split && ok)
-                  *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld + p.N_out) =
-                      __floats2bfloat162_rn(e0 - __low2float(h2), e1 - __high2float(h2));
+                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = __floats2bfloat162_rn(e0, e1);
               }
             }
           }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) {
-            if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);
-            else mbar_arrive(&tmem_empty[acc]);
-          }
-          acc ^= 1;
-          if (acc == 0) acc_phase ^= 1;
           continue;
         }
         float* wstat = ebias + MAX_BN;                          // [chalf][sub][which][128]
@@ -898,16 +906,17 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // distributed-shared-memory exchange only (no multicast: measured slower, see above).  Otherwise the launch runs unfused and
   // emits stats_out for sd_groupnorm_swish as before; *p_fused tells the caller which happened.
   {
-    static const int want_gn_fuse = [] { const char* e = getenv("SDB_GN_FUSE"); return e ? atoi(e) : 1; }();   // tuning knob
-    bool fuse = want_gn_fuse && p.gn_gamma != nullptr && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
+    static const int want_gn_fuse = [] { const char* e = getenv("SDB_GN_FUSE"); return e ? atoi(e) : 2; }();   // tuning knob: 0 off, 1 unit == image only, 2 + clusters
+    bool fuse = want_gn_fuse && p.gn_gamma != nullptr && !(flags & SD_GEMM_SPLIT3) && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
     if (fuse) {
       if (p.pair) {
         fuse = p.tiles_per_img == 2;
       } else {
-        // images spanning several units (32x32: four) need a thread-block cluster for the exchange.  Measured on B200
-        // (profiles/r02_notes.md): clusters of 4 CTAs with 204 KB of shared memory each do not all fit at once (148 SMs in GPCs of
-        // 16-20 SMs: fewer than 37 clusters are co-resident, the persistent grid runs a second wave) -- 119 -> 275 us at K = 1152.
-        // Off unless SDB_GN_FUSE=2 asks for it.
+        // images spanning several units (32x32: four) need a thread-block cluster for the exchange.  Clusters of 4 CTAs with 204 KB
+        // of shared memory each only fit where a GPC has 4 free SMs: 33 clusters (132 of 148 SMs) are co-resident on B200, and the
+        // persistent grid is sized to that (see the launch below; with 37 clusters the last four ran as a second wave, 119 -> 275 us).
+        // Kernel time is then break-even with conv + separate GroupNorm (178 vs 119 + 48 us at K = 1152, 344 vs 311 + 48 at K = 3456),
+        // but 268 MB of DRAM traffic per GroupNorm disappear, and the power-capped timestep gets 2 % faster (profiles/r02_notes.md).
         const int units_per_img = p.tiles_per_img / 2;
         fuse = (units_per_img == 1 || (want_gn_fuse >= 2 && (units_per_img == 2 || units_per_img == 4))) && (num_sms() % units_per_img) == 0;
         if (fuse && units_per_img > 1) { p.cluster = units_per_img; p.mcast = 1; }
@@ -1021,6 +1030,21 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     ++nattr;
   }
   if (nattr) { cfg.attrs = attr; cfg.numAttrs = nattr; }
+  if (p.cluster > 2 && !p.pair) {
+    // a persistent grid must be co-resident: clusters of 4 CTAs (204 KB of shared memory each = one CTA per SM) only fit where a GPC
+    // has 4 free SMs, so fewer than num_sms / 4 clusters may be active at once; ask the runtime and shrink the grid to that
+    static int max_active4 = -1;
+    if (max_active4 < 0) {
+      int n = 0;
+      cudaLaunchConfig_t q = cfg;
+      q.gridDim = dim3((unsigned)(num_sms() / p.cluster * p.cluster));
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_tcgen05_kernel<false>, &q) != cudaSuccess || n < 1) { n = num_sms() / p.cluster; cudaGetLastError(); }
+      max_active4 = n;
+      if (getenv("SDB_GEMM_VERBOSE")) fprintf(stderr, "[gemm] max active clusters of %d: %d (of %d)\n", p.cluster, n, num_sms() / p.cluster);
+    }
+    const int want = (int)cfg.gridDim.x / p.cluster;
+    if (want > max_active4) cfg.gridDim = dim3((unsigned)(max_active4 * p.cluster));
+  }
   if (p.pair) return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<true>, p), who);
   return check_cuda(cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<false>, p), who);
 }
