@@ -105,6 +105,8 @@ struct GemmParams {
   int stride2;                // 1: 3x3 stride-2 SAME conv (pad (0,1)): taps read input pixel (2*ho + kh, 2*wo + kw) through a TMA map
                               //    with element strides (1,2,2,1); the tile geometry (h_box, ...) is that of the OUTPUT image
   int up_phase;               // -1, or a*2+b: this launch computes output pixels (2i+a, 2j+b) of a fused nearest-x2 upsample + 3x3 conv
+  int up_all;                 // 1: ALL four phases in this launch -- the phase is the slowest digit of the tile index and selects the
+                              //    weight matrix (batch coordinate of the B map); up_phase is then only a ">= 0" marker
   int img_H, img_W;           // source image size (conv mode)
   int stats_tpi_total, stats_slot0;   // stats_out slot = img * stats_tpi_total + stats_slot0 + tile-in-image
   int imgs_in_tile;           // images covered by one 128-row tile (row-bias table rows), 1 when HW >= 128 or flat
@@ -228,7 +230,7 @@ __device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
 }
 
 // output row r (0..127) of m-tile `m_tile` -> validity and element offset of the row start in out / residual
-__device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int r, size_t& off) {
+__device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int r, size_t& off, int up_phase) {
   if (p.flat) {
     const int batch = m_tile / p.m_tiles_per_batch;
     const int rl = (m_tile - batch * p.m_tiles_per_batch) * BM + r;
@@ -239,7 +241,7 @@ __device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int 
   if (p.up_phase >= 0) {      // low-res pixel (img, i, j) -> output pixel (2i+a, 2j+b) of the 2H x 2W image
     const int img = m / p.HW, rem = m - img * p.HW;
     const int i = rem / p.img_W, j = rem - i * p.img_W;
-    off = ((size_t)(img * 2 * p.img_H + 2 * i + (p.up_phase >> 1)) * (2 * p.img_W) + 2 * j + (p.up_phase & 1)) * (size_t)p.out_ld;
+    off = ((size_t)(img * 2 * p.img_H + 2 * i + (up_phase >> 1)) * (2 * p.img_W) + 2 * j + (up_phase & 1)) * (size_t)p.out_ld;
   } else {
     off = (size_t)m * p.out_ld;
   }
@@ -268,7 +270,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
   const int csize = p.cluster;
   const int crank = csize > 1 ? (int)cluster_ctarank() : 0;
   const int cluster_id = blockIdx.x / csize, num_clusters = gridDim.x / csize;
-  const int total_tiles = ((m_units + csize - 1) / csize) * p.n_tiles;       // tile groups
+  const int tiles_pp = ((m_units + csize - 1) / csize) * p.n_tiles;          // tile groups (per upsample phase)
+  const int total_tiles = tiles_pp * (p.up_all ? 4 : 1);
   const int msize = p.mcast;                                                  // multicast group (1 = every CTA loads its own B tile)
   const uint16_t cmask = (uint16_t)((1u << msize) - 1u);
   const int nsub = p.dual ? 2 : 1;
@@ -340,8 +343,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         else tma_load_4d(map, dst, bar, c0, cw, ch, cimg);
       };
       for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-        const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
-        int c1[2], c2[2], c3[2], bz = 0;
+        const int ph = p.up_all ? tile / tiles_pp : p.up_phase;
+        const int tpp = p.up_all ? tile - ph * tiles_pp : tile;
+        const int m_group = tpp / p.n_tiles, n_tile = tpp - m_group * p.n_tiles, m_unit = m_group * csize + crank;
+        int c1[2], c2[2], c3[2], bz = p.up_all ? ph : 0;
         for (int sub = 0; sub < nsub; ++sub) {
           const int m_tile = m_unit * nsub + sub;     // may be == m_tiles for an odd tail: TMA zero-fills, epilogue masks
           if (p.flat) {
@@ -381,7 +386,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               for (int tw = 0; tw < tside; ++tw) {
                 int dh = 0, dw = 0;
                 if (tside == 3) { dh = th - 1; dw = tw - 1; }
-                else if (tside == 2) { dh = (p.up_phase >> 1) - 1 + th; dw = (p.up_phase & 1) - 1 + tw; }
+                else if (tside == 2) { dh = (ph >> 1) - 1 + th; dw = (ph & 1) - 1 + tw; }
                 for (int cb = 0; cb < cblocks; ++cb, ++kb) {
                   mbar_wait(&empty_bar[stage], phase ^ 1);
                   uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
@@ -486,7 +491,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
     uint32_t acc_phase = 0;
     uint32_t gn_it = 0;                            // tiles this CTA has normalised (parity selects the exchange buffer / barrier)
     for (int tile = cluster_id; tile < total_tiles; tile += num_clusters) {
-      const int m_group = tile / p.n_tiles, n_tile = tile - m_group * p.n_tiles, m_unit = m_group * csize + crank;
+      const int ph = p.up_all ? tile / tiles_pp : p.up_phase;
+      const int tpp = p.up_all ? tile - ph * tiles_pp : tile;
+      const int m_group = tpp / p.n_tiles, n_tile = tpp - m_group * p.n_tiles, m_unit = m_group * csize + crank;
+      const int stats_slot0 = p.up_all ? ph * p.tiles_per_img : p.stats_slot0;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const int row = q * 32 + lane;
@@ -668,7 +676,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             const int m_tile = m_tile0 + sub;
             if (m_tile < p.m_tiles && ch_base + n < p.N_out) {
               const float t = wstat[((0 * 2 + sub) * 2 + which) * BM + n] + wstat[((1 * 2 + sub) * 2 + which) * BM + n];
-              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + p.stats_slot0 + (m_tile % p.tiles_per_img);
+              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + stats_slot0 + (m_tile % p.tiles_per_img);
               p.stats_out[(slot * 2 + which) * p.N_out + ch_base + n] = t;
             }
           }
@@ -687,7 +695,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
         size_t row_off;
-        const bool row_ok = row_offset(p, m_tile, row, row_off);
+        const bool row_ok = row_offset(p, m_tile, row, row_off, ph);
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * MAX_BN + (uint32_t)sub * 128u;
         if (p.flags & SD_EPI_SOFTMAX) {
           // the whole score row (block_n == N <= 256 columns) sits in one TMEM lane: softmax over the row's diagonal block
@@ -811,7 +819,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               const int which = i >= vcols ? 1 : 0, n = i - which * vcols;
               const float t = wstat[(0 * 2 + which) * MAX_BN + n] + wstat[(1 * 2 + which) * MAX_BN + n] +
                               wstat[(2 * 2 + which) * MAX_BN + n] + wstat[(3 * 2 + which) * MAX_BN + n];
-              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + p.stats_slot0 + (m_tile % p.tiles_per_img);
+              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + stats_slot0 + (m_tile % p.tiles_per_img);
               p.stats_out[(slot * 2 + which) * p.N_out + n_base + n] = t;
             }
         }
@@ -851,7 +859,8 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   const int n_pad = (N + 15) / 16 * 16;
   p.block_n = n_pad < MAX_BN ? n_pad : MAX_BN;
   // few tiles (low-resolution layers): halve the N tile so more of the 148 SMs get work
-  if (!(flags & SD_EPI_SOFTMAX) && p.block_n > 128 && p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
+  const int phases = p.up_all ? 4 : 1;       // independent tile sets in one launch
+  if (!(flags & SD_EPI_SOFTMAX) && p.block_n > 128 && phases * p.m_tiles * ((n_pad + p.block_n - 1) / p.block_n) < num_sms()) p.block_n = 128;
   // 1x1 layers (NIN, attention projections; K = 256..512) are bound by the epilogue and the output write, not by the MMAs:
   // run them as N = 128 column blocks so they take the operand-swapped path below (64-byte store runs, thread-local GN sums)
   static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
@@ -864,7 +873,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
   // narrow N: pair two m-tiles per CTA tile so the B tile is fetched once per 256 rows (same smem traffic per
   // MMA cycle as the 128x256 tile, which runs near the tensor peak)
-  p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && p.m_tiles * p.n_tiles >= 2 * num_sms() &&
+  p.dual = (!(flags & SD_EPI_SOFTMAX) && p.block_n <= 128 && phases * p.m_tiles * p.n_tiles >= 2 * num_sms() &&
             (!p.flat || !p.b_batched || (p.m_tiles_per_batch % 2) == 0)) ? 1 : 0;
   // thread-block clusters (optional): consecutive m-units share the B tile (weights) through TMA multicast.  Built to
   // cut the L2->SM traffic per MMA (the kernel moves ~44-54 B/clk/SM of TMA traffic at 57-73 % tensor activity, the
@@ -884,7 +893,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     // 32 KB instead of 48 KB per K-block of a layer that is bound by the L2 -> SM feed
     static const int pair_min_tiles = [] { const char* e = getenv("SDB_GEMM_PAIR_MIN_TILES"); return e ? atoi(e) : 148; }();   // tuning knob
     if (want_pair && !p.dual && p.block_n == MAX_BN && !p.b_batched && !(flags & SD_EPI_SOFTMAX) &&
-        p.m_tiles * p.n_tiles >= pair_min_tiles) {
+        phases * p.m_tiles * p.n_tiles >= pair_min_tiles) {
       p.pair = 1;
       p.cluster = 2;
     }
@@ -1007,7 +1016,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
   const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
-  const int groups = ((m_units_h + p.cluster - 1) / p.cluster) * p.n_tiles;
+  const int groups = ((m_units_h + p.cluster - 1) / p.cluster) * p.n_tiles * phases;
   const int max_clusters = num_sms() / p.cluster;
   const int grid = (groups < max_clusters ? groups : max_clusters) * p.cluster;
   cudaLaunchConfig_t cfg{};
@@ -1072,7 +1081,8 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.tiles_per_img = (H * W >= BM) ? (H * W) / BM : 1;
   p.imgs_per_tile = (H * W >= BM) ? 1 : BM / (H * W);
   p.flat = 0;
-  p.up_phase = up_phase;
+  p.up_all = up_phase == 4 ? 1 : 0;          // 4: all phases of the fused upsample + conv in one launch
+  p.up_phase = p.up_all ? 0 : up_phase;
   p.stride2 = stride2;
   p.img_H = H;
   p.img_W = W;
@@ -1131,8 +1141,8 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.HW = H * W;
   p.m_tiles = (p.M_total + BM - 1) / BM;
   p.m_tiles_per_batch = 1;
-  const int rc = launch_gemm(p, N, K, Wt, (int)K, 0, 1, bias, rowbias, rowbias_ld, residual, flags, out, out_ld,
-                             (cudaStream_t)stream, who, stats_out);
+  const int rc = launch_gemm(p, N, K, Wt, (int)K, p.up_all ? (long long)N * K : 0, p.up_all ? 4 : 1, bias, rowbias, rowbias_ld,
+                             residual, flags, out, out_ld, (cudaStream_t)stream, who, stats_out);
   if (rc == SD_OK && gn && gn->fused) *gn->fused = p.gn_gamma != nullptr ? 1 : 0;
   return rc;
 }
@@ -1172,8 +1182,12 @@ extern "C" int sd_upconv_gemm(const void* x, int B, int H, int W, int C, const v
   if (stats_out && ((H * W) % BM) != 0) return fail(kErrInvalidArg, "sd_upconv_gemm: stats_out needs H*W % 128 == 0");
   const int tpi = (H * W >= BM) ? (H * W) / BM : 1;
   sd_gemm_src src{x, C, 4};
+  const int kmul = (flags & SD_GEMM_SPLIT3) ? 2 : 1;          // split: per phase [N, 2 * 4C] = [hi | lo]; out rows [hi(N) | lo(N)]
+  static const int one_launch = [] { const char* e = getenv("SDB_UPCONV_ONE_LAUNCH"); return e ? atoi(e) : 1; }();   // tuning knob
+  if (one_launch)      // the four phases as one persistent launch: one ramp / tail instead of four (K = 4C per phase is short)
+    return conv_gemm_impl(&src, 1, B, H, W, Wt4, N, bias, nullptr, 0, nullptr, flags, out, kmul * N, stats_out, stream, 4,
+                          4 * tpi, 0, "sd_upconv_gemm");
   for (int ph = 0; ph < 4; ++ph) {
-    const int kmul = (flags & SD_GEMM_SPLIT3) ? 2 : 1;        // split: per phase [N, 2 * 4C] = [hi | lo]; out rows [hi(N) | lo(N)]
     const __nv_bfloat16* w = reinterpret_cast<const __nv_bfloat16*>(Wt4) + (size_t)ph * N * 4 * C * kmul;
     int rc = conv_gemm_impl(&src, 1, B, H, W, w, N, bias, nullptr, 0, nullptr, flags, out, kmul * N, stats_out, stream, ph,
                             4 * tpi, ph * tpi, "sd_upconv_gemm");

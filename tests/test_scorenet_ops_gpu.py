@@ -520,3 +520,25 @@ def test_conv_gemm_with_fused_groupnorm(cuda, B, H, C, N, expect_fused, split):
     assert err <= tol, (err, err_unfused)
     if out.gn_fused and not split:
         assert err <= err_unfused * 1.05 + 1e-3      # normalising the fp32 accumulator is at least as accurate as the bf16 round trip
+
+
+@pytest.mark.parametrize("B,H,C,N", [(512, 16, 256, 256), (512, 8, 256, 256), (512, 4, 256, 256), (300, 16, 64, 128), (333, 8, 128, 64)])
+def test_upconv_gemm_large_batches_match_small_batches(cuda, B, H, C, N):
+    """The four phases of the fused upsample + conv run as ONE launch (phase = slowest digit of the tile index); at large batches
+    the tile modes change (cta_group::2 pairs, two-tile units).  Checked against the same op on sub-batches of 5, whose small-batch
+    path is pinned to the fp64 reference above; statistics against the output itself."""
+    g = torch.Generator().manual_seed(B + H + C + N)
+    x = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+    k = torch.randn(3, 3, C, N, generator=g) / math.sqrt(9 * C)
+    bias = torch.randn(N, generator=g).to(cuda)
+    w4 = ops.upconv_weights(k).bfloat16().to(cuda)
+    out = ops.upconv_gemm(x, w4, bias=bias, want_stats=True)
+    torch.cuda.synchronize()
+    for i in (0, 5, B - 5):
+        sub = ops.upconv_gemm(x[i:i + 5].contiguous(), w4, bias=bias)
+        assert (out[i:i + 5].float() - sub.float()).abs().max().item() <= 1e-2 * sub.float().abs().max().item(), i
+    if (H * H) % 128 == 0:
+        st, n = out.gn_stats
+        assert n == 4 * H * H // 128
+        assert torch.allclose(st[:, :, 0].sum(1), out.float().sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
+        assert torch.allclose(st[:, :, 1].sum(1), (out.float() ** 2).sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
