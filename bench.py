@@ -283,6 +283,8 @@ def run_b200(args):
     # ---- fused step kernel alone, L2 flushed between launches ----
     step_us, step_bytes = _step_kernel_time(sampler, ops, torch, noise_dev[0]) if not args.no_probes else (float("nan"), 4 * B * D * (M_MODELS + 3))
     step_gbs = step_bytes / (step_us * 1e-6) / 1e9
+    launch_us = _launch_floor_us(ops, torch, dev) if not args.no_probes else float("nan")
+    step_floor_us = launch_us + step_bytes / (hbm_peak * 1e9) * 1e6       # empty launch + the bytes at the measured copy peak
     # the same kernel at BASELINE config 3's single-GPU size (B = 8192, AND with the per-sample kappa solve, and OR)
     big = {}
     if rank == 0 and not args.no_probes:
@@ -333,6 +335,9 @@ def run_b200(args):
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                           "traffic": None, "kernel": "step_vpsde_kernel", "us_per_launch": step_us,
                           "bytes_per_launch": step_bytes, "peak_kind": f"{peak_kind} copy bandwidth",
+                          "launch_floor_us": launch_us, "floor_us": step_floor_us, "frac_of_floor": step_floor_us / step_us,
+                          "floor_note": "floor = in-graph empty-launch time (measured: back-to-back single-thread launches) + bytes / copy peak; "
+                                        "a 31 MB launch cannot reach the streaming peak because ~1/3 of its ideal duration is the launch itself",
                           "note": "4*B*D*(M+3) algorithmic bytes / average launch duration over round-robin input sets totalling > 2x the 126 MB L2 (every launch reads HBM), launches captured in one CUDA graph; at this batch (31 MB per launch) the kernel is ramp-bound, see roofline_step_b8192"},
         "roofline_step_b8192": {"bound": "hbm", "unit": "GB/s", "peak": hbm_peak, "bytes_per_launch": 4 * 8192 * D * (M_MODELS + 3),
                                 "and": big.get("and"), "or": big.get("or"),
@@ -582,20 +587,23 @@ def _config4_sd(torch, dev, ops, hbm_peak):
         if i >= 2:
             ts.append(s.elapsed_time(e) * 1e3 / (reps * R))
     us = statistics.median(ts)
+    launch_us = _launch_floor_us(ops, torch, dev)
+    floor_us = launch_us + set_bytes / (hbm_peak * 1e9) * 1e6
     return {"workload": "sd_latent_superdiff_and_b64_64x64x4_50steps", "batch": B, "n_steps": N,
             "loop_seconds": sec, "samples_per_s": B / sec, "ms_per_step": sec / N * 1e3,
             "unet": "random-init PyTorch stand-in (3 convs), 3 evaluations per step; diffusers / SD weights are absent",
             "step_kernel": {"kernel": "step_edm_kernel (sd_step_edm_cfg, AND)", "us_per_launch": us, "bytes_per_launch": set_bytes,
                             "GBps": set_bytes / (us * 1e-6) / 1e9, "frac_of_hbm_peak": set_bytes / (us * 1e-6) / 1e9 / hbm_peak,
-                            "floor_note": "25 MB per launch = 3.9 us at the copy peak; launch + one DRAM round trip is ~4-5 us"},
+                            "launch_floor_us": launch_us, "floor_us": floor_us, "frac_of_floor": floor_us / us,
+                            "floor_note": "floor = measured in-graph empty-launch time + 25 MB at the copy peak (3.9 us)"},
             "finite": bool(torch.isfinite(x).all())}
 
 
 def _recorded_traffic(B):
     """DRAM bytes (read + written) of one timestep's tensor-core launches at batch 512, from the committed ncu launch list
-    (profiles/r01d_step_traffic.json = tools/summarize_traffic.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+    (profiles/r02_step_traffic.json = tools/summarize_traffic.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
     of this bench; a profiler artefact, not measured in this run).  None at any other batch or when the file is absent."""
-    p = os.path.join(ROOT, "profiles", "r01d_step_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_step_traffic.json")
     if B != BATCH_PER_GPU or not os.path.exists(p):
         return None
     try:
@@ -707,6 +715,31 @@ def _gemm_only_time(sampler, ops, torch, reps=8):
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / reps, len(calls)
+
+
+def _launch_floor_us(ops, torch, dev, n=200):
+    """In-graph cost of one (empty) kernel launch: n back-to-back single-thread launches (sd_counter_add) in one CUDA graph.
+    The floor any per-timestep kernel pays before it moves its first byte."""
+    c = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.counter_add(c, 0)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.counter_add(c, 0)
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(n):
+            ops.counter_add(c, 0)
+    ts = []
+    for i in range(5):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); g.replay(); e.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append(s.elapsed_time(e) * 1e3 / n)
+    return statistics.median(ts)
 
 
 def _step_kernel_time(sampler, ops, torch, noise, B=None, mode=None):

@@ -56,6 +56,18 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// 1 / d in fp64 without the division subroutine: fp32 reciprocal as the seed, two Newton steps (4 DFMAs) -> ~1 ulp.  fp64
+// division / rsqrt compile to CALLs into slow-path routines whose latency (microseconds when they sit on a CTA's critical
+// path: profiles/r02_notes.md) dwarfs the arithmetic they replace.  Falls back to the true division outside fp32's range.
+__device__ __forceinline__ double fast_drcp(double d) {
+  const double ad = fabs(d);
+  if (!(ad > 1e-30 && ad < 1e30)) return 1.0 / d;
+  double x = (double)(1.0f / (float)d);
+  x = x * fma(-d, x, 2.0);
+  x = x * fma(-d, x, 2.0);
+  return x;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -582,24 +582,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           ++gn_it;
           const float gam = ch_ok ? p.gn_gamma[ch] : 0.f, bet = ch_ok ? p.gn_beta[ch] : 0.f;    // issued ahead of the barrier
           epi_bar();
-          // group statistics: ONE thread per group in fp64 like the stand-alone GroupNorm kernel.  (Every thread doing its own
-          // fp64 division / rsqrt made the launch epilogue-bound: ncu showed half of all stall samples as stall_math in the fp64
-          // subroutines -- 185 -> 206 us at 16x16 / K = 4608, 119 -> 275 us at 32x32 / K = 1152.)
+          // group statistics in fp32, every thread for its own channel's group (a handful of shared-memory reads and FMAs).
+          // fp64 here -- first per thread, then one thread per group behind a barrier -- put the fp64 division / rsqrt
+          // subroutines on the epilogue's critical path: ncu showed 40-55 % of all stall samples at that barrier and the tensor
+          // pipe fell from 93 % to 77 % at 16x16 / K = 4608.  flax's GroupNorm computes E[x^2] - E[x]^2 in fp32 as well.
           const int cpg = p.N_out >> 5;                                   // channels per group (32 groups); divides 128
-          float* gstat = xsum + 4 * BM;                                   // [group][mean, rstd]
-          if (et < BM / cpg) {
-            double gs = 0.0, gq = 0.0;
-            for (int cc = 0; cc < cpg; ++cc) { gs += (double)ctot[et * cpg + cc]; gq += (double)ctot[BM + et * cpg + cc]; }
-            const double gcnt = (double)p.HW * cpg;
-            const double gmean = gs / gcnt;
-            double gvar = gq / gcnt - gmean * gmean;                       // flax: E[x^2] - E[x]^2, clipped at 0
-            if (gvar < 0.0) gvar = 0.0;
-            gstat[2 * et] = (float)gmean;
-            gstat[2 * et + 1] = (float)(1.0 / sqrt(gvar + (double)p.gn_eps));
-          }
-          epi_bar();
-          const float rs = gstat[2 * (row / cpg) + 1] * gam;
-          const float sh = bet - gstat[2 * (row / cpg)] * rs;
+          const int g0 = (row / cpg) * cpg;
+          float gs = 0.f, gq = 0.f;
+          for (int cc = 0; cc < cpg; ++cc) { gs += ctot[g0 + cc]; gq += ctot[BM + g0 + cc]; }
+          const float ginv = 1.f / ((float)p.HW * (float)cpg);
+          const float gmean = gs * ginv;
+          const float gvar = fmaxf(fmaf(gq, ginv, -gmean * gmean), 0.f);  // flax: E[x^2] - E[x]^2, clipped at 0
+          const float rs = rsqrtf(gvar + p.gn_eps) * gam;
+          const float sh = bet - gmean * rs;
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = chalf * 32 + it * 64;

@@ -36,6 +36,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// 1 / sqrt(v) to fp32 accuracy: MUFU.RSQ (2 ulp) + one Newton step
+__device__ __forceinline__ float rstd_f32(float v) {
+  const float r = rsqrtf(v);
+  return r * fmaf(-0.5f * v * r, r, 1.5f);
+}
+
 // exact form for the FP32-faithful arm (SD_GEMM_SPLIT3 activations): ex2.approx + division, ~1e-6 relative
 __device__ __forceinline__ float swish_exact_f(float v) { return v / (1.f + __expf(-v)); }
 template <bool SPLIT>
@@ -91,6 +97,8 @@ struct GnParams {
   int nchunk, px_per_chunk;  // apply-pass chunking
   const float* gamma; const float* beta;
   float eps; int apply_swish;
+  double inv_n;                   // 1 / (HW * channels per group), formed on the host: the kernels multiply instead of calling the
+                                  // fp64 division subroutine (fp64 division / sqrt on the critical path cost microseconds per CTA)
   const float* part0; int nch0;   // per-source channel partials [B][nch][2][Csrc]
   const float* part1; int nch1;
   __nv_bfloat16* out;
@@ -170,12 +178,11 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __grid_constant__ G
       sum += (double)ch_tot[threadIdx.x * cpg + c];
       sq += (double)ch_tot[C + threadIdx.x * cpg + c];
     }
-    const double n = (double)p.HW * cpg;
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0
+    const double mean = sum * p.inv_n;
+    double var = sq * p.inv_n - mean * mean;      // flax: E[x^2] - E[x]^2, clipped at 0 (fp64 FMAs only: no division subroutine)
     if (var < 0.0) var = 0.0;
     g_stat[threadIdx.x * 2] = (float)mean;
-    g_stat[threadIdx.x * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+    g_stat[threadIdx.x * 2 + 1] = rstd_f32((float)var + p.eps);
   }
   __syncthreads();
   const int cv = threadIdx.x % VC, r = threadIdx.x / VC, rows_per_pass = blockDim.x / VC;
@@ -272,12 +279,11 @@ __global__ void __launch_bounds__(256) gn_small_kernel(const __grid_constant__ G
         sum += (double)part[t * 2];
         sq += (double)part[t * 2 + 1];
       }
-    const double n = (double)p.HW * cpg;
-    const double mean = sum / n;
-    double var = sq / n - mean * mean;
+    const double mean = sum * p.inv_n;
+    double var = sq * p.inv_n - mean * mean;
     if (var < 0.0) var = 0.0;
     g_stat[tid * 2] = (float)mean;
-    g_stat[tid * 2 + 1] = (float)(1.0 / sqrt(var + (double)p.eps));
+    g_stat[tid * 2 + 1] = rstd_f32((float)var + p.eps);
   }
   __syncthreads();
   const int grp = c0 / cpg;
@@ -683,6 +689,7 @@ int sd_groupnorm_swish_ex(const void* x0, int C0, const void* x1, int C1, int B,
   p.x0 = (const __nv_bfloat16*)x0; p.x1 = (const __nv_bfloat16*)x1;
   p.C0 = C0; p.C1 = C1; p.B = B; p.HW = HW;
   p.gamma = gamma; p.beta = beta; p.eps = eps; p.apply_swish = apply_swish;
+  p.inv_n = 1.0 / ((double)HW * (double)(C / 32));
   p.out = (__nv_bfloat16*)out;
   if (!stats0 && !stats1 && (C == 256 || C == 512) && ((size_t)HW * C / 8) % 256 == 0) {
     const size_t nv = (size_t)HW * C / 8 / 256;

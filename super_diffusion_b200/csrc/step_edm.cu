@@ -92,11 +92,11 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
   if (ode) {
     // clip_eval.py:383-385: kappa = [sigma (dlog_o - dlog_b) + <d, vo + vb> + lift/dsigma*sigma/N - <d, base>] / (g <d,d>)
     const double dl = (double)p.dlog[2 * sample] - (double)p.dlog[2 * sample + 1];
-    kappa = (sg * dl + (OO - BB) + (double)p.lift_term - BD) / (g * DD);
+    kappa = (sg * dl + (OO - BB) + (double)p.lift_term - BD) * fast_drcp(g * DD);
   } else if (p.mode == SD_MODE_AND) {
     // clip_eval.py:398-400 with dx_ind = 2 dsigma base + cn z
     const double num = fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term;
-    kappa = num / (2.0 * ds * g * DD);
+    kappa = num * fast_drcp(2.0 * ds * g * DD);
   } else if (p.mode == SD_MODE_OR) {
     // clip_eval.py:402: softmax([T (ll_obj + logp), T ll_bg])[0], fp32 like the reference
     const float z0 = p.temperature * (p.ll[2 * sample] + p.logp), z1 = p.temperature * p.ll[2 * sample + 1];
@@ -122,17 +122,17 @@ __global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ E
   if (crank == 0 && threadIdx.x == 0 && ode) {
     // clip_eval.py:389-390: ll_k += dsigma (dlog_k - sum (-v_k/sigma)(v_k - vf)),  <vo,vf> = OB + g k OD, <d,vf> = BD + g k DD
     const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);
-    p.ll[2 * sample] = p.ll[2 * sample] + (float)(ds * ((double)p.dlog[2 * sample] + (OO - o_vf) / sg));
-    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(ds * ((double)p.dlog[2 * sample + 1] + (BB - b_vf) / sg));
+    p.ll[2 * sample] = p.ll[2 * sample] + (float)(ds * ((double)p.dlog[2 * sample] + (OO - o_vf) * fast_drcp(sg)));
+    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(ds * ((double)p.dlog[2 * sample + 1] + (BB - b_vf) * fast_drcp(sg)));
     p.kappa_out[sample] = kf;
   } else if (crank == 0 && threadIdx.x == 0) {
     // <vo,dx> = 2ds(OB + g k OD) + cn OZ ; <vb,dx> = <vo,dx> - <d,dx>, <d,dx> = 2ds(BD + g k DD) + cn ZD
     const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
     const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
     const double b_dx = o_dx - d_dx;
-    const double q = (p.mode == SD_MODE_OR) ? (-ds / sg) : (-fabs(ds) / sg);   // :412-413 vs :409-410
-    p.ll[2 * sample] = p.ll[2 * sample] + (float)(-o_dx / sg + q * OO);
-    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(-b_dx / sg + q * BB);
+    const double q = (p.mode == SD_MODE_OR) ? (-ds * fast_drcp(sg)) : (-fabs(ds) * fast_drcp(sg));   // :412-413 vs :409-410
+    p.ll[2 * sample] = p.ll[2 * sample] + (float)(-o_dx * fast_drcp(sg) + q * OO);
+    p.ll[2 * sample + 1] = p.ll[2 * sample + 1] + (float)(-b_dx * fast_drcp(sg) + q * BB);
     p.kappa_out[sample] = kf;
   }
 }
@@ -258,11 +258,11 @@ __global__ void __launch_bounds__(256) step_edm_stream_kernel(const __grid_const
   if (two_pass) {
     if (ode) {
       // clip_eval.py:383-385
-      kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) / (g * DD);
+      kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) * fast_drcp(g * DD);
     } else {
       // clip_eval.py:398-400 with dx_ind = 2 dsigma base + cn z
       const double num = fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term;
-      kappa = num / (2.0 * ds * g * DD);
+      kappa = num * fast_drcp(2.0 * ds * g * DD);
     }
     kf = (float)kappa;
     for (int r0 = 0; r0 < nunits; r0 += NV * blockDim.x) {
@@ -293,15 +293,15 @@ __global__ void __launch_bounds__(256) step_edm_stream_kernel(const __grid_const
     if (ode) {
       // clip_eval.py:389-390
       const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);
-      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) / sg));
-      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) / sg));
+      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) * fast_drcp(sg)));
+      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) * fast_drcp(sg)));
     } else {
       const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
       const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
       const double b_dx = o_dx - d_dx;
-      const double q = (p.mode == SD_MODE_OR) ? (-ds / sg) : (-fabs(ds) / sg);   // :412-413 vs :409-410
-      p.ll[2 * sample] = ll0 + (float)(-o_dx / sg + q * OO);
-      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx / sg + q * BB);
+      const double q = (p.mode == SD_MODE_OR) ? (-ds * fast_drcp(sg)) : (-fabs(ds) * fast_drcp(sg));   // :412-413 vs :409-410
+      p.ll[2 * sample] = ll0 + (float)(-o_dx * fast_drcp(sg) + q * OO);
+      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx * fast_drcp(sg) + q * BB);
     }
     p.kappa_out[sample] = kf;
   }
@@ -368,7 +368,7 @@ __global__ void __launch_bounds__(kEdmSmemThreads, 1) step_edm_smem_kernel(const
   const double DD = t[0], BD = t[1], ZD = t[2], OO = t[3], BB = t[4], OB = t[5], OD = t[6], OZ = t[7];
   const double ds = p.dsigma, sg = p.sigma, g = p.g;
   double kappa;
-  if (ode) kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) / (g * DD);        // clip_eval.py:383-385
+  if (ode) kappa = (sg * ((double)dl0 - (double)dl1) + (OO - BB) + (double)p.lift_term - BD) * fast_drcp(g * DD);        // clip_eval.py:383-385
   else kappa = (fabs(ds) * (BB - OO) - (2.0 * ds * BD + (double)cn * ZD) + (double)p.lift_term) / (2.0 * ds * g * DD);   // :398-400
   const float kf = (float)kappa;
 #pragma unroll
@@ -386,15 +386,15 @@ __global__ void __launch_bounds__(kEdmSmemThreads, 1) step_edm_smem_kernel(const
   if (threadIdx.x == 0) {
     if (ode) {
       const double o_vf = OB + g * kappa * OD, b_vf = o_vf - (BD + g * kappa * DD);     // clip_eval.py:389-390
-      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) / sg));
-      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) / sg));
+      p.ll[2 * sample] = ll0 + (float)(ds * ((double)dl0 + (OO - o_vf) * fast_drcp(sg)));
+      p.ll[2 * sample + 1] = ll1 + (float)(ds * ((double)dl1 + (BB - b_vf) * fast_drcp(sg)));
     } else {
       const double o_dx = 2.0 * ds * (OB + g * kappa * OD) + (double)cn * OZ;
       const double d_dx = 2.0 * ds * (BD + g * kappa * DD) + (double)cn * ZD;
       const double b_dx = o_dx - d_dx;
       const double q = -fabs(ds) / sg;                                                     // :409-410
-      p.ll[2 * sample] = ll0 + (float)(-o_dx / sg + q * OO);
-      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx / sg + q * BB);
+      p.ll[2 * sample] = ll0 + (float)(-o_dx * fast_drcp(sg) + q * OO);
+      p.ll[2 * sample + 1] = ll1 + (float)(-b_dx * fast_drcp(sg) + q * BB);
     }
     p.kappa_out[sample] = kf;
   }

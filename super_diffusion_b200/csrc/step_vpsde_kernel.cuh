@@ -105,7 +105,7 @@ __device__ __forceinline__ void and_solve(const double* D, const double* E, doub
   constexpr int Md = M - 1;
   if (M == 1) { kappa[0] = 1.0; return; }
   if (M == 2) {
-    kappa[0] = (dtb * D[0] - c * E[0]) / (2.0 * dtb * D[0]);
+    kappa[0] = (dtb * D[0] - c * E[0]) * fast_drcp(2.0 * dtb * D[0]);
     kappa[1] = 1.0 - kappa[0];
     return;
   }
@@ -123,7 +123,7 @@ __device__ __forceinline__ void and_solve(const double* D, const double* E, doub
   double pinv[Md > 0 ? Md : 1];                   // reciprocal pivots, reused by the back substitution
 #pragma unroll
   for (int col = 0; col < Md; ++col) {
-    const double inv = 1.0 / U[col][col];
+    const double inv = fast_drcp(U[col][col]);
     pinv[col] = inv;
 #pragma unroll
     for (int r = col + 1; r < Md; ++r) {
@@ -168,7 +168,7 @@ __device__ __forceinline__ void and_solve_warp(const double* tot, double dtb, do
   double dinv = 1.0;
 #pragma unroll
   for (int col = 0; col < Md; ++col) {
-    const double inv = __drcp_rn(__shfl_sync(0xffffffffu, a[col], col));
+    const double inv = fast_drcp(__shfl_sync(0xffffffffu, a[col], col));
     const double f = a[col] * inv;
     if (lane == col) dinv = inv;                    // own (final) pivot, reciprocal
 #pragma unroll
@@ -198,7 +198,7 @@ __device__ __forceinline__ void and_increments_warp(const double* tot, const dou
   double mixF = 0.0;
 #pragma unroll
   for (int j = 0; j < Md; ++j) mixF += kappa_sh[j] * F[j];
-  const double inv_sigma = 1.0 / sigma;
+  const double inv_sigma = fast_drcp(sigma);
   const double Rm = (2.0 * dtb * (Gmm + mixF) + c * Nm - dtb * Gmm) * inv_sigma;
   if (lane < Md) {
     double acc = 0.0;
@@ -233,7 +233,7 @@ __device__ __forceinline__ void and_increments(const double* tot, const double* 
   double mixF = 0.0;
 #pragma unroll
   for (int j = 0; j < Md; ++j) mixF += kappa[j] * F[j];
-  const double inv_sigma = 1.0 / sigma;
+  const double inv_sigma = fast_drcp(sigma);
   const double Rm = (2.0 * dtb * (Gmm + mixF) + c * Nm - dtb * Gmm) * inv_sigma;
   R[Md] = Rm;
 #pragma unroll
@@ -389,7 +389,7 @@ __global__ void __launch_bounds__(256, ((M + 2) * NV * (VEC / 4) <= 12 && VEC ==
     const double* tot = block_cluster_sum<K, CLUSTER>(part, scratch);
     if (crank == 0 && threadIdx.x == 0) {
       double R[M];
-      const double inv_sigma = 1.0 / (double)sc.sigma;       // one fp64 division on the CTA's tail, not M
+      const double inv_sigma = fast_drcp((double)sc.sigma);       // one reciprocal on the CTA's tail, not M divisions
 #pragma unroll
       for (int i = 0; i < M; ++i) R[i] = tot[i] * inv_sigma;
       write_logq<M>(p, sc, sample, lqs, R);
