@@ -42,6 +42,9 @@ def build_parser():
     ap.add_argument("--num_batches", type=int, default=None, help="stop after this many batches (default: eval.num_samples)")
     ap.add_argument("--batch_size", type=int, default=None, help="override config.eval.batch_size")
     ap.add_argument("--dt", type=float, default=None, help="override the reference's dt = 5e-3 (cifar/eval_utils.py:75)")
+    ap.add_argument("--precision", default=None, choices=["bf16", "fp32"],
+                    help="score-net arm: bf16 (bf16 operands / activations, fp32 accumulation; default) or fp32 (FP32-faithful: the "
+                         "reference's fp32 arithmetic to ~1e-5, ~2.6x slower); sets config.model.precision")
     return ap
 
 
@@ -52,6 +55,8 @@ def launch(argv=None):
     config = load_config(args.config)
     if args.batch_size:
         config.eval.batch_size = args.batch_size
+    if args.precision:
+        config.model.precision = args.precision
     if "LOCAL_RANK" in os.environ and not torch.distributed.is_initialized():
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         torch.distributed.init_process_group("nccl")

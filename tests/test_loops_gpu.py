@@ -266,6 +266,42 @@ def test_cifar_or_steps_against_cpu_oracle(cuda):
     assert torch.equal(smp.weights.cpu()[clear].argmax(1), w_ref[clear].argmax(1))
 
 
+def test_cifar_or_200_steps_both_arms_against_the_fp64_oracle(cuda):
+    """The reference-default loop (cifar/eval_utils.py:75-77: 200 Euler-Maruyama steps, dt = 5e-3) with the REAL U-Net -- two
+    random-init score-nets, batch 64, SuperDiff-OR at the reference's T = 1e6 -- on both precision arms against the fp64 CPU
+    oracle trajectory committed as tests/golden/cifar_or_200step_oracle_float64.npz (tools/deviation_study.py --oracle; identical
+    x0 and noise from seeded CPU generators).  north_star: "final samples and log-density trajectories within rel 1e-3 in fp32
+    (stated separately for bf16 denoiser GEMMs)".  Measured (profiles/r02_deviation.md):
+        FP32-faithful arm: final samples 9.0e-6 (median) / 1.0e-5 (max) rel L2, log-density gap 1.1e-5 median / 2.5e-5 max
+        bf16 arm:          final samples 4.1e-3 / 4.4e-3,                         log-density gap 1.3e-3 median / 1.0e-2 max (step 1)
+    every sample follows the oracle's OR-winner sequence on both arms.  Gates: 1e-3 for the fp32 arm (the north_star's), and
+    1.5x the measured values for the bf16 arm."""
+    import numpy as np
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import deviation_study as dev
+    ref = dict(np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cifar_or_200step_oracle_float64.npz")))
+    B, n = int(ref["B"]), int(ref["n"])
+    x0, noise = dev.inputs(B, n)
+    cfg, mods, params = dev.models()
+    gates = {"fp32": dict(x=1e-3, gap_med=1e-3, gap_max=1e-3), "bf16": dict(x=6.6e-3, gap_med=2e-3, gap_max=1.5e-2)}
+    for prec, gate in gates.items():
+        nets = [m.bind(p, cuda, precision=prec) for m, p in zip(mods, params)]
+        smp = SuperDiffSampler(nets, B, mode="or", n_steps=n, dt=1.0 / n, temperature=1e6, device=cuda)
+        smp.capture()
+        smp.reset(x0.to(cuda))
+        lq, w = [], []
+        for i in range(n):
+            smp.step(noise[i].to(cuda))
+            lq.append(smp.logq.double().cpu().numpy()); w.append(smp.weights.double().cpu().numpy())
+        torch.cuda.synchronize()
+        row = dev.compare(prec, np.stack(lq), np.stack(w), smp.x.double().cpu().numpy(), ref)
+        assert row["winner_sequence_match_frac"] == 1.0, row
+        assert row["final_sample_rel_l2_max"] <= gate["x"], row
+        assert row["logq_gap_rel_err_median"] <= gate["gap_med"] and row["logq_gap_rel_err_max"] <= gate["gap_max"], row
+        del smp, nets
+
+
 def test_sd_latent_loop_against_cpu_oracle(cuda):
     """SD-style loop (clip_eval.py:348-415) with a small caller-supplied velocity network standing in for the UNet."""
     torch.manual_seed(0)
@@ -365,3 +401,24 @@ def test_cli_joint_eval_from_exported_checkpoints(cuda, tmp_path):
     d2 = cli.launch(["--config", "vpsde", "--workdir", str(tmp_path), "--mode", "eval_fid", "--batch_size", "4", "--num_batches", "1",
                      "--dt", "0.25"])
     assert d2.endswith(os.path.join("eval", "samples")) and os.path.exists(os.path.join(d2, "samples_0.npz"))
+
+
+def test_cli_deterministic_joint_eval_at_a_batch_that_does_not_fill_attention_tiles(cuda, tmp_path):
+    """--mode eval_joint_fid (deterministic SuperDiff-OR: get_joint_vf, Hutchinson divergence through the score-net JVP) with the
+    reference's kind of batch -- eval.batch_size = 100 there, 12 per GPU on 8 GPUs: not a multiple of the 8 images a 4x4 attention
+    tile packs.  The JVP pads the batch internally (it raised NotImplementedError before); --precision fp32 runs the stochastic
+    mode on the FP32-faithful arm."""
+    import numpy as np
+    from super_diffusion_b200 import checkpoint, main as cli
+    cfg = vpsde.get_config()
+    for i, seed in enumerate((1, 2)):
+        checkpoint.save_npz(tmp_path / f"m{i}.npz", mutils.init_model(seed, cfg, zero_init_scale=1.0)[1])
+    chk = f"{tmp_path / 'm0.npz'},{tmp_path / 'm1.npz'}"
+    d = cli.launch(["--config", "vpsde", "--workdir", str(tmp_path), "--mode", "eval_joint_fid", "--chkpts", chk, "--batch_size", "12",
+                    "--num_batches", "1", "--dt", "0.5"])
+    z = np.load(os.path.join(d, "samples_0.npz"))
+    assert z["samples"].shape == (12, 32, 32, 3) and int(z["num_steps"]) == 2
+    d = cli.launch(["--config", "vpsde", "--workdir", str(tmp_path), "--mode", "eval_joint_fid_stoch", "--chkpts", chk, "--batch_size", "12",
+                    "--num_batches", "1", "--dt", "0.5", "--precision", "fp32", "--eval_folder", "eval32"])
+    z = np.load(os.path.join(d, "samples_0.npz"))
+    assert z["samples"].shape == (12, 32, 32, 3)

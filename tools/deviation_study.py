@@ -7,7 +7,8 @@ real U-Net (two random-init score-nets, zero-init layers drawn at scale 1), Supe
 
   phase 1 (CPU, no GPU needed):  python tools/deviation_study.py --oracle [--dtype float64|float32] [--batch 64]
       runs the oracle loop (oracle/scorenet.py + oracle/steps.py::or_step_cifar_literal) and writes
-      profiles/r02_deviation_oracle_<dtype>.npz (log-density trajectory, weights trajectory, final samples).
+      tests/golden/cifar_or_200step_oracle_<dtype>.npz (log-density trajectory, weights trajectory, final samples; the fp64 file is
+      also the fixture of tests/test_loops_gpu.py::test_cifar_or_200_steps_both_arms_against_the_fp64_oracle).
   phase 2 (GPU box):              python tools/deviation_study.py --gpu
       runs the B200 sampler in both precisions on the same inputs and prints / writes the deviation table
       (profiles/r02_deviation.json, .md).
@@ -67,7 +68,7 @@ def run_oracle(args):
             lq_tr.append(logq.double().numpy().copy()); w_tr.append(w.double().numpy().copy())
             if i % 10 == 0:
                 print(f"step {i}/{n}  {time.time() - t0:.0f}s", flush=True)
-    path = os.path.join(ROOT, "profiles", f"r02_deviation_oracle_{args.dtype}.npz")
+    path = os.path.join(ROOT, "tests", "golden", f"cifar_or_200step_oracle_{args.dtype}.npz")
     np.savez_compressed(path, logq=np.stack(lq_tr), weights=np.stack(w_tr), x=x.double().numpy(), B=B, n=n,
                         seconds=time.time() - t0, threads=args.threads)
     print("wrote", path)
@@ -107,11 +108,11 @@ def run_gpu(args):
     cfg, mods, params = models()
     refs = {}
     for d in ("float64", "float32"):
-        p = os.path.join(ROOT, "profiles", f"r02_deviation_oracle_{d}.npz")
+        p = os.path.join(ROOT, "tests", "golden", f"cifar_or_200step_oracle_{d}.npz")
         if os.path.exists(p):
             refs[d] = dict(np.load(p))
     if "float64" not in refs:
-        raise SystemExit("run the --oracle phase first (profiles/r02_deviation_oracle_float64.npz)")
+        raise SystemExit("run the --oracle phase first (tests/golden/cifar_or_200step_oracle_float64.npz)")
     B, n = int(refs["float64"]["B"]), int(refs["float64"]["n"])
     x0, noise = inputs(B, n)
     rows = []
@@ -140,6 +141,11 @@ def run_gpu(args):
         md.append(f"| {k} | " + " | ".join("n/a" if r[k] is None else f"{r[k]:.3g}" for r in rows) + " |")
     txt = "\n".join(md)
     open(os.path.join(ROOT, "profiles", "r02_deviation.md"), "w").write(txt + "\n")
+    scratch = os.path.join(ROOT, "gpurun_out")          # the GPU box only sends gpurun_out/ back
+    if os.path.isdir(scratch):
+        import shutil
+        for f in ("r02_deviation.md", "r02_deviation.json"):
+            shutil.copy(os.path.join(ROOT, "profiles", f), os.path.join(scratch, f))
     print(txt)
 
 
