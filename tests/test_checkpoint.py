@@ -121,6 +121,7 @@ def test_orbax_directory_zarr_layout(tmp_path):
     """<workdir>/checkpoints/chkpt_<step>/default/<item>.<dotted key>/ (cifar/run_lib.py:43-52): the latest step is picked,
     params_ema is read leaf by leaf (chunked, gzip or raw), other State items are ignored."""
     cfg = vpsde.get_config()
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks, cfg.model.attn_resolutions = 64, (1, 2), 1, (16,)   # 1.5 M parameters
     _, params = mutils.init_model(3, cfg, zero_init_scale=1.0)
     flat = ckpt.flatten_params(params, sep=".")
     root = tmp_path / "checkpoints"
@@ -130,7 +131,7 @@ def test_orbax_directory_zarr_layout(tmp_path):
             a = (v * scale).numpy()
             chunks = [max(1, s // 2 + 1) for s in a.shape] if i % 3 == 0 else None
             _write_zarr_leaf(str(d / f"params_ema.{k}"), a, chunks=chunks, compressor="gzip" if i % 2 else None)
-        _write_zarr_leaf(str(d / "model_params.Conv_0.bias"), np.ones(128, dtype=np.float32))
+        _write_zarr_leaf(str(d / "model_params.Conv_0.bias"), np.ones(64, dtype=np.float32))
     got = ckpt.validate_params(ckpt.load_params(str(root)), cfg)
     for k, v in ckpt.flatten_params(got, sep=".").items():
         assert torch.equal(v, flat[k]), k
@@ -148,6 +149,7 @@ def test_orbax_directory_through_orbax_when_importable(tmp_path, monkeypatch):
     import sys
     import types
     cfg = vpsde.get_config()
+    cfg.model.nf, cfg.model.ch_mult, cfg.model.num_res_blocks, cfg.model.attn_resolutions = 64, (1, 2), 1, (16,)
     _, params = mutils.init_model(4, cfg, zero_init_scale=1.0)
     seen = {}
 
