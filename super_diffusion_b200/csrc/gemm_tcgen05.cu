@@ -31,6 +31,13 @@
 //   * 3x3 stride-1 segments are fed as activation slabs shared by the three vertical taps;
 //   * everything else (N < 128, flat / batched matrices, softmax epilogue of the attention probabilities used by the
 //     JVP path) runs unswapped with thread = pixel row.
+//
+// Round 2:
+//   * SD_GEMM_SPLIT3 (the FP32-faithful arm): operands are hi|lo bf16 pairs, every source contributes three K segments that
+//     share weight columns (seg_bk0), the epilogues write / read pairs -- conv_gemm_impl, batched_gemm_impl;
+//   * fused GroupNorm + swish epilogue for swapped tiles (sd_conv_gemm_gn): one TMEM pass, values parked as packed bf16
+//     registers, fp32 group statistics, 32x32 images exchange channel sums inside a thread-block cluster of 4 through DSMEM;
+//   * the four phases of the fused upsample + conv as one launch (up_all: phase = slowest digit of the tile index).
 #include "common.cuh"
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"
