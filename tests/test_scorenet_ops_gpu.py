@@ -542,3 +542,25 @@ def test_upconv_gemm_large_batches_match_small_batches(cuda, B, H, C, N):
         assert n == 4 * H * H // 128
         assert torch.allclose(st[:, :, 0].sum(1), out.float().sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
         assert torch.allclose(st[:, :, 1].sum(1), (out.float() ** 2).sum(dim=(1, 2)), rtol=2e-2, atol=1.0)
+
+
+def test_fused_groupnorm_is_deterministic_under_repetition(cuda):
+    """The cluster exchange of the fused GroupNorm epilogue (DSMEM reads ordered by cluster-scope mbarriers, double-buffered by
+    tile parity) and its register-parked pass: 30 repetitions of a multi-round launch give the same bits -- a missing barrier or a
+    buffer reused too early shows up as run-to-run differences long before it shows up in a tolerance."""
+    g = torch.Generator().manual_seed(7)
+    outs = {}
+    for (B, H, C, N) in ((592, 32, 128, 128), (700, 16, 256, 256)):
+        x = _bf(torch.randn(B, H, H, C, generator=g)).to(cuda)
+        w = _bf(torch.randn(N, 9 * C, generator=g) / math.sqrt(9 * C)).to(cuda)
+        rb = torch.randn(B, N, generator=g).to(cuda)
+        gam, bet = (1 + 0.2 * torch.randn(N, generator=g)).to(cuda), (0.1 * torch.randn(N, generator=g)).to(cuda)
+        first = None
+        for rep in range(30):
+            out = ops.conv_gemm([(x, 9)], w, rowbias=rb, want_stats=True, gn=(gam, bet))
+            assert out.gn_fused
+            if first is None:
+                first = out.clone()
+            else:
+                assert torch.equal(out, first), (B, H, rep)
+        assert torch.isfinite(first.float()).all()
