@@ -64,7 +64,8 @@ constexpr int MAX_SLABS = 3;           // 9-tap stride-1 segments that may be fe
 constexpr int EPI_WARPS = 8;               // two warps per TMEM lane quarter, each takes alternate 32-column groups
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int GEMM_THREADS = 64 + EPI_THREADS;
-constexpr int EBIAS_FLOATS = 9 * MAX_BN;           // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials
+constexpr int EBIAS_FLOATS = 12 * MAX_BN;          // bias + row-bias table (<= 8 images per tile); with stats_out: 1 row + [4 warps][2][256] column partials;
+                                                   // fused GroupNorm on pixel-row tiles: + gamma / beta table [2][256] + warp partials [8][2][32]
 constexpr size_t GEMM_SMEM = (size_t)RING_BYTES + EBIAS_FLOATS * 4 + 256 + 1024;  // + barriers + alignment slack
 
 struct GemmParams {
@@ -255,6 +256,124 @@ __device__ __forceinline__ bool row_offset(const GemmParams& p, int m_tile, int 
   return m < p.M_total;
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory"); }   // the epilogue warps only
+
+// Totals over the SEG lanes of an aligned lane group of V per-lane values (butterfly reduce-scatter; plain butterflies once
+// there are more lanes than values).  On return a lane holds max(1, V / SEG) totals in v[0..): those of the original values
+// ((lane % SEG) * V) / SEG + i.  Fixed order: deterministic.
+template <int V, int SEG>
+__device__ __forceinline__ void seg_reduce_scatter(float (&v)[V], int lane) {
+  int n = V;
+#pragma unroll
+  for (int o = SEG / 2; o >= 1; o >>= 1) {
+    if (n > 1) {
+      n >>= 1;
+      const bool upper = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        if (i < n) {
+          const float send = upper ? v[i] : v[i + n];
+          const float keep = upper ? v[i + n] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+    } else {
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+    }
+  }
+}
+
+// Fused GroupNorm + swish on a thread = pixel-row tile that holds whole images (8x8: two per tile, 4x4: eight): the statistics of
+// one (image, 8-channel group) are the sums over the image's rows -- a lane segment of one warp (4x4) or two warps (8x8) -- of a
+// thread's 8 adjacent columns.  NCH = 32-column chunks per thread (block_n / 64), HW = pixels per image.
+template <int NCH, int HW, bool PAIR>
+__device__ __forceinline__ void gn_rows_epilogue(const GemmParams& p, uint32_t taddr, int row, int q, int chalf, int lane, int warp_e, int et,
+                                                 const float* eb_row, float* gtab, float* wred, bool row_ok, size_t row_off, int n_base,
+                                                 uint64_t* tmem_empty_bar) {
+  constexpr int SEG = HW < 32 ? HW : 32;
+  for (int n = et; n < 2 * p.block_n; n += EPI_THREADS) {
+    const int which = n >= p.block_n ? 1 : 0, nn = n - which * p.block_n;
+    gtab[which * MAX_BN + nn] = (which ? p.gn_beta : p.gn_gamma)[n_base + nn];
+  }
+  uint32_t pk[NCH * 16];
+  const int segid = SEG == 16 ? lane >> 4 : 0;
+  const int idx0 = ((lane & (SEG - 1)) * 8) / SEG;           // which of a chunk's 8 totals this lane ends up holding
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = chalf * 32 + k * 64;
+    float s[8];                              // (sum, sum of squares) of the chunk's four 8-column groups
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint32_t r[16];                        // 16 columns at a time: the 64 parked registers leave little room (168 per thread)
+      tmem_ld16(taddr + c + h * 16, r);
+      tmem_wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const float x0 = __uint_as_float(r[2 * jj]) + eb_row[c + h * 16 + 2 * jj];
+        const float x1 = __uint_as_float(r[2 * jj + 1]) + eb_row[c + h * 16 + 2 * jj + 1];
+        const int g = h * 2 + jj / 4;                            // 8 adjacent columns = one group
+        s[2 * g] += x0 + x1;
+        s[2 * g + 1] = fmaf(x0, x0, fmaf(x1, x1, s[2 * g + 1]));
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+        pk[k * 16 + h * 8 + jj] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+    }
+    // totals over the rows of the image inside this warp (per chunk: 8 live values instead of 32)
+    seg_reduce_scatter<8, SEG>(s, lane);
+    wred[(warp_e * 2 + segid) * 32 + k * 8 + idx0] = s[0];
+  }
+  tcgen05_fence_before();                  // accumulator drained: hand it back to the MMA warp
+  __syncwarp();
+  if (lane == 0) {
+    if constexpr (PAIR) mbar_arrive_rank(tmem_empty_bar, 0);
+    else mbar_arrive(tmem_empty_bar);
+  }
+  epi_bar();
+  // this row's image: its lane segment (HW <= 32) or the two warps of its row-quarter pair (HW = 64), same column half
+  const float* t0 = wred + (warp_e * 2 + (SEG == 16 ? lane >> 4 : 0)) * 32;
+  const float* t1 = t0;
+  if (HW == 64) {
+    const int pw = chalf * 4 + (((q ^ 1) + 2) & 3);              // partner warp: same chalf, row quarter q ^ 1
+    t1 = wred + (pw * 2) * 32;
+  }
+  const float inv_n = 1.f / (float)(HW * 8);
+  __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + row_off + n_base;
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) {
+    const int c = chalf * 32 + k * 64;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float mean[2], rstd[2];              // the two groups of these 16 columns (statistics formed here: 32 fewer live registers)
+#pragma unroll
+      for (int gg = 0; gg < 2; ++gg) {
+        const int g = k * 4 + h * 2 + gg;
+        const float sm = HW == 64 ? t0[2 * g] + t1[2 * g] : t0[2 * g];
+        const float sq = HW == 64 ? t0[2 * g + 1] + t1[2 * g + 1] : t0[2 * g + 1];
+        mean[gg] = sm * inv_n;
+        rstd[gg] = rsqrtf(fmaxf(fmaf(sq, inv_n, -mean[gg] * mean[gg]), 0.f) + p.gn_eps);      // flax: E[x^2] - E[x]^2, clipped at 0
+      }
+      uint32_t w[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int gg = jj / 4, cc = c + h * 16 + 2 * jj;
+        const uint32_t u = pk[k * 16 + h * 8 + jj];
+        const float sc0 = rstd[gg] * gtab[cc], sc1 = rstd[gg] * gtab[cc + 1];
+        float y0 = fmaf(__uint_as_float(u << 16) - mean[gg], sc0, gtab[MAX_BN + cc]);
+        float y1 = fmaf(__uint_as_float(u & 0xFFFF0000u) - mean[gg], sc1, gtab[MAX_BN + cc + 1]);
+        if (p.gn_swish) { y0 = swish_tanh_f(y0); y1 = swish_tanh_f(y1); }
+        const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+        w[jj] = *reinterpret_cast<const uint32_t*>(&h2);
+      }
+      if (row_ok) {
+        uint4* op = reinterpret_cast<uint4*>(orow + c + h * 16);
+        op[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+    }
+  }
+  epi_bar();                               // bias / gamma tables and the warp partials are rewritten by the next tile
+}
 
 // PAIR = true is a separate instantiation: a kernel that contains cta_group::2 instructions can only be launched as
 // a cluster of 2 ("cluster misconfiguration" otherwise), so the single-CTA kernel must not contain them.
@@ -694,6 +813,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (acc == 0) acc_phase ^= 1;
         continue;
       }
+      bool released = false;                       // the fused-GroupNorm path hands the accumulator back itself (early)
       for (int sub = 0; sub < nsub; ++sub) {
         const int m_tile = m_unit * nsub + sub;
         size_t row_off;
@@ -794,6 +914,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         if (use_tab) epi_bar();
         // ---- phase 1: this thread's row
         const float* eb_row = eb + ((p.imgs_in_tile > 1) ? (row / p.HW) * MAX_BN : 0);
+        if (p.gn_gamma != nullptr) {
+          // fused GroupNorm + swish, thread = pixel-row form (host: one sub-tile, N = 256, whole 8x8 / 4x4 images per tile)
+          float* gtab = ebias + 8 * MAX_BN;
+          float* wred = gtab + 2 * MAX_BN;
+          const int warp_e = warp - 2;
+          // pairs always run 256-column tiles, single CTAs reach this path with 128-column tiles (see launch_gemm)
+          if constexpr (PAIR) {
+            if (p.HW == 64) gn_rows_epilogue<4, 64, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+            else gn_rows_epilogue<4, 16, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+          } else {
+            if (p.HW == 64) gn_rows_epilogue<2, 64, false>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+            else gn_rows_epilogue<2, 16, false>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+          }
+          released = true;
+          continue;
+        }
         const bool do_stats = p.stats_out != nullptr;         // host guarantees one image per tile and N_out % 16 == 0
         float* wstat = ebias + MAX_BN;                          // [4 warps][2][MAX_BN]
         for (int c = chalf * 32; c < p.block_n; c += 64) {
@@ -827,11 +963,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         }
         if (use_tab || do_stats) epi_bar();   // table / partials are rewritten by the next (sub-)tile
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);     // the leader's MMA warp waits for both CTAs' epilogues
-        else mbar_arrive(&tmem_empty[acc]);
+      if (!released) {
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_rank(&tmem_empty[acc], 0);     // the leader's MMA warp waits for both CTAs' epilogues
+          else mbar_arrive(&tmem_empty[acc]);
+        }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -933,6 +1071,12 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
         if (fuse && units_per_img > 1) { p.cluster = units_per_img; p.mcast = 1; }
       }
     }
+    // thread = pixel-row tiles that hold whole images (8x8: two per tile, 4x4: eight; N = 256 so that a group is 8 adjacent columns)
+    if (!fuse && want_gn_fuse && p.gn_gamma != nullptr && !(flags & (SD_GEMM_SPLIT3 | SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) &&
+        !residual && !p.swap && !p.dual && !p.flat && p.up_phase < 0 && !p.stride2 && N == MAX_BN &&
+        p.block_n == (p.pair ? MAX_BN : 128) && (p.HW == 16 || p.HW == 64) && p.imgs_per_tile == BM / p.HW &&
+        (out_ld % 8) == 0 && p.cluster == (p.pair ? 2 : 1))
+      fuse = true;
     if (!fuse) p.gn_gamma = nullptr;
   }
   {

@@ -484,7 +484,13 @@ def test_conv_gemm_pair_two_images_per_tile(cuda):
     (600, 16, 128, 128, True),     # dual-swapped, unit == image (no exchange)
     (512, 32, 256, 128, None),     # K = 2304 (the widest 32x32 conv1 of the up path takes 384 channels; 256 here)
     (8, 32, 128, 128, False),      # too few tiles for the swapped shapes: unfused fallback, raw output + stats
-    (64, 8, 256, 256, False),      # low resolution: several images per tile
+    (64, 8, 256, 256, True),       # thread = pixel-row tiles holding whole images: 8x8, two per 128-row tile, 128-column tiles
+    (512, 8, 512, 256, True),      # ... cta_group::2 pairs with 256-column tiles (the benched 8x8 layers)
+    (37, 8, 256, 256, True),       # ... ragged last tile
+    (512, 4, 512, 256, True),      # 4x4: eight images per tile, statistics inside 16-lane segments
+    (2048, 4, 256, 256, True),     # ... in pair mode
+    (9, 4, 256, 256, True),        # ... one image in the last tile
+    (16, 8, 128, 128, False),      # N = 128: groups of 4 channels are not covered by the pixel-row form
 ])
 def test_conv_gemm_with_fused_groupnorm(cuda, B, H, C, N, expect_fused, split):
     """sd_conv_gemm_gn: conv3x3 + per-sample (time-embedding) bias -> GroupNorm(32) -> swish in one launch, against the fp64
