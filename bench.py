@@ -332,7 +332,7 @@ def run_b200(args):
                              "the step's tensor-core launches (every conv / NIN / Dense / attention product), measured by replaying exactly those launches alone in a CUDA "
                              "graph (events on the launching stream, 8 replays); share_of_step = that time / ms_per_step; "
                              "achieved_eager (events around every python call of an eager pass) includes host launch gaps; since round 2 the "
-                             "same launches also carry the GroupNorm + swish of 22 layers per forward (fused epilogue, sd_conv_gemm_gn), which "
+                             "same launches also carry the GroupNorm (+ swish) of 33 layers per forward (fused epilogue, sd_conv_gemm_gn), which "
                              "used to be separate memory-bound passes outside this figure (SDB_GN_FUSE=0 restores them: higher frac, slower step)"},
         "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": step_gbs / hbm_peak,
                           "traffic": None, "kernel": "step_vpsde_kernel", "us_per_launch": step_us,

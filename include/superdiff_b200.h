@@ -181,17 +181,22 @@ int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W
                                      needs H*W % 128 == 0 and N % 16 == 0 */,
                  void* stream);
 
-/* sd_conv_gemm whose output feeds ONLY act(GroupNorm(.)) -- conv1 of a ResnetBlockDDPM (cifar/models/layers.py:552-558:
- * h = conv3x3(h); h += Dense(temb); h = act(normalize(h))): where the tile shape allows it the 32-group statistics of the whole
- * image are formed inside the GEMM epilogue (channel sums are thread-local in the [channel][pixel] epilogue; the tiles of one
- * 32x32 image exchange theirs through distributed shared memory inside a thread-block cluster of 4) and `out` receives
- * swish(GN(conv) * gamma + beta) directly: the raw conv output is never written or re-read.  *fused_host = 1 then.  Where the
- * shape does not allow it (small batches, low resolutions) the call behaves exactly like sd_conv_gemm -- `out` = raw conv output,
- * `stats_out` = per-tile channel sums -- and *fused_host = 0: the caller runs sd_groupnorm_swish itself. */
+/* sd_conv_gemm with the GroupNorm (+ swish) that consumes its output fused into the epilogue -- conv1 of a ResnetBlockDDPM
+ * (cifar/models/layers.py:552-558: h = conv3x3(h); h += Dense(temb); h = act(normalize(h))), and conv2 / the first conv when the
+ * next layer starts with a GroupNorm of that tensor (the next block's act(normalize(x)) at :552, an AttnBlock's normalize(x) at
+ * :498, the final act(normalize(h)) of cifar/models/ddpm.py:98).  Where the tile shape allows it the 32-group statistics of the
+ * whole image are formed inside the GEMM epilogue (channel sums are thread-local in the [channel][pixel] epilogue; the tiles of one
+ * 32x32 image exchange theirs through distributed shared memory inside a thread-block cluster of 4; pixel-row tiles that hold whole
+ * 8x8 / 4x4 images reduce over lane segments) and `out` receives [swish](GN(conv) * gamma + beta) directly: *fused_host = 1.
+ * raw_out (optional): a second output, the raw conv result (bf16, layout of `out`), for tensors that also stay on the residual
+ * stream; `stats_out` then carries the raw tensor's channel sums (per 256-pixel unit: the second 128-pixel slot of a unit is 0).
+ * Where the shape does not allow fusion (small batches, N != 256 at low resolution, split precision) the call behaves like
+ * sd_conv_gemm and *fused_host = 0: the raw result (+ stats_out) lands in raw_out when it is given, else in `out`, and the caller
+ * runs sd_groupnorm_swish itself. */
 int sd_conv_gemm_gn(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W, const void* Wt, int N,
                     const float* bias, const float* rowbias, int rowbias_ld, unsigned flags, void* out, int out_ld,
                     float* stats_out, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_swish,
-                    int* fused_host, void* stream);
+                    void* raw_out, int* fused_host, void* stream);
 
 /* 3x3 stride-2 SAME conv of the Downsample block (cifar/models/layers.py:526-537; flax pads (0,1) on even sizes):
  * out[b,ho,wo,n] = sum_{kh,kw,c} x[b, 2ho+kh, 2wo+kw, c] * Wt[n, (kh*3+kw)*C + c] + bias[n], x = 0 outside.

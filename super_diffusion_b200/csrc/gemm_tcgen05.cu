@@ -95,6 +95,8 @@ struct GemmParams {
   const float* gn_beta;       //    with the 32-group statistics of the whole image formed in the epilogue
   float gn_eps;
   int gn_swish;
+  __nv_bfloat16* gn_raw_out;  // optional second output of a fused launch: the raw (un-normalised) conv result, bf16, same layout / ld as
+                              //    `out` -- for tensors that stay on the residual stream while their GroupNorm feeds the next layer
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   int swap;                   // 1 (dual, conv mode, N = 128): operands swapped inside the MMA -- D^T[128 channels x 256 pixels] =
                               //    W[128 x K] * X^T: ONE M=128, N=256 instruction per K step instead of two N=128 ones (see launch_gemm)
@@ -369,6 +371,11 @@ __device__ __forceinline__ void gn_rows_epilogue(const GemmParams& p, uint32_t t
         uint4* op = reinterpret_cast<uint4*>(orow + c + h * 16);
         op[0] = make_uint4(w[0], w[1], w[2], w[3]);
         op[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        if (p.gn_raw_out != nullptr) {       // second output: the raw tensor, straight from the parked bf16 pairs
+          uint4* rp = reinterpret_cast<uint4*>(p.gn_raw_out + row_off + n_base + c + h * 16);
+          rp[0] = make_uint4(pk[k * 16 + h * 8 + 0], pk[k * 16 + h * 8 + 1], pk[k * 16 + h * 8 + 2], pk[k * 16 + h * 8 + 3]);
+          rp[1] = make_uint4(pk[k * 16 + h * 8 + 4], pk[k * 16 + h * 8 + 5], pk[k * 16 + h * 8 + 6], pk[k * 16 + h * 8 + 7]);
+        }
       }
     }
   }
@@ -693,6 +700,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           epi_bar();
           const int gbuf = (int)(gn_it & 1u);
           const int gw = et / BM, gn_n = et - gw * BM;                   // threads 0..255: (which, channel)
+          const float unit_tot = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];    // this unit's channel total (raw stats)
           if (xchg) {
             xsum[(gbuf * 2 + gw) * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
             epi_bar();                                                    // every channel sum of this CTA is written ...
@@ -742,6 +750,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;
                 if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = __floats2bfloat162_rn(e0, e1);
               }
+              if (p.gn_raw_out != nullptr) {
+                // second output: the raw tensor (already bf16 in the parked registers).  A parked word is (pixel j, pixel j+1) of
+                // this thread's channel; a stored word is (channel even, channel odd) of one pixel: swap halves with the lane partner.
+                __nv_bfloat16* rrow = p.gn_raw_out + (ch & ~1) + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const uint32_t mine = pk[it * 16 + h * 8 + jj];
+                  const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
+                  const uint32_t word = odd ? __byte_perm(mine, other, 0x3276) : __byte_perm(mine, other, 0x5410);
+                  if (ok) *reinterpret_cast<uint32_t*>(rrow + (size_t)(2 * jj) * p.out_ld) = word;
+                }
+              }
+            }
+          }
+          if (p.gn_raw_out != nullptr && p.stats_out != nullptr) {
+            // channel sums of the raw tensor for later GroupNorms over it (skip connections): the unit's totals go to its first
+            // 128-pixel tile's slot, zeros to the second's (consumers add the slots of an image)
+            const int m_tile = m_tile0;
+            if (m_tile < p.m_tiles && ch_base + gn_n < p.N_out) {
+              const float t = unit_tot;
+              const size_t slot = (size_t)(m_tile / p.tiles_per_img) * p.stats_tpi_total + stats_slot0 + (m_tile % p.tiles_per_img);
+              p.stats_out[(slot * 2 + gw) * p.N_out + ch_base + gn_n] = t;
+              if (m_tile + 1 < p.m_tiles) p.stats_out[((slot + 1) * 2 + gw) * p.N_out + ch_base + gn_n] = 0.f;
             }
           }
           continue;
@@ -1056,7 +1087,10 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // emits stats_out for sd_groupnorm_swish as before; *p_fused tells the caller which happened.
   {
     static const int want_gn_fuse = [] { const char* e = getenv("SDB_GN_FUSE"); return e ? atoi(e) : 2; }();   // tuning knob: 0 off, 1 unit == image only, 2 + clusters
-    bool fuse = want_gn_fuse && p.gn_gamma != nullptr && !(flags & SD_GEMM_SPLIT3) && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
+    // the fused epilogue is ~3x the plain one per tile: only worth it where the tile's MMAs hide it (K >= 1024; the first conv, one
+    // 64-wide K block, went from 72 to 157 us fused against a 54 us GroupNorm pass)
+    const bool long_k = p.num_kb >= 16;
+    bool fuse = long_k && want_gn_fuse && p.gn_gamma != nullptr && !(flags & SD_GEMM_SPLIT3) && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
     if (fuse) {
       if (p.pair) {
         fuse = p.tiles_per_img == 2;
@@ -1072,12 +1106,16 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
       }
     }
     // thread = pixel-row tiles that hold whole images (8x8: two per tile, 4x4: eight; N = 256 so that a group is 8 adjacent columns)
-    if (!fuse && want_gn_fuse && p.gn_gamma != nullptr && !(flags & (SD_GEMM_SPLIT3 | SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) &&
+    if (!fuse && long_k && want_gn_fuse && p.gn_gamma != nullptr && !(flags & (SD_GEMM_SPLIT3 | SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) &&
         !residual && !p.swap && !p.dual && !p.flat && p.up_phase < 0 && !p.stride2 && N == MAX_BN &&
         p.block_n == (p.pair ? MAX_BN : 128) && (p.HW == 16 || p.HW == 64) && p.imgs_per_tile == BM / p.HW &&
         (out_ld % 8) == 0 && p.cluster == (p.pair ? 2 : 1))
       fuse = true;
-    if (!fuse) p.gn_gamma = nullptr;
+    if (!fuse) {
+      if (p.gn_raw_out) out = p.gn_raw_out;      // unfused: the raw result goes where the caller expects the raw tensor
+      p.gn_gamma = nullptr;
+      p.gn_raw_out = nullptr;
+    }
   }
   {
     // ring slot = A region + the B rows this CTA receives; slab mode (see the kernel) packs three vertical taps per slot
@@ -1144,7 +1182,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   p.out_ld = out_ld;
   p.flags = flags;
   p.imgs_in_tile = (!p.flat && p.HW < BM) ? BM / p.HW : 1;
-  p.stats_out = p.gn_gamma ? nullptr : stats_out;        // a fused GroupNorm epilogue needs no channel sums downstream
+  p.stats_out = (p.gn_gamma && !p.gn_raw_out) ? nullptr : stats_out;   // a fused GroupNorm epilogue needs no channel sums downstream unless the raw tensor is kept too
   if (stats_out && ((p.flat ? (p.M_per_batch % BM) != 0 : (p.HW % BM) != 0) || (N % 16) != 0 || (flags & SD_EPI_SOFTMAX)))
     return fail(kErrInvalidArg, std::string(who) + ": stats_out needs whole 128-row tiles per image / batch entry and N a multiple of 16");
   const int out_align = (flags & SD_EPI_OUT_F32) ? 4 : 8;
@@ -1206,7 +1244,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
 
 }  // namespace sdb
 
-struct GnFuse { const float* gamma; const float* beta; float eps; int swish; int* fused; };
+struct GnFuse { const float* gamma; const float* beta; float eps; int swish; int* fused; void* raw_out; };
 
 static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
                           const float* bias, const float* rowbias, int rowbias_ld, const void* residual,
@@ -1282,7 +1320,10 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.nseg = nseg;
   p.num_kb = (int)(K / BK);
   p.slab_B = B;
-  if (gn && gn->gamma && gn->beta) { p.gn_gamma = gn->gamma; p.gn_beta = gn->beta; p.gn_eps = gn->eps; p.gn_swish = gn->swish; }
+  if (gn && gn->gamma && gn->beta) {
+    p.gn_gamma = gn->gamma; p.gn_beta = gn->beta; p.gn_eps = gn->eps; p.gn_swish = gn->swish;
+    p.gn_raw_out = reinterpret_cast<__nv_bfloat16*>(gn->raw_out);
+  }
   p.M_total = B * H * W;
   p.HW = H * W;
   p.m_tiles = (p.M_total + BM - 1) / BM;
@@ -1303,9 +1344,10 @@ extern "C" int sd_conv_gemm(const sd_gemm_src* srcs, int num_srcs, int B, int H,
 extern "C" int sd_conv_gemm_gn(const sd_gemm_src* srcs, int num_srcs, int B, int H, int W, const void* Wt, int N,
                                const float* bias, const float* rowbias, int rowbias_ld, unsigned flags, void* out, int out_ld,
                                float* stats_out, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_swish,
-                               int* fused_host, void* stream) {
+                               void* raw_out, int* fused_host, void* stream) {
   if (!gn_gamma || !gn_beta || !fused_host) return sdb::fail(sdb::kErrInvalidArg, "sd_conv_gemm_gn: null GroupNorm parameters / fused flag");
-  GnFuse gn{gn_gamma, gn_beta, gn_eps, gn_swish, fused_host};
+  if (raw_out && (((uintptr_t)raw_out % 16) != 0 || raw_out == out)) return sdb::fail(sdb::kErrInvalidArg, "sd_conv_gemm_gn: raw_out must be a distinct 16-byte aligned buffer");
+  GnFuse gn{gn_gamma, gn_beta, gn_eps, gn_swish, fused_host, raw_out};
   return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, nullptr, flags, out, out_ld, stats_out, stream, -1,
                         0, 0, "sd_conv_gemm_gn", 0, &gn);
 }

@@ -158,7 +158,15 @@ int layout(const sd_scorenet_desc& d, Net& net) {
 }
 
 // Activation in the workspace: NHWC bf16 plus the per-128-pixel-tile channel sums its producer emitted (if any).
-struct Act { void* p = nullptr; int H = 0, W = 0, C = 0; float* stats = nullptr; int nchunk = 0; };
+struct Act {
+  void* p = nullptr; int H = 0, W = 0, C = 0; float* stats = nullptr; int nchunk = 0;
+  // GroupNorm of THIS tensor pre-computed (or to be computed) for its first consumer: norm_key = that GroupNorm's scale vector;
+  // norm_p = its output buffer (== p when the tensor itself was normalised in place: no other reader of the raw form);
+  // norm_valid = the producing GEMM's epilogue already filled it (sd_conv_gemm_gn fused)
+  void* norm_p = nullptr; const float* norm_key = nullptr; bool norm_valid = false;
+};
+// the GroupNorm that consumes a conv's output first (models/ddpm.py::gn_after)
+struct GnNext { const float* gamma = nullptr; const float* beta = nullptr; bool swish = true; bool keep_raw = true; };
 
 struct Runner {
   const sd_scorenet_desc& d;
@@ -248,6 +256,42 @@ struct Runner {
     return o;
   }
 
+  // act(GroupNorm(x)) for x's first consumer: the buffer its producer reserved (already filled when the producer's epilogue
+  // fused the normalisation), else a separate pass.  The returned Act owns the buffer like any GroupNorm output.
+  Act gn_first(Act& x, const float* gamma, const float* beta, bool swish) {
+    if (x.norm_p && x.norm_key == gamma && x.norm_p != x.p) {
+      Act o; o.H = x.H; o.W = x.W; o.C = x.C; o.p = x.norm_p;
+      if (!x.norm_valid && live())
+        check(sd_groupnorm_swish_ex(x.p, x.C, nullptr, 0, B, x.H * x.W, gamma, beta, 1e-6f, swish ? 1 : 0, x.stats, x.nchunk, nullptr, 0,
+                                    gn_scratch, gn_scratch_floats, o.p, fl(), st));
+      x.norm_p = nullptr;
+      return o;
+    }
+    return gn(x, nullptr, gamma, beta, swish);
+  }
+
+  // conv whose output's first consumer is the GroupNorm `next` (may be null): sd_conv_gemm_gn with the raw tensor kept as a second
+  // output (keep_raw) or normalised in place.  The normalised buffer is reserved whether or not the launch fuses, so the arena sees
+  // one allocation sequence (the workspace dry run cannot know the tile shape).
+  Act conv_next(const sd_gemm_src* srcs, int nsrc, int H, int W, const void* Wt, int N, const float* bias, const GnNext* next) {
+    if (!next || !next->gamma) return conv(srcs, nsrc, H, W, Wt, N, bias, nullptr, 0, true);
+    Act o = new_act(H, W, N);                 // normalised output (keep_raw) or the only output
+    Act raw;
+    if (next->keep_raw) raw = new_act(H, W, N);
+    Act& st_owner = next->keep_raw ? raw : o;
+    want_stats(st_owner, H * W / 128);
+    int fused = 0;
+    if (live())
+      check(sd_conv_gemm_gn(srcs, nsrc, B, H, W, Wt, N, bias, nullptr, 0, fl(), o.p, N * sm(), st_owner.stats, next->gamma, next->beta, 1e-6f,
+                            next->swish ? 1 : 0, next->keep_raw ? raw.p : nullptr, &fused, st));
+    if (next->keep_raw) {
+      raw.norm_p = o.p; raw.norm_key = next->gamma; raw.norm_valid = fused != 0;
+      return raw;
+    }
+    if (fused) { o.norm_p = o.p; o.norm_key = next->gamma; o.norm_valid = true; release(o.stats); o.stats = nullptr; }
+    return o;
+  }
+
   Act conv(const sd_gemm_src* srcs, int nsrc, int H, int W, const void* Wt, int N, const float* bias, const float* rowbias,
            int rb_ld, bool stats) {
     Act o = new_act(H, W, N);
@@ -258,16 +302,16 @@ struct Runner {
 
   // ResnetBlockDDPM (layers.py:540-565): GN+swish -> conv3x3 + temb bias -> GN+swish -> conv3x3 + shortcut.  The second GroupNorm
   // runs inside conv1's epilogue where the tile shape allows it (sd_conv_gemm_gn): 3 launches instead of 4.
-  Act res_block(const Act& x0, const Act* x1, int i, const float* rowbias) {
+  Act res_block(Act& x0, const Act* x1, int i, const float* rowbias, const GnNext* next = nullptr) {
     const ResW& r = net.res[i];
-    Act a1 = gn(x0, x1, r.g1, r.be1, true);
+    Act a1 = x1 ? gn(x0, x1, r.g1, r.be1, true) : gn_first(x0, r.g1, r.be1, true);
     sd_gemm_src s1[1] = {{a1.p, a1.C, 9}};
     Act h1 = new_act(x0.H, x0.W, r.cout);
     want_stats(h1, x0.H * x0.W / 128);
     int fused = 0;
     if (live())
       check(sd_conv_gemm_gn(s1, 1, B, x0.H, x0.W, r.w1, r.cout, nullptr, rowbias ? rowbias + r.off : nullptr, net.dense_n, fl(), h1.p,
-                            r.cout * sm(), h1.stats, r.g2, r.be2, 1e-6f, 1, &fused, st));
+                            r.cout * sm(), h1.stats, r.g2, r.be2, 1e-6f, 1, nullptr, &fused, st));
     release(a1);
     Act a2;
     if (fused) {
@@ -283,14 +327,14 @@ struct Runner {
       release(h1);
     }
     sd_gemm_src s2[3] = {{a2.p, a2.C, 9}, {x0.p, x0.C, 1}, {x1 ? x1->p : nullptr, x1 ? x1->C : 0, 1}};
-    Act o = conv(s2, x1 ? 3 : 2, x0.H, x0.W, r.w2, r.cout, r.b2, nullptr, 0, true);
+    Act o = conv_next(s2, x1 ? 3 : 2, x0.H, x0.W, r.w2, r.cout, r.b2, next);
     release(a2);
     return o;
   }
 
   // AttnBlock (layers.py:493-511) with the projections folded at export time: GN -> q' = NIN(h) -> V'^T = (Wv Wo)^T h^T ->
   // fused softmax(q' h^T) V' + bias + x
-  Act attn_block(const Act& x, int i) {
+  Act attn_block(Act& x, int i) {
     const AttnW& a = net.attn[i];
     const int S = x.H * x.W, C = x.C;
     const int g = S >= 128 ? 1 : 128 / S;
@@ -303,7 +347,7 @@ struct Runner {
         rc = fail(kErrUnsupported, "sd_scorenet_forward: attention needs 16..256 pixels per image and C <= 256 (multiple of 64)");
       return x;
     }
-    Act h = gn(x, nullptr, a.g, a.be, false);
+    Act h = gn_first(x, a.g, a.be, false);
     if (live() && nb * g > B)
       check(check_cuda(cudaMemsetAsync(static_cast<char*>(h.p) + (size_t)B * S * C * 2 * sm(), 0, (size_t)(nb * g - B) * S * C * 2 * sm(), st),
                        "sd_scorenet_forward: zeroing the attention padding"));
@@ -363,18 +407,45 @@ struct Runner {
     // first conv (ddpm.py:71) on the tensor cores: hi/lo-split im2col K-block
     void* cols = alloc((size_t)B * H0 * H0 * 64 * 2 * sm());
     if (live()) check(sd_im2col_in_ex(x, B, H0, H0, d.channels, cols, fl(), st));
+    // the GroupNorm that first consumes the tensor produced by plan[k] (stage: which ResBlock of a mid op; k = -1: the first conv);
+    // gamma == nullptr when that consumer is not a plain GroupNorm of this tensor alone -- same rule as models/ddpm.py::gn_after
+    const std::vector<Op>& plan = net.plan;
+    auto gn_after = [&](int k, int stage) {
+      GnNext g;
+      auto attn_gn = [&](int ai) { g.gamma = net.attn[ai].g; g.beta = net.attn[ai].be; g.swish = false; g.keep_raw = true; };
+      if (k >= 0) {
+        const Op& op = plan[k];
+        if (op.kind == OP_DOWN_BLOCK && op.b >= 0) { attn_gn(op.b); return g; }
+        if (op.kind == OP_MID) { if (stage == 0) attn_gn(op.b); return g; }
+        if (op.kind == OP_UP_BLOCK) {
+          if (k + 1 == (int)plan.size()) { g.gamma = net.out_g; g.beta = net.out_be; g.swish = true; g.keep_raw = false; }
+          else if (plan[k + 1].kind == OP_ATTN) attn_gn(plan[k + 1].a);
+          return g;
+        }
+      }
+      if (k + 1 < (int)plan.size() && (plan[k + 1].kind == OP_DOWN_BLOCK || plan[k + 1].kind == OP_MID) &&
+          (k < 0 || plan[k].kind == OP_DOWN_BLOCK)) {
+        const ResW& r = net.res[plan[k + 1].a];
+        g.gamma = r.g1; g.beta = r.be1; g.swish = true; g.keep_raw = true;
+      }
+      return g;
+    };
     sd_gemm_src s0[1] = {{cols, 64, 1}};
-    Act h = conv(s0, 1, H0, H0, net.conv_in_w64, nf, net.conv_in_b, nullptr, 0, true);
+    GnNext n0 = gn_after(-1, 0);
+    Act h = conv_next(s0, 1, H0, H0, net.conv_in_w64, nf, net.conv_in_b, &n0);
     release(cols);
     std::vector<Act> hs{h};
-    for (const Op& op : net.plan) {
+    for (int k = 0; k < (int)plan.size(); ++k) {
+      const Op& op = plan[k];
       if (rc != SD_OK) return;
       switch (op.kind) {
-        case OP_DOWN_BLOCK:
-          h = res_block(hs.back(), nullptr, op.a, rowbias);
+        case OP_DOWN_BLOCK: {
+          GnNext nx = gn_after(k, 0);
+          h = res_block(hs.back(), nullptr, op.a, rowbias, &nx);
           if (op.b >= 0) { Act r = h; h = attn_block(r, op.b); if (h.p != r.p) release(r); }
           hs.push_back(h);
           break;
+        }
         case OP_DOWNSAMPLE: {
           const DownW& w = net.down[op.a];
           const Act& src = hs.back();
@@ -386,10 +457,11 @@ struct Runner {
           break;
         }
         case OP_MID: {
-          Act r0 = res_block(hs.back(), nullptr, op.a, rowbias);        // its input stays alive as a skip connection
+          GnNext n1 = gn_after(k, 0), n2 = gn_after(k, 1);
+          Act r0 = res_block(hs.back(), nullptr, op.a, rowbias, &n1);        // its input stays alive as a skip connection
           Act a0 = attn_block(r0, op.b);
           if (a0.p != r0.p) release(r0);
-          h = res_block(a0, nullptr, op.c, rowbias);
+          h = res_block(a0, nullptr, op.c, rowbias, &n2);
           release(a0);
           break;
         }
@@ -397,7 +469,8 @@ struct Runner {
           Act skip = hs.back();
           hs.pop_back();
           Act prev = h;
-          h = res_block(prev, &skip, op.a, rowbias);
+          GnNext nx = gn_after(k, 0);
+          h = res_block(prev, &skip, op.a, rowbias, &nx);
           if (prev.p != skip.p) release(prev);
           release(skip);
           break;
@@ -423,11 +496,17 @@ struct Runner {
       }
     }
     if (rc != SD_OK) return;
-    Act a = gn(h, nullptr, net.out_g, net.out_be, true);
-    release(h);
+    Act a;
+    if (h.norm_p == h.p && h.norm_key == net.out_g && h.norm_valid) {
+      a = h;                                   // normalised in the last conv's epilogue: the raw tensor had no other reader
+      h.p = nullptr; h.stats = nullptr;
+    } else {
+      a = gn(h, nullptr, net.out_g, net.out_be, true);
+      release(h);
+    }
     sd_gemm_src so[1] = {{a.p, a.C, 9}};
     if (live())
-      check(sd_conv_gemm(so, 1, B, h.H, h.W, net.out_w, d.channels, net.out_b, nullptr, 0, nullptr, SD_EPI_OUT_F32 | fl(), out, d.channels,
+      check(sd_conv_gemm(so, 1, B, a.H, a.W, net.out_w, d.channels, net.out_b, nullptr, 0, nullptr, SD_EPI_OUT_F32 | fl(), out, d.channels,
                          nullptr, st));
   }
 };

@@ -187,19 +187,41 @@ class _Bound:
         self.dense_n = off
 
     # -- forward ---------------------------------------------------------------
-    def _res(self, srcs, i, rowbias):
+    @staticmethod
+    def _pre_normalised(x, gamma):
+        """The tensor a producing GEMM already normalised for the GroupNorm whose scale is `gamma` (fused epilogue), or None."""
+        if getattr(x, "gn_norm", None) is not None and getattr(x, "gn_norm_key", None) == id(gamma):
+            return x.gn_norm
+        return None
+
+    def _conv_then_gn(self, srcs, weight, next_gn, **kw):
+        """conv_gemm whose output's first consumer is a GroupNorm (`next_gn` = (gamma, beta, swish, keep_raw) or None): tags the
+        result so that the consumer finds the pre-normalised tensor (`_pre_normalised`)."""
+        if next_gn is None:
+            return ops.conv_gemm(srcs, weight, want_stats=True, split=self.split, **kw)
+        out = ops.conv_gemm(srcs, weight, want_stats=True, split=self.split, gn=next_gn, **kw)
+        if next_gn[3]:                       # raw tensor returned, normalised one attached (None when the launch did not fuse)
+            out.gn_norm_key = id(next_gn[0])
+        elif out.gn_fused:                   # the tensor itself is normalised (its raw form has no other reader)
+            out.gn_norm, out.gn_norm_key = out, id(next_gn[0])
+        return out
+
+    def _res(self, srcs, i, rowbias, next_gn=None):
         r = self.res[i]
         x0 = srcs[0]
         x1 = srcs[1] if len(srcs) > 1 else None
         sp = self.split
-        a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1, split=sp)
+        a1 = self._pre_normalised(x0, r["g1"]) if x1 is None else None
+        if a1 is None:
+            a1 = ops.groupnorm_swish(x0, r["g1"], r["be1"], x1=x1, split=sp)
         # conv1 + temb bias, then act(normalize(.)) (layers.py:553-557): the GroupNorm runs inside the GEMM epilogue where the tile
         # shape lets one CTA / cluster see the whole image (sd_conv_gemm_gn), as its own pass otherwise
         h1 = ops.conv_gemm([(a1, 9)], r["w1"], rowbias=rowbias[:, r["off"]:r["off"] + r["cout"]], want_stats=True, split=sp,
                            gn=(r["g2"], r["be2"]))
         a2 = h1 if h1.gn_fused else ops.groupnorm_swish(h1, r["g2"], r["be2"], split=sp)
-        # NIN shortcut (C_in != C_out) or identity residual: both are extra 1-tap K segments of the same GEMM
-        return ops.conv_gemm([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], bias=r["b2"], want_stats=True, split=sp)
+        # NIN shortcut (C_in != C_out) or identity residual: both are extra 1-tap K segments of the same GEMM; the GroupNorm of the
+        # layer that follows (next block, attention block, output head) runs in this GEMM's epilogue where the tile shape allows
+        return self._conv_then_gn([(a2, 9)] + [(s, 1) for s in srcs], r["w2"], next_gn, bias=r["b2"])
 
     def _attn_split(self, x, i):
         """AttnBlock in the FP32-faithful arm: same folded algebra, every product as a 3 x bf16 split GEMM, the softmax in fp32
@@ -232,7 +254,9 @@ class _Bound:
         a = self.attn[i]
         B, H, W, C = x.shape
         S = H * W
-        h = ops.groupnorm_swish(x, a["g"], a["be"], swish=False)
+        h = self._pre_normalised(x, a["g"])
+        if h is None:
+            h = ops.groupnorm_swish(x, a["g"], a["be"], swish=False)
         g = max(1, 128 // S)              # low resolution: pack g images per 128-row tensor-core tile
         if S < 16 or B % g or (g * S) % 16:
             qkv = ops.conv_gemm([(h, 1)], a["w_qkv"], bias=a["b_qkv"])
@@ -261,12 +285,41 @@ class _Bound:
         if not (x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()):
             raise ValueError("x must be a contiguous float32 CUDA tensor (NHWC)")
         rowbias = self._rowbias(t, x, y, sched, step_counter)
-        h = self._conv_in(x, self.conv_in_b, True)
+        plan = self.plan
+
+        def gn_after(k, stage=0):
+            """(gamma, beta, swish, keep_raw) of the GroupNorm that first consumes the tensor produced by plan[k] (stage: which of a
+            'mid' op's two ResBlocks; k = -1: the first conv), or None when that consumer is not a plain GroupNorm of this tensor
+            alone (skip concatenation, down / upsample, an attention block's output)."""
+            if k >= 0:
+                op = plan[k]
+                if op[0] == "down_block" and op[2] is not None:
+                    a = self.attn[op[2]]
+                    return (a["g"], a["be"], False, True)
+                if op[0] == "mid":
+                    if stage == 0:
+                        a = self.attn[op[2]]
+                        return (a["g"], a["be"], False, True)
+                    return None
+                if op[0] == "up_block":
+                    if k + 1 == len(plan):
+                        return (self.out_g, self.out_be, True, False)          # output head: the raw tensor has no other reader
+                    if plan[k + 1][0] == "attn":
+                        a = self.attn[plan[k + 1][1]]
+                        return (a["g"], a["be"], False, True)
+                    return None
+            nxt = plan[k + 1] if k + 1 < len(plan) else None
+            if nxt is not None and nxt[0] in ("down_block", "mid") and (k < 0 or plan[k][0] == "down_block"):
+                r = self.res[nxt[1]]
+                return (r["g1"], r["be1"], True, True)
+            return None
+
+        h = self._conv_in(x, self.conv_in_b, True, gn_after(-1))
         hs = [h]
-        for op in self.plan:
+        for k, op in enumerate(plan):
             kind = op[0]
             if kind == "down_block":
-                h = self._res([hs[-1]], op[1], rowbias)
+                h = self._res([hs[-1]], op[1], rowbias, gn_after(k))
                 if op[2] is not None:
                     h = self._attn(h, op[2])
                 hs.append(h)
@@ -275,26 +328,30 @@ class _Bound:
                 h = ops.conv_gemm_s2(hs[-1], d["w"], bias=d["b"], want_stats=True, split=self.split)
                 hs.append(h)
             elif kind == "mid":
-                h = self._res([hs[-1]], op[1], rowbias)
+                h = self._res([hs[-1]], op[1], rowbias, gn_after(k, 0))
                 h = self._attn(h, op[2])
-                h = self._res([h], op[3], rowbias)
+                h = self._res([h], op[3], rowbias, gn_after(k, 1))
             elif kind == "up_block":
-                h = self._res([h, hs.pop()], op[1], rowbias)
+                h = self._res([h, hs.pop()], op[1], rowbias, gn_after(k))
             elif kind == "attn":
                 h = self._attn(h, op[1])
             elif kind == "upsample":
                 u = self.up[op[1]]
                 h = ops.upconv_gemm(h, u["w4"], bias=u["b"], want_stats=True, split=self.split)
         assert not hs
-        a = ops.groupnorm_swish(h, self.out_g, self.out_be, split=self.split)
+        a = self._pre_normalised(h, self.out_g)
+        if a is None:
+            a = ops.groupnorm_swish(h, self.out_g, self.out_be, split=self.split)
         return ops.conv_gemm([(a, 9)], self.out_w, bias=self.out_b, out_f32=True, n_out=self.n_img, out=out, split=self.split)
 
-    def _conv_in(self, x, bias, want_stats):
+    def _conv_in(self, x, bias, want_stats, next_gn=None):
         """conv3x3(x, nf) (ddpm.py:71).  Tensor-core form: 166 -> ~55 us at batch 512 and the GEMM epilogue emits the channel
         sums the first GroupNorm needs; the CUDA-core kernel remains for inputs the gather does not cover."""
         if self.conv_in_tc:
-            return ops.conv_gemm([(ops.im2col_in(x, split=self.split), 1)], self.conv_in_w64, bias=bias, want_stats=want_stats,
-                                 split=self.split)
+            cols = ops.im2col_in(x, split=self.split)
+            if next_gn is not None and want_stats:
+                return self._conv_then_gn([(cols, 1)], self.conv_in_w64, next_gn, bias=bias)
+            return ops.conv_gemm([(cols, 1)], self.conv_in_w64, bias=bias, want_stats=want_stats, split=self.split)
         return ops.conv_in(x, self.conv_in_w, bias)
 
     def _rowbias(self, t, x, y, sched, step_counter):

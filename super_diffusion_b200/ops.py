@@ -252,14 +252,25 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     if want_stats and (H * W) % 128 == 0 and N % 16 == 0 and not out_f32 and B > 0:
         stats = torch.empty(B, (H * W) // 128, 2, N, device=x0.device, dtype=torch.float32)
     if gn is not None:
+        # gn = (gamma, beta[, swish[, keep_raw]]): keep_raw asks for the raw tensor as a second output (it stays on the residual
+        # stream); the return value is then the RAW tensor with `.gn_norm` = the normalised one (None when the launch did not fuse)
         if residual is not None or out_f32 or swish:
             raise ValueError("gn fusion: no residual / fp32 output / extra swish")
+        gn_swish = bool(gn[2]) if len(gn) > 2 else True
+        keep_raw = bool(gn[3]) if len(gn) > 3 else False
+        raw = torch.empty_like(out) if keep_raw else None
         fused = ctypes.c_int(0)
         rc = lib.sd_conv_gemm_gn(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld, flags, _ptr(out),
-                                 out.shape[-1], _ptr(stats), _ptr(_f32c(gn[0], "gamma")), _ptr(_f32c(gn[1], "beta")), 1e-6, 1,
-                                 ctypes.byref(fused), _stream())
+                                 out.shape[-1], _ptr(stats), _ptr(_f32c(gn[0], "gamma")), _ptr(_f32c(gn[1], "beta")), 1e-6, int(gn_swish),
+                                 _ptr(raw), ctypes.byref(fused), _stream())
         _lib.check(rc, "sd_conv_gemm_gn")
-        out.gn_fused = bool(fused.value)
+        if keep_raw:
+            norm = out if fused.value else None
+            out = raw
+            out.gn_norm = norm
+            out.gn_fused = False           # `out` is the raw tensor: its gn_stats (below) are valid either way
+        else:
+            out.gn_fused = bool(fused.value)
     else:
         rc = lib.sd_conv_gemm(arr, len(srcs), B, H, W, _ptr(weight), N, _ptr(bias), _ptr(rowbias), rb_ld,
                               _ptr(residual), flags, _ptr(out), out.shape[-1], _ptr(stats), _stream())

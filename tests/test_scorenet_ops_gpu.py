@@ -526,6 +526,19 @@ def test_conv_gemm_with_fused_groupnorm(cuda, B, H, C, N, expect_fused, split):
     assert err <= tol, (err, err_unfused)
     if out.gn_fused and not split:
         assert err <= err_unfused * 1.05 + 1e-3      # normalising the fp32 accumulator is at least as accurate as the bf16 round trip
+    # second form: the raw tensor is kept as well (it stays on the residual stream), no swish (an attention block's GroupNorm)
+    both = ops.conv_gemm([(xs, 9)], ws, rowbias=rowbias.to(cuda), want_stats=True, split=split, gn=(gamma.to(cuda), beta.to(cuda), False, True))
+    torch.cuda.synchronize()
+    assert (both.gn_norm is not None) == expect_fused
+    assert torch.equal(both, raw), "the raw second output must be the unfused conv output bit for bit"
+    href = y                                          # GroupNorm without swish
+    hn = both.gn_norm if both.gn_norm is not None else ops.groupnorm_swish(both, gamma.to(cuda), beta.to(cuda), swish=False, split=split)
+    assert ((merge(hn).double().cpu() - href).abs().max() / href.abs().max()).item() <= tol
+    if hasattr(both, "gn_stats") and hasattr(raw, "gn_stats"):
+        sb, sr = both.gn_stats[0].double().sum(1), raw.gn_stats[0].double().sum(1)       # per image: [B, 2, N]
+        assert torch.allclose(sb, sr, rtol=1e-5, atol=1e-2)
+        a_raw = ops.groupnorm_swish(both, gamma.to(cuda), beta.to(cuda), split=split)      # a later GroupNorm over the kept raw tensor
+        assert (merge(a_raw).float() - merge(unfused).float()).abs().max().item() <= 2e-2 * merge(unfused).float().abs().max().item()
 
 
 @pytest.mark.parametrize("B,H,C,N", [(512, 16, 256, 256), (512, 8, 256, 256), (512, 4, 256, 256), (300, 16, 64, 128), (333, 8, 128, 64)])

@@ -65,7 +65,9 @@ def describe(name, a, k, r):
         N = w.shape[0] if k.get("n_out") is None else k["n_out"]
         Mrows = t0.shape[0] * t0.shape[1] * t0.shape[2]
         segs = "+".join(f"{tp}x{s.shape[3]}" for s, tp in srcs)
-        tag = (" +GN fused" if getattr(r, "gn_fused", False) else " (GN unfused)") if k.get("gn") is not None else ""
+        fusedp = getattr(r, "gn_fused", False) or getattr(r, "gn_norm", None) is not None
+        keep = len(k["gn"]) > 3 and k["gn"][3] if k.get("gn") is not None else False
+        tag = ((" +GN fused" + (" +raw" if keep else "")) if fusedp else " (GN unfused)") if k.get("gn") is not None else ""
         return (f"conv_gemm H{t0.shape[1]} [{segs}] N{N}" + (" stats" if k.get("want_stats") else "") + tag, 2.0 * Mrows * N * K,
                 sum(nbytes(s) for s, _ in srcs) + nbytes(w) + nbytes(r))
     if name == "conv_gemm_s2":
