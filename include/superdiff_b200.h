@@ -198,6 +198,11 @@ int sd_conv_gemm_gn(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, in
                     float* stats_out, const float* gn_gamma, const float* gn_beta, float gn_eps, int gn_swish,
                     void* raw_out, int* fused_host, void* stream);
 
+/* How far sd_conv_gemm_gn may fuse: 0 = never (always the separate GroupNorm pass), 1 = only where one CTA / CTA pair holds the
+ * image, 2 = also through thread-block clusters (default; environment SDB_GN_FUSE).  Process-wide; returns the previous level.
+ * Callers that branch on *fused_host need nothing else; bench.py uses it to time the same launches both ways. */
+int sd_set_gn_fuse(int level);
+
 /* 3x3 stride-2 SAME conv of the Downsample block (cifar/models/layers.py:526-537; flax pads (0,1) on even sizes):
  * out[b,ho,wo,n] = sum_{kh,kw,c} x[b, 2ho+kh, 2wo+kw, c] * Wt[n, (kh*3+kw)*C + c] + bias[n], x = 0 outside.
  * The stride lives in the TMA descriptor (element strides 2 along w and h), so no im2col buffer is materialised.

@@ -47,6 +47,7 @@ SIGNATURES = {
     "sd_conv_gemm": (_I, [ctypes.POINTER(GemmSrc), _I, _I, _I, _I, _V, _I, _V, _V, _I, _V, _U, _V, _I, _V, _V]),
     "sd_conv_gemm_gn": (_I, [ctypes.POINTER(GemmSrc), _I, _I, _I, _I, _V, _I, _V, _V, _I, _U, _V, _I, _V, _V, _V, _F, _I,
                              _V, ctypes.POINTER(_I), _V]),
+    "sd_set_gn_fuse": (_I, [_I]),
     "sd_conv_gemm_s2": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),
     "sd_upconv_gemm": (_I, [_V, _I, _I, _I, _I, _V, _I, _V, _U, _V, _V, _V]),
     "sd_groupnorm_swish": (_I, [_V, _I, _V, _I, _I, _I, _V, _V, _F, _I, _V, _I, _V, _I, _V, _SZ, _V, _V]),

@@ -41,6 +41,7 @@
 #include "common.cuh"
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 
@@ -1019,6 +1020,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 // ---- host side -----------------------------------------------------------------
 
 
+// SDB_GN_FUSE, overridable at run time (sd_set_gn_fuse: bench.py measures the same launches with and without the fused epilogue)
+static std::atomic<int> g_gn_fuse{-1};
+static int gn_fuse_level() {
+  int v = g_gn_fuse.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("SDB_GN_FUSE");
+    v = e ? atoi(e) : 2;
+    g_gn_fuse.store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, long long strideB, int nbatchB,
                        const float* bias, const float* rowbias, int rowbias_ld, const void* residual, unsigned flags,
                        void* out, int out_ld, cudaStream_t st, const char* who, float* stats_out = nullptr) {
@@ -1086,7 +1099,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // distributed-shared-memory exchange only (no multicast: measured slower, see above).  Otherwise the launch runs unfused and
   // emits stats_out for sd_groupnorm_swish as before; *p_fused tells the caller which happened.
   {
-    static const int want_gn_fuse = [] { const char* e = getenv("SDB_GN_FUSE"); return e ? atoi(e) : 2; }();   // tuning knob: 0 off, 1 unit == image only, 2 + clusters
+    const int want_gn_fuse = gn_fuse_level();   // tuning knob (SDB_GN_FUSE / sd_set_gn_fuse): 0 off, 1 unit == image only, 2 + clusters
     // the fused epilogue is ~3x the plain one per tile: only worth it where the tile's MMAs hide it (K >= 1024; the first conv, one
     // 64-wide K block, went from 72 to 157 us fused against a 54 us GroupNorm pass)
     const bool long_k = p.num_kb >= 16;
@@ -1350,6 +1363,13 @@ extern "C" int sd_conv_gemm_gn(const sd_gemm_src* srcs, int num_srcs, int B, int
   GnFuse gn{gn_gamma, gn_beta, gn_eps, gn_swish, fused_host, raw_out};
   return conv_gemm_impl(srcs, num_srcs, B, H, W, Wt, N, bias, rowbias, rowbias_ld, nullptr, flags, out, out_ld, stats_out, stream, -1,
                         0, 0, "sd_conv_gemm_gn", 0, &gn);
+}
+
+extern "C" int sd_set_gn_fuse(int level) {
+  if (level < 0 || level > 2) return sdb::fail(sdb::kErrInvalidArg, "sd_set_gn_fuse: level must be 0, 1 or 2");
+  const int prev = sdb::gn_fuse_level();
+  sdb::g_gn_fuse.store(level, std::memory_order_relaxed);
+  return prev;
 }
 
 extern "C" int sd_conv_gemm_s2(const void* x, int B, int H_in, int W_in, int C, const void* Wt, int N, const float* bias,

@@ -282,6 +282,14 @@ def conv_gemm(srcs, weight, bias=None, rowbias=None, residual=None, swish=False,
     return out
 
 
+def set_gn_fuse(level):
+    """sd_set_gn_fuse: 0 / 1 / 2 (see the header); returns the previous level."""
+    prev = _lib.load().sd_set_gn_fuse(int(level))
+    if prev < 0:
+        _lib.check(prev, "sd_set_gn_fuse")
+    return prev
+
+
 def conv_gemm_s2(x, weight, bias=None, out=None, want_stats=False, split=False):
     """3x3 stride-2 SAME conv (flax pad (0,1)) with the stride in the TMA descriptor (sd_conv_gemm_s2).
     x: bf16 [B,H,W,C]; weight: bf16 [N, 9C]."""
