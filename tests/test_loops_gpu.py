@@ -273,9 +273,9 @@ def test_cifar_or_200_steps_both_arms_against_the_fp64_oracle(cuda):
     x0 and noise from seeded CPU generators).  north_star: "final samples and log-density trajectories within rel 1e-3 in fp32
     (stated separately for bf16 denoiser GEMMs)".  Measured (profiles/r02_deviation.md):
         FP32-faithful arm: final samples 9.0e-6 (median) / 1.0e-5 (max) rel L2, log-density gap 1.1e-5 median / 2.5e-5 max
-        bf16 arm:          final samples 4.1e-3 / 4.4e-3,                         log-density gap 1.3e-3 median / 1.0e-2 max (step 1)
+        bf16 arm:          final samples 4.1e-3 / 4.4e-3,                         log-density gap 1.3e-3 median / 1.3e-2 max (step 1)
     every sample follows the oracle's OR-winner sequence on both arms.  Gates: 1e-3 for the fp32 arm (the north_star's), and
-    1.5x the measured values for the bf16 arm."""
+    <= 1.5x the measured values for the bf16 arm."""
     import numpy as np
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
@@ -284,7 +284,7 @@ def test_cifar_or_200_steps_both_arms_against_the_fp64_oracle(cuda):
     B, n = int(ref["B"]), int(ref["n"])
     x0, noise = dev.inputs(B, n)
     cfg, mods, params = dev.models()
-    gates = {"fp32": dict(x=1e-3, gap_med=1e-3, gap_max=1e-3), "bf16": dict(x=6.6e-3, gap_med=2e-3, gap_max=1.5e-2)}
+    gates = {"fp32": dict(x=1e-3, gap_med=1e-3, gap_max=1e-3), "bf16": dict(x=6.6e-3, gap_med=2e-3, gap_max=1.9e-2)}
     for prec, gate in gates.items():
         nets = [m.bind(p, cuda, precision=prec) for m, p in zip(mods, params)]
         smp = SuperDiffSampler(nets, B, mode="or", n_steps=n, dt=1.0 / n, temperature=1e6, device=cuda)
