@@ -17,6 +17,7 @@
 #include "common.cuh"
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"
+#include <cstdlib>
 
 namespace sdb {
 
@@ -313,6 +314,314 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_kernel(const __grid_c
   }
 }
 
+
+// =====================================================================================================================
+// v2 (C == 256, block % 16 == 0): the same four phases, software-pipelined over two tiles so that neither the tensor pipe nor
+// the epilogue warps wait for each other, and with every pass over tensor memory made once:
+//
+//   * ONE pass over S: a thread pulls its 128 (64 at Sp = 128) scores into registers with back-to-back tcgen05.ld and releases the
+//     S accumulator at once (s_free) -- the issuer starts the NEXT tile's Q K^T while this tile's max / exp run on registers
+//     (v1 read S twice from tensor memory, 64 B/clk, and kept it until the probabilities were written);
+//   * P V is issued with the operand roles exchanged: O^T[channel][query] = V^T[channel][key] . P[query][key]^T, two M = 128
+//     channel halves, N = 128 queries (the bytes in shared memory are the same).  An epilogue thread now owns ONE channel:
+//     bias is a register, the GroupNorm channel sums are thread-local (v1: a 31-shuffle reduce-scatter per 16 columns -- 35 %
+//     of all stall samples in profiles/r01d_ncu_attn_core_phases.txt), a lane-pair exchange packs channel pairs so each store /
+//     residual load instruction touches two 64-byte runs of the NHWC rows;
+//   * the epilogue warps drain O of tile i-1 AFTER the softmax of tile i: P V of tile i-1 runs under softmax i, Q K^T of tile
+//     i+1 under the drain, and the TMA ring keeps streaming through all of it.
+//
+// Issue order on the tensor pipe: S0, S1, PV0, S2, PV1, ...   (the producer loads in the same order)
+// Barriers: s_full / s_free (S accumulator), p_ready (P in shared memory) / o_full (also "P may be overwritten"), o_free.
+constexpr int AC2_AUX_FLOATS = 2 * 256 /* row max [parity][row][half] */ + 2 * 256 /* row sum */ + 128 /* 1 / sum */;
+constexpr size_t AC2_SMEM = (size_t)AC_STAGES * AC_STAGE_BYTES + AC_P_BYTES + AC2_AUX_FLOATS * 4 + 256 + 1024;
+
+template <int SP>
+__global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __grid_constant__ AttnCoreParams p) {
+  constexpr int C = 256;
+  constexpr int NCH = SP / 64;                 // 32-column chunks of S per thread (two threads per row take alternate chunks)
+  constexpr int KB1 = C / AC_BK, KB2 = SP / AC_BK, M_TILES = SP / AC_BM;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* pbuf = smem + (size_t)AC_STAGES * AC_STAGE_BYTES;
+  float* aux = reinterpret_cast<float*>(pbuf + AC_P_BYTES);
+  float* xmax = aux;                    // [2][128][2]
+  float* xsum = aux + 512;              // [2][128][2]
+  float* inv_sh = aux + 1024;           // [128]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux + AC2_AUX_FLOATS);
+  uint64_t* empty_bar = full_bar + AC_STAGES;
+  uint64_t* s_full = empty_bar + AC_STAGES;
+  uint64_t* s_free = s_full + 1;
+  uint64_t* p_ready = s_free + 1;
+  uint64_t* o_full = p_ready + 1;
+  uint64_t* o_free = o_full + 1;
+  uint32_t* tmem_ptr_sh = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_local = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;    // grid <= tiles: >= 1
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.q_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.k_map) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.v_map) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < AC_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(s_full, 1); mbar_init(s_free, AC_EPI_WARPS); mbar_init(p_ready, AC_EPI_WARPS);
+      mbar_init(o_full, 1); mbar_init(o_free, AC_EPI_WARPS);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_sh)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_sh;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;     // O^T: channel half h in columns [256 + 128 h, +128)
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer: QK(0), [QK(k+1), V(k)] ... =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      auto load_qk = [&](int tile) {
+        const int b = tile / M_TILES, mt = tile - b * M_TILES;
+        for (int kb = 0; kb < KB1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * AC_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)(AC_BM + SP) * AC_BK * 2);
+          tma_load_3d(&p.q_map, st, &full_bar[stage], kb * AC_BK, mt * AC_BM, b);
+          tma_load_3d(&p.k_map, st + AC_BM * AC_BK * 2, &full_bar[stage], kb * AC_BK, 0, b);
+          if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      };
+      load_qk((int)blockIdx.x);
+      for (int k = 0; k < n_local; ++k) {
+        const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+        if (k + 1 < n_local) load_qk(tile + (int)gridDim.x);
+        const int b = tile / M_TILES;
+        if (p.residual)     // the tile's residual rows (64 KB, contiguous) are read by the drain one tile later: pull them into L2 now --
+                            // ncu showed 2/3 of the drain's stall samples waiting for these words to arrive from HBM
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + (size_t)tile * AC_BM * C), "r"(AC_BM * C * 2) : "memory");
+        for (int kb = 0; kb < KB2; ++kb) {          // V^T: one 64-key block of all 256 channels
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + (size_t)stage * AC_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], (uint32_t)C * AC_BK * 2);
+          tma_load_3d(&p.v_map, st, &full_bar[stage], kb * AC_BK, 0, b);
+          if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer: S0, [S(k+1), PV(k)] ... =====================
+      const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(SP >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(AC_BM >> 3) << 17) | ((uint32_t)(AC_BM >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      auto issue_s = [&]() {
+        for (int kb = 0; kb < KB1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)stage * AC_STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_sw128(sa), b_desc = umma_desc_sw128(sa + AC_BM * AC_BK * 2);
+#pragma unroll
+          for (int k = 0; k < AC_BK / 16; ++k)
+            umma_bf16(tmem_S, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(s_full);
+      };
+      issue_s();
+      for (int k = 0; k < n_local; ++k) {
+        if (k + 1 < n_local) {
+          mbar_wait(s_free, k & 1);                  // every epilogue warp holds its part of S(k) in registers
+          tcgen05_fence_after();
+          issue_s();
+        }
+        mbar_wait(p_ready, k & 1);                   // P(k) is in shared memory (generic-proxy writes fenced by the writers)
+        if (k > 0) mbar_wait(o_free, (k - 1) & 1);   // O(k-1) has been drained
+        tcgen05_fence_after();
+        for (int kb = 0; kb < KB2; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sv = smem_u32(smem + (size_t)stage * AC_STAGE_BYTES);
+          const uint64_t p_desc = umma_desc_sw128(smem_u32(pbuf) + (uint32_t)kb * (AC_BM * AC_BK * 2));
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {              // channel half h: A = its 128 rows of the V^T tile, B = the 128 query rows of P
+            const uint64_t v_desc = umma_desc_sw128(sv + (uint32_t)h * (AC_BM * AC_BK * 2));
+#pragma unroll
+            for (int k4 = 0; k4 < AC_BK / 16; ++k4)
+              umma_bf16(tmem_O + (uint32_t)h * 128u, v_desc + (uint64_t)(k4 * 2), p_desc + (uint64_t)(k4 * 2), idesc2, (kb | k4) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax + epilogue (warps 2..9) =====================
+    const int q = warp & 3;                        // TMEM lane quarter
+    const int chalf = (warp - 2) >> 2;             // softmax: alternate 32-column chunks of the row; drain: channel half
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const bool odd = (lane & 1) != 0;
+    const int ch = chalf * 128 + row, chp = ch & ~1;                  // drain: this thread's channel / its even-odd pair
+    const float bv0 = p.bias ? p.bias[chp] : 0.f, bv1 = p.bias ? p.bias[chp + 1] : 0.f;
+    const uint32_t tS = tmem_S + ((uint32_t)(q * 32) << 16);
+    const uint32_t tO = tmem_O + (uint32_t)chalf * 128u + ((uint32_t)(q * 32) << 16);
+
+    auto load_res = [&](int tile, int ci, uint32_t (&res)[16]) {      // residual words of queries [32 ci, 32 ci + 32) of `tile`
+      if (!p.residual) return;
+      const int b = tile / M_TILES, mt = tile - b * M_TILES;
+      const __nv_bfloat16* rb = p.residual + ((size_t)b * SP + (size_t)mt * AC_BM) * (size_t)C + (size_t)chp + (odd ? C : 0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        res[j] = __ldg(reinterpret_cast<const unsigned int*>(rb + (size_t)(ci * 32 + 2 * j) * C));
+    };
+    // O^T of tile `tile` -> out rows: value (channel ch, query c) scaled by 1 / sum(c); a lane pair exchanges so that the even
+    // lane holds channels (chp, chp + 1) of query c, the odd lane those of query c + 1; + bias + residual, bf16x2 stores.
+    auto drain = [&](int tile, uint32_t (&rc)[16]) {         // rc: the residual words of the first 32 queries, already in flight
+      const int b = tile / M_TILES, mt = tile - b * M_TILES;
+      const size_t base = ((size_t)b * SP + (size_t)mt * AC_BM) * (size_t)C + (size_t)chp;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        const int c = ci * 32;
+        uint32_t r[2][16], rn[16];
+        tmem_ld16(tO + c, r[0]);
+        tmem_ld16(tO + c + 16, r[1]);
+        if (ci < 3) load_res(tile, ci + 1, rn);     // one chunk ahead: its latency hides behind this chunk's arithmetic and stores
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {             // queries c + 2j, c + 2j + 1
+          const float2 iv = *reinterpret_cast<const float2*>(inv_sh + c + 2 * j);
+          const float a0 = __uint_as_float(r[j >> 3][(2 * j) & 15]) * iv.x, a1 = __uint_as_float(r[j >> 3][(2 * j + 1) & 15]) * iv.y;
+          const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
+          float e0 = (odd ? recv : a0) + bv0, e1 = (odd ? a1 : recv) + bv1;
+          if (p.residual) {
+            e0 += __uint_as_float(rc[j] << 16);
+            e1 += __uint_as_float(rc[j] & 0xFFFF0000u);
+          }
+          s0 += e0; q0 = fmaf(e0, e0, q0);
+          s1 += e1; q1 = fmaf(e1, e1, q1);
+          *reinterpret_cast<__nv_bfloat162*>(p.out + base + (size_t)(c + 2 * j + (odd ? 1 : 0)) * C) = __floats2bfloat162_rn(e0, e1);
+        }
+        if (ci < 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) rc[j] = rn[j];
+        }
+      }
+      if (p.stats_out) {                           // channel totals over the tile's 128 queries: mine + the lane partner's
+        const float t0 = s0 + __shfl_xor_sync(0xffffffffu, s0, 1), t1 = s1 + __shfl_xor_sync(0xffffffffu, s1, 1);
+        const float u0 = q0 + __shfl_xor_sync(0xffffffffu, q0, 1), u1 = q1 + __shfl_xor_sync(0xffffffffu, q1, 1);
+        float* so = p.stats_out + ((size_t)b * M_TILES + mt) * 2 * C;
+        so[ch] = odd ? t1 : t0;
+        so[C + ch] = odd ? u1 : u0;
+      }
+    };
+
+    // iteration k: softmax of tile k (k < n_local), then the drain of tile k - 1 (k > 0) -- one copy of each in the code
+    int prev = -1;
+    for (int k = 0; k <= n_local; ++k) {
+      const bool has = k < n_local;
+      const int tile = (int)blockIdx.x + k * (int)gridDim.x;
+      const int par = k & 1;
+      if (has) {
+        const int mt = tile % M_TILES;
+        const int rl = mt * AC_BM + row;                                   // row within the batch entry
+        const int lo = (rl / p.block) * p.block, hi = lo + p.block;         // this row's softmax block of key columns
+        mbar_wait(s_full, par);
+        tcgen05_fence_after();
+        uint32_t s[NCH * 2][16];
+#pragma unroll
+        for (int it = 0; it < NCH; ++it) {
+          tmem_ld16(tS + chalf * 32 + it * 64, s[2 * it]);
+          tmem_ld16(tS + chalf * 32 + it * 64 + 16, s[2 * it + 1]);
+        }
+        tmem_wait_ld();
+        tcgen05_fence_before();                      // S is in registers: the next tile's Q K^T may overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s_free);
+        float mx = -INFINITY;
+#pragma unroll
+        for (int g = 0; g < NCH * 2; ++g) {          // block % 16 == 0: a 16-column group is inside or outside the row's block as a whole
+          const int c16 = chalf * 32 + (g >> 1) * 64 + (g & 1) * 16;
+          const bool in = c16 >= lo && c16 < hi;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float v = in ? __uint_as_float(s[g][j]) : -INFINITY;
+            s[g][j] = __float_as_uint(v);
+            mx = fmaxf(mx, v);
+          }
+        }
+        xmax[par * 256 + row * 2 + chalf] = mx;
+        ac_epi_bar();
+        mx = fmaxf(xmax[par * 256 + row * 2], xmax[par * 256 + row * 2 + 1]);     // finite: the row's own column is inside its block
+        const float mxs = mx * sl2;
+        // e = exp(scale (s - max)) once per element, kept UNNORMALISED as packed bf16 pairs (1 / sum is applied to the output column)
+        uint32_t pk[NCH * 16];
+        float sum = 0.f;
+#pragma unroll
+        for (int g = 0; g < NCH * 2; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float e0 = exp2f(fmaf(__uint_as_float(s[g][2 * j]), sl2, -mxs));
+            const float e1 = exp2f(fmaf(__uint_as_float(s[g][2 * j + 1]), sl2, -mxs));
+            sum += e0 + e1;
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
+            pk[g * 8 + j] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+        xsum[par * 256 + row * 2 + chalf] = sum;
+        if (k > 0) {
+          mbar_wait(o_full, par ^ 1);                // P V of the previous tile has retired: P may be overwritten, O(k-1) is complete
+          tcgen05_fence_after();
+        }
+#pragma unroll
+        for (int g = 0; g < NCH * 2; ++g) {
+          const int c = chalf * 32 + (g >> 1) * 64;                        // the chunk's first key
+          uint8_t* blk = pbuf + (size_t)(c >> 6) * (AC_BM * AC_BK * 2) + (size_t)row * 128;     // [128 x 64]-key block, this row
+          // two 16-byte pieces (8 keys each) of the row's 128-byte line, XOR-swizzled with (row & 7) like TMA's SWIZZLE_128B
+          const int ch0 = ((c & 63) >> 3) + (g & 1) * 2;
+          *reinterpret_cast<uint4*>(blk + (((ch0) ^ (row & 7)) << 4)) = make_uint4(pk[g * 8], pk[g * 8 + 1], pk[g * 8 + 2], pk[g * 8 + 3]);
+          *reinterpret_cast<uint4*>(blk + (((ch0 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[g * 8 + 4], pk[g * 8 + 5], pk[g * 8 + 6], pk[g * 8 + 7]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy smem writes -> visible to the tensor core
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready);
+      } else {
+        mbar_wait(o_full, par ^ 1);                  // the last tile's P V
+        tcgen05_fence_after();
+        ac_epi_bar();                                // its row sums are visible (the other iterations have the row-max barrier)
+      }
+      if (k > 0) {
+        uint32_t res[16];
+        load_res(prev, 0, res);                      // first chunk of the residual: in flight across the barrier
+        if (et < AC_BM) inv_sh[et] = 1.f / (xsum[(par ^ 1) * 256 + et * 2] + xsum[(par ^ 1) * 256 + et * 2 + 1]);
+        ac_epi_bar();
+        drain(prev, res);
+        if (has) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(o_free);
+        }
+      }
+      prev = tile;
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 }  // namespace sdb
 
 extern "C" int sd_attention_core(const void* Q, int ldq, long long strideQ, const void* K, int ldk, long long strideK,
@@ -346,9 +655,22 @@ extern "C" int sd_attention_core(const void* Q, int ldq, long long strideQ, cons
   p.scale = scale; p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out; p.stats_out = stats_out;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC_SMEM); });
+  static bool force_v1 = false;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_core_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
+    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_core_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
+    const char* e = getenv("SDB_ATTN_V1");          // A/B switch for tools/layer_bench.py: the round-1 kernel
+    force_v1 = e != nullptr && e[0] == '1';
+  });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "sd_attention_core");
   const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
+  if (C == 256 && (block % 16) == 0 && scale > 0.f && !force_v1) {
+    // the score-net's own shape (cifar/models/layers.py:505-511 at 256 channels): two-tile software pipeline, see attn_core_v2_kernel
+    if (S == 256) attn_core_v2_kernel<256><<<grid, AC_THREADS, AC2_SMEM, (cudaStream_t)stream>>>(p);
+    else attn_core_v2_kernel<128><<<grid, AC_THREADS, AC2_SMEM, (cudaStream_t)stream>>>(p);
+    return check_cuda(cudaGetLastError(), "sd_attention_core launch");
+  }
   attn_core_kernel<<<grid, AC_THREADS, AC_SMEM, (cudaStream_t)stream>>>(p);
   return check_cuda(cudaGetLastError(), "sd_attention_core launch");
 }
