@@ -30,6 +30,7 @@ constexpr size_t AC_SMEM = (size_t)AC_STAGES * AC_STAGE_BYTES + AC_P_BYTES + AC_
 
 struct AttnCoreParams {
   CUtensorMap q_map, k_map, v_map;      // Q: (C, Sp, nb) box (64, 128, 1); K: (C, Sp, nb) box (64, Sp, 1); V^T: (Sp, C, nb) box (64, C, 1)
+  CUtensorMap r_map, i_map;             // v2: residual (C, Sp, nb) box (64, 128, 1); identity tiles (64, 256) box (64, 128)
   int nb, Sp, C, block, tiles;
   float scale;
   const float* bias;                    // [C] or null
@@ -327,12 +328,27 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_kernel(const __grid_c
 //     bias is a register, the GroupNorm channel sums are thread-local (v1: a 31-shuffle reduce-scatter per 16 columns -- 35 %
 //     of all stall samples in profiles/r01d_ncu_attn_core_phases.txt), a lane-pair exchange packs channel pairs so each store /
 //     residual load instruction touches two 64-byte runs of the NHWC rows;
+//   * the probabilities are normalised BEFORE they are rounded to bf16 (row sums exchanged through shared memory), so the
+//     residual can ride the P V accumulation as four extra K-blocks  O^T[ch] += I[ch][k] x[query][k]  (identity tile x the
+//     residual rows, both through the TMA ring; exact: 1.0 * bf16 into fp32) -- with 4-byte residual loads in the drain, ncu
+//     showed 2/3 (HBM) resp. 1/4 (after an L2 prefetch) of all epilogue stall samples waiting for those words;
 //   * the epilogue warps drain O of tile i-1 AFTER the softmax of tile i: P V of tile i-1 runs under softmax i, Q K^T of tile
 //     i+1 under the drain, and the TMA ring keeps streaming through all of it.
 //
 // Issue order on the tensor pipe: S0, S1, PV0, S2, PV1, ...   (the producer loads in the same order)
 // Barriers: s_full / s_free (S accumulator), p_ready (P in shared memory) / o_full (also "P may be overwritten"), o_free.
-constexpr int AC2_AUX_FLOATS = 2 * 256 /* row max [parity][row][half] */ + 2 * 256 /* row sum */ + 128 /* 1 / sum */;
+// Two [128 x 64] bf16 tiles with ones at (row == 64 j + column), j = 0, 1: the A operand that adds 64 channels of the residual
+// tile to one 128-channel half of O^T inside the P V accumulation (constant-initialised: no allocation, no init launch).
+struct IdentTiles {
+  uint16_t v[2 * 128 * 64];
+  constexpr IdentTiles() : v{} {
+    for (int j = 0; j < 2; ++j)
+      for (int c = 0; c < 64; ++c) v[(j * 128 + j * 64 + c) * 64 + c] = 0x3F80;      // bf16 1.0
+  }
+};
+__device__ const IdentTiles g_attn_ident{};
+
+constexpr int AC2_AUX_FLOATS = 2 * 256 /* row max [parity][row][half] */ + 2 * 256 /* row sum */;
 constexpr size_t AC2_SMEM = (size_t)AC_STAGES * AC_STAGE_BYTES + AC_P_BYTES + AC2_AUX_FLOATS * 4 + 256 + 1024;
 
 template <int SP>
@@ -346,7 +362,6 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
   float* aux = reinterpret_cast<float*>(pbuf + AC_P_BYTES);
   float* xmax = aux;                    // [2][128][2]
   float* xsum = aux + 512;              // [2][128][2]
-  float* inv_sh = aux + 1024;           // [128]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux + AC2_AUX_FLOATS);
   uint64_t* empty_bar = full_bar + AC_STAGES;
   uint64_t* s_full = empty_bar + AC_STAGES;
@@ -401,15 +416,23 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
         const int tile = (int)blockIdx.x + k * (int)gridDim.x;
         if (k + 1 < n_local) load_qk(tile + (int)gridDim.x);
         const int b = tile / M_TILES;
-        if (p.residual)     // the tile's residual rows (64 KB, contiguous) are read by the drain one tile later: pull them into L2 now --
-                            // ncu showed 2/3 of the drain's stall samples waiting for these words to arrive from HBM
-          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p.residual + (size_t)tile * AC_BM * C), "r"(AC_BM * C * 2) : "memory");
         for (int kb = 0; kb < KB2; ++kb) {          // V^T: one 64-key block of all 256 channels
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + (size_t)stage * AC_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], (uint32_t)C * AC_BK * 2);
           tma_load_3d(&p.v_map, st, &full_bar[stage], kb * AC_BK, 0, b);
           if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (p.residual) {
+          const int mt = tile - b * M_TILES;
+          for (int kb = 0; kb < KB1; ++kb) {        // residual: identity tile (kb & 1) + 64 channels of the tile's 128 rows
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + (size_t)stage * AC_STAGE_BYTES;
+            mbar_expect_tx(&full_bar[stage], (uint32_t)2 * AC_BM * AC_BK * 2);
+            tma_load_2d(&p.i_map, st, &full_bar[stage], 0, (kb & 1) * AC_BM);
+            tma_load_3d(&p.r_map, st + AC_BM * AC_BK * 2, &full_bar[stage], kb * AC_BK, mt * AC_BM, b);
+            if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -459,6 +482,19 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
           umma_commit(&empty_bar[stage]);
           if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (p.residual) {
+          for (int kb = 0; kb < KB1; ++kb) {         // + residual channels [64 kb, +64) into channel half kb / 2
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t sr = smem_u32(smem + (size_t)stage * AC_STAGE_BYTES);
+            const uint64_t i_desc = umma_desc_sw128(sr), x_desc = umma_desc_sw128(sr + AC_BM * AC_BK * 2);
+#pragma unroll
+            for (int k4 = 0; k4 < AC_BK / 16; ++k4)
+              umma_bf16(tmem_O + (uint32_t)(kb >> 1) * 128u, i_desc + (uint64_t)(k4 * 2), x_desc + (uint64_t)(k4 * 2), idesc2, 1u);
+            umma_commit(&empty_bar[stage]);
+            if (++stage == AC_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
         umma_commit(o_full);
       }
     }
@@ -467,7 +503,6 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
     const int q = warp & 3;                        // TMEM lane quarter
     const int chalf = (warp - 2) >> 2;             // softmax: alternate 32-column chunks of the row; drain: channel half
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
     const float sl2 = p.scale * 1.4426950408889634f;
     const bool odd = (lane & 1) != 0;
     const int ch = chalf * 128 + row, chp = ch & ~1;                  // drain: this thread's channel / its even-odd pair
@@ -475,45 +510,27 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
     const uint32_t tS = tmem_S + ((uint32_t)(q * 32) << 16);
     const uint32_t tO = tmem_O + (uint32_t)chalf * 128u + ((uint32_t)(q * 32) << 16);
 
-    auto load_res = [&](int tile, int ci, uint32_t (&res)[16]) {      // residual words of queries [32 ci, 32 ci + 32) of `tile`
-      if (!p.residual) return;
+    // O^T of tile `tile` (already normalised, residual included) -> out rows: a lane pair exchanges so that the even lane holds
+    // channels (chp, chp + 1) of query c, the odd lane those of query c + 1; + bias, bf16x2 stores, thread-local channel sums.
+    auto drain = [&](int tile) {
       const int b = tile / M_TILES, mt = tile - b * M_TILES;
-      const __nv_bfloat16* rb = p.residual + ((size_t)b * SP + (size_t)mt * AC_BM) * (size_t)C + (size_t)chp + (odd ? C : 0);
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        res[j] = __ldg(reinterpret_cast<const unsigned int*>(rb + (size_t)(ci * 32 + 2 * j) * C));
-    };
-    // O^T of tile `tile` -> out rows: value (channel ch, query c) scaled by 1 / sum(c); a lane pair exchanges so that the even
-    // lane holds channels (chp, chp + 1) of query c, the odd lane those of query c + 1; + bias + residual, bf16x2 stores.
-    auto drain = [&](int tile, uint32_t (&rc)[16]) {         // rc: the residual words of the first 32 queries, already in flight
-      const int b = tile / M_TILES, mt = tile - b * M_TILES;
-      const size_t base = ((size_t)b * SP + (size_t)mt * AC_BM) * (size_t)C + (size_t)chp;
+      const size_t base = ((size_t)b * SP + (size_t)mt * AC_BM) * (size_t)C + (size_t)chp + (odd ? C : 0);
       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
       for (int ci = 0; ci < 4; ++ci) {
         const int c = ci * 32;
-        uint32_t r[2][16], rn[16];
+        uint32_t r[2][16];
         tmem_ld16(tO + c, r[0]);
         tmem_ld16(tO + c + 16, r[1]);
-        if (ci < 3) load_res(tile, ci + 1, rn);     // one chunk ahead: its latency hides behind this chunk's arithmetic and stores
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {             // queries c + 2j, c + 2j + 1
-          const float2 iv = *reinterpret_cast<const float2*>(inv_sh + c + 2 * j);
-          const float a0 = __uint_as_float(r[j >> 3][(2 * j) & 15]) * iv.x, a1 = __uint_as_float(r[j >> 3][(2 * j + 1) & 15]) * iv.y;
+          const float a0 = __uint_as_float(r[j >> 3][(2 * j) & 15]), a1 = __uint_as_float(r[j >> 3][(2 * j + 1) & 15]);
           const float recv = __shfl_xor_sync(0xffffffffu, odd ? a0 : a1, 1);
-          float e0 = (odd ? recv : a0) + bv0, e1 = (odd ? a1 : recv) + bv1;
-          if (p.residual) {
-            e0 += __uint_as_float(rc[j] << 16);
-            e1 += __uint_as_float(rc[j] & 0xFFFF0000u);
-          }
+          const float e0 = (odd ? recv : a0) + bv0, e1 = (odd ? a1 : recv) + bv1;
           s0 += e0; q0 = fmaf(e0, e0, q0);
           s1 += e1; q1 = fmaf(e1, e1, q1);
-          *reinterpret_cast<__nv_bfloat162*>(p.out + base + (size_t)(c + 2 * j + (odd ? 1 : 0)) * C) = __floats2bfloat162_rn(e0, e1);
-        }
-        if (ci < 3) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) rc[j] = rn[j];
+          *reinterpret_cast<__nv_bfloat162*>(p.out + base + (size_t)(c + 2 * j) * C) = __floats2bfloat162_rn(e0, e1);
         }
       }
       if (p.stats_out) {                           // channel totals over the tile's 128 queries: mine + the lane partner's
@@ -563,20 +580,28 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
         ac_epi_bar();
         mx = fmaxf(xmax[par * 256 + row * 2], xmax[par * 256 + row * 2 + 1]);     // finite: the row's own column is inside its block
         const float mxs = mx * sl2;
-        // e = exp(scale (s - max)) once per element, kept UNNORMALISED as packed bf16 pairs (1 / sum is applied to the output column)
-        uint32_t pk[NCH * 16];
+        // e = exp(scale (s - max)) once per element (kept in the S registers); the row sum is exchanged with the partner thread
+        // and the probabilities are normalised before they are rounded to bf16
         float sum = 0.f;
 #pragma unroll
         for (int g = 0; g < NCH * 2; ++g)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float e0 = exp2f(fmaf(__uint_as_float(s[g][2 * j]), sl2, -mxs));
-            const float e1 = exp2f(fmaf(__uint_as_float(s[g][2 * j + 1]), sl2, -mxs));
-            sum += e0 + e1;
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(e0, e1);
-            pk[g * 8 + j] = *reinterpret_cast<const uint32_t*>(&hh);
+          for (int j = 0; j < 16; ++j) {
+            const float e = exp2f(fmaf(__uint_as_float(s[g][j]), sl2, -mxs));
+            sum += e;
+            s[g][j] = __float_as_uint(e);
           }
         xsum[par * 256 + row * 2 + chalf] = sum;
+        ac_epi_bar();
+        const float inv = 1.f / (xsum[par * 256 + row * 2] + xsum[par * 256 + row * 2 + 1]);
+        uint32_t pk[NCH * 16];
+#pragma unroll
+        for (int g = 0; g < NCH * 2; ++g)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(s[g][2 * j]) * inv, __uint_as_float(s[g][2 * j + 1]) * inv);
+            pk[g * 8 + j] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
         if (k > 0) {
           mbar_wait(o_full, par ^ 1);                // P V of the previous tile has retired: P may be overwritten, O(k-1) is complete
           tcgen05_fence_after();
@@ -597,14 +622,9 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_v2_kernel(const __gri
       } else {
         mbar_wait(o_full, par ^ 1);                  // the last tile's P V
         tcgen05_fence_after();
-        ac_epi_bar();                                // its row sums are visible (the other iterations have the row-max barrier)
       }
       if (k > 0) {
-        uint32_t res[16];
-        load_res(prev, 0, res);                      // first chunk of the residual: in flight across the barrier
-        if (et < AC_BM) inv_sh[et] = 1.f / (xsum[(par ^ 1) * 256 + et * 2] + xsum[(par ^ 1) * 256 + et * 2 + 1]);
-        ac_epi_bar();
-        drain(prev, res);
+        drain(prev);
         if (has) {
           tcgen05_fence_before();
           __syncwarp();
@@ -666,6 +686,23 @@ extern "C" int sd_attention_core(const void* Q, int ldq, long long strideQ, cons
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "sd_attention_core");
   const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
   if (C == 256 && (block % 16) == 0 && scale > 0.f && !force_v1) {
+    if (residual) {
+      // the residual rides the P V accumulation: its rows as a TMA operand + the constant identity tiles
+      cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)S, (cuuint64_t)batch};
+      cuuint64_t sr[2] = {(cuuint64_t)C * 2, (cuuint64_t)S * C * 2};
+      cuuint32_t boxr[3] = {AC_BK, AC_BM, 1};
+      int rc = encode_map(&p.r_map, residual, 3, dims, sr, boxr);
+      static void* ident = nullptr;
+      static std::once_flag ionce;
+      static cudaError_t ierr = cudaSuccess;
+      std::call_once(ionce, [] { ierr = cudaGetSymbolAddress(&ident, g_attn_ident); });
+      if (ierr != cudaSuccess) return check_cuda(ierr, "sd_attention_core (identity tiles)");
+      cuuint64_t dimi[2] = {AC_BK, 2 * AC_BM};
+      cuuint64_t si[1] = {AC_BK * 2};
+      cuuint32_t boxi[2] = {AC_BK, AC_BM};
+      if (rc == SD_OK) rc = encode_map(&p.i_map, ident, 2, dimi, si, boxi);
+      if (rc != SD_OK) return rc;
+    }
     // the score-net's own shape (cifar/models/layers.py:505-511 at 256 channels): two-tile software pipeline, see attn_core_v2_kernel
     if (S == 256) attn_core_v2_kernel<256><<<grid, AC_THREADS, AC2_SMEM, (cudaStream_t)stream>>>(p);
     else attn_core_v2_kernel<128><<<grid, AC_THREADS, AC2_SMEM, (cudaStream_t)stream>>>(p);
