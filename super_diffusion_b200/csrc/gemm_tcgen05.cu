@@ -951,9 +951,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           float* gtab = ebias + 8 * MAX_BN;
           float* wred = gtab + 2 * MAX_BN;
           const int warp_e = warp - 2;
-          // pairs always run 256-column tiles, single CTAs reach this path with 128-column tiles (see launch_gemm)
+          // pairs run 256-column tiles (or 128 below 148 tiles), single CTAs reach this path with 128-column tiles (see launch_gemm)
           if constexpr (PAIR) {
-            if (p.HW == 64) gn_rows_epilogue<4, 64, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+            if (p.block_n == 128) {              // halved-N pairs (4x4 level below 148 tiles)
+              if (p.HW == 64) gn_rows_epilogue<2, 64, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+              else gn_rows_epilogue<2, 16, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
+            } else if (p.HW == 64) gn_rows_epilogue<4, 64, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
             else gn_rows_epilogue<4, 16, true>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
           } else {
             if (p.HW == 64) gn_rows_epilogue<2, 64, false>(p, taddr, row, q, chalf, lane, warp_e, et, eb_row, gtab, wred, row_ok, row_off, n_base, &tmem_empty[acc]);
@@ -1081,6 +1084,15 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
       p.pair = 1;
       p.cluster = 2;
     }
+    // low-resolution layers whose N = 256 was halved above to spread < 148 tiles over the SMs (4x4 level at batch 512: 64 m-tiles
+    // x 2): as pairs of M = 256 pixels x N = 128 channels each SM still owns one 128 x 128 accumulator but receives its pixel tile
+    // and 64 weight rows (24 KB) instead of 128 (32 KB) per K-block -- these launches run at 2.5x their MMA time on the L2 -> SM feed
+    static const int want_pair128 = [] { const char* e = getenv("SDB_GEMM_PAIR128"); return e ? atoi(e) : 1; }();   // tuning knob
+    if (want_pair && want_pair128 && !p.pair && !p.dual && p.cluster == 1 && p.block_n == 128 && n_pad == MAX_BN && !p.flat &&
+        !p.b_batched && !(flags & SD_EPI_SOFTMAX) && p.m_tiles >= 2) {
+      p.pair = 1;
+      p.cluster = 2;
+    }
   }
   // N = 128 conv layers (all 32x32 layers of the score-net): as two 128 x 128 x 16 instructions per K step (dual) the tensor
   // pipe ran at 45-60 % -- every 64-clk instruction re-reads its 4 KB A tile AND the 4 KB weight tile from shared memory
@@ -1121,7 +1133,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     // thread = pixel-row tiles that hold whole images (8x8: two per tile, 4x4: eight; N = 256 so that a group is 8 adjacent columns)
     if (!fuse && long_k && want_gn_fuse && p.gn_gamma != nullptr && !(flags & (SD_GEMM_SPLIT3 | SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) &&
         !residual && !p.swap && !p.dual && !p.flat && p.up_phase < 0 && !p.stride2 && N == MAX_BN &&
-        p.block_n == (p.pair ? MAX_BN : 128) && (p.HW == 16 || p.HW == 64) && p.imgs_per_tile == BM / p.HW &&
+        (p.block_n == 128 || (p.pair && p.block_n == MAX_BN)) && (p.HW == 16 || p.HW == 64) && p.imgs_per_tile == BM / p.HW &&
         (out_ld % 8) == 0 && p.cluster == (p.pair ? 2 : 1))
       fuse = true;
     if (!fuse) {
