@@ -42,6 +42,7 @@
 #include "tcgen05_util.cuh"
 #include "../../include/superdiff_b200.h"
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 
@@ -98,6 +99,11 @@ struct GemmParams {
   int gn_swish;
   __nv_bfloat16* gn_raw_out;  // optional second output of a fused launch: the raw (un-normalised) conv result, bf16, same layout / ld as
                               //    `out` -- for tensors that stay on the residual stream while their GroupNorm feeds the next layer
+  int gx_units;               // > 1: the gx_units CTAs that hold one image (consecutive blockIdx, same tile round) exchange their GroupNorm
+                              //    channel sums through global memory (gx_data / gx_cnt) instead of a thread-block cluster: clusters of 4
+                              //    CTAs at one CTA per SM only fit 33 times on the 148 SMs (GPCs of 18-20 SMs), plain CTAs use all of them
+  float* gx_data;             // [2 * grid / gx_units slots][gx_units][2][128] channel sums
+  int* gx_cnt;                // [slots][2]: arrivals, readers done (self-resetting: the last reader zeroes both)
   int dual;                   // 1: each CTA tile is TWO adjacent 128-row m-tiles sharing one B tile (block_n <= 128)
   int swap;                   // 1 (dual, conv mode, N = 128): operands swapped inside the MMA -- D^T[128 channels x 256 pixels] =
                               //    W[128 x K] * X^T: ONE M=128, N=256 instruction per K step instead of two N=128 ones (see launch_gemm)
@@ -702,6 +708,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           const int gbuf = (int)(gn_it & 1u);
           const int gw = et / BM, gn_n = et - gw * BM;                   // threads 0..255: (which, channel)
           const float unit_tot = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];    // this unit's channel total (raw stats)
+          int* gx_done = nullptr;
           if (xchg) {
             xsum[(gbuf * 2 + gw) * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
             epi_bar();                                                    // every channel sum of this CTA is written ...
@@ -711,12 +718,43 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             float t = 0.f;
             for (int r = 0; r < csize; ++r) t += ld_dsmem_f32(&xsum[(gbuf * 2 + gw) * BM + gn_n], (uint32_t)r);    // fixed order
             ctot[gw * BM + gn_n] = t;
+          } else if (p.gx_units > 1) {
+            // exchange through global memory: the image's gx_units CTAs are consecutive blocks in the same tile round (the grid is
+            // a multiple of gx_units and co-resident: cooperative launch); a group alternates between two slots, so a slot is
+            // reused only after its last reader has zeroed the counters (that reader arrives at the next round after the reset)
+            const int U = p.gx_units, u = (int)blockIdx.x % U;
+            const int slot = ((int)blockIdx.x / U) * 2 + gbuf;
+            float* gd = p.gx_data + (size_t)slot * U * 2 * BM;
+            int* cnt = p.gx_cnt + slot * 2;
+            gd[u * 2 * BM + et] = unit_tot;                                 // et == gw * 128 + gn_n
+            epi_bar();
+            if (et == 0) {
+              __threadfence();                                             // the CTA's sums (ordered by the barrier) before the arrival
+              atomicAdd(cnt, 1);
+              const long long t0 = clock64();
+              while (*reinterpret_cast<volatile int*>(cnt) < U) {
+                __nanosleep(64);
+                if (clock64() - t0 > 4000000000LL) __trap();              // peers not resident: a launch failure, never a hung GPU
+              }
+              __threadfence();
+            }
+            epi_bar();
+            float t = 0.f;
+            for (int r = 0; r < U; ++r) t += __ldcg(gd + r * 2 * BM + et);  // fixed order; L2 (the peers' writes are not in this SM's L1)
+            ctot[gw * BM + gn_n] = t;
+            gx_done = cnt + 1;
           } else {
             ctot[gw * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
           }
           ++gn_it;
           const float gam = ch_ok ? p.gn_gamma[ch] : 0.f, bet = ch_ok ? p.gn_beta[ch] : 0.f;    // issued ahead of the barrier
           epi_bar();
+          if (gx_done != nullptr && et == 0) {                             // every thread of this CTA has read the slot
+            if (atomicAdd(gx_done, 1) == p.gx_units - 1) {
+              gx_done[-1] = 0; gx_done[0] = 0;
+              __threadfence();
+            }
+          }
           // group statistics in fp32, every thread for its own channel's group (a handful of shared-memory reads and FMAs).
           // fp64 here -- first per thread, then one thread per group behind a barrier -- put the fp64 division / rsqrt
           // subroutines on the epilogue's critical path: ncu showed 40-55 % of all stall samples at that barrier and the tensor
@@ -1035,6 +1073,25 @@ static int gn_fuse_level() {
   return v;
 }
 
+// Exchange area of the global-memory GroupNorm exchange (GemmParams::gx_units): one region per stream that issues such launches
+// (launches on one stream are serialised, so a region has one user at a time), 2 slots per group of CTAs.
+constexpr int GX_REGIONS = 8, GX_MAX_GROUPS = 128, GX_MAX_UNITS = 4;
+__device__ float g_gx_data[GX_REGIONS * GX_MAX_GROUPS * 2 * GX_MAX_UNITS * 2 * BM];
+__device__ int g_gx_cnt[GX_REGIONS * GX_MAX_GROUPS * 2 * 2];
+
+// -> region index of `st`, or -1 when more than GX_REGIONS distinct streams have asked (the launch then uses clusters)
+static int gx_region_of(cudaStream_t st) {
+  static std::mutex mu;
+  static cudaStream_t seen[GX_REGIONS];
+  static int nseen = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < nseen; ++i)
+    if (seen[i] == st) return i;
+  if (nseen == GX_REGIONS) return -1;
+  seen[nseen] = st;
+  return nseen++;
+}
+
 static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, long long strideB, int nbatchB,
                        const float* bias, const float* rowbias, int rowbias_ld, const void* residual, unsigned flags,
                        void* out, int out_ld, cudaStream_t st, const char* who, float* stats_out = nullptr) {
@@ -1127,7 +1184,31 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
         // but 268 MB of DRAM traffic per GroupNorm disappear, and the power-capped timestep gets 2 % faster (profiles/r02_notes.md).
         const int units_per_img = p.tiles_per_img / 2;
         fuse = (units_per_img == 1 || (want_gn_fuse >= 2 && (units_per_img == 2 || units_per_img == 4))) && (num_sms() % units_per_img) == 0;
-        if (fuse && units_per_img > 1) { p.cluster = units_per_img; p.mcast = 1; }
+        if (fuse && units_per_img > 1) {
+          // default: plain CTAs on every SM exchanging through global memory (cooperative launch); SDB_GN_GX=0 or no free region:
+          // the cluster + distributed-shared-memory form on the 33 co-resident clusters of 4
+          static const int want_gx = [] { const char* e = getenv("SDB_GN_GX"); return e ? atoi(e) : 1; }();   // tuning knob
+          static float* gx_data = nullptr;
+          static int* gx_cnt = nullptr;
+          static std::once_flag gx_once;
+          std::call_once(gx_once, [] {
+            void *d = nullptr, *c = nullptr;
+            if (cudaGetSymbolAddress(&d, g_gx_data) == cudaSuccess && cudaGetSymbolAddress(&c, g_gx_cnt) == cudaSuccess) {
+              gx_data = reinterpret_cast<float*>(d);
+              gx_cnt = reinterpret_cast<int*>(c);
+            } else {
+              cudaGetLastError();
+            }
+          });
+          const int region = (want_gx && gx_data && p.n_tiles == 1 && num_sms() / units_per_img <= GX_MAX_GROUPS) ? gx_region_of(st) : -1;
+          if (region >= 0) {
+            p.gx_units = units_per_img;
+            p.gx_data = gx_data + (size_t)region * GX_MAX_GROUPS * 2 * GX_MAX_UNITS * 2 * BM;
+            p.gx_cnt = gx_cnt + (size_t)region * GX_MAX_GROUPS * 2 * 2;
+          } else {
+            p.cluster = units_per_img; p.mcast = 1;
+          }
+        }
       }
     }
     // thread = pixel-row tiles that hold whole images (8x8: two per tile, 4x4: eight; N = 256 so that a group is 8 adjacent columns)
@@ -1227,14 +1308,20 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;
   const int groups = ((m_units_h + p.cluster - 1) / p.cluster) * p.n_tiles * phases;
   const int max_clusters = num_sms() / p.cluster;
-  const int grid = (groups < max_clusters ? groups : max_clusters) * p.cluster;
+  int grid = (groups < max_clusters ? groups : max_clusters) * p.cluster;
+  if (p.gx_units > 1) grid = grid / p.gx_units * p.gx_units;     // whole images per tile round (the tile count is a multiple of gx_units)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = GEMM_SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[3];
   int nattr = 0;
+  if (p.gx_units > 1) {        // the CTAs of an image wait for each other: the whole (persistent, <= 1 CTA per SM) grid must be co-resident
+    attr[nattr].id = cudaLaunchAttributeCooperative;
+    attr[nattr].val.cooperative = 1;
+    ++nattr;
+  }
   if (p.cluster > 1) {
     attr[nattr].id = cudaLaunchAttributeClusterDimension;
     attr[nattr].val.clusterDim.x = p.cluster;
