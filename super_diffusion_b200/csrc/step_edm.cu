@@ -9,6 +9,7 @@
 // HBM bytes per sample: 4*D*6.
 #include "common.cuh"
 #include <cstdlib>
+#include <cstdio>
 #include "../../include/superdiff_b200.h"
 
 namespace sdb {
@@ -27,8 +28,8 @@ constexpr int SD_EDM_MODE_AND_ODE = 100;   // internal: deterministic AND (clip_
 // reductions (all per sample):
 //  0 dd=<d,d>  1 bd=<base,d>  2 zd=<z,d>  3 oo=<vo,vo>  4 bb=<vb,vb>  5 ob=<vo,base>  6 od=<vo,d>  7 oz=<vo,z>
 //  with d = vo - vb, base = vu + g (vb - vu)
-template <int NV, bool CLUSTER>
-__global__ void __launch_bounds__(256) step_edm_kernel(const __grid_constant__ EdmParams p) {
+template <int NV, bool CLUSTER, int MAXT = 256>
+__global__ void __launch_bounds__(MAXT) step_edm_kernel(const __grid_constant__ EdmParams p) {
   extern __shared__ double scratch[];
   unsigned csize = 1, crank = 0;
   if (CLUSTER) {
@@ -415,8 +416,18 @@ static cudaError_t launch_edm(const EdmParams& p, int threads, int cluster, cuda
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (threads > 512) {
+      if constexpr (NV <= 2) return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, true, 1024>, p);
+      else return cudaErrorInvalidConfiguration;          // 4 float4 per thread x 5 arrays do not fit 64 registers
+    }
+    if (threads > 256) return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, true, 512>, p);
     return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, true>, p);
   }
+  if (threads > 512) {
+    if constexpr (NV <= 2) return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, false, 1024>, p);
+    else return cudaErrorInvalidConfiguration;
+  }
+  if (threads > 256) return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, false, 512>, p);
   return cudaLaunchKernelEx(&cfg, step_edm_kernel<NV, false>, p);
 }
 
@@ -474,8 +485,22 @@ static int step_edm_impl(const float* latents, const float* z, const float* v_ob
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_c = c; best_t = t; best_nv = n; }
       }
   if (best_cost < 0) return fail(kErrUnsupported, "sd_step_edm_cfg: D too large (max 8*256*2 float4 per sample)");
+  // few samples (BASELINE config 4: batch 64): clusters of 4 CTAs with four float4 per thread instead of clusters of 8 with two --
+  // half as many CTAs to schedule, the same bytes in flight per SM: 10.9 -> 8.6 us at batch 64; at batch 96 the order flips
+  // (12.7 vs 14.5 us), so only while the grid stays within two CTAs per SM (profiles/r04j_edm_shapes.txt)
+  if (best_c == 8 && best_t == 256 && best_nv == 2 && (long)B * 4 <= 2L * 148 && (long)4 * 256 * 4 >= nunits) { best_c = 4; best_nv = 4; }
+  // SDB_EDM_SHAPE="cluster,threads,nv" forces a launch shape (tools/edm_sweep.py --shape); it must hold the sample
+  static const char* shape_env = getenv("SDB_EDM_SHAPE");
+  if (shape_env && *shape_env) {
+    int c = 0, t = 0, n = 0;
+    if (sscanf(shape_env, "%d,%d,%d", &c, &t, &n) == 3 && (c == 1 || c == 2 || c == 4 || c == 8) && t >= 64 && t <= 1024 && (t % 32) == 0 &&
+        (n == 1 || n == 2 || n == 4) && (long)c * t * n >= nunits && !(n == 4 && t > 512)) {
+      best_c = c; best_t = t; best_nv = n;
+    }
+  }
   cudaError_t err = best_nv == 1 ? launch_edm<1>(p, best_t, best_c, (cudaStream_t)stream)
-                                 : launch_edm<2>(p, best_t, best_c, (cudaStream_t)stream);
+                  : best_nv == 2 ? launch_edm<2>(p, best_t, best_c, (cudaStream_t)stream)
+                                 : launch_edm<4>(p, best_t, best_c, (cudaStream_t)stream);
   return check_cuda(err, "sd_step_edm_cfg launch");
 }
 

@@ -421,6 +421,21 @@ def test_conv_in_tensor_core_form(cuda, B, H, Cin, Cout):
     _close(old, ref, rtol=2e-2)
 
 
+@pytest.mark.parametrize("B,H,W,Cin", [(3, 12, 12, 3), (2, 32, 32, 2), (600, 32, 32, 3), (5, 8, 64, 1)])
+def test_im2col_in_gather_any_geometry(cuda, B, H, W, Cin):
+    """sd_im2col_in alone: tile form (image rows staged in shared memory, eight lanes per pixel) where 128 % W == 0 and whole rows
+    make a 128-pixel tile, one thread per pixel otherwise; more tiles than the grid; hi + lo reproduces the fp32 neighbourhood."""
+    g = torch.Generator().manual_seed(B + H + W + Cin)
+    x = torch.randn(B, H, W, Cin, generator=g) * 3.0
+    a = ops.im2col_in(x.to(cuda)).float().cpu()
+    xp = F.pad(x.permute(0, 3, 1, 2), (1, 1, 1, 1))
+    nb = torch.stack([xp[:, :, kh:kh + H, kw:kw + W] for kh in range(3) for kw in range(3)], dim=1)   # [B, 9, Cin, H, W]
+    nb = nb.permute(0, 3, 4, 1, 2).reshape(B, H, W, 9 * Cin)
+    assert torch.allclose(a[..., :9 * Cin] + a[..., 9 * Cin:18 * Cin], nb, rtol=2e-5, atol=1e-6)
+    assert torch.equal(a[..., :9 * Cin], nb.bfloat16().float())
+    assert (a[..., 18 * Cin:] == 0).all()
+
+
 @pytest.mark.parametrize("nb,Sp,block,C,stats", [(5, 256, 256, 256, True), (150, 256, 256, 256, True), (6, 128, 64, 256, False),
                                                   (7, 128, 16, 256, False), (3, 128, 128, 128, True)])
 def test_attention_core_fused(cuda, nb, Sp, block, C, stats):
@@ -583,3 +598,22 @@ def test_fused_groupnorm_is_deterministic_under_repetition(cuda):
             else:
                 assert torch.equal(out, first), (B, H, rep)
         assert torch.isfinite(first.float()).all()
+
+
+@pytest.mark.parametrize("env,select", [
+    ({"SDB_GN_GX": "0"}, "test_conv_gemm_with_fused_groupnorm and (296-32 or 297-32) and False"),     # cluster-of-4 + DSMEM exchange
+    ({"SDB_GN_GX": "0"}, "test_fused_groupnorm_is_deterministic_under_repetition"),
+    ({"SDB_ATTN_V1": "1"}, "test_attention_core_fused"),                                              # the round-1 attention kernel
+    ({"SDB_GEMM_PAIR128": "0"}, "test_conv_gemm_with_fused_groupnorm and 512-4-512 and False"),       # single-CTA 128-column tiles at 4x4
+])
+def test_fallback_kernels_behind_tuning_knobs(cuda, env, select):
+    """The launch shapes that are no longer the default stay reachable (more than 8 streams asking for the global-memory
+    GroupNorm exchange fall back to clusters; C != 256 attention takes the v1 kernel): the same parity tests in a child process
+    with the knob set (the knobs are read once per process)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-m", "gpu", "-x", "-q", "-k", f"({select}) and not fallback",
+                        "-p", "no:cacheprovider"], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout, r.stdout[-500:]
