@@ -833,23 +833,40 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             for (int h = 0; h < 2; ++h) {
               float v[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float x = __uint_as_float(r[h][j]) + bv;
-                v[j] = x;
-                ssum += x;
-                ssq = fmaf(x, x, ssq);
+              for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[h][j]) + bv;
+              if (do_stats) {                    // uniform: 1x1 projections and shortcut-free layers carry no GroupNorm sums
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  ssum += v[j];
+                  ssq = fmaf(v[j], v[j], ssq);
+                }
               }
               __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
               const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;    // tiles are whole (HW % 256 == 0)
+              // The exchange first (every lane takes part), then ONE branch around the eight stores: with the test inside the
+              // loop the compiler emitted a branch + reconvergence pair per store (ncu: 13.5 instructions per element, 2.6 of
+              // them control flow, in launches whose four K-blocks cannot hide this epilogue).
+              float e0[8], e1[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
-                const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;       // channels (ch & ~1, ch | 1) of one pixel
-                const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0, e1);
-                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = h2;
-                if (split && ok)
-                  *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld + p.N_out) =
-                      __floats2bfloat162_rn(e0 - __low2float(h2), e1 - __high2float(h2));
+              for (int j = 0; j < 8; ++j) {
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[2 * j] : v[2 * j + 1], 1);
+                e0[j] = odd ? recv : v[2 * j];                                          // channels (ch & ~1, ch | 1) of one pixel
+                e1[j] = odd ? v[2 * j + 1] : recv;
+              }
+              if (ok) {
+                const size_t ld2 = 2 * (size_t)p.out_ld;
+                if (!split) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * ld2) = __floats2bfloat162_rn(e0[j], e1[j]);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(e0[j], e1[j]);
+                    *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * ld2) = h2;
+                    *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * ld2 + p.N_out) =
+                        __floats2bfloat162_rn(e0[j] - __low2float(h2), e1[j] - __high2float(h2));
+                  }
+                }
               }
             }
             if (do_stats && (it & 1)) {
