@@ -783,22 +783,33 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
               }
               __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
               const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;
+              const size_t ld2 = 2 * (size_t)p.out_ld;
+              // exchange first (every lane takes part), then one branch around the eight stores (see the plain epilogue below)
+              uint32_t wn[8];
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[j] : v[j + 1], 1);
-                const float e0 = odd ? recv : v[j], e1 = odd ? v[j + 1] : recv;
-                if (ok) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * p.out_ld) = __floats2bfloat162_rn(e0, e1);
+              for (int j = 0; j < 8; ++j) {
+                const float recv = __shfl_xor_sync(0xffffffffu, odd ? v[2 * j] : v[2 * j + 1], 1);
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(odd ? recv : v[2 * j], odd ? v[2 * j + 1] : recv);
+                wn[j] = *reinterpret_cast<const uint32_t*>(&h2);
+              }
+              if (ok) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint32_t*>(orow + (size_t)j * ld2) = wn[j];
               }
               if (p.gn_raw_out != nullptr) {
                 // second output: the raw tensor (already bf16 in the parked registers).  A parked word is (pixel j, pixel j+1) of
                 // this thread's channel; a stored word is (channel even, channel odd) of one pixel: swap halves with the lane partner.
                 __nv_bfloat16* rrow = p.gn_raw_out + (ch & ~1) + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+                uint32_t wr[8];
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                   const uint32_t mine = pk[it * 16 + h * 8 + jj];
                   const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 1);
-                  const uint32_t word = odd ? __byte_perm(mine, other, 0x3276) : __byte_perm(mine, other, 0x5410);
-                  if (ok) *reinterpret_cast<uint32_t*>(rrow + (size_t)(2 * jj) * p.out_ld) = word;
+                  wr[jj] = odd ? __byte_perm(mine, other, 0x3276) : __byte_perm(mine, other, 0x5410);
+                }
+                if (ok) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) *reinterpret_cast<uint32_t*>(rrow + (size_t)jj * ld2) = wr[jj];
                 }
               }
             }
