@@ -154,6 +154,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # NCCL_DEBUG=VERSION (set on the GPU boxes) prints "NCCL version ..." on stdout ahead of the result: stdout carries ONE JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     hbm_peak, tf_peak, peak_kind = _peaks()
