@@ -10,6 +10,8 @@
 //   phase 2   O[128 x C]   = P . (V^T)^T             A operand = P from shared memory, B = V^T tiles by TMA, TMEM cols [256, 256+C)
 //   epilogue  + bias + residual -> bf16 out, optional per-tile channel sums for the following GroupNorm
 //
+// (This header describes attn_core_kernel, the round-1 form that still serves C != 256; the score-net's own shape, C = 256, takes
+// attn_core_v2_kernel further down: the same phases software-pipelined over two tiles.)
 // One CTA per SM, persistent over (batch entry, 128-row query tile); the MMA issuer starts the next tile's phase 1 as soon as
 // this tile's phase 2 is issued (S is free by then), so it overlaps the epilogue; warp 0 = TMA producer (runs ahead through a 3-stage ring,
 // so the V^T tiles of phase 2 and the next tile's Q / K arrive during the softmax), warp 1 = MMA issuer, warps 2..9 = softmax +
@@ -326,8 +328,8 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_kernel(const __grid_c
 //   * P V is issued with the operand roles exchanged: O^T[channel][query] = V^T[channel][key] . P[query][key]^T, two M = 128
 //     channel halves, N = 128 queries (the bytes in shared memory are the same).  An epilogue thread now owns ONE channel:
 //     bias is a register, the GroupNorm channel sums are thread-local (v1: a 31-shuffle reduce-scatter per 16 columns -- 35 %
-//     of all stall samples in profiles/r01d_ncu_attn_core_phases.txt), a lane-pair exchange packs channel pairs so each store /
-//     residual load instruction touches two 64-byte runs of the NHWC rows;
+//     of all stall samples in profiles/r01d_ncu_attn_core_phases.txt), a lane-pair exchange packs channel pairs so each store
+//     instruction touches two 64-byte runs of the NHWC rows;
 //   * the probabilities are normalised BEFORE they are rounded to bf16 (row sums exchanged through shared memory), so the
 //     residual can ride the P V accumulation as four extra K-blocks  O^T[ch] += I[ch][k] x[query][k]  (identity tile x the
 //     residual rows, both through the TMA ring; exact: 1.0 * bf16 into fp32) -- with 4-byte residual loads in the drain, ncu
@@ -337,6 +339,7 @@ __global__ void __launch_bounds__(AC_THREADS, 1) attn_core_kernel(const __grid_c
 //
 // Issue order on the tensor pipe: S0, S1, PV0, S2, PV1, ...   (the producer loads in the same order)
 // Barriers: s_full / s_free (S accumulator), p_ready (P in shared memory) / o_full (also "P may be overwritten"), o_free.
+
 // Two [128 x 64] bf16 tiles with ones at (row == 64 j + column), j = 0, 1: the A operand that adds 64 channels of the residual
 // tile to one 128-channel half of O^T inside the P V accumulation (constant-initialised: no allocation, no init launch).
 struct IdentTiles {
@@ -692,11 +695,21 @@ extern "C" int sd_attention_core(const void* Q, int ldq, long long strideQ, cons
       cuuint64_t sr[2] = {(cuuint64_t)C * 2, (cuuint64_t)S * C * 2};
       cuuint32_t boxr[3] = {AC_BK, AC_BM, 1};
       int rc = encode_map(&p.r_map, residual, 3, dims, sr, boxr);
-      static void* ident = nullptr;
-      static std::once_flag ionce;
-      static cudaError_t ierr = cudaSuccess;
-      std::call_once(ionce, [] { ierr = cudaGetSymbolAddress(&ident, g_attn_ident); });
-      if (ierr != cudaSuccess) return check_cuda(ierr, "sd_attention_core (identity tiles)");
+      // a __device__ variable has one instance per device: look the address up per device (cached)
+      static void* ident_of[64] = {};
+      static std::mutex imu;
+      int dev = 0;
+      cudaGetDevice(&dev);
+      void* ident = nullptr;
+      {
+        std::lock_guard<std::mutex> lock(imu);
+        if (dev < 0 || dev >= 64) return fail(kErrUnsupported, "sd_attention_core: device ordinal out of range");
+        if (!ident_of[dev]) {
+          const cudaError_t ierr = cudaGetSymbolAddress(&ident_of[dev], g_attn_ident);
+          if (ierr != cudaSuccess) { ident_of[dev] = nullptr; return check_cuda(ierr, "sd_attention_core (identity tiles)"); }
+        }
+        ident = ident_of[dev];
+      }
       cuuint64_t dimi[2] = {AC_BK, 2 * AC_BM};
       cuuint64_t si[1] = {AC_BK * 2};
       cuuint32_t boxi[2] = {AC_BK, AC_BM};

@@ -1216,18 +1216,30 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
           // default: plain CTAs on every SM exchanging through global memory (cooperative launch); SDB_GN_GX=0 or no free region:
           // the cluster + distributed-shared-memory form on the 33 co-resident clusters of 4
           static const int want_gx = [] { const char* e = getenv("SDB_GN_GX"); return e ? atoi(e) : 1; }();   // tuning knob
-          static float* gx_data = nullptr;
-          static int* gx_cnt = nullptr;
-          static std::once_flag gx_once;
-          std::call_once(gx_once, [] {
-            void *d = nullptr, *c = nullptr;
-            if (cudaGetSymbolAddress(&d, g_gx_data) == cudaSuccess && cudaGetSymbolAddress(&c, g_gx_cnt) == cudaSuccess) {
-              gx_data = reinterpret_cast<float*>(d);
-              gx_cnt = reinterpret_cast<int*>(c);
-            } else {
-              cudaGetLastError();
+          // __device__ variables have one instance per device: addresses looked up per device (cached)
+          static float* gx_data_of[64] = {};
+          static int* gx_cnt_of[64] = {};
+          static std::mutex gx_mu;
+          float* gx_data = nullptr;
+          int* gx_cnt = nullptr;
+          {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::lock_guard<std::mutex> lock(gx_mu);
+            if (dev >= 0 && dev < 64) {
+              if (!gx_data_of[dev]) {
+                void *d = nullptr, *c = nullptr;
+                if (cudaGetSymbolAddress(&d, g_gx_data) == cudaSuccess && cudaGetSymbolAddress(&c, g_gx_cnt) == cudaSuccess) {
+                  gx_data_of[dev] = reinterpret_cast<float*>(d);
+                  gx_cnt_of[dev] = reinterpret_cast<int*>(c);
+                } else {
+                  cudaGetLastError();
+                }
+              }
+              gx_data = gx_data_of[dev];
+              gx_cnt = gx_cnt_of[dev];
             }
-          });
+          }
           const int region = (want_gx && gx_data && p.n_tiles == 1 && num_sms() / units_per_img <= GX_MAX_GROUPS) ? gx_region_of(st) : -1;
           if (region >= 0) {
             p.gx_units = units_per_img;
