@@ -86,6 +86,7 @@ struct GemmParams {
   int seg_C[MAX_SEGS], seg_ld[MAX_SEGS], slab_B;
   int slab;                   // 1: the 3x3 stride-1 segments (seg_slab >= 0) are fed as activation slabs shared by the three vertical taps
   int slab_bytes, a_region_bytes;   // bytes of one slab; bytes reserved for A at the start of a ring slot
+  int slab_taps;              // vertical taps that share one slab: 3 (3x3 conv) or 2 (the 2x2-tap phases of the fused upsample + conv)
   CUtensorMap a_slab_map[MAX_SLABS];     // per slab segment: map with a (64, W, hb+2, 1) box
   int num_stages, stage_bytes; // operand ring geometry: stage_bytes = A bytes + B bytes of one K-block (1 KB multiple)
   int pair;                   // 1 (with cluster == 2, non-dual): the two CTAs form one tcgen05 cta_group::2 pair -- M = 256 (two m-tiles),
@@ -505,15 +506,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           const int kb_base = p.seg_bk0[seg];           // K-block index (weight column / 64) where the segment starts
           if (p.slab && p.seg_slab[seg] >= 0) {
             const CUtensorMap* smap = &p.a_slab_map[p.seg_slab[seg]];
-            const uint32_t tx = (PAIR ? 2u : 1u) * ((uint32_t)p.slab_bytes + 3u * b_cta_bytes);
+            const int nt = p.slab_taps;             // 3: 3x3 conv; 2: the 2x2 taps of upsample phase ph
+            const uint32_t tx = (PAIR ? 2u : 1u) * ((uint32_t)p.slab_bytes + (uint32_t)nt * b_cta_bytes);
+            // first slab row / column shift of tap column kw: (c2 - 1, kw - 1) for the 3x3 conv; the phase's taps read source rows
+            // (ph >> 1) - 1 + {0, 1} and columns (ph & 1) - 1 + {0, 1} of the low-resolution image (same as the per-tap path below)
+            const int r0 = nt == 3 ? c2[0] - 1 : c2[0] + (ph >> 1) - 1;
+            const int w0 = nt == 3 ? -1 : (ph & 1) - 1;
             for (int cb = 0; cb < cblocks; ++cb)
-              for (int kw = 0; kw < 3; ++kw) {
+              for (int kw = 0; kw < nt; ++kw) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* sa = smem + (size_t)stage * STAGE_BYTES;
                 if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[stage], tx);
-                load_a(smap, sa, &full_bar[stage], cb * BK, kw - 1, c2[0] - 1, c3[0]);
-                for (int kh = 0; kh < 3; ++kh)
-                  load_b(sa + b_off + kh * b_tile_bytes, &full_bar[stage], (kb_base + (kh * 3 + kw) * cblocks + cb) * BK, n_tile, bz);
+                load_a(smap, sa, &full_bar[stage], cb * BK, w0 + kw, r0, c3[0]);
+                for (int kh = 0; kh < nt; ++kh)
+                  load_b(sa + b_off + kh * b_tile_bytes, &full_bar[stage], (kb_base + (kh * nt + kw) * cblocks + cb) * BK, n_tile, bz);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
               }
           } else {
@@ -563,8 +569,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
         uint32_t accumulate = 0;
         for (int seg = 0; seg < p.nseg; ++seg) {
           const bool slab = p.slab && p.seg_slab[seg] >= 0;
-          const int nsteps = slab ? p.seg_cblocks[seg] * 3 : p.seg_taps[seg] * p.seg_cblocks[seg];
-          const int groups = slab ? 3 : 1;
+          const int nsteps = slab ? p.seg_cblocks[seg] * p.slab_taps : p.seg_taps[seg] * p.seg_cblocks[seg];
+          const int groups = slab ? p.slab_taps : 1;
           for (int st = 0; st < nsteps; ++st) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
@@ -852,7 +858,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                   ssq = fmaf(v[j], v[j], ssq);
                 }
               }
-              __nv_bfloat16* orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+              // first pixel of this lane (even lanes take pixel P, odd lanes P + 1) and the address step between consecutive pixels.
+              // Upsample phase (a, b) of the fused upsample + conv: low-resolution pixel (img, i, j) lands on (2i + a, 2j + b) of
+              // the 2H x 2W output, so a 16-pixel group (one low-resolution row or a part of one: img_W % 16 == 0) is a run of
+              // output pixels with stride 2.
+              size_t pstep = (size_t)p.out_ld;
+              __nv_bfloat16* orow;
+              if (p.up_phase >= 0) {
+                size_t off;
+                row_offset(p, 0, (int)(pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))), off, ph);       // m_tile 0 + row = the pixel index
+                orow = obase + off;
+                pstep = 2 * (size_t)p.out_ld;
+              } else {
+                orow = obase + (pix0 + (size_t)(c + h * 16 + (odd ? 1 : 0))) * (size_t)p.out_ld;
+              }
               const bool ok = pair_ok && pix0 + (size_t)(c + h * 16 + 15) < (size_t)p.M_total;    // tiles are whole (HW % 256 == 0)
               // The exchange first (every lane takes part), then ONE branch around the eight stores: with the test inside the
               // loop the compiler emitted a branch + reconvergence pair per store (ncu: 13.5 instructions per element, 2.6 of
@@ -865,7 +884,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
                 e1[j] = odd ? v[2 * j + 1] : recv;
               }
               if (ok) {
-                const size_t ld2 = 2 * (size_t)p.out_ld;
+                const size_t ld2 = 2 * pstep;
                 if (!split) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) *reinterpret_cast<__nv_bfloat162*>(orow + (size_t)j * ld2) = __floats2bfloat162_rn(e0[j], e1[j]);
@@ -1138,7 +1157,10 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   static const int want_swap = [] { const char* e = getenv("SDB_GEMM_SWAP"); return e ? atoi(e) : 1; }();   // tuning knob
   bool all_1tap = !p.flat;
   for (int sgi = 0; sgi < p.nseg; ++sgi) all_1tap = all_1tap && p.seg_taps[sgi] == 1;
-  const bool swap_epi_ok = want_swap && !p.flat && p.up_phase < 0 && !p.stride2 && (N % 128) == 0 && p.imgs_per_tile == 1 &&
+  // upsample phases: the strided-pixel store of the swapped epilogue needs a 16-pixel group inside one low-resolution row
+  static const int want_swap_up = [] { const char* e = getenv("SDB_GEMM_SWAP_UP"); return e ? atoi(e) : 1; }();   // tuning knob
+  const bool up_ok = p.up_phase < 0 || (want_swap_up && (p.img_W % 16) == 0 && N == MAX_BN);
+  const bool swap_epi_ok = want_swap && !p.flat && up_ok && !p.stride2 && (N % 128) == 0 && p.imgs_per_tile == 1 &&
                            (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
                            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0;
   if (swap_epi_ok && all_1tap && N > 128) p.block_n = 128;
@@ -1277,16 +1299,17 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     if (want_slab && any_cand && (p.dual || p.pair) && (p.mcast == 1 || p.pair) && p.imgs_per_tile == 1 &&
         (nsub_h == 1 || (p.tiles_per_img % 2) == 0)) {
       const int hb = nsub_h * p.h_box;
-      const int slab_bytes = (hb + 2) * p.img_W * BK * 2;
+      const int nt = p.slab_taps;                // vertical taps per slab: hb + nt - 1 image rows
+      const int slab_bytes = (hb + nt - 1) * p.img_W * BK * 2;
       int a_region = slab_bytes > nsub_h * A_BYTES ? slab_bytes : nsub_h * A_BYTES;
       a_region = (a_region + 1023) / 1024 * 1024;
-      if (2 * (a_region + 3 * b_cta) <= RING_BYTES && hb + 2 <= 256) {
+      if (2 * (a_region + nt * b_cta) <= RING_BYTES && hb + nt - 1 <= 256) {
         for (int sgi = 0; sgi < p.nseg; ++sgi) {
           if (p.seg_slab[sgi] < 0) continue;
           const cuuint64_t ld = (cuuint64_t)p.seg_ld[sgi];
           cuuint64_t dims[4] = {(cuuint64_t)p.seg_C[sgi], (cuuint64_t)p.img_W, (cuuint64_t)p.img_H, (cuuint64_t)p.slab_B};
           cuuint64_t strides[3] = {ld * 2, ld * 2 * p.img_W, ld * 2 * p.img_W * p.img_H};
-          cuuint32_t box[4] = {BK, (cuuint32_t)p.img_W, (cuuint32_t)(hb + 2), 1};
+          cuuint32_t box[4] = {BK, (cuuint32_t)p.img_W, (cuuint32_t)(hb + nt - 1), 1};
           int rc = encode_map(&p.a_slab_map[p.seg_slab[sgi]], p.seg_src[sgi], 4, dims, strides, box);
           if (rc != SD_OK) return rc;
         }
@@ -1294,7 +1317,7 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
         p.slab = 1;
         p.slab_bytes = slab_bytes;
         p.a_region_bytes = a_region;
-        groups = 3;
+        groups = nt;
       }
     }
     if (!slab_on)
@@ -1448,7 +1471,11 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
       p.seg_cblocks[nseg] = src.C / BK;
       p.seg_bk0[nseg] = (int)(((term == 2 ? K_half : 0) + k_off) / BK);
       p.seg_src[nseg] = base; p.seg_C[nseg] = src.C; p.seg_ld[nseg] = ld;
-      if (src.taps == 9 && !stride2 && up_phase < 0 && nslab < MAX_SLABS) p.seg_slab[nseg] = nslab++;
+      // slab candidates: 3x3 stride-1 segments; the 2x2-tap phases of the fused upsample + conv (two vertical taps per slab:
+      // 9 instead of 16 image rows per (channel block, tap column) at 16x16 -- that launch is bound by the L2 -> SM feed)
+      static const int want_slab_up = [] { const char* e = getenv("SDB_GEMM_SLAB_UP"); return e ? atoi(e) : 1; }();   // tuning knob
+      if (((src.taps == 9 && !stride2 && up_phase < 0) || (src.taps == 4 && up_phase >= 0 && want_slab_up)) && nslab < MAX_SLABS)
+        p.seg_slab[nseg] = nslab++;
       int rc;
       const cuuint64_t l2 = (cuuint64_t)ld * 2;
       if (stride2) {
@@ -1472,6 +1499,7 @@ static int conv_gemm_impl(const sd_gemm_src* srcs, int num_srcs, int B, int H, i
   p.nseg = nseg;
   p.num_kb = (int)(K / BK);
   p.slab_B = B;
+  p.slab_taps = up_phase >= 0 ? 2 : 3;
   if (gn && gn->gamma && gn->beta) {
     p.gn_gamma = gn->gamma; p.gn_beta = gn->beta; p.gn_eps = gn->eps; p.gn_swish = gn->swish;
     p.gn_raw_out = reinterpret_cast<__nv_bfloat16*>(gn->raw_out);
