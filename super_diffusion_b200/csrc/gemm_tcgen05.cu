@@ -1160,7 +1160,8 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // upsample phases: the strided-pixel store of the swapped epilogue needs a 16-pixel group inside one low-resolution row
   static const int want_swap_up = [] { const char* e = getenv("SDB_GEMM_SWAP_UP"); return e ? atoi(e) : 1; }();   // tuning knob
   const bool up_ok = p.up_phase < 0 || (want_swap_up && (p.img_W % 16) == 0 && N == MAX_BN);
-  const bool swap_epi_ok = want_swap && !p.flat && up_ok && !p.stride2 && (N % 128) == 0 && p.imgs_per_tile == 1 &&
+  static const int want_swap_s2 = [] { const char* e = getenv("SDB_GEMM_SWAP_S2"); return e ? atoi(e) : 1; }();   // tuning knob: stride-2 convs swapped too
+  const bool swap_epi_ok = want_swap && !p.flat && up_ok && (!p.stride2 || want_swap_s2) && (N % 128) == 0 && p.imgs_per_tile == 1 &&
                            (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
                            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0;
   if (swap_epi_ok && all_1tap && N > 128) p.block_n = 128;
