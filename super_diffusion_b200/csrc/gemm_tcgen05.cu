@@ -1161,8 +1161,14 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   static const int want_swap_up = [] { const char* e = getenv("SDB_GEMM_SWAP_UP"); return e ? atoi(e) : 1; }();   // tuning knob
   const bool up_ok = p.up_phase < 0 || (want_swap_up && (p.img_W % 16) == 0 && N == MAX_BN);
   static const int want_swap_s2 = [] { const char* e = getenv("SDB_GEMM_SWAP_S2"); return e ? atoi(e) : 1; }();   // tuning knob: stride-2 convs swapped too
-  const bool swap_epi_ok = want_swap && !p.flat && up_ok && (!p.stride2 || want_swap_s2) && (N % 128) == 0 && p.imgs_per_tile == 1 &&
-                           (p.tiles_per_img % 2) == 0 && !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
+  // several images per 128-pixel tile (8x8, 4x4): a 256-pixel unit spans images, which the swapped epilogue allows when nothing in
+  // it is per image -- no time-embedding row bias, no per-tile channel sums, no fused GroupNorm (those launches keep the
+  // thread = pixel-row form, whose fused epilogue holds whole images per tile)
+  static const int want_swap_multi = [] { const char* e = getenv("SDB_GEMM_SWAP_MULTI"); return e ? atoi(e) : 1; }();   // tuning knob
+  const bool unit_ok = p.imgs_per_tile == 1 ? (p.tiles_per_img % 2) == 0
+                                            : (want_swap_multi && !rowbias && !stats_out && p.gn_gamma == nullptr && p.up_phase < 0);
+  const bool swap_epi_ok = want_swap && !p.flat && up_ok && (!p.stride2 || want_swap_s2) && (N % 128) == 0 && unit_ok &&
+                           !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
                            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0;
   if (swap_epi_ok && all_1tap && N > 128) p.block_n = 128;
   p.n_tiles = (n_pad + p.block_n - 1) / p.block_n;
