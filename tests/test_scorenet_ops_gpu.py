@@ -295,7 +295,9 @@ def test_upconv_gemm_equals_upsample_then_conv(cuda, B, H, C, N):
         assert (a.float() - b.float()).abs().max().item() <= 6.5e-2
 
 
-@pytest.mark.parametrize("B,H,C,N", [(3, 32, 128, 128), (5, 16, 256, 256), (9, 8, 256, 256), (40, 32, 64, 64)])
+@pytest.mark.parametrize("B,H,C,N", [(3, 32, 128, 128), (5, 16, 256, 256), (9, 8, 256, 256), (40, 32, 64, 64),
+                                     (600, 32, 64, 128),      # 1200 output tiles: two-tile units, operands swapped ([channel][pixel] epilogue)
+                                     (600, 16, 64, 256)])     # 8x8 outputs, 300 tiles: cta_group::2 pairs, swapped, a unit spans four images
 def test_conv_gemm_stride2_tma(cuda, B, H, C, N):
     """Downsample conv (cifar/models/layers.py:533): 3x3, stride 2, SAME => pad (0,1); stride carried by the TMA descriptor.
     Also equals the explicit im2col gather + 1x1 GEMM path."""
@@ -474,6 +476,28 @@ def test_attention_core_fused(cuda, nb, Sp, block, C, stats):
     _close(out2, ref2)
 
 
+@pytest.mark.parametrize("B,H,C,N,taps", [(600, 8, 64, 256, 9), (601, 8, 128, 256, 1), (2400, 4, 64, 256, 9), (1200, 8, 64, 128, 1)])
+def test_conv_gemm_swapped_units_spanning_images(cuda, B, H, C, N, taps):
+    """Low-resolution layers at batches that give >= 148 tiles: operand-swapped 256-pixel units that span several images (8x8: four,
+    4x4: sixteen) -- allowed because nothing in these epilogues is per image (bias only); 3x3 + identity-free 1-tap segment, 1x1
+    layers as two 128-channel column blocks, an odd tile count; against the fp64 convolution."""
+    g = torch.Generator().manual_seed(B + H + C + N + taps)
+    x = _bf(torch.randn(B, H, H, C, generator=g))
+    x1 = _bf(torch.randn(B, H, H, C, generator=g))
+    K = taps * C
+    w = _bf(torch.cat([torch.randn(N, K, generator=g) / math.sqrt(K), torch.randn(N, C, generator=g) / math.sqrt(C)], dim=1))
+    bias = torch.randn(N, generator=g)
+    out = ops.conv_gemm([(x.to(cuda), taps), (x1.to(cuda), 1)], w.to(cuda), bias=bias.to(cuda))
+    torch.cuda.synchronize()
+    wd = w.double()
+    if taps == 9:
+        ref = F.conv2d(x.double().permute(0, 3, 1, 2), wd[:, :K].reshape(N, 3, 3, C).permute(0, 3, 1, 2), padding=1).permute(0, 2, 3, 1)
+    else:
+        ref = torch.einsum("bhwc,nc->bhwn", x.double(), wd[:, :K])
+    ref = ref + torch.einsum("bhwc,nc->bhwn", x1.double(), wd[:, K:]) + bias.double()
+    _close(out, ref)
+
+
 def test_conv_gemm_pair_two_images_per_tile(cuda):
     """8x8 level at a batch that gives 148..295 m-tiles: cta_group::2 pairs with TWO images per 128-row tile (row-bias table
     with two rows per CTA), 1-tap segments, odd pair count."""
@@ -605,6 +629,8 @@ def test_fused_groupnorm_is_deterministic_under_repetition(cuda):
     ({"SDB_GN_GX": "0"}, "test_fused_groupnorm_is_deterministic_under_repetition"),
     ({"SDB_ATTN_V1": "1"}, "test_attention_core_fused"),                                              # the round-1 attention kernel
     ({"SDB_GEMM_PAIR128": "0"}, "test_conv_gemm_with_fused_groupnorm and 512-4-512 and False"),       # single-CTA 128-column tiles at 4x4
+    ({"SDB_GEMM_SWAP_UP": "0", "SDB_GEMM_SLAB_UP": "0", "SDB_GEMM_SWAP_S2": "0", "SDB_GEMM_SWAP_MULTI": "0"},
+     "test_upconv_gemm_large_batches or test_conv_gemm_stride2_tma or test_conv_gemm_swapped_units_spanning_images"),   # thread = pixel-row forms
 ])
 def test_fallback_kernels_behind_tuning_knobs(cuda, env, select):
     """The launch shapes that are no longer the default stay reachable (more than 8 streams asking for the global-memory
