@@ -498,6 +498,27 @@ def test_conv_gemm_swapped_units_spanning_images(cuda, B, H, C, N, taps):
     _close(out, ref)
 
 
+@pytest.mark.parametrize("B,N", [(300, 3), (37, 3), (301, 10)])
+def test_conv_gemm_narrow_fp32_output(cuda, B, N):
+    """The output head (3x3 conv to `num_channels` = 3 fp32 channels, cifar/models/ddpm.py:98-100) at batches with two-tile
+    units and below, and a 10-channel variant: against the fp64 convolution, and the large batch against itself in small batches.
+    (Padding the three weight rows to the M = 128 operand of the swapped form was measured and dropped: 202 us vs 121 us at
+    batch 512 -- the zero-filled weight tiles cost the same shared-memory traffic as a full 128-channel layer.)"""
+    H, C = 32, 64
+    g = torch.Generator().manual_seed(B + N)
+    x = _bf(torch.randn(B, H, H, C, generator=g))
+    w = _bf(torch.randn(16, 9 * C, generator=g) / math.sqrt(9 * C))
+    bias = torch.randn(16, generator=g)
+    out = ops.conv_gemm([(x.to(cuda), 9)], w.to(cuda), bias=bias.to(cuda), out_f32=True, n_out=N)
+    torch.cuda.synchronize()
+    assert out.shape == (B, H, H, N) and out.dtype == torch.float32
+    ref = F.conv2d(x.double().permute(0, 3, 1, 2), w[:N].double().reshape(N, 3, 3, C).permute(0, 3, 1, 2), bias[:N].double(),
+                   padding=1).permute(0, 2, 3, 1)
+    assert torch.allclose(out.cpu().double(), ref, rtol=1e-4, atol=1e-4)
+    small = ops.conv_gemm([(x[:5].contiguous().to(cuda), 9)], w.to(cuda), bias=bias.to(cuda), out_f32=True, n_out=N)
+    assert torch.allclose(out[:5], small, rtol=1e-5, atol=1e-5)
+
+
 def test_conv_gemm_pair_two_images_per_tile(cuda):
     """8x8 level at a batch that gives 148..295 m-tiles: cta_group::2 pairs with TWO images per 128-row tile (row-bias table
     with two rows per CTA), 1-tap segments, odd pair count."""
