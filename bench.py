@@ -635,9 +635,9 @@ def _config4_sd(torch, dev, ops, hbm_peak):
 
 def _recorded_traffic(B):
     """DRAM bytes (read + written) of one timestep's tensor-core launches at batch 512, from the committed ncu launch list
-    (profiles/r04_step_traffic.json = tools/summarize_traffic.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+    (profiles/r05_step_traffic.json = tools/summarize_traffic.py over `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
     of this bench; a profiler artefact, not measured in this run).  None at any other batch or when the file is absent."""
-    p = os.path.join(ROOT, "profiles", "r04_step_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r05_step_traffic.json")
     if B != BATCH_PER_GPU or not os.path.exists(p):
         return None
     try:
