@@ -680,8 +680,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           float* ctot = gsum + 4 * BM;             // [which][128]: channel totals over the image
           float* xsum = ctot + 2 * BM;             // [parity][which][128]: this CTA's channel sums, read by its cluster peers
           const bool xchg = !PAIR && csize > 1;
+          // several images per unit (8x8: HW = 64, a 256-pixel unit holds four): the 64-column chunk `it` IS image `it` -- this
+          // thread holds 32 of its pixels, the partner warp (other chalf) the other 32 -- so bias, sums and statistics are per chunk
+          const bool mi = p.imgs_per_tile > 1;
+          float bvi[4] = {bv, bv, bv, bv};
+          if (mi && ch_ok && p.rowbias) {
+            const int img0 = (int)(pix0 / p.HW), img_last = (p.M_total - 1) / p.HW;
+            const float b0 = p.bias ? p.bias[ch] : 0.f;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) bvi[it] = b0 + p.rowbias[(size_t)min(img0 + it, img_last) * p.rowbias_ld + ch];
+          }
           uint32_t pk[64];
-          float ssum = 0.f, ssq = 0.f;
+          float ps[4], pq[4];
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = chalf * 32 + it * 64;
@@ -689,16 +699,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
             tmem_ld16(taddr + c, r[0]);
             tmem_ld16(taddr + c + 16, r[1]);
             tmem_wait_ld();
+            float ssum = 0.f, ssq = 0.f;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
-                const float x0 = __uint_as_float(r[h][2 * jj]) + bv, x1 = __uint_as_float(r[h][2 * jj + 1]) + bv;
+                const float x0 = __uint_as_float(r[h][2 * jj]) + bvi[it], x1 = __uint_as_float(r[h][2 * jj + 1]) + bvi[it];
                 ssum += x0 + x1;
                 ssq = fmaf(x0, x0, fmaf(x1, x1, ssq));
                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
                 pk[it * 16 + h * 8 + jj] = *reinterpret_cast<const uint32_t*>(&h2);
               }
+            ps[it] = ssum; pq[it] = ssq;
           }
           tcgen05_fence_before();                  // accumulator drained: hand it back to the MMA warp now
           __syncwarp();
@@ -708,12 +720,39 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           }
           acc ^= 1;
           if (acc == 0) acc_phase ^= 1;
-          gsum[(chalf * 2 + 0) * BM + row] = ssum;
-          gsum[(chalf * 2 + 1) * BM + row] = ssq;
+          float rs4[4], sh4[4];
+          const int gw = et / BM, gn_n = et - gw * BM;                   // threads 0..255: (which, channel)
+          float unit_tot = 0.f;                                          // this unit's channel total (raw stats; single-image units)
+          if (mi) {
+            float* gmi = ebias;                    // [image][chalf][which][128]
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              gmi[((it * 2 + chalf) * 2 + 0) * BM + row] = ps[it];
+              gmi[((it * 2 + chalf) * 2 + 1) * BM + row] = pq[it];
+            }
+            const float gam_m = ch_ok ? p.gn_gamma[ch] : 0.f, bet_m = ch_ok ? p.gn_beta[ch] : 0.f;    // issued ahead of the barrier
+            epi_bar();
+            const int cpg_m = p.N_out >> 5, g0_m = (row / cpg_m) * cpg_m;
+            const float ginv_m = 1.f / ((float)p.HW * (float)cpg_m);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              float gs = 0.f, gq = 0.f;
+              for (int cc = 0; cc < cpg_m; ++cc) {
+                gs += gmi[((it * 2 + 0) * 2 + 0) * BM + g0_m + cc] + gmi[((it * 2 + 1) * 2 + 0) * BM + g0_m + cc];
+                gq += gmi[((it * 2 + 0) * 2 + 1) * BM + g0_m + cc] + gmi[((it * 2 + 1) * 2 + 1) * BM + g0_m + cc];
+              }
+              const float gmean = gs * ginv_m;
+              const float gvar = fmaxf(fmaf(gq, ginv_m, -gmean * gmean), 0.f);
+              rs4[it] = rsqrtf(gvar + p.gn_eps) * gam_m;
+              sh4[it] = bet_m - gmean * rs4[it];
+            }
+            epi_bar();                             // every thread has read the sums before the next unit overwrites them
+          } else {
+          gsum[(chalf * 2 + 0) * BM + row] = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          gsum[(chalf * 2 + 1) * BM + row] = (pq[0] + pq[1]) + (pq[2] + pq[3]);
           epi_bar();
           const int gbuf = (int)(gn_it & 1u);
-          const int gw = et / BM, gn_n = et - gw * BM;                   // threads 0..255: (which, channel)
-          const float unit_tot = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];    // this unit's channel total (raw stats)
+          unit_tot = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
           int* gx_done = nullptr;
           if (xchg) {
             xsum[(gbuf * 2 + gw) * BM + gn_n] = gsum[(0 * 2 + gw) * BM + gn_n] + gsum[(1 * 2 + gw) * BM + gn_n];
@@ -775,6 +814,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
           const float rs = rsqrtf(gvar + p.gn_eps) * gam;
           const float sh = bet - gmean * rs;
 #pragma unroll
+          for (int it = 0; it < 4; ++it) { rs4[it] = rs; sh4[it] = sh; }
+          }      // !mi
+#pragma unroll
           for (int it = 0; it < 4; ++it) {
             const int c = chalf * 32 + it * 64;
 #pragma unroll
@@ -783,7 +825,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tcgen05_kernel(const __g
 #pragma unroll
               for (int jj = 0; jj < 8; ++jj) {
                 const uint32_t w = pk[it * 16 + h * 8 + jj];
-                const float y0 = fmaf(__uint_as_float(w << 16), rs, sh), y1 = fmaf(__uint_as_float(w & 0xFFFF0000u), rs, sh);
+                const float y0 = fmaf(__uint_as_float(w << 16), rs4[it], sh4[it]), y1 = fmaf(__uint_as_float(w & 0xFFFF0000u), rs4[it], sh4[it]);
                 v[2 * jj] = p.gn_swish ? swish_tanh_f(y0) : y0;
                 v[2 * jj + 1] = p.gn_swish ? swish_tanh_f(y1) : y1;
               }
@@ -1165,8 +1207,14 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
   // it is per image -- no time-embedding row bias, no per-tile channel sums, no fused GroupNorm (those launches keep the
   // thread = pixel-row form, whose fused epilogue holds whole images per tile)
   static const int want_swap_multi = [] { const char* e = getenv("SDB_GEMM_SWAP_MULTI"); return e ? atoi(e) : 1; }();   // tuning knob
+  // ... or, at 8x8 (a 256-pixel unit = four whole images, one per 64-column chunk of the accumulator), the fused GroupNorm epilogue
+  // with per-chunk bias and statistics (the conditions repeat the fuse test further down: a swapped multi-image launch with a
+  // GroupNorm or a row bias must end up fused)
+  const bool mi_fuse_ok = want_swap_multi >= 1 && p.gn_gamma != nullptr && gn_fuse_level() >= 1 && !(flags & SD_GEMM_SPLIT3) && p.num_kb >= 16 &&
+                          p.HW == 64 && !stats_out && p.up_phase < 0 && !p.stride2 && (N % 32) == 0 && (BM % (N / 32)) == 0 && (N % 128) == 0 &&
+                          getenv("SDB_GN_MULTI_SWAP_OFF") == nullptr;
   const bool unit_ok = p.imgs_per_tile == 1 ? (p.tiles_per_img % 2) == 0
-                                            : (want_swap_multi && !rowbias && !stats_out && p.gn_gamma == nullptr && p.up_phase < 0);
+                                            : ((want_swap_multi && !rowbias && !stats_out && p.gn_gamma == nullptr && p.up_phase < 0) || mi_fuse_ok);
   const bool swap_epi_ok = want_swap && !p.flat && up_ok && (!p.stride2 || want_swap_s2) && (N % 128) == 0 && unit_ok &&
                            !(flags & (SD_EPI_OUT_F32 | SD_EPI_SOFTMAX | SD_EPI_SWISH)) && !residual &&
                            (out_ld % 2) == 0 && ((uintptr_t)out % 4) == 0;
@@ -1230,7 +1278,9 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
     // 64-wide K block, went from 72 to 157 us fused against a 54 us GroupNorm pass)
     const bool long_k = p.num_kb >= 16;
     bool fuse = long_k && want_gn_fuse && p.gn_gamma != nullptr && !(flags & SD_GEMM_SPLIT3) && p.swap && (N % 32) == 0 && (BM % (N / 32)) == 0 && p.cluster == (p.pair ? 2 : 1);
-    if (fuse) {
+    if (fuse && p.imgs_per_tile > 1) {
+      fuse = mi_fuse_ok;                       // 8x8: four whole images per unit, statistics per 64-column chunk (no exchange)
+    } else if (fuse) {
       if (p.pair) {
         fuse = p.tiles_per_img == 2;
       } else {

@@ -545,7 +545,7 @@ def test_conv_gemm_pair_two_images_per_tile(cuda):
     (512, 32, 256, 128, None),     # K = 2304 (the widest 32x32 conv1 of the up path takes 384 channels; 256 here)
     (8, 32, 128, 128, False),      # too few tiles for the swapped shapes: unfused fallback, raw output + stats
     (64, 8, 256, 256, True),       # thread = pixel-row tiles holding whole images: 8x8, two per 128-row tile, 128-column tiles
-    (512, 8, 512, 256, True),      # ... cta_group::2 pairs with 256-column tiles (the benched 8x8 layers)
+    (512, 8, 512, 256, True),      # ... at >= 148 tiles: cta_group::2 pairs, operands swapped, four images per unit with per-chunk statistics
     (37, 8, 256, 256, True),       # ... ragged last tile
     (512, 4, 512, 256, True),      # 4x4: eight images per tile, statistics inside 16-lane segments
     (2048, 4, 256, 256, True),     # ... in pair mode
@@ -652,6 +652,7 @@ def test_fused_groupnorm_is_deterministic_under_repetition(cuda):
     ({"SDB_GEMM_PAIR128": "0"}, "test_conv_gemm_with_fused_groupnorm and 512-4-512 and False"),       # single-CTA 128-column tiles at 4x4
     ({"SDB_GEMM_SWAP_UP": "0", "SDB_GEMM_SLAB_UP": "0", "SDB_GEMM_SWAP_S2": "0", "SDB_GEMM_SWAP_MULTI": "0"},
      "test_upconv_gemm_large_batches or test_conv_gemm_stride2_tma or test_conv_gemm_swapped_units_spanning_images"),   # thread = pixel-row forms
+    ({"SDB_GN_MULTI_SWAP_OFF": "1"}, "test_conv_gemm_with_fused_groupnorm and (512-8-512 or 64-8-256 or 37-8-256) and False"),   # 8x8 fused GroupNorm, pixel-row form
 ])
 def test_fallback_kernels_behind_tuning_knobs(cuda, env, select):
     """The launch shapes that are no longer the default stay reachable (more than 8 streams asking for the global-memory
