@@ -153,10 +153,14 @@ def run_b200(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    result_fd = None
     if world > 1:
-        # NCCL_DEBUG=VERSION (set on the GPU boxes) prints "NCCL version ..." on stdout ahead of the result: stdout carries ONE JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG=VERSION (set on the GPU boxes) makes NCCL print "NCCL version ..." on stdout when the communicator is created
+        # (NCCL_DEBUG_FILE does not move it); stdout carries ONE JSON line, so everything else this process and its libraries
+        # write to file descriptor 1 goes to stderr and the result is written to the saved descriptor at the end
+        sys.stdout.flush()
+        result_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     _lib.require_device()
     hbm_peak, tf_peak, peak_kind = _peaks()
@@ -392,7 +396,11 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": sample_b / (N_STEPS * sec), "unit": "samples/s", "cores": threads, "kind": "port",
                                 "sample": f"{k_cpu} timed steps at batch {sample_b} (2 fp32 oracle score-net forwards + OR step each, "
                                           f"{sec * k_cpu:.1f} s of CPU work), scaled linearly to {N_STEPS} steps"}
-    print(json.dumps(line), flush=True)
+    if result_fd is not None:
+        sys.stdout.flush()
+        os.write(result_fd, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
