@@ -185,9 +185,11 @@ int sd_conv_gemm(const sd_gemm_src* srcs_host, int num_srcs, int B, int H, int W
  * (cifar/models/layers.py:552-558: h = conv3x3(h); h += Dense(temb); h = act(normalize(h))), and conv2 / the first conv when the
  * next layer starts with a GroupNorm of that tensor (the next block's act(normalize(x)) at :552, an AttnBlock's normalize(x) at
  * :498, the final act(normalize(h)) of cifar/models/ddpm.py:98).  Where the tile shape allows it the 32-group statistics of the
- * whole image are formed inside the GEMM epilogue (channel sums are thread-local in the [channel][pixel] epilogue; the tiles of one
- * 32x32 image exchange theirs through distributed shared memory inside a thread-block cluster of 4; pixel-row tiles that hold whole
- * 8x8 / 4x4 images reduce over lane segments) and `out` receives [swish](GN(conv) * gamma + beta) directly: *fused_host = 1.
+ * whole image are formed inside the GEMM epilogue (channel sums are thread-local in the [channel][pixel] epilogue; the four CTAs of
+ * one 32x32 image exchange theirs through global memory inside a cooperative launch -- or, with SDB_GN_GX=0 / on more than 8
+ * streams, through distributed shared memory inside a thread-block cluster of 4; a unit of four 8x8 images keeps per-image sums;
+ * pixel-row tiles that hold whole 8x8 / 4x4 images reduce over lane segments) and `out` receives [swish](GN(conv) * gamma + beta)
+ * directly: *fused_host = 1.
  * raw_out (optional): a second output, the raw conv result (bf16, layout of `out`), for tensors that also stay on the residual
  * stream; `stats_out` then carries the raw tensor's channel sums (per 256-pixel unit: the second 128-pixel slot of a unit is 0).
  * Where the shape does not allow fusion (small batches, N != 256 at low resolution, split precision) the call behaves like
@@ -241,7 +243,9 @@ int sd_batched_gemm_stats(const void* A, int lda, long long strideA, const void*
  * with the softmax restricted to the diagonal block of `block` key columns row i belongs to (block < S packs S/block small
  * images into one batch entry).  Q, K: bf16 [batch][S][ld] (channel-contiguous), Vt: bf16 [batch][C][ldv] = V transposed
  * (key-contiguous), residual / out: bf16 [batch][S][C]; S in {128, 256}, C in {64, 128, 192, 256}.  The probability matrix
- * stays in shared memory (softmax epilogue writes the UMMA A operand of the second product).  stats_out (optional, block == S):
+ * stays in shared memory (the softmax writes the UMMA operand of the second product).  C = 256 with block % 16 == 0 (the
+ * score-net's shape) takes the two-tile software-pipelined kernel, in which the residual is accumulated on the tensor cores
+ * (residual rows must be contiguous: [batch][S][C]).  stats_out (optional, block == S):
  * fp32 [batch][S/128][2][C] channel sums of out for sd_groupnorm_swish. */
 int sd_attention_core(const void* Q, int ldq, long long strideQ, const void* K, int ldk, long long strideK,
                       const void* Vt, int ldv, long long strideV, int batch, int S, int C, float scale, int block,
