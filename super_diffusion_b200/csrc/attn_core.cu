@@ -676,16 +676,14 @@ extern "C" int sd_attention_core(const void* Q, int ldq, long long strideQ, cons
   }
   p.nb = batch; p.Sp = S; p.C = C; p.block = block; p.tiles = batch * (S / AC_BM);
   p.scale = scale; p.bias = bias; p.residual = (const __nv_bfloat16*)residual; p.out = (__nv_bfloat16*)out; p.stats_out = stats_out;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  static bool force_v1 = false;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_core_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
-    if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(attn_core_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
-    const char* e = getenv("SDB_ATTN_V1");          // A/B switch for tools/layer_bench.py: the round-1 kernel
-    force_v1 = e != nullptr && e[0] == '1';
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(attn_core_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_v2_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_core_v2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AC2_SMEM);
+    return e;
   });
+  static const bool force_v1 = [] { const char* e = getenv("SDB_ATTN_V1"); return e != nullptr && e[0] == '1'; }();   // A/B switch: the round-1 kernel
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "sd_attention_core");
   const int grid = p.tiles < num_sms() ? p.tiles : num_sms();
   if (C == 256 && (block % 16) == 0 && scale > 0.f && !force_v1) {

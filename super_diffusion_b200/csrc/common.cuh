@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <utility>
 
@@ -18,6 +19,22 @@ int check_cuda(cudaError_t e, const char* what);
 constexpr int kErrInvalidArg = -1;
 constexpr int kErrUnsupported = -2;
 constexpr int kErrCuda = -3;
+
+// Kernel function attributes (cudaFuncAttributeMaxDynamicSharedMemorySize ...) belong to a device's context: a process that drives
+// several GPUs has to set them once per device, not once per process.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  cudaError_t err[64] = {};
+  template <typename F>
+  cudaError_t run(F&& fn) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!done[dev]) { err[dev] = fn(); done[dev] = true; }
+    return err[dev];
+  }
+};
 
 // ---- streaming 128-bit global accesses ---------------------------------------
 // Inputs of the fused step are read exactly once: keep them out of L1.

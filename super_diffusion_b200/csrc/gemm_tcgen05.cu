@@ -1417,12 +1417,11 @@ static int launch_gemm(GemmParams& p, int N, long K, const void* Wt, int ldb, lo
                       (p.out_batch_stride % out_align == 0);
   if (!vec_ok && N >= 16) return fail(kErrInvalidArg, std::string(who) + ": out/residual/bias must be 16-byte aligned (ld multiple of 8 bf16 / 4 fp32)");
 
-  static std::once_flag attr_once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+  static PerDeviceOnce attr_once;
+  const cudaError_t attr_err = attr_once.run([] {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM);
+    return e;
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, who);
   const int m_units_h = p.dual ? (p.m_tiles + 1) / 2 : p.m_tiles;

@@ -862,14 +862,13 @@ int sd_conv_in(const float* x, int B, int H, int W, int Cin, const float* w_hwio
   if (Cout < 32 || Cout % 32 || Cout > 512) return fail(kErrInvalidArg, "sd_conv_in: Cout must be a multiple of 32, <= 512");
   if (B == 0) return SD_OK;
   const size_t smem = sizeof(float) * ((size_t)9 * Cin * Cout + Cout);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static PerDeviceOnce attr_once;
+  attr_once.run([] {
     cudaFuncSetAttribute(conv_in_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(conv_in_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(conv_in_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_done = true;
-  }
+    return cudaFuncSetAttribute(conv_in_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  });
   const size_t total = (((size_t)B * H * W + 31) / 32) * 32 * (Cout / 32);
   const unsigned grid = grid_for(total, 256);
   cudaStream_t st = (cudaStream_t)stream;

@@ -665,3 +665,30 @@ def test_fallback_kernels_behind_tuning_knobs(cuda, env, select):
                         "-p", "no:cacheprovider"], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert " passed" in r.stdout and "no tests ran" not in r.stdout, r.stdout[-500:]
+
+
+def test_device_global_buffers_are_per_device(cuda):
+    """The GroupNorm exchange area and the attention identity tiles are `__device__` variables (one instance per device): one
+    process driving two GPUs must get the same bits on both.  Skipped on single-GPU boxes."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    g = torch.Generator().manual_seed(5)
+    B = 160
+    x = _bf(torch.randn(B, 32, 32, 128, generator=g))
+    w = _bf(torch.randn(128, 9 * 128, generator=g) / math.sqrt(9 * 128))
+    rb = torch.randn(B, 128, generator=g)
+    gam, bet = 1 + 0.2 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    q = _bf(torch.randn(8, 256, 256, generator=g))
+    k = _bf(torch.randn(8, 256, 256, generator=g))
+    vt = _bf(torch.randn(8, 256, 256, generator=g))
+    res = _bf(torch.randn(8, 256, 256, generator=g))
+    outs = []
+    for d in (1, 0):                       # the second device first: a cached device-0 address would fault or miscompute here
+        dev = torch.device("cuda", d)
+        with torch.cuda.device(dev):
+            o = ops.conv_gemm([(x.to(dev), 9)], w.to(dev), rowbias=rb.to(dev), want_stats=True, gn=(gam.to(dev), bet.to(dev)))
+            a = ops.attention_core(q.to(dev), k.to(dev), vt.to(dev), 256 ** -0.5, block=256, residual=res.to(dev), C=256)
+            torch.cuda.synchronize(dev)
+            assert o.gn_fused
+            outs.append((o.cpu(), a.cpu()))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
